@@ -1,0 +1,76 @@
+/* Host-driver C API (ctypes-facing) used by tests/ and bench.py.
+ *
+ * This is NOT the drop-in boundary (that is include/saamge_b200.h, the C ABI of
+ * the CUDA library).  It is a thin handle-based wrapper over the C++ host
+ * mirror of the reference's tg_ / ml_ entry points (saamge_b200/host), playing the
+ * role of the reference's test drivers (amg/test/mltest/mltest.cpp): generate a
+ * problem, partition it, build the hierarchy, run PCG, and read back any
+ * intermediate object for comparison with the oracle.
+ */
+#ifndef SAAMGE_B200_DRIVER_H
+#define SAAMGE_B200_DRIVER_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Options of the mltest driver that matter on the hot path
+ * (amg/test/mltest/mltest.cpp:332-404) + MultilevelParameters (amg/inc/ml.hpp:59-114). */
+typedef struct
+{
+    int num_levels;          /* total levels, >= 2 (--num-levels) */
+    int first_elems_per_agg; /* --first-elems-per-agg */
+    int elems_per_agg;       /* --elems-per-agg (coarser levels) */
+    int first_nu_pro;        /* --first-nu-pro */
+    int nu_pro;              /* --nu-pro */
+    int nu_relax;            /* --nu-relax, SAS polynomial degree 3*nu+1 */
+    double first_theta;      /* --first-theta */
+    double theta;            /* --theta */
+    int avoid_ess_bdr_dofs;  /* MultilevelParameters::avoid_ess_bdr_dofs (always 1 upstream) */
+    int partition_kind;      /* 0 = METIS k-way (reference), 1 = regular blocks (fixtures) */
+    int block[3];            /* block edge in elements per direction, finest level (partition_kind 1) */
+    int coarse_block;        /* fine AEs per coarse AE per direction (partition_kind 1) */
+    int testmesh_inject;     /* 1 = add the all-ones vector on AE 0 (amg/src/interp.cpp:510-524) */
+} sa_drv_params_t;
+
+void sa_drv_default_params(sa_drv_params_t *p);
+
+/* ---- problem (input producer) ---- */
+void *sa_drv_problem_create(int dim, int nx, int ny, int nz, int order, int coef_kind,
+                            double contrast, uint64_t seed);
+void sa_drv_problem_destroy(void *prob);
+/* Fine-level partition + relations; returns number of AEs. */
+int sa_drv_problem_partition(void *prob, const sa_drv_params_t *p);
+
+/* ---- hierarchy through the B200 path (sa_gpu_* C ABI underneath) ---- */
+/* device: CUDA device ordinal.  ae_shard / ae_nshards: this process handles AEs
+ * of shard ae_shard out of ae_nshards in the local spectral stage of the finest
+ * level (0,1 = all). */
+void *sa_drv_ml_build(void *prob, const sa_drv_params_t *p, int device);
+/* Runs PCG with the V-cycle preconditioner on the device; returns iterations
+ * (negative on failure, amg/src/mfem_addons.cpp:201,232). */
+int sa_drv_ml_pcg(void *hier, int maxiter, double rtol, double atol);
+/* Pull every level's device results into the host record (for comparisons). */
+int sa_drv_ml_download(void *hier);
+void sa_drv_hier_destroy(void *hier);
+
+/* ---- generic read access (problem, relations, hierarchy records) ----
+ * obj   : problem or hierarchy handle
+ * name  : e.g. "A.I", "elem_to_dof.J", "AE_to_dof.I", "mises", "evals", "evects",
+ *         "tent_interp.I", "Ac.A", "pcg.brr", "timing.<stage>" ...
+ * level : hierarchy level (0 = finest); ignored for problem-only arrays
+ * dtype : 0 = int32, 1 = int64, 2 = float64, 3 = int8
+ * Returns 0 on success, nonzero if the name is unknown. */
+int sa_drv_get(void *obj, const char *name, int level, const void **ptr, int64_t *count,
+               int *dtype);
+/* Scalars by name ("ND", "nparts", "num_mises", "num_levels", "pcg.iterations",
+ * "time.<stage>" in seconds, ...).  Returns NaN for unknown names. */
+double sa_drv_get_scalar(void *obj, const char *name, int level);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif
