@@ -2,7 +2,7 @@
 #   saamge_b200/lib/libsaamge_b200.so   CUDA kernels + C ABI (include/saamge_b200.h), sm_100a
 #   saamge_b200/lib/libsaamge_host.so   C++ host mirror of the reference API + driver API
 #   oracle/liboracle.so                 CPU oracle (test infrastructure only)
-CXX ?= g++
+CXX := g++
 NVCC ?= /usr/local/cuda/bin/nvcc
 CUDA_HOME ?= /usr/local/cuda
 CXXFLAGS = -O2 -g -fPIC -fopenmp -std=c++14 -Wall -Wno-unknown-pragmas

@@ -1,0 +1,197 @@
+/* saamge_b200 -- C ABI of the B200 (sm_100a) implementation of SAAMGE's spectral
+ * AMGe hot path.  This is the drop-in boundary: plain pointers and sizes, no C++
+ * or torch types.  A maintainer of the reference binds these entry points from
+ * the reference's own C++ at the call sites cited with each function (see
+ * INTEGRATION.md for the stubs).  All file:line citations are relative to the
+ * reference tree (amg/...).
+ *
+ * Conventions
+ *   - every function returns 0 on success, nonzero on failure; sa_gpu_last_error()
+ *     gives the message.  The reference has no error codes (SA_ASSERT aborts,
+ *     amg/inc/common.hpp:635-647); the C++ shim maps nonzero to that behaviour.
+ *   - host pointers in, host pointers out, caller allocated; nothing passed in is
+ *     retained after the call returns (data is copied to the device).
+ *   - index data int32, floating point FP64, dense blocks column-major
+ *     (mfem::Table / SparseMatrix / DenseMatrix layouts).
+ *   - one context per GPU; a context and the levels created from it are not
+ *     re-entrant (the reference is single threaded per rank as well).
+ */
+#ifndef SAAMGE_B200_H
+#define SAAMGE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sa_gpu_ctx sa_gpu_ctx;
+typedef struct sa_gpu_level sa_gpu_level;
+typedef struct sa_gpu_solver sa_gpu_solver;
+
+/* ---- context ---- */
+int sa_gpu_ctx_create(int device, sa_gpu_ctx **ctx);
+void sa_gpu_ctx_destroy(sa_gpu_ctx *ctx);
+const char *sa_gpu_last_error(void);
+/* cudaStream_t of the context as an opaque pointer (for event timing in bench.py) */
+void *sa_gpu_ctx_stream(sa_gpu_ctx *ctx);
+int sa_gpu_ctx_sync(sa_gpu_ctx *ctx);
+/* number of kernel launches issued through this context so far */
+int64_t sa_gpu_ctx_launch_count(sa_gpu_ctx *ctx);
+/* ms between two points: call with begin!=0 to record the start event, then with
+   begin==0 to record the end event, synchronise and return elapsed ms (CUDA events
+   on the context's stream) */
+double sa_gpu_ctx_timer(sa_gpu_ctx *ctx, int begin);
+
+/* ---- one level: the integer data contract agg_partitioning_relations_t
+ *      (amg/inc/aggregates.hpp:120-179) + operator + element matrices ---- */
+typedef struct
+{
+    int ND;        /* dofs */
+    int NE;        /* elements (fine elements, or finer AEs on coarse levels) */
+    int nparts;    /* AEs */
+    int num_mises; /* MISes */
+    const int *elem_to_dof_I, *elem_to_dof_J;
+    const int *dof_to_elem_I, *dof_to_elem_J; /* rows ascending */
+    const int *AE_to_elem_I, *AE_to_elem_J;   /* rows ascending */
+    const int *AE_to_dof_I, *AE_to_dof_J;     /* local dof order inside each AE */
+    const int *dof_to_AE_I, *dof_to_AE_J;
+    const int *dof_id_inAE;                   /* parallel to dof_to_AE_J */
+    const int *partitioning;                  /* element -> AE */
+    const char *agg_flags;                    /* AGG_* bit flags per dof */
+    const int *mis_to_dof_I, *mis_to_dof_J;   /* rows ascending */
+    const int *mis_to_AE_I, *mis_to_AE_J;
+    const int *AE_to_mis_I, *AE_to_mis_J;     /* rows ascending */
+    const int *mises;                         /* dof -> MIS */
+    /* operator of this level (CSR).  NULL => use the coarse operator Ac that
+       sa_gpu_rap left on the device in the finer level. */
+    const int *A_I, *A_J;
+    const double *A_data;
+    /* dense element blocks (ElementMatrixDenseArray / what
+       ElementMatrixStandardGeometric::GetMatrix returns, amg/src/elmat.cpp:68-88,
+       242-253), element e at elmat[elmat_off[e]], size RowSize(e)^2, column-major.
+       NULL => use the blocks sa_gpu_coarse_elmats left on the device in the finer
+       level (ElementMatrixParallelCoarse, amg/src/elmat.cpp:105-195). */
+    const double *elmat;
+    const int64_t *elmat_off; /* NE+1 */
+    /* 1: agg_build_AE_stiffm_with_global (amg/src/aggregates.cpp:855-945,
+          bdr_cond_imposed = assemble_ess_diag = true, amg/src/elmat.cpp:51-52)
+       0: agg_build_AE_stiffm (amg/src/aggregates.cpp:959-1086) */
+    int assemble_with_global;
+    /* (coarse levels) finer MIS -> first coarse dof, finer num_mises+1 entries;
+       needed by sa_gpu_coarse_elmats */
+    const int *mis_coarsedofoffsets;
+} sa_gpu_level_desc;
+
+/* Copies the description to the device.  \a finer may be NULL (finest level). */
+int sa_gpu_level_create(sa_gpu_ctx *ctx, const sa_gpu_level_desc *desc, sa_gpu_level *finer,
+                        sa_gpu_level **level);
+void sa_gpu_level_destroy(sa_gpu_level *level);
+
+/* ---- setup: local spectral stage ---- */
+
+/* Replaces the loop of interp_compute_vectors (amg/src/interp.cpp:387-556):
+ * for every AE in [ae_begin, ae_end): BuildAEStiff (a2/a3), weighted-l1 D
+ * (mbox_snd_D_sparse_from_sparse, amg/src/mbox.cpp:913-949), and the eigenpairs of
+ * A z = lambda D z with lambda in (-1, theta] that the reference obtains from
+ * dsygvx (xpacks_calc_lower_eigens_dense, amg/src/xpacks.cpp:222-314; at least one
+ * pair is always returned).  inject_ones_ae0 reproduces the mltest fixture
+ * (amg/src/interp.cpp:510-524).  Results stay on the device. */
+int sa_gpu_local_spectral(sa_gpu_level *level, double theta, int ae_begin, int ae_end,
+                          int inject_ones_ae0);
+/* number of accepted vectors per AE (cut_evects_arr[i]->Width()), nparts ints */
+int sa_gpu_get_spectral_counts(sa_gpu_level *level, int *ae_m);
+/* evals: sum(m_i) doubles (AE-major, ascending per AE; an injected vector has no
+ * eigenvalue), evects: sum(n_i*m_i) doubles (cut_evects_arr[i], column-major),
+ * D: sum(n_i) doubles (rhs_matrices_arr[i] diagonal).  Any pointer may be NULL. */
+int sa_gpu_get_spectral(sa_gpu_level *level, double *evals, double *evects, double *D);
+/* Overwrites the device-resident eigenvectors of AEs [ae_begin, ae_end) (used when
+ * the AE loop was sharded over several GPUs and the pieces were exchanged by the
+ * caller).  Layout as returned by sa_gpu_get_spectral. */
+int sa_gpu_set_spectral(sa_gpu_level *level, int ae_begin, int ae_end, const int *ae_m,
+                        const double *evals, const double *evects, const double *D);
+/* assembled dense AE matrix (n x n column-major) of one AE -- the value of
+ * ElementMatrixProvider::BuildAEStiff(part) (amg/inc/elmat.hpp:71) */
+int sa_gpu_build_AE_stiff(sa_gpu_level *level, int part, double *dense_out);
+
+/* ---- setup: tentative prolongator ---- */
+
+/* Replaces ContribTent::contrib_mises (amg/src/contrib.cpp:699-714) +
+ * contrib_tent_finalize (:73-95): per MIS restrict (agg_restrict_to_agg_enforce,
+ * amg/src/aggregates.cpp:1143-1179), boundary filter (:102-163), column
+ * normalisation + thin SVD + rank cut sigma_i > 1e-10 sigma_0 (xpack_svd_dense_arr,
+ * xpack_orth_set, amg/src/xpacks.cpp:494-620), insertion (:170-194).
+ * mis_numcoarsedof: num_mises ints out.  *NDc: number of coarse dofs. */
+int sa_gpu_tentative_P(sa_gpu_level *level, int avoid_ess_bdr_dofs, int *mis_numcoarsedof,
+                       int *NDc);
+/* mis_tent_interps (amg/inc/interp.hpp:93): block of MIS i is s_i x k_i
+ * column-major; total size sum(s_i*k_i). */
+int sa_gpu_get_mis_tent(sa_gpu_level *level, double *mis_tent);
+
+/* ---- setup: operators ---- */
+
+/* mbox_build_Dinv_neg_parallel_matrix (amg/src/mbox.cpp:1839-1861) */
+int sa_gpu_build_Dinv_neg(sa_gpu_level *level);
+/* interp_smooth (amg/src/interp.cpp:172-229): P = prod_k (I + roots[k]^-1 Dinv_neg A) P_tent,
+ * then restr = P^T (tg_smooth_interp, amg/inc/tg.hpp:678-693).  degree 0 => P = P_tent. */
+int sa_gpu_smooth_P(sa_gpu_level *level, int degree, const double *roots);
+/* tg_coarse_matr (amg/inc/tg.hpp:695-709): Ac = P^T A P */
+int sa_gpu_rap(sa_gpu_level *level);
+/* ElementMatrixParallelCoarse::GetMatrix for every finer AE (amg/src/elmat.cpp:105-195):
+ * coarse element matrices P_e^T A_AE(e) P_e, kept on the device of \a coarse. */
+int sa_gpu_coarse_elmats(sa_gpu_level *finer, sa_gpu_level *coarse);
+/* read back: nc_e^2 doubles per finer AE, column-major, concatenated */
+int sa_gpu_get_coarse_elmats(sa_gpu_level *coarse, double *celmat);
+
+/* CSR read-back.  which: 0 = A, 1 = tentative P, 2 = P, 3 = restr (P^T), 4 = Ac */
+enum { SA_GPU_MAT_A = 0, SA_GPU_MAT_PTENT = 1, SA_GPU_MAT_P = 2, SA_GPU_MAT_R = 3, SA_GPU_MAT_AC = 4 };
+int sa_gpu_get_csr_sizes(sa_gpu_level *level, int which, int *rows, int *cols, int *nnz);
+int sa_gpu_get_csr(sa_gpu_level *level, int which, int *I, int *J, double *data);
+int sa_gpu_get_Dinv_neg(sa_gpu_level *level, double *dinv_neg);
+
+/* ---- solve ---- */
+
+/* y = M x with M one of the level's matrices (HypreParMatrix::Mult); host buffers */
+int sa_gpu_spmv(sa_gpu_level *level, int which, const double *x, double *y);
+/* smpr_compute_poly (amg/inc/smpr.hpp:319-339): for i < degree:
+ *   x += roots[i]^-1 * Dinv_neg .* (A x - b);  host buffers, x in/out */
+int sa_gpu_poly_smooth(sa_gpu_level *level, const double *b, double *x, int degree,
+                       const double *roots);
+
+/* Chains the levels into a V-cycle (ml_impose_cycle, amg/src/ml.cpp:361-377) with the
+ * SAS polynomial smoother of degree 3*nu_relax+1 (smpr_sas_poly_roots,
+ * amg/src/smpr.cpp:282-306; sa_gpu_build_Dinv_neg must have been called on every
+ * level) and an exact coarsest solve (dense Cholesky of the last Ac; the
+ * reference's --coarse-direct option, amg/src/tg.cpp:991-998). */
+int sa_gpu_solver_create(sa_gpu_ctx *ctx, sa_gpu_level **levels, int nlevels, int nu_relax,
+                         sa_gpu_solver **solver);
+void sa_gpu_solver_destroy(sa_gpu_solver *solver);
+/* VCycleSolver::Mult (amg/src/solve.cpp:309-323) = tg_cycle_atb from x = 0
+ * (amg/src/tg.cpp:91-132); host buffers */
+int sa_gpu_vcycle(sa_gpu_solver *solver, const double *b, double *x);
+/* kalchev_pcg (amg/src/mfem_addons.cpp:106-248, zero_rhs = false) with the V-cycle as
+ * preconditioner.  x in/out (initial guess).  *iters follows the reference's
+ * convention (negative = no convergence / SPD breakdown).  brr_hist (optional)
+ * receives (B r, r) per iteration, at most hist_cap entries; *hist_len entries written. */
+int sa_gpu_pcg(sa_gpu_solver *solver, const double *b, double *x, int maxiter, double rtol,
+               double atol, int *iters, double *brr_hist, int hist_cap, int *hist_len);
+/* device-resident variant used for kernel-only timing: b and x already on the
+ * device (allocated by sa_gpu_solver_upload) */
+int sa_gpu_solver_upload(sa_gpu_solver *solver, const double *b, const double *x0);
+int sa_gpu_pcg_resident(sa_gpu_solver *solver, int maxiter, double rtol, double atol,
+                        int *iters);
+int sa_gpu_solver_download(sa_gpu_solver *solver, double *x);
+
+/* ---- micro-benchmarks used by bench.py for the roofline denominators ---- */
+/* runs `reps` SpMVs y = A x on device-resident vectors; returns ms per SpMV */
+double sa_gpu_bench_spmv(sa_gpu_level *level, int which, int reps);
+/* runs `reps` fused smoother steps; returns ms per step */
+double sa_gpu_bench_smoother(sa_gpu_level *level, int reps);
+/* measured FP64 FMA peak of this GPU in TFLOP/s (dependent-free DFMA loop) */
+double sa_gpu_bench_fp64_peak(sa_gpu_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -1,0 +1,204 @@
+"""saamge_b200 -- B200-native spectral AMGe hot path (LLNL/saamge's local spectral
+stage + V-cycle/PCG solve), Python loader.
+
+The product is the CUDA library ``lib/libsaamge_b200.so`` (C ABI in
+``include/saamge_b200.h``) and the C++ host mirror of the reference's tg_/ml_
+interface ``lib/libsaamge_host.so``.  This module only loads them through ctypes
+and wraps the driver C API (``include/saamge_b200_driver.h``) that tests and
+``bench.py`` use.  There is no CPU fallback: building a hierarchy without a CUDA
+device aborts with the library's error message.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_DIR = os.path.join(_HERE, "lib")
+GPU_LIB = os.path.join(LIB_DIR, "libsaamge_b200.so")
+HOST_LIB = os.path.join(LIB_DIR, "libsaamge_host.so")
+
+_gpu = None
+_host = None
+
+
+class Params(ctypes.Structure):
+    """sa_drv_params_t (include/saamge_b200_driver.h)."""
+
+    _fields_ = [
+        ("num_levels", ctypes.c_int),
+        ("first_elems_per_agg", ctypes.c_int),
+        ("elems_per_agg", ctypes.c_int),
+        ("first_nu_pro", ctypes.c_int),
+        ("nu_pro", ctypes.c_int),
+        ("nu_relax", ctypes.c_int),
+        ("first_theta", ctypes.c_double),
+        ("theta", ctypes.c_double),
+        ("avoid_ess_bdr_dofs", ctypes.c_int),
+        ("partition_kind", ctypes.c_int),
+        ("block", ctypes.c_int * 3),
+        ("coarse_block", ctypes.c_int),
+        ("testmesh_inject", ctypes.c_int),
+    ]
+
+
+def gpu_lib():
+    """The CUDA library (C ABI).  Raises if it has not been built."""
+    global _gpu
+    if _gpu is None:
+        if not os.path.exists(GPU_LIB):
+            raise RuntimeError(
+                "saamge_b200: %s is missing -- run `make` (or __graft_entry__.build()); "
+                "there is no fallback path" % GPU_LIB
+            )
+        _gpu = ctypes.CDLL(GPU_LIB, mode=ctypes.RTLD_GLOBAL)
+        _gpu.sa_gpu_last_error.restype = ctypes.c_char_p
+        _gpu.sa_gpu_ctx_launch_count.restype = ctypes.c_int64
+        _gpu.sa_gpu_ctx_launch_count.argtypes = [ctypes.c_void_p]
+        _gpu.sa_gpu_ctx_timer.restype = ctypes.c_double
+        _gpu.sa_gpu_ctx_timer.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        _gpu.sa_gpu_bench_spmv.restype = ctypes.c_double
+        _gpu.sa_gpu_bench_spmv.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        _gpu.sa_gpu_bench_smoother.restype = ctypes.c_double
+        _gpu.sa_gpu_bench_smoother.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        _gpu.sa_gpu_bench_fp64_peak.restype = ctypes.c_double
+        _gpu.sa_gpu_bench_fp64_peak.argtypes = [ctypes.c_void_p]
+    return _gpu
+
+
+def host_lib():
+    global _host
+    if _host is None:
+        gpu_lib()
+        if not os.path.exists(HOST_LIB):
+            raise RuntimeError("saamge_b200: %s is missing -- run `make`" % HOST_LIB)
+        h = ctypes.CDLL(HOST_LIB, mode=ctypes.RTLD_GLOBAL)
+        h.sa_drv_default_params.argtypes = [ctypes.POINTER(Params)]
+        h.sa_drv_problem_create.restype = ctypes.c_void_p
+        h.sa_drv_problem_create.argtypes = [ctypes.c_int] * 6 + [ctypes.c_double, ctypes.c_uint64]
+        h.sa_drv_problem_destroy.argtypes = [ctypes.c_void_p]
+        h.sa_drv_problem_partition.argtypes = [ctypes.c_void_p, ctypes.POINTER(Params)]
+        h.sa_drv_ml_build.restype = ctypes.c_void_p
+        h.sa_drv_ml_build.argtypes = [ctypes.c_void_p, ctypes.POINTER(Params), ctypes.c_int]
+        h.sa_drv_ml_pcg.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double]
+        h.sa_drv_ml_download.argtypes = [ctypes.c_void_p]
+        h.sa_drv_hier_destroy.argtypes = [ctypes.c_void_p]
+        h.sa_drv_get.argtypes = [
+            ctypes.c_void_p,
+            ctypes.c_char_p,
+            ctypes.c_int,
+            ctypes.POINTER(ctypes.c_void_p),
+            ctypes.POINTER(ctypes.c_int64),
+            ctypes.POINTER(ctypes.c_int),
+        ]
+        h.sa_drv_get_scalar.restype = ctypes.c_double
+        h.sa_drv_get_scalar.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]
+        if hasattr(h, "sa_drv_bench_create"):
+            h.sa_drv_bench_create.restype = ctypes.c_void_p
+            h.sa_drv_bench_create.argtypes = [ctypes.c_void_p, ctypes.POINTER(Params), ctypes.c_int]
+            h.sa_drv_bench_destroy.argtypes = [ctypes.c_void_p]
+            h.sa_drv_bench_step.restype = ctypes.c_double
+            h.sa_drv_bench_step.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+            h.sa_drv_bench_scalar.restype = ctypes.c_double
+            h.sa_drv_bench_scalar.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+        _host = h
+    return _host
+
+
+_DTYPES = {0: np.int32, 1: np.int64, 2: np.float64, 3: np.int8}
+
+
+def _get(handle, name, level=0):
+    h = host_lib()
+    ptr = ctypes.c_void_p()
+    cnt = ctypes.c_int64()
+    dt = ctypes.c_int()
+    rc = h.sa_drv_get(handle, name.encode(), level, ctypes.byref(ptr), ctypes.byref(cnt), ctypes.byref(dt))
+    if rc != 0:
+        raise KeyError("%s (level %d): rc=%d" % (name, level, rc))
+    n = cnt.value
+    dtype = _DTYPES[dt.value]
+    if n == 0:
+        return np.zeros(0, dtype=dtype)
+    buf = (ctypes.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr.value)
+    return np.frombuffer(buf, dtype=dtype).copy()
+
+
+def default_params(**kw):
+    p = Params()
+    host_lib().sa_drv_default_params(ctypes.byref(p))
+    for k, v in kw.items():
+        if k == "block":
+            for i in range(3):
+                p.block[i] = v[i]
+        else:
+            setattr(p, k, v)
+    return p
+
+
+class Problem:
+    """Structured Q1/Q2 diffusion problem + finest-level partition (host inputs)."""
+
+    def __init__(self, dim, n, order=1, coef_kind=0, contrast=1e6, seed=12345, nyz=None):
+        ny, nz = (n, n) if nyz is None else nyz
+        self.handle = host_lib().sa_drv_problem_create(dim, n, ny, nz, order, coef_kind, contrast, seed)
+        self.dim, self.n, self.order = dim, n, order
+
+    def partition(self, params):
+        return host_lib().sa_drv_problem_partition(self.handle, ctypes.byref(params))
+
+    def get(self, name, level=0):
+        return _get(self.handle, name, level)
+
+    def scalar(self, name, level=0):
+        return host_lib().sa_drv_get_scalar(self.handle, name.encode(), level)
+
+    def close(self):
+        if self.handle:
+            host_lib().sa_drv_problem_destroy(self.handle)
+            self.handle = None
+
+
+class Hierarchy:
+    """Handle on a built hierarchy (product or oracle) -- read access only."""
+
+    def __init__(self, handle):
+        self.handle = handle
+
+    def get(self, name, level=0):
+        return _get(self.handle, name, level)
+
+    def scalar(self, name, level=0):
+        return host_lib().sa_drv_get_scalar(self.handle, name.encode(), level)
+
+    def csr(self, name, level=0):
+        import scipy.sparse as sp
+
+        I = self.get(name + ".I", level)
+        J = self.get(name + ".J", level)
+        A = self.get(name + ".A", level)
+        ncols = int(J.max()) + 1 if len(J) else 0
+        if name in ("tent_interp", "interp"):
+            ncols = int(self.scalar("NDc", level))
+        elif name == "Ac":
+            ncols = len(I) - 1
+        return sp.csr_matrix((A, J, I), shape=(len(I) - 1, ncols))
+
+    def close(self):
+        if self.handle:
+            host_lib().sa_drv_hier_destroy(self.handle)
+            self.handle = None
+
+
+def ml_build(problem, params, device=0):
+    """ml_produce_data through the B200 path; returns a Hierarchy."""
+    h = host_lib().sa_drv_ml_build(problem.handle, ctypes.byref(params), device)
+    return Hierarchy(h)
+
+
+def ml_pcg(hier, maxiter=1000, rtol=1e-12, atol=0.0):
+    return host_lib().sa_drv_ml_pcg(hier.handle, maxiter, rtol, atol)
+
+
+def ml_download(hier):
+    return host_lib().sa_drv_ml_download(hier.handle)

@@ -1,0 +1,134 @@
+// Device-side assembly of one AE's dense local matrix, executed cooperatively by
+// one thread block.  One thread owns one row of the tile, so every entry is summed
+// by a single thread in ascending element order: deterministic, no atomics, and
+// the same summation order as the CPU path.
+//   mode with_global = 1: agg_build_AE_stiffm_with_global + agg_assemble_value
+//                         (amg/src/aggregates.cpp:855-945, 68-184)
+//   mode with_global = 0: agg_build_AE_stiffm (amg/src/aggregates.cpp:959-1086)
+#ifndef SA_ASSEMBLE_CUH
+#define SA_ASSEMBLE_CUH
+
+#include "sa_gpu_internal.cuh"
+
+#define SA_AGG_BETWEEN_AES_FLAG 0x01
+#define SA_AGG_ON_ESS_DOMAIN_BORDER_FLAG 0x02
+
+/// agg_map_id_glob_to_AE (amg/inc/aggregates.hpp:653-673)
+__device__ __forceinline__ int sa_dev_map_id_glob_to_AE(const LevelTables &L, int glob_id,
+                                                        int part)
+{
+    const int b = L.d2AE_I[glob_id], e = L.d2AE_I[glob_id + 1];
+    for (int p = b; p < e; ++p)
+        if (L.d2AE_J[p] == part)
+            return L.dof_id_inAE[p];
+    return -1;
+}
+
+/// agg_assemble_value (amg/src/aggregates.cpp:68-184): sum over the elements of
+/// AE `part` containing both dofs of the element-matrix entry (di, dj).
+__device__ __forceinline__ double sa_dev_assemble_value(const LevelTables &L, int di, int dj,
+                                                        int part)
+{
+    double value = 0.;
+    const int bi = L.d2e_I[di], ei = L.d2e_I[di + 1];
+    for (int p = bi; p < ei; ++p)
+    {
+        const int elno = L.d2e_J[p];
+        if (L.partitioning[elno] != part)
+            continue;
+        const int eb = L.e2d_I[elno];
+        const int ndofs = L.e2d_I[elno + 1] - eb;
+        int dii = -1, djj = -1;
+        for (int k = 0; k < ndofs; ++k)
+        {
+            const int g = L.e2d_J[eb + k];
+            if (g == di)
+                dii = k;
+            if (g == dj)
+                djj = k;
+        }
+        if (djj < 0)
+            continue; // element does not contain dj
+        value += L.elmat[L.elmat_off[elno] + (int64_t)djj * ndofs + dii];
+    }
+    return value;
+}
+
+/// Fills the n x n column-major tile T (leading dimension ld) with the matrix of AE
+/// `part`.  All threads of the block must call; ends with __syncthreads().
+static __device__ void sa_dev_assemble_AE(const LevelTables &L, int part, double *T, int ld)
+{
+    const int rb = L.AE2d_I[part];
+    const int n = L.AE2d_I[part + 1] - rb;
+    const int *dofs = L.AE2d_J + rb;
+    for (int64_t q = threadIdx.x; q < (int64_t)n * ld; q += blockDim.x)
+        T[q] = 0.;
+    __syncthreads();
+    if (L.with_global)
+    {
+        for (int i = threadIdx.x; i < n; i += blockDim.x)
+        {
+            const int glob_dof = dofs[i];
+            const char fi = L.agg_flags[glob_dof];
+            const int ab = L.A_I[glob_dof], ae = L.A_I[glob_dof + 1];
+            for (int p = ab; p < ae; ++p)
+            {
+                const int glob_neigh = L.A_J[p];
+                const int local_neigh = sa_dev_map_id_glob_to_AE(L, glob_neigh, part);
+                if (local_neigh < 0)
+                    continue;
+                const char fj = L.agg_flags[glob_neigh];
+                const bool both_iface = (fi & SA_AGG_BETWEEN_AES_FLAG) && (fj & SA_AGG_BETWEEN_AES_FLAG);
+                const bool ess = (fi & SA_AGG_ON_ESS_DOMAIN_BORDER_FLAG) ||
+                                 (fj & SA_AGG_ON_ESS_DOMAIN_BORDER_FLAG);
+                // bdr_cond_imposed = assemble_ess_diag = true (amg/src/elmat.cpp:51-52)
+                if (both_iface && !(ess && !(glob_neigh == glob_dof)))
+                {
+                    // the reference assembles (i, j) for i <= j and mirrors the value
+                    const double value = (i <= local_neigh)
+                                             ? sa_dev_assemble_value(L, glob_dof, glob_neigh, part)
+                                             : sa_dev_assemble_value(L, glob_neigh, glob_dof, part);
+                    T[i + (int64_t)ld * local_neigh] = value;
+                }
+                else
+                    T[i + (int64_t)ld * local_neigh] = L.A_data[p];
+            }
+        }
+    }
+    else
+    {
+        for (int i = threadIdx.x; i < n; i += blockDim.x)
+        {
+            const int g = dofs[i];
+            const int bi = L.d2e_I[g], ei = L.d2e_I[g + 1];
+            for (int p = bi; p < ei; ++p)
+            {
+                const int elem = L.d2e_J[p];
+                if (L.partitioning[elem] != part)
+                    continue;
+                const int eb = L.e2d_I[elem];
+                const int sz = L.e2d_I[elem + 1] - eb;
+                int k = -1;
+                for (int q = 0; q < sz; ++q)
+                    if (L.e2d_J[eb + q] == g)
+                    {
+                        k = q;
+                        break;
+                    }
+                const double *Ke = L.elmat + L.elmat_off[elem];
+                for (int j = 0; j < sz; ++j)
+                {
+                    const double el = Ke[(int64_t)j * sz + k];
+                    if (0. != el)
+                    {
+                        const int local_j = sa_dev_map_id_glob_to_AE(L, L.e2d_J[eb + j], part);
+                        T[i + (int64_t)ld * local_j] += el;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+#endif

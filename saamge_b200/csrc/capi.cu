@@ -1,0 +1,382 @@
+// Context / level lifetime, read-back and micro-benchmark entry points of the C ABI
+// (include/saamge_b200.h).
+#include <algorithm>
+#include <cmath>
+
+#include "sa_gpu_internal.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void sa_gpu_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *sa_gpu_last_error(void) { return g_err; }
+
+extern "C" int sa_gpu_ctx_create(int device, sa_gpu_ctx **out)
+{
+    SA_API_BEGIN
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        SA_FAIL("sa_gpu_ctx_create: no CUDA device available (%s); this library has no CPU "
+                "fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev)
+        SA_FAIL("sa_gpu_ctx_create: device %d out of range (%d devices)", device, ndev);
+    SA_CUDA(cudaSetDevice(device));
+    sa_gpu_ctx *ctx = new sa_gpu_ctx;
+    ctx->device = device;
+    cudaDeviceProp prop;
+    SA_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    SA_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    SA_CUDA(cudaEventCreate(&ctx->ev0));
+    SA_CUDA(cudaEventCreate(&ctx->ev1));
+    *out = ctx;
+    SA_API_END
+}
+
+extern "C" void sa_gpu_ctx_destroy(sa_gpu_ctx *ctx)
+{
+    if (!ctx)
+        return;
+    cudaSetDevice(ctx->device);
+    if (ctx->ev0)
+        cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1)
+        cudaEventDestroy(ctx->ev1);
+    if (ctx->stream)
+        cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" void *sa_gpu_ctx_stream(sa_gpu_ctx *ctx) { return (void *)ctx->stream; }
+
+extern "C" int sa_gpu_ctx_sync(sa_gpu_ctx *ctx)
+{
+    SA_API_BEGIN
+    SA_CUDA(cudaStreamSynchronize(ctx->stream));
+    SA_API_END
+}
+
+extern "C" int64_t sa_gpu_ctx_launch_count(sa_gpu_ctx *ctx) { return ctx->launches; }
+
+extern "C" double sa_gpu_ctx_timer(sa_gpu_ctx *ctx, int begin)
+{
+    if (begin)
+    {
+        cudaEventRecord(ctx->ev0, ctx->stream);
+        return 0.;
+    }
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    cudaEventSynchronize(ctx->ev1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    return (double)ms;
+}
+
+static void upload_table(DevBuf<int> &dI, DevBuf<int> &dJ, const int *I, const int *J, int rows,
+                         cudaStream_t st)
+{
+    dI.upload(I, (size_t)rows + 1, st);
+    dJ.upload(J, (size_t)I[rows], st);
+}
+
+extern "C" int sa_gpu_level_create(sa_gpu_ctx *ctx, const sa_gpu_level_desc *d,
+                                   sa_gpu_level *finer, sa_gpu_level **out)
+{
+    SA_API_BEGIN
+    SA_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    sa_gpu_level *L = new sa_gpu_level;
+    struct Guard
+    {
+        sa_gpu_level *l;
+        ~Guard() { delete l; }
+    } g{L};
+    L->ctx = ctx;
+    L->finer = finer;
+    L->ND = d->ND;
+    L->NE = d->NE;
+    L->nparts = d->nparts;
+    L->num_mises = d->num_mises;
+    L->with_global = d->assemble_with_global;
+    upload_table(L->e2d_I, L->e2d_J, d->elem_to_dof_I, d->elem_to_dof_J, d->NE, st);
+    upload_table(L->d2e_I, L->d2e_J, d->dof_to_elem_I, d->dof_to_elem_J, d->ND, st);
+    upload_table(L->AE2e_I, L->AE2e_J, d->AE_to_elem_I, d->AE_to_elem_J, d->nparts, st);
+    upload_table(L->AE2d_I, L->AE2d_J, d->AE_to_dof_I, d->AE_to_dof_J, d->nparts, st);
+    upload_table(L->d2AE_I, L->d2AE_J, d->dof_to_AE_I, d->dof_to_AE_J, d->ND, st);
+    L->dof_id_inAE.upload(d->dof_id_inAE, (size_t)d->dof_to_AE_I[d->ND], st);
+    L->partitioning.upload(d->partitioning, d->NE, st);
+    L->agg_flags.upload(d->agg_flags, d->ND, st);
+    upload_table(L->mis2d_I, L->mis2d_J, d->mis_to_dof_I, d->mis_to_dof_J, d->num_mises, st);
+    upload_table(L->mis2AE_I, L->mis2AE_J, d->mis_to_AE_I, d->mis_to_AE_J, d->num_mises, st);
+    upload_table(L->AE2mis_I, L->AE2mis_J, d->AE_to_mis_I, d->AE_to_mis_J, d->nparts, st);
+    L->mises.upload(d->mises, d->ND, st);
+    L->h_AE2d_I.assign(d->AE_to_dof_I, d->AE_to_dof_I + d->nparts + 1);
+    L->h_mis2d_I.assign(d->mis_to_dof_I, d->mis_to_dof_I + d->num_mises + 1);
+    L->h_mis2AE_I.assign(d->mis_to_AE_I, d->mis_to_AE_I + d->num_mises + 1);
+    L->h_mis2AE_J.assign(d->mis_to_AE_J, d->mis_to_AE_J + d->mis_to_AE_I[d->num_mises]);
+    L->h_e2d_I.assign(d->elem_to_dof_I, d->elem_to_dof_I + d->NE + 1);
+    if (d->A_I)
+    {
+        L->A_own.rows = L->A_own.cols = d->ND;
+        L->A_own.nnz = d->A_I[d->ND];
+        L->A_own.I.upload(d->A_I, (size_t)d->ND + 1, st);
+        L->A_own.J.upload(d->A_J, L->A_own.nnz, st);
+        L->A_own.A.upload(d->A_data, L->A_own.nnz, st);
+        L->A = &L->A_own;
+    }
+    else
+    {
+        if (!finer || !finer->have_Ac)
+            SA_FAIL("sa_gpu_level_create: no operator given and the finer level has no Ac");
+        if (finer->Ac.rows != d->ND)
+            SA_FAIL("sa_gpu_level_create: finer Ac has %d rows, level has %d dofs",
+                    finer->Ac.rows, d->ND);
+        L->A = &finer->Ac;
+    }
+    if (d->elmat)
+    {
+        L->h_elmat_off.assign(d->elmat_off, d->elmat_off + d->NE + 1);
+        L->elmat_off.upload(d->elmat_off, (size_t)d->NE + 1, st);
+        L->elmat.upload(d->elmat, (size_t)d->elmat_off[d->NE], st);
+        L->have_elmat = true;
+    }
+    if (d->mis_coarsedofoffsets && finer)
+        L->h_mis_coarsedofoffsets.assign(d->mis_coarsedofoffsets,
+                                         d->mis_coarsedofoffsets + finer->num_mises + 1);
+    SA_CUDA(cudaStreamSynchronize(st));
+    g.l = nullptr;
+    *out = L;
+    SA_API_END
+}
+
+extern "C" void sa_gpu_level_destroy(sa_gpu_level *level)
+{
+    if (!level)
+        return;
+    cudaSetDevice(level->ctx->device);
+    delete level;
+}
+
+static DevCsr *pick(sa_gpu_level *lev, int which)
+{
+    switch (which)
+    {
+    case SA_GPU_MAT_A:
+        return lev->A;
+    case SA_GPU_MAT_PTENT:
+        return lev->have_tent ? &lev->Ptent : nullptr;
+    case SA_GPU_MAT_P:
+        return lev->have_P ? &lev->P : nullptr;
+    case SA_GPU_MAT_R:
+        return lev->have_P ? &lev->R : nullptr;
+    case SA_GPU_MAT_AC:
+        return lev->have_Ac ? &lev->Ac : nullptr;
+    }
+    return nullptr;
+}
+
+extern "C" int sa_gpu_get_csr_sizes(sa_gpu_level *lev, int which, int *rows, int *cols, int *nnz)
+{
+    SA_API_BEGIN
+    DevCsr *M = pick(lev, which);
+    if (!M)
+        SA_FAIL("sa_gpu_get_csr_sizes: matrix %d not available", which);
+    *rows = M->rows;
+    *cols = M->cols;
+    *nnz = M->nnz;
+    SA_API_END
+}
+
+extern "C" int sa_gpu_get_csr(sa_gpu_level *lev, int which, int *I, int *J, double *data)
+{
+    SA_API_BEGIN
+    DevCsr *M = pick(lev, which);
+    if (!M)
+        SA_FAIL("sa_gpu_get_csr: matrix %d not available", which);
+    cudaStream_t st = lev->ctx->stream;
+    if (I)
+        M->I.download(I, (size_t)M->rows + 1, st);
+    if (J)
+        M->J.download(J, M->nnz, st);
+    if (data)
+        M->A.download(data, M->nnz, st);
+    SA_CUDA(cudaStreamSynchronize(st));
+    SA_API_END
+}
+
+extern "C" int sa_gpu_get_Dinv_neg(sa_gpu_level *lev, double *dinv_neg)
+{
+    SA_API_BEGIN
+    if (!lev->have_Dinv)
+        SA_FAIL("sa_gpu_get_Dinv_neg: not built");
+    lev->Dinv_neg.download(dinv_neg, lev->ND, lev->ctx->stream);
+    SA_CUDA(cudaStreamSynchronize(lev->ctx->stream));
+    SA_API_END
+}
+
+extern "C" int sa_gpu_spmv(sa_gpu_level *lev, int which, const double *x, double *y)
+{
+    SA_API_BEGIN
+    DevCsr *M = pick(lev, which);
+    if (!M)
+        SA_FAIL("sa_gpu_spmv: matrix %d not available", which);
+    cudaStream_t st = lev->ctx->stream;
+    lev->vx.upload(x, M->cols, st);
+    lev->vy.ensure(M->rows);
+    dev_spmv(lev->ctx, *M, lev->vx.p, lev->vy.p);
+    lev->vy.download(y, M->rows, st);
+    SA_CUDA(cudaStreamSynchronize(st));
+    SA_API_END
+}
+
+extern "C" int sa_gpu_poly_smooth(sa_gpu_level *lev, const double *b, double *x, int degree,
+                                  const double *roots)
+{
+    SA_API_BEGIN
+    if (!lev->have_Dinv)
+        SA_FAIL("sa_gpu_poly_smooth: sa_gpu_build_Dinv_neg has not been called");
+    cudaStream_t st = lev->ctx->stream;
+    const int n = lev->ND;
+    lev->vb.upload(b, n, st);
+    lev->vx.upload(x, n, st);
+    lev->vy.ensure(n);
+    double *cur = lev->vx.p, *alt = lev->vy.p;
+    for (int i = 0; i < degree; ++i)
+    {
+        dev_smoother_step(lev->ctx, *lev->A, lev->Dinv_neg.p, lev->vb.p, cur, alt, 1. / roots[i], 0);
+        std::swap(cur, alt);
+    }
+    SA_CUDA(cudaMemcpyAsync(x, cur, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SA_CUDA(cudaStreamSynchronize(st));
+    SA_API_END
+}
+
+/* ------------------------------------------------------- micro-benchmarks */
+
+__global__ void k_fill(double *x, int n, double v)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        x[i] = v + 1e-3 * (i & 1023);
+}
+
+extern "C" double sa_gpu_bench_spmv(sa_gpu_level *lev, int which, int reps)
+{
+    try
+    {
+        DevCsr *M = pick(lev, which);
+        if (!M)
+            return -1.;
+        sa_gpu_ctx *ctx = lev->ctx;
+        lev->vx.ensure(std::max(M->cols, M->rows));
+        lev->vy.ensure(std::max(M->cols, M->rows));
+        SA_LAUNCH(ctx, k_fill, (M->cols + 255) / 256, 256, 0, lev->vx.p, M->cols, 1.0);
+        for (int i = 0; i < 3; ++i)
+            dev_spmv(ctx, *M, lev->vx.p, lev->vy.p);
+        SA_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+        for (int i = 0; i < reps; ++i)
+            dev_spmv(ctx, *M, lev->vx.p, lev->vy.p);
+        SA_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+        SA_CUDA(cudaEventSynchronize(ctx->ev1));
+        float ms = 0.f;
+        SA_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        return (double)ms / reps;
+    }
+    catch (...)
+    {
+        return -1.;
+    }
+}
+
+extern "C" double sa_gpu_bench_smoother(sa_gpu_level *lev, int reps)
+{
+    try
+    {
+        if (!lev->have_Dinv || !lev->A)
+            return -1.;
+        sa_gpu_ctx *ctx = lev->ctx;
+        const int n = lev->ND;
+        lev->vx.ensure(n);
+        lev->vy.ensure(n);
+        lev->vb.ensure(n);
+        SA_LAUNCH(ctx, k_fill, (n + 255) / 256, 256, 0, lev->vx.p, n, 0.0);
+        SA_LAUNCH(ctx, k_fill, (n + 255) / 256, 256, 0, lev->vb.p, n, 1.0);
+        double *cur = lev->vx.p, *alt = lev->vy.p;
+        for (int i = 0; i < 3; ++i)
+        {
+            dev_smoother_step(ctx, *lev->A, lev->Dinv_neg.p, lev->vb.p, cur, alt, 0.5, 0);
+            std::swap(cur, alt);
+        }
+        SA_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+        for (int i = 0; i < reps; ++i)
+        {
+            dev_smoother_step(ctx, *lev->A, lev->Dinv_neg.p, lev->vb.p, cur, alt, 0.5, 0);
+            std::swap(cur, alt);
+        }
+        SA_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+        SA_CUDA(cudaEventSynchronize(ctx->ev1));
+        float ms = 0.f;
+        SA_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        return (double)ms / reps;
+    }
+    catch (...)
+    {
+        return -1.;
+    }
+}
+
+// 8 independent DFMA chains per thread
+__global__ void k_fp64_peak(double *out, int iters)
+{
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1., a2 = a0 + 2., a3 = a0 + 3., a4 = a0 + 4.,
+           a5 = a0 + 5., a6 = a0 + 6., a7 = a0 + 7.;
+    const double m = 1.0000001, c = 1e-7;
+    for (int i = 0; i < iters; ++i)
+    {
+        a0 = fma(a0, m, c);
+        a1 = fma(a1, m, c);
+        a2 = fma(a2, m, c);
+        a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c);
+        a5 = fma(a5, m, c);
+        a6 = fma(a6, m, c);
+        a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+extern "C" double sa_gpu_bench_fp64_peak(sa_gpu_ctx *ctx)
+{
+    try
+    {
+        const int blocks = ctx->num_sms * 8, threads = 256, iters = 1 << 14;
+        DevBuf<double> out;
+        out.alloc((size_t)blocks * threads);
+        SA_LAUNCH(ctx, k_fp64_peak, blocks, threads, 0, out.p, iters);
+        double best = 0.;
+        for (int rep = 0; rep < 5; ++rep)
+        {
+            SA_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+            SA_LAUNCH(ctx, k_fp64_peak, blocks, threads, 0, out.p, iters);
+            SA_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+            SA_CUDA(cudaEventSynchronize(ctx->ev1));
+            float ms = 0.f;
+            SA_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+            const double flops = 2. * 8. * iters * (double)blocks * threads;
+            best = std::max(best, flops / (ms * 1e-3) / 1e12);
+        }
+        return best;
+    }
+    catch (...)
+    {
+        return -1.;
+    }
+}

@@ -1,0 +1,880 @@
+// Local spectral stage on the device:
+//   k_assemble_tridiag : one thread block per AE -- assemble the AE matrix
+//                        (assemble.cuh), weighted-l1 D, symmetric scaling
+//                        A^ = D^-1/2 A D^-1/2 (B of the generalized problem is diagonal,
+//                        so dsygvx's dpotrf/dsygst collapse to a scaling), Householder
+//                        tridiagonalisation (lower, unblocked, the dsytd2 recurrences)
+//   k_count            : one thread per AE   -- Sturm count at theta -> m
+//   k_bisect           : one thread per eigenvalue -- bisection (dstebz)
+//   k_inverse_iter     : one warp per AE, one lane per eigenvalue -- pivoted LU of
+//                        (T - lambda I), 3 solves, modified Gram-Schmidt inside clusters (dstein)
+//   k_back_transform   : one warp per vector -- apply the reflectors (dormtr) and
+//                        un-scale by D^-1/2, so that z^T D z = 1 like dsygvx returns
+// Reference call chain replaced: interp_compute_vectors (amg/src/interp.cpp:387-556) ->
+// BuildAEStiff -> Eigensolver::SolveDirect (amg/src/spectral.cpp:124-237) ->
+// xpacks_calc_lower_eigens_dense (amg/src/xpacks.cpp:222-314).
+#include <algorithm>
+#include <cfloat>
+#include <numeric>
+
+#include "assemble.cuh"
+#include "sa_gpu_internal.cuh"
+#include "tridiag_math.cuh"
+
+namespace
+{
+
+/* per-chunk work arrays (device); "slot" = position of the AE inside the chunk */
+struct ChunkDev
+{
+    const int *ae_of_slot; // slot -> AE id
+    const int64_t *voff;   // slot -> offset of the n x n reflector block in V
+    const int *doff;       // slot -> offset into d/e/tau/sinv arrays
+    double *V;
+    double *d, *e, *tau, *sinv;
+    int *status; // per slot: 0 ok, 1 nonpositive diagonal, 2 nonfinite
+};
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+    for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+/// Sum over the block; result returned to every thread.  sbuf: >= 33 doubles.
+__device__ __forceinline__ double block_sum(double v, double *sbuf)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads(); // protect sbuf from the previous use
+    if (lane == 0)
+        sbuf[w] = v;
+    __syncthreads();
+    if (w == 0)
+    {
+        double t = (lane < (int)((blockDim.x + 31) >> 5)) ? sbuf[lane] : 0.;
+        t = warp_sum(t);
+        if (lane == 0)
+            sbuf[32] = t;
+    }
+    __syncthreads();
+    return sbuf[32];
+}
+
+// One block per slot of the list.  tile_in_smem: tile lives in dynamic shared
+// memory (n <= nmax_smem), otherwise directly in the V block of the AE.
+__global__ void k_assemble_tridiag(LevelTables L, ChunkDev C, const int *slot_list, int nslots,
+                                   int tile_in_smem, double *ae_D)
+{
+    extern __shared__ double sm[];
+    const int slot = slot_list[blockIdx.x];
+    const int part = C.ae_of_slot[slot];
+    const int rb = L.AE2d_I[part];
+    const int n = L.AE2d_I[part + 1] - rb;
+    double *Vout = C.V + C.voff[slot];
+    // shared layout: [reduction 40][v n][w n][dg n] [tile n*n if in smem]
+    double *sbuf = sm;
+    double *v = sm + 40;
+    double *w = v + n;
+    double *dg = w + n;
+    double *T = tile_in_smem ? (dg + n) : Vout;
+    const int ld = n;
+    double *dd = C.d + C.doff[slot], *ee = C.e + C.doff[slot], *tt = C.tau + C.doff[slot],
+           *sinv = C.sinv + C.doff[slot];
+
+    sa_dev_assemble_AE(L, part, T, ld);
+
+    // weighted-l1 diagonal D_ii = sum_j |a_ij| sqrt(a_ii / a_jj)  (amg/src/mbox.cpp:913-949)
+    int bad = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+    {
+        const double a = T[i + (int64_t)ld * i];
+        dg[i] = a;
+        if (!(a > 0.))
+            bad = 1;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+    {
+        const double di = dg[i];
+        double sum = 0.;
+        for (int j = 0; j < n; ++j)
+        {
+            const double a = T[i + (int64_t)ld * j];
+            if (a != 0.)
+                sum += fabs(a) * sqrt(di / dg[j]);
+        }
+        ae_D[rb + i] = sum;
+        const double s = 1. / sqrt(sum);
+        w[i] = s;
+        sinv[i] = s;
+        if (!(sum > 0.) || !isfinite(sum))
+            bad = 1;
+    }
+    __syncthreads();
+    if (__syncthreads_or(bad))
+    {
+        if (threadIdx.x == 0)
+            C.status[slot] = 1;
+        return;
+    }
+    // A^ = D^-1/2 A D^-1/2
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+    {
+        const double si = w[i];
+        for (int j = 0; j < n; ++j)
+            T[i + (int64_t)ld * j] *= si * w[j];
+    }
+    __syncthreads();
+
+    // Householder tridiagonalisation, lower triangle convention of dsytd2:
+    // H(k) annihilates A(k+2:n-1, k); reflector stored below the subdiagonal.
+    for (int k = 0; k < n - 1; ++k)
+    {
+        double part2 = 0.;
+        for (int i = k + 2 + threadIdx.x; i < n; i += blockDim.x)
+        {
+            const double x = T[i + (int64_t)ld * k];
+            part2 += x * x;
+        }
+        const double xnorm2 = block_sum(part2, sbuf);
+        const double alpha = T[(k + 1) + (int64_t)ld * k];
+        double tau = 0., beta = alpha, scal = 0.;
+        if (xnorm2 > 0.)
+        {
+            beta = -copysign(sqrt(alpha * alpha + xnorm2), alpha);
+            tau = (beta - alpha) / beta;
+            scal = 1. / (alpha - beta);
+        }
+        __syncthreads(); // everyone has read alpha before the column is overwritten
+        for (int i = k + 1 + threadIdx.x; i < n; i += blockDim.x)
+        {
+            const double vi = (i == k + 1) ? 1. : T[i + (int64_t)ld * k] * scal;
+            v[i] = vi;
+            if (i > k + 1)
+                T[i + (int64_t)ld * k] = vi; // keep the reflector in place
+        }
+        if (threadIdx.x == 0)
+        {
+            dd[k] = T[k + (int64_t)ld * k];
+            ee[k] = beta;
+            tt[k] = tau;
+        }
+        __syncthreads();
+        if (tau != 0.)
+        {
+            // p = tau * A22 v ; w = p - (tau/2)(p.v) v ; A22 -= v w^T + w v^T
+            double pv = 0.;
+            for (int i = k + 1 + threadIdx.x; i < n; i += blockDim.x)
+            {
+                double s = 0.;
+                for (int j = k + 1; j < n; ++j)
+                    s += T[i + (int64_t)ld * j] * v[j];
+                s *= tau;
+                w[i] = s;
+                pv += s * v[i];
+            }
+            const double pvs = block_sum(pv, sbuf);
+            const double alpha2 = -0.5 * tau * pvs;
+            for (int i = k + 1 + threadIdx.x; i < n; i += blockDim.x)
+                w[i] += alpha2 * v[i];
+            __syncthreads();
+            for (int i = k + 1 + threadIdx.x; i < n; i += blockDim.x)
+            {
+                const double vi = v[i], wi = w[i];
+                for (int j = k + 1; j < n; ++j)
+                    T[i + (int64_t)ld * j] -= vi * w[j] + wi * v[j];
+            }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0)
+    {
+        dd[n - 1] = T[(n - 1) + (int64_t)ld * (n - 1)];
+        ee[n - 1] = 0.;
+        tt[n - 1] = 0.;
+    }
+    __syncthreads();
+    if (tile_in_smem)
+    {
+        // only the reflectors (strictly below the subdiagonal) are needed later
+        for (int64_t q = threadIdx.x; q < (int64_t)n * n; q += blockDim.x)
+            Vout[q] = T[q];
+    }
+}
+
+// one thread per slot: number of eigenvalues in (-1, theta] and search bounds
+__global__ void k_count(ChunkDev C, const int *AE2d_I, int nslots, double theta, int inject_ae0,
+                        int *nev, int *m_total, double *glo, double *ghi, double *tnorm_out)
+{
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= nslots)
+        return;
+    const int part = C.ae_of_slot[slot];
+    const int n = AE2d_I[part + 1] - AE2d_I[part];
+    const double *d = C.d + C.doff[slot];
+    double *e = C.e + C.doff[slot];
+    if (C.status[slot])
+    {
+        nev[slot] = 0;
+        m_total[slot] = 0;
+        return;
+    }
+    double gl, gu, e2max;
+    sa_gershgorin(n, d, e, &gl, &gu, &e2max);
+    const double tn = fmax(fabs(gl), fabs(gu));
+    const double pivmin = DBL_MIN * fmax(1., e2max);
+    // dstebz widens the Gershgorin interval
+    gl = gl - 2.1 * tn * DBL_EPSILON * n - 2.1 * 2. * pivmin;
+    gu = gu + 2.1 * tn * DBL_EPSILON * n + 2.1 * pivmin;
+    // e2 is kept in tau's place?  no: squared on the fly in the bisection kernel
+    int cnt_hi = 0, cnt_lo = 0;
+    {
+        // counts with e^2 formed on the fly
+        double q = d[0] - theta, ql = d[0] - (-1.);
+        if (fabs(q) < pivmin) q = -pivmin;
+        if (fabs(ql) < pivmin) ql = -pivmin;
+        cnt_hi += (q <= 0.);
+        cnt_lo += (ql <= 0.);
+        for (int i = 1; i < n; ++i)
+        {
+            const double e2 = e[i - 1] * e[i - 1];
+            q = d[i] - e2 / q - theta;
+            ql = d[i] - e2 / ql - (-1.);
+            if (fabs(q) < pivmin) q = -pivmin;
+            if (fabs(ql) < pivmin) ql = -pivmin;
+            cnt_hi += (q <= 0.);
+            cnt_lo += (ql <= 0.);
+        }
+    }
+    int m = cnt_hi - cnt_lo;
+    double hi = theta, lo = fmin(gl, -1.);
+    if (cnt_lo > 0)
+        lo = -1.; // eigenvalues <= -1 are excluded (vl = -1)
+    if (m <= 0)
+    {
+        // atleast_one: the reference re-runs dsygvx with range 'I', il = iu = 1
+        m = 1;
+        cnt_lo = 0;
+        lo = gl;
+        hi = gu;
+    }
+    nev[slot] = m;
+    m_total[slot] = m + ((inject_ae0 && part == 0) ? 1 : 0);
+    glo[slot] = lo;
+    ghi[slot] = hi;
+    tnorm_out[slot] = tn;
+    // index of the first wanted eigenvalue is cnt_lo (0-based); stash it in tau[n-1]
+    C.tau[C.doff[slot] + n - 1] = (double)cnt_lo;
+}
+
+// one thread per wanted eigenvalue.  ev_slot/ev_idx map the flat eigenvalue index
+// to (slot, j).
+__global__ void k_bisect(ChunkDev C, const int *AE2d_I, const int *ev_slot, const int *ev_idx,
+                         int nev_total, const double *glo, const double *ghi,
+                         const double *tnorm, const int64_t *eval_off_slot, double *evals)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nev_total)
+        return;
+    const int slot = ev_slot[t];
+    const int j = ev_idx[t];
+    const int part = C.ae_of_slot[slot];
+    const int n = AE2d_I[part + 1] - AE2d_I[part];
+    const double *d = C.d + C.doff[slot];
+    const double *e = C.e + C.doff[slot];
+    const int first = (int)C.tau[C.doff[slot] + n - 1];
+    const int target = first + j; // want the eigenvalue with exactly `target` eigenvalues below it
+    double e2max = 0.;
+    for (int i = 0; i + 1 < n; ++i)
+        e2max = fmax(e2max, e[i] * e[i]);
+    const double pivmin = DBL_MIN * fmax(1., e2max);
+    double lo = glo[slot], hi = ghi[slot];
+    const double tn = tnorm[slot];
+    const double atol = 2. * DBL_EPSILON * tn + 2. * pivmin;
+    for (int it = 0; it < 200; ++it)
+    {
+        const double mid = 0.5 * (lo + hi);
+        if (hi - lo <= atol || mid <= lo || mid >= hi)
+            break;
+        int cnt = 0;
+        double q = d[0] - mid;
+        if (fabs(q) < pivmin) q = -pivmin;
+        cnt += (q <= 0.);
+        for (int i = 1; i < n; ++i)
+        {
+            q = d[i] - (e[i - 1] * e[i - 1]) / q - mid;
+            if (fabs(q) < pivmin) q = -pivmin;
+            cnt += (q <= 0.);
+        }
+        if (cnt <= target)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    evals[eval_off_slot[slot] + j] = 0.5 * (lo + hi);
+}
+
+// one warp per slot; lanes = eigenvalues (blocks of 32).  ws: per-warp workspace
+// of 4 double arrays + 1 int array, each 32*nmax entries, interleaved by lane.
+__global__ void k_inverse_iter(ChunkDev C, const int *AE2d_I, int nslots, const int *nev,
+                               const int64_t *eval_off_slot, const double *evals,
+                               const int64_t *evect_off_slot, double *evects,
+                               const double *tnorm, double *ws_d, int *ws_i, int nmax)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    double *u0inv = ws_d + (size_t)warp_global * 4 * 32 * nmax;
+    double *u1 = u0inv + (size_t)32 * nmax;
+    double *u2 = u1 + (size_t)32 * nmax;
+    double *mult = u2 + (size_t)32 * nmax;
+    int *swp = ws_i + (size_t)warp_global * 32 * nmax;
+
+    for (int slot = warp_global; slot < nslots; slot += nwarps)
+    {
+        const int m = nev[slot];
+        if (m <= 0)
+            continue;
+        const int part = C.ae_of_slot[slot];
+        const int n = AE2d_I[part + 1] - AE2d_I[part];
+        const double *d = C.d + C.doff[slot];
+        const double *e = C.e + C.doff[slot];
+        const double *lam = evals + eval_off_slot[slot];
+        double *Z = evects + evect_off_slot[slot];
+        const double tn = fmax(tnorm[slot], DBL_MIN);
+        const double pivtol = DBL_EPSILON * tn;
+        const double ortol = 1e-3 * tn; // dstein: ORTOL = ODM3 * ONENRM
+
+        if (n == 1)
+        {
+            if (lane == 0)
+                Z[0] = 1.;
+            continue;
+        }
+        for (int jb = 0; jb < m; jb += 32)
+        {
+            const int j = jb + lane;
+            const bool active = j < m;
+            // dstein: separate (nearly) equal eigenvalues so the shifted systems differ
+            double xj = 0.;
+            int gpind = 0; // first vector of the cluster of j
+            if (active)
+            {
+                double xprev = lam[0];
+                for (int q = 1; q <= j; ++q)
+                {
+                    double x = lam[q];
+                    const double pertol = 10. * fabs(DBL_EPSILON * x);
+                    if (x - xprev < pertol)
+                        x = xprev + pertol;
+                    if (fabs(x - xprev) > ortol)
+                        gpind = q;
+                    xprev = x;
+                }
+                xj = xprev;
+                sa_tridiag_lu_factor(n, d, e, xj, pivtol, u0inv + lane, u1 + lane, u2 + lane,
+                                     mult + lane, swp + lane, 32);
+                for (int i = 0; i < n; ++i)
+                    Z[i + (int64_t)n * j] =
+                        sa_hash_uniform(((uint64_t)part << 32) ^ ((uint64_t)j << 16) ^ (uint64_t)i);
+            }
+            __syncwarp();
+            for (int its = 0; its < 3; ++its)
+            {
+                if (active)
+                    sa_tridiag_lu_solve(n, u0inv + lane, u1 + lane, u2 + lane, mult + lane,
+                                        swp + lane, 32, Z + (int64_t)n * j, 1);
+                __syncwarp();
+                // modified Gram-Schmidt inside clusters + normalisation, vector by vector
+                const int jend = min(m, jb + 32);
+                for (int jj = jb; jj < jend; ++jj)
+                {
+                    const int gp = __shfl_sync(0xffffffffu, gpind, jj - jb);
+                    double *zj = Z + (int64_t)n * jj;
+                    for (int q = gp; q < jj; ++q)
+                    {
+                        const double *zq = Z + (int64_t)n * q;
+                        double s = 0.;
+                        for (int i = lane; i < n; i += 32)
+                            s += zq[i] * zj[i];
+                        s = warp_sum(s);
+                        for (int i = lane; i < n; i += 32)
+                            zj[i] -= s * zq[i];
+                        __syncwarp();
+                    }
+                    double s = 0., amax = 0.;
+                    for (int i = lane; i < n; i += 32)
+                        amax = fmax(amax, fabs(zj[i]));
+                    for (int o = 16; o > 0; o >>= 1)
+                        amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+                    const double sc = (amax > 0.) ? 1. / amax : 1.;
+                    for (int i = lane; i < n; i += 32)
+                    {
+                        const double t = zj[i] * sc;
+                        s += t * t;
+                    }
+                    s = warp_sum(s);
+                    const double nrm = (s > 0.) ? sc / sqrt(s) : 0.;
+                    for (int i = lane; i < n; i += 32)
+                        zj[i] *= nrm;
+                    __syncwarp();
+                }
+            }
+        }
+    }
+}
+
+// grid.x = slots; each warp of the block handles vectors w, w + nwarps, ...
+__global__ void k_back_transform(ChunkDev C, const int *AE2d_I, const int *nev, const int *m_total,
+                                 const int64_t *evect_off_slot, double *evects)
+{
+    const int slot = blockIdx.x;
+    const int m = nev[slot];
+    const int part = C.ae_of_slot[slot];
+    const int n = AE2d_I[part + 1] - AE2d_I[part];
+    const double *V = C.V + C.voff[slot];
+    const double *tau = C.tau + C.doff[slot];
+    const double *sinv = C.sinv + C.doff[slot];
+    double *Z = evects + evect_off_slot[slot];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int j = w; j < m; j += nw)
+    {
+        double *z = Z + (int64_t)n * j;
+        for (int k = n - 3; k >= 0; --k)
+        {
+            const double t = tau[k];
+            if (t == 0.)
+                continue;
+            const double *vk = V + (int64_t)n * k;
+            double s = 0.;
+            for (int i = k + 1 + lane; i < n; i += 32)
+                s += ((i == k + 1) ? 1. : vk[i]) * z[i];
+            s = warp_sum(s) * t;
+            for (int i = k + 1 + lane; i < n; i += 32)
+                z[i] -= s * ((i == k + 1) ? 1. : vk[i]);
+            __syncwarp();
+        }
+        for (int i = lane; i < n; i += 32)
+            z[i] *= sinv[i];
+    }
+    // mltest fixture: extra all-ones vector (amg/src/interp.cpp:510-524)
+    if (m_total[slot] > m)
+        for (int i = threadIdx.x; i < n; i += blockDim.x)
+            Z[i + (int64_t)n * m] = 1.0;
+}
+
+__global__ void k_check_finite(const double *x, int64_t n, int *flag)
+{
+    int bad = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        if (!isfinite(x[i]))
+            bad = 1;
+    if (bad)
+        *flag = 1;
+}
+
+__global__ void k_assemble_only(LevelTables L, int part, double *out)
+{
+    const int n = L.AE2d_I[part + 1] - L.AE2d_I[part];
+    sa_dev_assemble_AE(L, part, out, n);
+}
+
+} // namespace
+
+LevelTables sa_gpu_level::tables() const
+{
+    LevelTables T;
+    T.ND = ND;
+    T.NE = NE;
+    T.nparts = nparts;
+    T.num_mises = num_mises;
+    T.e2d_I = e2d_I.p;
+    T.e2d_J = e2d_J.p;
+    T.d2e_I = d2e_I.p;
+    T.d2e_J = d2e_J.p;
+    T.AE2e_I = AE2e_I.p;
+    T.AE2e_J = AE2e_J.p;
+    T.AE2d_I = AE2d_I.p;
+    T.AE2d_J = AE2d_J.p;
+    T.d2AE_I = d2AE_I.p;
+    T.d2AE_J = d2AE_J.p;
+    T.dof_id_inAE = dof_id_inAE.p;
+    T.partitioning = partitioning.p;
+    T.agg_flags = agg_flags.p;
+    T.mis2d_I = mis2d_I.p;
+    T.mis2d_J = mis2d_J.p;
+    T.mis2AE_I = mis2AE_I.p;
+    T.mis2AE_J = mis2AE_J.p;
+    T.AE2mis_I = AE2mis_I.p;
+    T.AE2mis_J = AE2mis_J.p;
+    T.mises = mises.p;
+    T.A_I = A ? A->I.p : nullptr;
+    T.A_J = A ? A->J.p : nullptr;
+    T.A_data = A ? A->A.p : nullptr;
+    T.elmat = elmat.p;
+    T.elmat_off = elmat_off.p;
+    T.with_global = with_global;
+    return T;
+}
+
+extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_begin, int ae_end,
+                                     int inject_ones_ae0)
+{
+    SA_API_BEGIN
+    sa_gpu_ctx *ctx = lev->ctx;
+    cudaStream_t st = ctx->stream;
+    if (!lev->have_elmat)
+        SA_FAIL("sa_gpu_local_spectral: level has no element matrices");
+    if (lev->with_global && !lev->A)
+        SA_FAIL("sa_gpu_local_spectral: with_global assembly needs the operator");
+    ae_begin = std::max(0, ae_begin);
+    ae_end = std::min(lev->nparts, ae_end);
+    const int nparts = lev->nparts;
+    const std::vector<int> &AI = lev->h_AE2d_I;
+    LevelTables L = lev->tables();
+
+    if (lev->h_ae_m.size() != (size_t)nparts)
+    {
+        lev->h_ae_m.assign(nparts, 0);
+        lev->h_ae_nev.assign(nparts, 0);
+    }
+    lev->ae_D.ensure(AI[nparts]);
+
+    // chunks of consecutive AEs bounded by the reflector storage budget
+    const size_t budget_doubles = (size_t)3 << 30; // 24 GB of reflectors per chunk
+    int nmax_smem = 0;
+    {
+        // n*n + 3n + 40 doubles must fit
+        const size_t cap = ctx->smem_optin / sizeof(double);
+        int n = 1;
+        while ((size_t)(n + 1) * (n + 1) + 3 * (size_t)(n + 1) + 40 <= cap)
+            ++n;
+        nmax_smem = n;
+    }
+
+    struct PieceResult
+    {
+        int a0, a1;
+        std::vector<int> nev, mtot;
+        DevBuf<double> evals, evects;
+        std::vector<int64_t> eval_off, evect_off;
+    };
+    std::vector<PieceResult *> pieces;
+    struct PieceGuard
+    {
+        std::vector<PieceResult *> &p;
+        ~PieceGuard()
+        {
+            for (size_t i = 0; i < p.size(); ++i)
+                delete p[i];
+        }
+    } guard{pieces};
+
+    int a0 = ae_begin;
+    while (a0 < ae_end)
+    {
+        size_t vtot = 0;
+        int a1 = a0;
+        while (a1 < ae_end)
+        {
+            const size_t n = AI[a1 + 1] - AI[a1];
+            if (a1 > a0 && vtot + n * n > budget_doubles)
+                break;
+            vtot += n * n;
+            ++a1;
+        }
+        const int ns = a1 - a0;
+        std::vector<int> h_ae(ns), h_doff(ns);
+        std::vector<int64_t> h_voff(ns);
+        int64_t vo = 0;
+        int dofftot = 0, nmax = 1;
+        for (int s = 0; s < ns; ++s)
+        {
+            const int n = AI[a0 + s + 1] - AI[a0 + s];
+            h_ae[s] = a0 + s;
+            h_voff[s] = vo;
+            h_doff[s] = dofftot;
+            vo += (int64_t)n * n;
+            dofftot += n;
+            nmax = std::max(nmax, n);
+        }
+        DevBuf<int> d_ae, d_doff, d_status;
+        DevBuf<int64_t> d_voff;
+        DevBuf<double> d_V, d_d, d_e, d_tau, d_sinv;
+        d_ae.upload(h_ae.data(), ns, st);
+        d_doff.upload(h_doff.data(), ns, st);
+        d_voff.upload(h_voff.data(), ns, st);
+        d_status.alloc(ns);
+        d_status.zero(st);
+        d_V.alloc(vo);
+        d_d.alloc(dofftot);
+        d_e.alloc(dofftot);
+        d_tau.alloc(dofftot);
+        d_sinv.alloc(dofftot);
+        ChunkDev C;
+        C.ae_of_slot = d_ae.p;
+        C.voff = d_voff.p;
+        C.doff = d_doff.p;
+        C.V = d_V.p;
+        C.d = d_d.p;
+        C.e = d_e.p;
+        C.tau = d_tau.p;
+        C.sinv = d_sinv.p;
+        C.status = d_status.p;
+
+        // size buckets: slots sorted by n (largest first); shared-memory tiles for
+        // n <= nmax_smem with the dynamic shared size of the bucket's largest n
+        std::vector<int> order(ns);
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+            return (AI[a0 + x + 1] - AI[a0 + x]) > (AI[a0 + y + 1] - AI[a0 + y]);
+        });
+        DevBuf<int> d_order;
+        d_order.upload(order.data(), ns, st);
+        const int bucket_edges[] = {32, 48, 64, 80, 96, 112, 128, 144, 160, nmax_smem};
+        int pos = 0;
+        // large (global-memory tile) bucket first
+        {
+            int cnt = 0;
+            while (pos + cnt < ns && (AI[a0 + order[pos + cnt] + 1] - AI[a0 + order[pos + cnt]]) > nmax_smem)
+                ++cnt;
+            if (cnt)
+            {
+                const int nb = AI[a0 + order[pos] + 1] - AI[a0 + order[pos]];
+                const size_t smem = (size_t)(3 * nb + 40) * sizeof(double);
+                SA_CUDA(cudaFuncSetAttribute(k_assemble_tridiag,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)ctx->smem_optin));
+                SA_LAUNCH(ctx, k_assemble_tridiag, cnt, 512, smem, L, C, d_order.p + pos, cnt, 0,
+                          lev->ae_D.p);
+                pos += cnt;
+            }
+        }
+        for (int b = (int)(sizeof(bucket_edges) / sizeof(int)) - 1; b >= 0 && pos < ns; --b)
+        {
+            const int lo_edge = (b == 0) ? 0 : std::min(bucket_edges[b - 1], nmax_smem);
+            int cnt = 0;
+            while (pos + cnt < ns && (AI[a0 + order[pos + cnt] + 1] - AI[a0 + order[pos + cnt]]) > lo_edge)
+                ++cnt;
+            if (!cnt)
+                continue;
+            const int nb = AI[a0 + order[pos] + 1] - AI[a0 + order[pos]];
+            const size_t smem = ((size_t)nb * nb + 3 * (size_t)nb + 40) * sizeof(double);
+            SA_CUDA(cudaFuncSetAttribute(k_assemble_tridiag,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)ctx->smem_optin));
+            const int threads = nb <= 64 ? 64 : (nb <= 128 ? 128 : 192);
+            SA_LAUNCH(ctx, k_assemble_tridiag, cnt, threads, smem, L, C, d_order.p + pos, cnt, 1,
+                      lev->ae_D.p);
+            pos += cnt;
+        }
+
+        // counts
+        DevBuf<int> d_nev, d_mtot;
+        DevBuf<double> d_glo, d_ghi, d_tn;
+        d_nev.alloc(ns);
+        d_mtot.alloc(ns);
+        d_glo.alloc(ns);
+        d_ghi.alloc(ns);
+        d_tn.alloc(ns);
+        SA_LAUNCH(ctx, k_count, (ns + 127) / 128, 128, 0, C, lev->AE2d_I.p, ns, theta,
+                  inject_ones_ae0, d_nev.p, d_mtot.p, d_glo.p, d_ghi.p, d_tn.p);
+        PieceResult *pr = new PieceResult;
+        pieces.push_back(pr);
+        pr->a0 = a0;
+        pr->a1 = a1;
+        pr->nev.resize(ns);
+        pr->mtot.resize(ns);
+        std::vector<int> h_status(ns);
+        d_nev.download(pr->nev.data(), ns, st);
+        d_mtot.download(pr->mtot.data(), ns, st);
+        d_status.download(h_status.data(), ns, st);
+        SA_CUDA(cudaStreamSynchronize(st));
+        for (int s = 0; s < ns; ++s)
+            if (h_status[s])
+                SA_FAIL("sa_gpu_local_spectral: AE %d has a non-positive diagonal "
+                        "(SA_ASSERT(diag > 0.) in mbox_snd_D_sparse_from_sparse)",
+                        a0 + s);
+        pr->eval_off.assign(ns + 1, 0);
+        pr->evect_off.assign(ns + 1, 0);
+        std::vector<int> ev_slot, ev_idx;
+        for (int s = 0; s < ns; ++s)
+        {
+            const int n = AI[a0 + s + 1] - AI[a0 + s];
+            pr->eval_off[s + 1] = pr->eval_off[s] + pr->nev[s];
+            pr->evect_off[s + 1] = pr->evect_off[s] + (int64_t)n * pr->mtot[s];
+            for (int j = 0; j < pr->nev[s]; ++j)
+            {
+                ev_slot.push_back(s);
+                ev_idx.push_back(j);
+            }
+        }
+        const int nev_total = (int)pr->eval_off[ns];
+        DevBuf<int> d_ev_slot, d_ev_idx;
+        DevBuf<int64_t> d_eval_off, d_evect_off;
+        d_ev_slot.upload(ev_slot.data(), nev_total, st);
+        d_ev_idx.upload(ev_idx.data(), nev_total, st);
+        d_eval_off.upload(pr->eval_off.data(), ns + 1, st);
+        d_evect_off.upload(pr->evect_off.data(), ns + 1, st);
+        pr->evals.alloc(nev_total);
+        pr->evects.alloc(pr->evect_off[ns]);
+        SA_LAUNCH(ctx, k_bisect, (nev_total + 127) / 128, 128, 0, C, lev->AE2d_I.p, d_ev_slot.p,
+                  d_ev_idx.p, nev_total, d_glo.p, d_ghi.p, d_tn.p, d_eval_off.p, pr->evals.p);
+        // inverse iteration
+        {
+            // resident warps bounded by workspace: 4 double + 1 int arrays of 32*nmax
+            const size_t per_warp = (size_t)32 * nmax * (4 * sizeof(double) + sizeof(int));
+            size_t warps = std::min<size_t>((size_t)ctx->num_sms * 16, (size_t)ns);
+            const size_t ws_budget = (size_t)4 << 30;
+            warps = std::max<size_t>(1, std::min(warps, ws_budget / per_warp));
+            const int wpb = 4;
+            const int blocks = (int)((warps + wpb - 1) / wpb);
+            DevBuf<double> ws_d;
+            DevBuf<int> ws_i;
+            ws_d.alloc((size_t)blocks * wpb * 4 * 32 * nmax);
+            ws_i.alloc((size_t)blocks * wpb * 32 * nmax);
+            SA_LAUNCH(ctx, k_inverse_iter, blocks, wpb * 32, 0, C, lev->AE2d_I.p, ns, d_nev.p,
+                      d_eval_off.p, pr->evals.p, d_evect_off.p, pr->evects.p, d_tn.p, ws_d.p,
+                      ws_i.p, nmax);
+            SA_LAUNCH(ctx, k_back_transform, ns, 128, 0, C, lev->AE2d_I.p, d_nev.p, d_mtot.p,
+                      d_evect_off.p, pr->evects.p);
+            SA_CUDA(cudaStreamSynchronize(st)); // workspace freed at scope exit
+        }
+        a0 = a1;
+    }
+
+    // merge the pieces into the level's flat arrays (range [ae_begin, ae_end) only)
+    for (size_t p = 0; p < pieces.size(); ++p)
+        for (int s = 0; s < pieces[p]->a1 - pieces[p]->a0; ++s)
+        {
+            lev->h_ae_m[pieces[p]->a0 + s] = pieces[p]->mtot[s];
+            lev->h_ae_nev[pieces[p]->a0 + s] = pieces[p]->nev[s];
+        }
+    lev->h_eval_off.assign(nparts + 1, 0);
+    lev->h_evect_off.assign(nparts + 1, 0);
+    for (int i = 0; i < nparts; ++i)
+    {
+        const int n = AI[i + 1] - AI[i];
+        lev->h_eval_off[i + 1] = lev->h_eval_off[i] + lev->h_ae_nev[i];
+        lev->h_evect_off[i + 1] = lev->h_evect_off[i] + (int64_t)n * lev->h_ae_m[i];
+    }
+    // (re)allocate the flat arrays; a partial range keeps nothing outside it, so
+    // sharded callers use sa_gpu_set_spectral for the other ranges afterwards
+    lev->evals.alloc(lev->h_eval_off[nparts]);
+    lev->evects.alloc(lev->h_evect_off[nparts]);
+    for (size_t p = 0; p < pieces.size(); ++p)
+    {
+        PieceResult *pr = pieces[p];
+        const int ns = pr->a1 - pr->a0;
+        if (pr->eval_off[ns])
+            SA_CUDA(cudaMemcpyAsync(lev->evals.p + lev->h_eval_off[pr->a0], pr->evals.p,
+                                    pr->eval_off[ns] * sizeof(double), cudaMemcpyDeviceToDevice,
+                                    st));
+        if (pr->evect_off[ns])
+            SA_CUDA(cudaMemcpyAsync(lev->evects.p + lev->h_evect_off[pr->a0], pr->evects.p,
+                                    pr->evect_off[ns] * sizeof(double), cudaMemcpyDeviceToDevice,
+                                    st));
+    }
+    lev->ae_m.upload(lev->h_ae_m.data(), nparts, st);
+    lev->evect_off.upload(lev->h_evect_off.data(), nparts + 1, st);
+    lev->eval_off.upload(lev->h_eval_off.data(), nparts + 1, st);
+    // fail loudly on non-finite vectors
+    {
+        DevBuf<int> flag;
+        flag.alloc(1);
+        flag.zero(st);
+        if (lev->h_evect_off[nparts])
+            SA_LAUNCH(ctx, k_check_finite, ctx->num_sms * 4, 256, 0, lev->evects.p,
+                      lev->h_evect_off[nparts], flag.p);
+        int h = 0;
+        flag.download(&h, 1, st);
+        SA_CUDA(cudaStreamSynchronize(st));
+        if (h)
+            SA_FAIL("sa_gpu_local_spectral: non-finite eigenvector entries");
+    }
+    lev->have_spectral = true;
+    SA_API_END
+}
+
+extern "C" int sa_gpu_get_spectral_counts(sa_gpu_level *lev, int *ae_m)
+{
+    SA_API_BEGIN
+    if (!lev->have_spectral)
+        SA_FAIL("sa_gpu_get_spectral_counts: no spectral data");
+    std::copy(lev->h_ae_m.begin(), lev->h_ae_m.end(), ae_m);
+    SA_API_END
+}
+
+extern "C" int sa_gpu_get_spectral(sa_gpu_level *lev, double *evals, double *evects, double *D)
+{
+    SA_API_BEGIN
+    if (!lev->have_spectral)
+        SA_FAIL("sa_gpu_get_spectral: no spectral data");
+    cudaStream_t st = lev->ctx->stream;
+    if (evals)
+        lev->evals.download(evals, lev->h_eval_off[lev->nparts], st);
+    if (evects)
+        lev->evects.download(evects, lev->h_evect_off[lev->nparts], st);
+    if (D)
+        lev->ae_D.download(D, lev->h_AE2d_I[lev->nparts], st);
+    SA_CUDA(cudaStreamSynchronize(st));
+    SA_API_END
+}
+
+extern "C" int sa_gpu_set_spectral(sa_gpu_level *lev, int ae_begin, int ae_end, const int *ae_m,
+                                   const double *evals, const double *evects, const double *D)
+{
+    SA_API_BEGIN
+    // Replaces the whole set when [ae_begin, ae_end) == [0, nparts); a partial range
+    // requires counts that match what the level already holds.
+    cudaStream_t st = lev->ctx->stream;
+    const int nparts = lev->nparts;
+    const std::vector<int> &AI = lev->h_AE2d_I;
+    if (ae_begin == 0 && ae_end == nparts)
+    {
+        lev->h_ae_m.assign(ae_m, ae_m + nparts);
+        lev->h_ae_nev = lev->h_ae_m;
+        lev->h_eval_off.assign(nparts + 1, 0);
+        lev->h_evect_off.assign(nparts + 1, 0);
+        for (int i = 0; i < nparts; ++i)
+        {
+            lev->h_eval_off[i + 1] = lev->h_eval_off[i] + ae_m[i];
+            lev->h_evect_off[i + 1] = lev->h_evect_off[i] + (int64_t)(AI[i + 1] - AI[i]) * ae_m[i];
+        }
+        lev->evects.upload(evects, lev->h_evect_off[nparts], st);
+        if (evals)
+            lev->evals.upload(evals, lev->h_eval_off[nparts], st);
+        else
+            lev->evals.alloc(lev->h_eval_off[nparts]);
+        if (D)
+            lev->ae_D.upload(D, AI[nparts], st);
+        lev->ae_m.upload(lev->h_ae_m.data(), nparts, st);
+        lev->evect_off.upload(lev->h_evect_off.data(), nparts + 1, st);
+        lev->eval_off.upload(lev->h_eval_off.data(), nparts + 1, st);
+        SA_CUDA(cudaStreamSynchronize(st));
+        lev->have_spectral = true;
+    }
+    else
+        SA_FAIL("sa_gpu_set_spectral: only the full range is supported");
+    SA_API_END
+}
+
+extern "C" int sa_gpu_build_AE_stiff(sa_gpu_level *lev, int part, double *dense_out)
+{
+    SA_API_BEGIN
+    if (part < 0 || part >= lev->nparts)
+        SA_FAIL("sa_gpu_build_AE_stiff: bad AE index %d", part);
+    if (!lev->have_elmat)
+        SA_FAIL("sa_gpu_build_AE_stiff: level has no element matrices");
+    const int n = lev->h_AE2d_I[part + 1] - lev->h_AE2d_I[part];
+    DevBuf<double> out;
+    out.alloc((size_t)n * n);
+    LevelTables L = lev->tables();
+    SA_LAUNCH(lev->ctx, k_assemble_only, 1, 256, 0, L, part, out.p);
+    out.download(dense_out, (size_t)n * n, lev->ctx->stream);
+    SA_CUDA(cudaStreamSynchronize(lev->ctx->stream));
+    SA_API_END
+}

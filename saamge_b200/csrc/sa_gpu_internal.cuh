@@ -1,0 +1,218 @@
+// Internal declarations shared by the CUDA translation units.
+#ifndef SA_GPU_INTERNAL_CUH
+#define SA_GPU_INTERNAL_CUH
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/saamge_b200.h"
+
+void sa_gpu_set_error(const char *fmt, ...);
+
+#define SA_CUDA(call)                                                              \
+    do {                                                                           \
+        cudaError_t e__ = (call);                                                  \
+        if (e__ != cudaSuccess) {                                                  \
+            sa_gpu_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,         \
+                             cudaGetErrorString(e__));                             \
+            throw std::runtime_error("cuda");                                      \
+        }                                                                          \
+    } while (0)
+
+#define SA_FAIL(...)                                                               \
+    do {                                                                           \
+        sa_gpu_set_error(__VA_ARGS__);                                             \
+        throw std::runtime_error("sa_gpu");                                        \
+    } while (0)
+
+// every extern "C" body is wrapped so no exception crosses the C ABI
+#define SA_API_BEGIN try {
+#define SA_API_END                                                                 \
+    }                                                                              \
+    catch (const std::exception &ex__)                                             \
+    {                                                                              \
+        if (std::strcmp(ex__.what(), "cuda") != 0 &&                               \
+            std::strcmp(ex__.what(), "sa_gpu") != 0)                               \
+            sa_gpu_set_error("exception: %s", ex__.what());                        \
+        return 1;                                                                  \
+    }                                                                              \
+    return 0;
+
+template <class T> struct DevBuf
+{
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release()
+    {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    void alloc(size_t count)
+    {
+        release();
+        n = count;
+        SA_CUDA(cudaMalloc((void **)&p, (count ? count : 1) * sizeof(T)));
+    }
+    void ensure(size_t count)
+    {
+        if (count > n || !p)
+            alloc(count);
+    }
+    void upload(const T *h, size_t count, cudaStream_t s)
+    {
+        ensure(count);
+        n = count;
+        if (count)
+            SA_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    void download(T *h, size_t count, cudaStream_t s) const
+    {
+        if (count)
+            SA_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
+    }
+    void zero(cudaStream_t s)
+    {
+        if (n)
+            SA_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+    }
+    void swap(DevBuf &o)
+    {
+        std::swap(p, o.p);
+        std::swap(n, o.n);
+    }
+};
+
+struct DevCsr
+{
+    int rows = 0, cols = 0, nnz = 0;
+    DevBuf<int> I, J;
+    DevBuf<double> A;
+    void swap(DevCsr &o)
+    {
+        std::swap(rows, o.rows);
+        std::swap(cols, o.cols);
+        std::swap(nnz, o.nnz);
+        I.swap(o.I);
+        J.swap(o.J);
+        A.swap(o.A);
+    }
+};
+
+struct sa_gpu_ctx
+{
+    int device = 0;
+    int num_sms = 148;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int64_t launches = 0;
+};
+
+#define SA_LAUNCH(ctx, kernel, grid, block, smem, ...)                             \
+    do {                                                                           \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);           \
+        (ctx)->launches++;                                                         \
+        SA_CUDA(cudaGetLastError());                                               \
+    } while (0)
+
+/* device view of the integer tables of a level */
+struct LevelTables
+{
+    int ND, NE, nparts, num_mises;
+    const int *e2d_I, *e2d_J;
+    const int *d2e_I, *d2e_J;
+    const int *AE2e_I, *AE2e_J;
+    const int *AE2d_I, *AE2d_J;
+    const int *d2AE_I, *d2AE_J, *dof_id_inAE;
+    const int *partitioning;
+    const char *agg_flags;
+    const int *mis2d_I, *mis2d_J;
+    const int *mis2AE_I, *mis2AE_J;
+    const int *AE2mis_I, *AE2mis_J;
+    const int *mises;
+    const int *A_I, *A_J;
+    const double *A_data;
+    const double *elmat;
+    const int64_t *elmat_off;
+    int with_global;
+};
+
+struct sa_gpu_level
+{
+    sa_gpu_ctx *ctx = nullptr;
+    sa_gpu_level *finer = nullptr;
+    int ND = 0, NE = 0, nparts = 0, num_mises = 0;
+    int with_global = 0;
+    // host copies of the small index arrays needed for bucketing
+    std::vector<int> h_AE2d_I, h_mis2d_I, h_mis2AE_I, h_mis2AE_J, h_e2d_I;
+    std::vector<int> h_mis_coarsedofoffsets; // finer MIS -> coarse dof (coarse levels)
+    // device tables
+    DevBuf<int> e2d_I, e2d_J, d2e_I, d2e_J, AE2e_I, AE2e_J, AE2d_I, AE2d_J, d2AE_I, d2AE_J,
+        dof_id_inAE, partitioning, mis2d_I, mis2d_J, mis2AE_I, mis2AE_J, AE2mis_I, AE2mis_J,
+        mises, mis_cdof_off;
+    DevBuf<char> agg_flags;
+    // operator: own copy (finest) or alias of finer->Ac
+    DevCsr A_own;
+    DevCsr *A = nullptr;
+    // element matrices: own (finest) or produced by sa_gpu_coarse_elmats
+    DevBuf<double> elmat;
+    DevBuf<int64_t> elmat_off;
+    std::vector<int64_t> h_elmat_off;
+    bool have_elmat = false;
+    // local spectral results
+    bool have_spectral = false;
+    std::vector<int> h_ae_m;             // accepted vectors per AE (incl. injected)
+    std::vector<int> h_ae_nev;           // eigenvalues per AE
+    std::vector<int64_t> h_evect_off;    // nparts+1
+    std::vector<int64_t> h_eval_off;     // nparts+1
+    DevBuf<int> ae_m;
+    DevBuf<int64_t> evect_off, eval_off;
+    DevBuf<double> evals, evects, ae_D;  // ae_D offsets = AE2d_I
+    double max_residual = 0.;
+    // tentative P
+    bool have_tent = false;
+    int avoid_ess = 1;
+    std::vector<int> h_mis_ncd;          // mis_numcoarsedof
+    std::vector<int64_t> h_mis_off;      // num_mises+1 (s*k)
+    DevBuf<int> mis_ncd, mis_cd_off;     // coarse dof offsets per MIS (num_mises+1)
+    DevBuf<int64_t> mis_off;
+    DevBuf<double> mis_tent;
+    int NDc = 0;
+    DevCsr Ptent, P, R, Ac;
+    bool have_P = false, have_Ac = false;
+    DevBuf<double> Dinv_neg;
+    bool have_Dinv = false;
+    // scratch vectors for host-buffer SpMV / smoother calls and micro-benchmarks
+    DevBuf<double> vx, vy, vb;
+
+    LevelTables tables() const;
+};
+
+/* ---- sparse.cu ---- */
+void dev_csr_transpose(sa_gpu_ctx *ctx, const DevCsr &A, DevCsr &At);
+void dev_spgemm(sa_gpu_ctx *ctx, const DevCsr &A, const DevCsr &B, DevCsr &C);
+void dev_spmv(sa_gpu_ctx *ctx, const DevCsr &A, const double *x, double *y);
+/* y = b - A x */
+void dev_residual(sa_gpu_ctx *ctx, const DevCsr &A, const double *x, const double *b, double *y);
+/* y += A x */
+void dev_spmv_add(sa_gpu_ctx *ctx, const DevCsr &A, const double *x, double *y);
+/* xout = xin + mult * dinv_neg .* (A xin - b);  first==1: xin == 0 (skips the SpMV) */
+void dev_smoother_step(sa_gpu_ctx *ctx, const DevCsr &A, const double *dinv_neg, const double *b,
+                       const double *xin, double *xout, double mult, int xin_is_zero);
+void dev_exclusive_scan_i32(sa_gpu_ctx *ctx, const int *in, int *out, int n); // out has n+1
+void dev_exclusive_scan_i64(sa_gpu_ctx *ctx, const int64_t *in, int64_t *out, int n);
+
+#endif

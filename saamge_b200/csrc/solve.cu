@@ -1,0 +1,467 @@
+// Solve phase on the device: SAS polynomial
+// smoother (smpr_sym_poly / smpr_compute_poly, amg/src/smpr.cpp:213-234,
+// amg/inc/smpr.hpp:319-339), V-cycle (tg_cycle_atb, amg/src/tg.cpp:91-132;
+// VCycleSolver::Mult, amg/src/solve.cpp:309-323; ml_impose_cycle, amg/src/ml.cpp:361-377),
+// PCG (kalchev_pcg, amg/src/mfem_addons.cpp:106-248) and the exact coarsest solve that
+// stands in for the reference's --coarse-direct UMFPACK solver (amg/src/tg.cpp:991-998).
+#include <algorithm>
+#include <cmath>
+
+#include "sa_gpu_internal.cuh"
+
+struct SolverLevel
+{
+    sa_gpu_level *lev = nullptr;
+    DevBuf<double> b, xa, xb, r; // rhs, ping/pong iterate, residual (size ND of the level)
+};
+
+struct sa_gpu_solver
+{
+    sa_gpu_ctx *ctx = nullptr;
+    std::vector<SolverLevel *> L;
+    int degree = 0;
+    std::vector<double> roots;
+    // coarsest
+    int nc = 0;
+    DevBuf<double> Ainv; // dense nc x nc
+    DevBuf<double> bc, xc;
+    // PCG work vectors on level 0
+    DevBuf<double> pb, px, pr, pd, pz;
+    DevBuf<double> dots; // device scalars
+    ~sa_gpu_solver()
+    {
+        for (size_t i = 0; i < L.size(); ++i)
+            delete L[i];
+    }
+};
+
+namespace
+{
+
+__global__ void k_densify(int n, const int *I, const int *J, const double *A, double *D)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n)
+        return;
+    for (int p = I[r]; p < I[r + 1]; ++p)
+        D[r + (int64_t)n * J[p]] = A[p];
+}
+
+// single block, right-looking Cholesky of the lower triangle (column-major)
+__global__ void k_cholesky(int n, double *A, int *info)
+{
+    __shared__ double piv;
+    for (int k = 0; k < n; ++k)
+    {
+        if (threadIdx.x == 0)
+        {
+            const double a = A[k + (int64_t)n * k];
+            if (!(a > 0.))
+            {
+                *info = k + 1;
+                piv = 0.;
+            }
+            else
+            {
+                piv = sqrt(a);
+                A[k + (int64_t)n * k] = piv;
+            }
+        }
+        __syncthreads();
+        const double pv = piv;
+        if (pv == 0.)
+            return;
+        const double inv = 1. / pv;
+        for (int i = k + 1 + threadIdx.x; i < n; i += blockDim.x)
+            A[i + (int64_t)n * k] *= inv;
+        __syncthreads();
+        // trailing update: column j gets -= L[j,k] * L[j:n,k]
+        const int64_t rem = n - k - 1;
+        for (int64_t t = threadIdx.x; t < rem * rem; t += blockDim.x)
+        {
+            const int i = k + 1 + (int)(t % rem);
+            const int j = k + 1 + (int)(t / rem);
+            if (i >= j)
+                A[i + (int64_t)n * j] -= A[i + (int64_t)n * k] * A[j + (int64_t)n * k];
+        }
+        __syncthreads();
+    }
+}
+
+// thread per column j of the inverse: solve L y = e_j, L^T x = y; X stored row-major
+// (X[j + n*i] = x_i) so that writes coalesce
+__global__ void k_chol_inverse(int n, const double *Lm, double *X)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n)
+        return;
+    for (int i = 0; i < n; ++i)
+    {
+        double s = (i == j) ? 1. : 0.;
+        if (i >= j)
+        {
+            for (int k = j; k < i; ++k)
+                s -= Lm[i + (int64_t)n * k] * X[j + (int64_t)n * k];
+            s /= Lm[i + (int64_t)n * i];
+        }
+        else
+            s = 0.;
+        X[j + (int64_t)n * i] = s;
+    }
+    for (int i = n - 1; i >= 0; --i)
+    {
+        double s = X[j + (int64_t)n * i];
+        for (int k = i + 1; k < n; ++k)
+            s -= Lm[k + (int64_t)n * i] * X[j + (int64_t)n * k];
+        X[j + (int64_t)n * i] = s / Lm[i + (int64_t)n * i];
+    }
+}
+
+__global__ void k_symmetrize(int n, const double *X, double *S)
+{
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= (int64_t)n * n)
+        return;
+    const int i = (int)(t % n), j = (int)(t / n);
+    S[t] = 0.5 * (X[i + (int64_t)n * j] + X[j + (int64_t)n * i]);
+}
+
+// y = S x, S dense symmetric n x n; one warp per row (rows read as columns: coalesced)
+__global__ void k_dense_symv(int n, const double *S, const double *x, double *y)
+{
+    const int lane = threadIdx.x & 31;
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= n)
+        return;
+    const double *col = S + (int64_t)n * row;
+    double s = 0.;
+    for (int i = lane; i < n; i += 32)
+        s += col[i] * x[i];
+    for (int o = 16; o > 0; o >>= 1)
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0)
+        y[row] = s;
+}
+
+// out[slot] = sum a_i b_i (two-stage: per-block partials then atomicAdd)
+__global__ void k_dot(int n, const double *a, const double *b, double *out)
+{
+    __shared__ double sh[32];
+    double s = 0.;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        s += a[i] * b[i];
+    for (int o = 16; o > 0; o >>= 1)
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0)
+        sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32)
+    {
+        double t = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.;
+        for (int o = 16; o > 0; o >>= 1)
+            t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0)
+            atomicAdd(out, t);
+    }
+}
+
+// x += alpha d ; r -= alpha z
+__global__ void k_pcg_update(int n, double alpha, const double *d, const double *z, double *x,
+                             double *r)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    x[i] = x[i] + alpha * d[i];
+    r[i] = r[i] - alpha * z[i];
+}
+
+// d = z + beta d
+__global__ void k_pcg_dir(int n, double beta, const double *z, double *d)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    d[i] = z[i] + beta * d[i];
+}
+
+double dev_dot(sa_gpu_solver *S, int n, const double *a, const double *b)
+{
+    sa_gpu_ctx *ctx = S->ctx;
+    SA_CUDA(cudaMemsetAsync(S->dots.p, 0, sizeof(double), ctx->stream));
+    const int blocks = std::max(1, std::min(ctx->num_sms * 4, (n + 255) / 256));
+    SA_LAUNCH(ctx, k_dot, blocks, 256, 0, n, a, b, S->dots.p);
+    double h = 0.;
+    SA_CUDA(cudaMemcpyAsync(&h, S->dots.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SA_CUDA(cudaStreamSynchronize(ctx->stream));
+    return h;
+}
+
+// smpr_compute_poly on device buffers; result ends in *xcur (pointer swap)
+void dev_poly_smooth(sa_gpu_ctx *ctx, const DevCsr &A, const double *dinv, const double *b,
+                     double **xcur, double **xalt, int degree, const double *roots,
+                     bool x_is_zero)
+{
+    for (int i = 0; i < degree; ++i)
+    {
+        const double mult = 1. / roots[i];
+        dev_smoother_step(ctx, A, dinv, b, *xcur, *xalt, mult, (x_is_zero && i == 0) ? 1 : 0);
+        std::swap(*xcur, *xalt);
+    }
+}
+
+// tg_cycle_atb on level l; rhs in SL.b; result pointer returned (xa or xb)
+double *dev_vcycle(sa_gpu_solver *S, int l)
+{
+    sa_gpu_ctx *ctx = S->ctx;
+    SolverLevel &SL = *S->L[l];
+    sa_gpu_level *lev = SL.lev;
+    const DevCsr &A = *lev->A;
+    double *xcur = SL.xa.p, *xalt = SL.xb.p;
+    // x = 0 (iterative_mode == false); pre-smoother
+    dev_poly_smooth(ctx, A, lev->Dinv_neg.p, SL.b.p, &xcur, &xalt, S->degree, S->roots.data(),
+                    true);
+    // res = b - A x ; resc = restr * res
+    dev_residual(ctx, A, xcur, SL.b.p, SL.r.p);
+    double *xc = nullptr;
+    if (l + 1 < (int)S->L.size())
+    {
+        SolverLevel &SC = *S->L[l + 1];
+        dev_spmv(ctx, lev->R, SL.r.p, SC.b.p);
+        xc = dev_vcycle(S, l + 1);
+    }
+    else
+    {
+        dev_spmv(ctx, lev->R, SL.r.p, S->bc.p);
+        SA_LAUNCH(ctx, k_dense_symv, (S->nc + 7) / 8, 256, 0, S->nc, S->Ainv.p, S->bc.p, S->xc.p);
+        xc = S->xc.p;
+    }
+    // x += interp * xc
+    dev_spmv_add(ctx, lev->P, xc, xcur);
+    // post-smoother
+    dev_poly_smooth(ctx, A, lev->Dinv_neg.p, SL.b.p, &xcur, &xalt, S->degree, S->roots.data(),
+                    false);
+    return xcur;
+}
+
+} // namespace
+
+extern "C" int sa_gpu_solver_create(sa_gpu_ctx *ctx, sa_gpu_level **levels, int nlevels,
+                                    int nu_relax, sa_gpu_solver **out)
+{
+    SA_API_BEGIN
+    if (nlevels < 1 || nu_relax < 1)
+        SA_FAIL("sa_gpu_solver_create: bad arguments");
+    sa_gpu_solver *S = new sa_gpu_solver;
+    S->ctx = ctx;
+    struct Guard
+    {
+        sa_gpu_solver *s;
+        ~Guard() { delete s; }
+    } g{S};
+    cudaStream_t st = ctx->stream;
+    // smpr_sas_poly_roots (amg/src/smpr.cpp:282-306)
+    {
+        const int nu = nu_relax, twonu = 2 * nu;
+        const double denom = (double)(2 * nu + 1);
+        S->degree = twonu + nu + 1;
+        S->roots.resize(S->degree);
+        for (int i = 0; i <= twonu; ++i)
+        {
+            const double val = cos(((double)i * M_PI) / denom);
+            S->roots[i] = val * val;
+        }
+        for (int i = 1; i <= nu; ++i)
+        {
+            const double val = sin(((double)i * M_PI) / denom);
+            S->roots[i + twonu] = val * val;
+        }
+    }
+    for (int l = 0; l < nlevels; ++l)
+    {
+        sa_gpu_level *lev = levels[l];
+        if (!lev->have_Ac || !lev->have_P || !lev->have_Dinv)
+            SA_FAIL("sa_gpu_solver_create: level %d is not fully set up", l);
+        SolverLevel *SL = new SolverLevel;
+        S->L.push_back(SL);
+        SL->lev = lev;
+        SL->b.alloc(lev->ND);
+        SL->xa.alloc(lev->ND);
+        SL->xb.alloc(lev->ND);
+        SL->r.alloc(lev->ND);
+    }
+    // exact coarsest solve: dense inverse of the last Ac through Cholesky
+    {
+        const DevCsr &Ac = levels[nlevels - 1]->Ac;
+        const int n = Ac.rows;
+        if (n > 20000)
+            SA_FAIL("sa_gpu_solver_create: coarsest operator has %d rows; the exact dense "
+                    "coarsest solve supports at most 20000 -- add levels", n);
+        S->nc = n;
+        DevBuf<double> Lm, X;
+        DevBuf<int> info;
+        Lm.alloc((size_t)n * n);
+        Lm.zero(st);
+        X.alloc((size_t)n * n);
+        info.alloc(1);
+        info.zero(st);
+        S->Ainv.alloc((size_t)n * n);
+        S->bc.alloc(n);
+        S->xc.alloc(n);
+        if (n)
+        {
+            SA_LAUNCH(ctx, k_densify, (n + 255) / 256, 256, 0, n, Ac.I.p, Ac.J.p, Ac.A.p, Lm.p);
+            SA_LAUNCH(ctx, k_cholesky, 1, 1024, 0, n, Lm.p, info.p);
+            SA_LAUNCH(ctx, k_chol_inverse, (n + 63) / 64, 64, 0, n, Lm.p, X.p);
+            const int64_t nn = (int64_t)n * n;
+            SA_LAUNCH(ctx, k_symmetrize, (unsigned)((nn + 255) / 256), 256, 0, n, X.p, S->Ainv.p);
+        }
+        int h = 0;
+        info.download(&h, 1, st);
+        SA_CUDA(cudaStreamSynchronize(st));
+        if (h)
+            SA_FAIL("sa_gpu_solver_create: coarsest operator is not positive definite "
+                    "(pivot %d)", h);
+    }
+    const int n0 = levels[0]->ND;
+    S->pb.alloc(n0);
+    S->px.alloc(n0);
+    S->pr.alloc(n0);
+    S->pd.alloc(n0);
+    S->pz.alloc(n0);
+    S->dots.alloc(4);
+    g.s = nullptr;
+    *out = S;
+    SA_API_END
+}
+
+extern "C" void sa_gpu_solver_destroy(sa_gpu_solver *S) { delete S; }
+
+extern "C" int sa_gpu_vcycle(sa_gpu_solver *S, const double *b, double *x)
+{
+    SA_API_BEGIN
+    cudaStream_t st = S->ctx->stream;
+    const int n = S->L[0]->lev->ND;
+    S->L[0]->b.upload(b, n, st);
+    double *res = dev_vcycle(S, 0);
+    SA_CUDA(cudaMemcpyAsync(x, res, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SA_CUDA(cudaStreamSynchronize(st));
+    SA_API_END
+}
+
+// B.Mult(r, z) with device vectors of level 0
+static void precond(sa_gpu_solver *S, const double *r, double *z)
+{
+    cudaStream_t st = S->ctx->stream;
+    const int n = S->L[0]->lev->ND;
+    SA_CUDA(cudaMemcpyAsync(S->L[0]->b.p, r, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice,
+                            st));
+    double *res = dev_vcycle(S, 0);
+    SA_CUDA(cudaMemcpyAsync(z, res, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+}
+
+// kalchev_pcg on device-resident S->pb (b) and S->px (x)
+static int pcg_resident(sa_gpu_solver *S, int max_num_iter, double RTOLERANCE, double ATOLERANCE,
+                        double *brr_hist, int hist_cap, int *hist_len)
+{
+    sa_gpu_ctx *ctx = S->ctx;
+    const DevCsr &A = *S->L[0]->lev->A;
+    const int dim = A.rows;
+    const int tb = 256, gb = (dim + tb - 1) / tb;
+    double *x = S->px.p, *b = S->pb.p, *r = S->pr.p, *d = S->pd.p, *z = S->pz.p;
+    int i, iters = 0, hl = 0;
+    double r0, den, nom, betanom = 0., alpha, beta;
+
+    dev_residual(ctx, A, x, b, r); // r = b - A x
+    precond(S, r, z);
+    SA_CUDA(cudaMemcpyAsync(d, z, (size_t)dim * sizeof(double), cudaMemcpyDeviceToDevice,
+                            ctx->stream));
+    nom = dev_dot(S, dim, z, r);
+    if (brr_hist && hl < hist_cap)
+        brr_hist[hl++] = nom;
+    if (hist_len)
+        *hist_len = hl;
+    if ((r0 = nom * RTOLERANCE) < ATOLERANCE)
+        r0 = ATOLERANCE;
+    if (nom < r0)
+        return -1;
+    dev_spmv(ctx, A, d, z);
+    den = dev_dot(S, dim, z, d);
+    if (0. == den)
+        return -1;
+    for (i = 1; i <= max_num_iter; i++)
+    {
+        alpha = nom / den;
+        SA_LAUNCH(ctx, k_pcg_update, gb, tb, 0, dim, alpha, d, z, x, r);
+        precond(S, r, z);
+        betanom = dev_dot(S, dim, r, z);
+        if (brr_hist && hl < hist_cap)
+            brr_hist[hl++] = betanom;
+        if (betanom < 0.0)
+        {
+            iters = -i;
+            break;
+        }
+        if (betanom < r0)
+        {
+            iters = i;
+            break;
+        }
+        beta = betanom / nom;
+        SA_LAUNCH(ctx, k_pcg_dir, gb, tb, 0, dim, beta, z, d);
+        dev_spmv(ctx, A, d, z);
+        den = dev_dot(S, dim, d, z);
+        nom = betanom;
+    }
+    if (i > max_num_iter)
+        iters = -(i - 1);
+    if (hist_len)
+        *hist_len = hl;
+    return iters;
+}
+
+extern "C" int sa_gpu_pcg(sa_gpu_solver *S, const double *b, double *x, int maxiter, double rtol,
+                          double atol, int *iters, double *brr_hist, int hist_cap, int *hist_len)
+{
+    SA_API_BEGIN
+    cudaStream_t st = S->ctx->stream;
+    const int n = S->L[0]->lev->ND;
+    S->pb.upload(b, n, st);
+    S->px.upload(x, n, st);
+    *iters = pcg_resident(S, maxiter, rtol, atol, brr_hist, hist_cap, hist_len);
+    S->px.download(x, n, st);
+    SA_CUDA(cudaStreamSynchronize(st));
+    SA_API_END
+}
+
+extern "C" int sa_gpu_solver_upload(sa_gpu_solver *S, const double *b, const double *x0)
+{
+    SA_API_BEGIN
+    cudaStream_t st = S->ctx->stream;
+    const int n = S->L[0]->lev->ND;
+    S->pb.upload(b, n, st);
+    if (x0)
+        S->px.upload(x0, n, st);
+    else
+        S->px.zero(st);
+    SA_CUDA(cudaStreamSynchronize(st));
+    SA_API_END
+}
+
+extern "C" int sa_gpu_pcg_resident(sa_gpu_solver *S, int maxiter, double rtol, double atol,
+                                   int *iters)
+{
+    SA_API_BEGIN
+    *iters = pcg_resident(S, maxiter, rtol, atol, nullptr, 0, nullptr);
+    SA_CUDA(cudaStreamSynchronize(S->ctx->stream));
+    SA_API_END
+}
+
+extern "C" int sa_gpu_solver_download(sa_gpu_solver *S, double *x)
+{
+    SA_API_BEGIN
+    S->px.download(x, S->L[0]->lev->ND, S->ctx->stream);
+    SA_CUDA(cudaStreamSynchronize(S->ctx->stream));
+    SA_API_END
+}

@@ -1,0 +1,538 @@
+// Tentative prolongator on the device:
+//   k_mis_svd       : one warp per MIS -- restrict the eigenvectors of every AE that
+//                     contains the MIS to the MIS's dofs (agg_restrict_to_agg_enforce,
+//                     amg/src/aggregates.cpp:1143-1179; concatenation order of
+//                     CommunicateEigenvectors, amg/src/contrib.cpp:501-546), boundary
+//                     filter (contrib_filter_boundary, amg/src/contrib.cpp:102-163),
+//                     column normalisation (xpack_svd_dense_arr, amg/src/xpacks.cpp:533-559),
+//                     thin SVD by one-sided Jacobi (the reference calls dgesvd 'S','N';
+//                     only U and sigma are needed), rank cut sigma_i > 1e-10 sigma_0
+//                     (xpack_orth_set, amg/src/xpacks.cpp:591-620)
+//   k_mis_finalize  : sort by sigma, write mis_tent_interps blocks
+//   k_ptent_count / k_ptent_fill : contrib_tent_insert_simple + contrib_tent_finalize
+//                     (amg/src/contrib.cpp:170-194, 73-95) -> CSR tentative P
+//   k_coarse_elmat  : ElementMatrixParallelCoarse::GetMatrix (amg/src/elmat.cpp:105-195)
+#include <algorithm>
+#include <cfloat>
+
+#include "assemble.cuh"
+#include "sa_gpu_internal.cuh"
+
+namespace
+{
+
+__device__ __forceinline__ double wsum(double v)
+{
+    for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+struct MisWork
+{
+    const int64_t *xoff; // MIS -> offset of its s x c work matrix
+    const int *coff;     // MIS -> offset of its c singular values
+    double *X;
+    double *sig;
+    int *ncols; // columns kept after filtering (c')
+    int *ncd;   // numcoarsedof
+};
+
+__global__ void k_mis_svd(LevelTables L, MisWork W, const int *ae_m, const int64_t *evect_off,
+                          const double *evects, int avoid_ess, int nmis)
+{
+    const int lane = threadIdx.x & 31;
+    const int mis = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (mis >= nmis)
+        return;
+    const int db = L.mis2d_I[mis];
+    const int s = L.mis2d_I[mis + 1] - db;
+    const int *mdofs = L.mis2d_J + db;
+    double *X = W.X + W.xoff[mis];
+    double *sig = W.sig + W.coff[mis];
+
+    // MIS entirely on the essential boundary -> no coarse dofs (amg/src/contrib.cpp:578-605)
+    if (avoid_ess)
+    {
+        int interior = 0;
+        for (int r = lane; r < s; r += 32)
+            if (!(L.agg_flags[mdofs[r]] & SA_AGG_ON_ESS_DOMAIN_BORDER_FLAG))
+                interior = 1;
+        if (!__any_sync(0xffffffffu, interior))
+        {
+            if (lane == 0)
+            {
+                W.ncols[mis] = 0;
+                W.ncd[mis] = 0;
+            }
+            return;
+        }
+    }
+    if (s == 1)
+    {
+        // amg/src/contrib.cpp:607-612
+        if (lane == 0)
+        {
+            W.ncols[mis] = 1;
+            W.ncd[mis] = 1;
+            X[0] = 1.0;
+            sig[0] = 1.0;
+        }
+        return;
+    }
+    // gather + filter + normalise, column by column
+    int c = 0;
+    for (int p = L.mis2AE_I[mis]; p < L.mis2AE_I[mis + 1]; ++p)
+    {
+        const int ae = L.mis2AE_J[p];
+        const int n = L.AE2d_I[ae + 1] - L.AE2d_I[ae];
+        const int m = ae_m[ae];
+        const double *E = evects + evect_off[ae];
+        for (int v = 0; v < m; ++v)
+        {
+            double *xc = X + (int64_t)s * c;
+            double nrm2 = 0.;
+            int nz = 0;
+            for (int r = lane; r < s; r += 32)
+            {
+                const int dof = mdofs[r];
+                double a = 0.;
+                if (!(avoid_ess && (L.agg_flags[dof] & SA_AGG_ON_ESS_DOMAIN_BORDER_FLAG)))
+                    a = E[sa_dev_map_id_glob_to_AE(L, dof, ae) + (int64_t)n * v];
+                xc[r] = a;
+                nrm2 += a * a;
+                nz |= (a != 0.);
+            }
+            nrm2 = wsum(nrm2);
+            nz = __any_sync(0xffffffffu, nz);
+            const double norm = sqrt(nrm2);
+            // all-zero columns are dropped by the filter, (near) zero norms by the SVD wrapper
+            if (!nz || norm <= 0. + 1e-10)
+                continue;
+            const double inv = 1. / norm;
+            for (int r = lane; r < s; r += 32)
+                xc[r] = xc[r] / norm;
+            (void)inv;
+            ++c;
+        }
+    }
+    __syncwarp();
+    if (c == 0)
+    {
+        if (lane == 0)
+        {
+            W.ncols[mis] = 0;
+            W.ncd[mis] = 0;
+        }
+        return;
+    }
+    // one-sided Jacobi (Hestenes): rotate column pairs until mutually orthogonal
+    const double tol = 4. * DBL_EPSILON;
+    for (int sweep = 0; sweep < 60; ++sweep)
+    {
+        int rotated = 0;
+        for (int p = 0; p < c - 1; ++p)
+            for (int q = p + 1; q < c; ++q)
+            {
+                double *xp = X + (int64_t)s * p;
+                double *xq = X + (int64_t)s * q;
+                double a = 0., b = 0., g = 0.;
+                for (int r = lane; r < s; r += 32)
+                {
+                    const double up = xp[r], uq = xq[r];
+                    a += up * up;
+                    b += uq * uq;
+                    g += up * uq;
+                }
+                a = wsum(a);
+                b = wsum(b);
+                g = wsum(g);
+                if (g == 0. || fabs(g) <= tol * sqrt(a * b))
+                    continue;
+                rotated = 1;
+                const double zeta = (b - a) / (2. * g);
+                const double t = copysign(1., zeta) / (fabs(zeta) + sqrt(1. + zeta * zeta));
+                const double cs = 1. / sqrt(1. + t * t);
+                const double sn = cs * t;
+                for (int r = lane; r < s; r += 32)
+                {
+                    const double up = xp[r], uq = xq[r];
+                    xp[r] = cs * up - sn * uq;
+                    xq[r] = sn * up + cs * uq;
+                }
+                __syncwarp();
+            }
+        if (!rotated)
+            break;
+    }
+    // singular values = column norms
+    double smax = 0.;
+    for (int q = 0; q < c; ++q)
+    {
+        const double *xq = X + (int64_t)s * q;
+        double a = 0.;
+        for (int r = lane; r < s; r += 32)
+            a += xq[r] * xq[r];
+        a = sqrt(wsum(a));
+        if (lane == 0)
+            sig[q] = a;
+        smax = fmax(smax, a);
+    }
+    // xpack_orth_set: keep sigma_i > eps * sigma_0; at most min(s, c) singular values exist
+    const double cut = 1.e-10 * smax;
+    int k = 0;
+    for (int q = 0; q < c; ++q)
+    {
+        const double *xq = X + (int64_t)s * q;
+        double a = 0.;
+        for (int r = lane; r < s; r += 32)
+            a += xq[r] * xq[r];
+        a = sqrt(wsum(a));
+        if (a > cut)
+            ++k;
+    }
+    k = min(k, min(s, c));
+    if (lane == 0)
+    {
+        W.ncols[mis] = c;
+        W.ncd[mis] = k;
+    }
+}
+
+// one warp per MIS: place the k columns with the largest singular values, in
+// descending order, normalised, into the compact mis_tent array
+__global__ void k_mis_finalize(LevelTables L, MisWork W, const int64_t *mis_off, double *mis_tent,
+                               int nmis)
+{
+    const int lane = threadIdx.x & 31;
+    const int mis = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (mis >= nmis)
+        return;
+    const int s = L.mis2d_I[mis + 1] - L.mis2d_I[mis];
+    const int c = W.ncols[mis];
+    const int k = W.ncd[mis];
+    if (k == 0)
+        return;
+    const double *X = W.X + W.xoff[mis];
+    const double *sig = W.sig + W.coff[mis];
+    double *U = mis_tent + mis_off[mis];
+    for (int q = 0; q < c; ++q)
+    {
+        const double sq = sig[q];
+        int rank = 0;
+        for (int o = lane; o < c; o += 32)
+        {
+            const double so = sig[o];
+            rank += (so > sq) || (so == sq && o < q);
+        }
+        for (int o = 16; o > 0; o >>= 1)
+            rank += __shfl_xor_sync(0xffffffffu, rank, o);
+        if (rank >= k)
+            continue;
+        const double inv = 1. / sq;
+        for (int r = lane; r < s; r += 32)
+            U[r + (int64_t)s * rank] = X[r + (int64_t)s * q] * inv;
+    }
+}
+
+__global__ void k_ptent_count(LevelTables L, const int *ncd, int avoid_ess, int *rowcnt)
+{
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= L.ND)
+        return;
+    const bool ess = avoid_ess && (L.agg_flags[d] & SA_AGG_ON_ESS_DOMAIN_BORDER_FLAG);
+    rowcnt[d] = ess ? 0 : ncd[L.mises[d]];
+}
+
+__global__ void k_ptent_fill(LevelTables L, const int *ncd, const int *cdoff,
+                             const int64_t *mis_off, const double *mis_tent, const int *PI, int *PJ,
+                             double *PA)
+{
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= L.ND)
+        return;
+    const int b = PI[d], cnt = PI[d + 1] - b;
+    if (!cnt)
+        return;
+    const int mis = L.mises[d];
+    const int db = L.mis2d_I[mis];
+    const int s = L.mis2d_I[mis + 1] - db;
+    // position of d inside the (ascending) MIS row
+    int lo = 0, hi = s - 1;
+    while (lo < hi)
+    {
+        const int mid = (lo + hi) >> 1;
+        if (L.mis2d_J[db + mid] < d)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    const double *U = mis_tent + mis_off[mis];
+    for (int c = 0; c < cnt; ++c)
+    {
+        PJ[b + c] = cdoff[mis] + c;
+        PA[b + c] = U[lo + (int64_t)s * c];
+    }
+}
+
+/* coarse element matrices ------------------------------------------------- */
+
+struct CoarseElmatArgs
+{
+    const int *ce2d_I, *ce2d_J; // coarse elem_to_dof (rows = finer AEs)
+    const int *cdof_mis;        // coarse dof -> finer MIS
+    const int *cdoff;           // finer MIS -> first coarse dof
+    const int64_t *mis_off;
+    const double *mis_tent;
+    const int64_t *out_off;
+    double *out;
+    double *scratch;            // per block: tile n*n + W n*nc
+    int64_t scratch_stride;
+    int max_mis;                // largest MIS size (shared buffers)
+};
+
+__global__ void k_coarse_elmat(LevelTables L, CoarseElmatArgs C, int nparts)
+{
+    extern __shared__ double sm[];
+    double *ubuf = sm;                              // max_mis
+    int *lidbuf = (int *)(sm + C.max_mis);          // max_mis
+    for (int e = blockIdx.x; e < nparts; e += gridDim.x)
+    {
+        const int n = L.AE2d_I[e + 1] - L.AE2d_I[e];
+        const int cb = C.ce2d_I[e];
+        const int nc = C.ce2d_I[e + 1] - cb;
+        if (nc == 0)
+            continue;
+        double *T = C.scratch + (int64_t)blockIdx.x * C.scratch_stride;
+        double *Wm = T + (int64_t)n * n;
+        sa_dev_assemble_AE(L, e, T, n);
+        // W = A_AE * P_e, column by column
+        for (int lc = 0; lc < nc; ++lc)
+        {
+            const int cd = C.ce2d_J[cb + lc];
+            const int mis = C.cdof_mis[cd];
+            const int idx = cd - C.cdoff[mis];
+            const int db = L.mis2d_I[mis];
+            const int s = L.mis2d_I[mis + 1] - db;
+            const double *U = C.mis_tent + C.mis_off[mis] + (int64_t)s * idx;
+            for (int r = threadIdx.x; r < s; r += blockDim.x)
+            {
+                lidbuf[r] = sa_dev_map_id_glob_to_AE(L, L.mis2d_J[db + r], e);
+                ubuf[r] = U[r];
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < n; i += blockDim.x)
+            {
+                double acc = 0.;
+                for (int r = 0; r < s; ++r)
+                    acc += T[i + (int64_t)n * lidbuf[r]] * ubuf[r];
+                Wm[i + (int64_t)n * lc] = acc;
+            }
+            __syncthreads();
+        }
+        // out = P_e^T W
+        double *out = C.out + C.out_off[e];
+        for (int lc1 = 0; lc1 < nc; ++lc1)
+        {
+            const int cd = C.ce2d_J[cb + lc1];
+            const int mis = C.cdof_mis[cd];
+            const int idx = cd - C.cdoff[mis];
+            const int db = L.mis2d_I[mis];
+            const int s = L.mis2d_I[mis + 1] - db;
+            const double *U = C.mis_tent + C.mis_off[mis] + (int64_t)s * idx;
+            for (int r = threadIdx.x; r < s; r += blockDim.x)
+            {
+                lidbuf[r] = sa_dev_map_id_glob_to_AE(L, L.mis2d_J[db + r], e);
+                ubuf[r] = U[r];
+            }
+            __syncthreads();
+            for (int lc2 = threadIdx.x; lc2 < nc; lc2 += blockDim.x)
+            {
+                double acc = 0.;
+                for (int r = 0; r < s; ++r)
+                    acc += ubuf[r] * Wm[lidbuf[r] + (int64_t)n * lc2];
+                out[lc1 + (int64_t)nc * lc2] = acc;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+} // namespace
+
+extern "C" int sa_gpu_tentative_P(sa_gpu_level *lev, int avoid_ess_bdr_dofs,
+                                  int *mis_numcoarsedof, int *NDc_out)
+{
+    SA_API_BEGIN
+    sa_gpu_ctx *ctx = lev->ctx;
+    cudaStream_t st = ctx->stream;
+    if (!lev->have_spectral)
+        SA_FAIL("sa_gpu_tentative_P: run sa_gpu_local_spectral first");
+    const int nmis = lev->num_mises;
+    LevelTables L = lev->tables();
+    lev->avoid_ess = avoid_ess_bdr_dofs;
+
+    // work-matrix offsets: s x c per MIS, c = sum of m over the AEs containing it
+    std::vector<int64_t> xoff(nmis + 1, 0);
+    std::vector<int> coff(nmis + 1, 0);
+    for (int mis = 0; mis < nmis; ++mis)
+    {
+        const int s = lev->h_mis2d_I[mis + 1] - lev->h_mis2d_I[mis];
+        int c = 0;
+        for (int p = lev->h_mis2AE_I[mis]; p < lev->h_mis2AE_I[mis + 1]; ++p)
+            c += lev->h_ae_m[lev->h_mis2AE_J[p]];
+        c = std::max(c, 1);
+        xoff[mis + 1] = xoff[mis] + (int64_t)s * c;
+        coff[mis + 1] = coff[mis] + c;
+    }
+    DevBuf<int64_t> d_xoff;
+    DevBuf<int> d_coff, d_ncols;
+    DevBuf<double> d_X, d_sig;
+    d_xoff.upload(xoff.data(), nmis + 1, st);
+    d_coff.upload(coff.data(), nmis + 1, st);
+    d_X.alloc(xoff[nmis]);
+    d_sig.alloc(coff[nmis]);
+    d_ncols.alloc(nmis);
+    lev->mis_ncd.alloc(nmis);
+    MisWork W;
+    W.xoff = d_xoff.p;
+    W.coff = d_coff.p;
+    W.X = d_X.p;
+    W.sig = d_sig.p;
+    W.ncols = d_ncols.p;
+    W.ncd = lev->mis_ncd.p;
+    const int wpb = 4;
+    SA_LAUNCH(ctx, k_mis_svd, (nmis + wpb - 1) / wpb, wpb * 32, 0, L, W, lev->ae_m.p,
+              lev->evect_off.p, lev->evects.p, avoid_ess_bdr_dofs, nmis);
+    lev->h_mis_ncd.resize(nmis);
+    lev->mis_ncd.download(lev->h_mis_ncd.data(), nmis, st);
+    SA_CUDA(cudaStreamSynchronize(st));
+
+    lev->h_mis_off.assign(nmis + 1, 0);
+    std::vector<int> cdoff(nmis + 1, 0);
+    for (int mis = 0; mis < nmis; ++mis)
+    {
+        const int s = lev->h_mis2d_I[mis + 1] - lev->h_mis2d_I[mis];
+        lev->h_mis_off[mis + 1] = lev->h_mis_off[mis] + (int64_t)s * lev->h_mis_ncd[mis];
+        cdoff[mis + 1] = cdoff[mis] + lev->h_mis_ncd[mis];
+    }
+    lev->NDc = cdoff[nmis];
+    lev->mis_off.upload(lev->h_mis_off.data(), nmis + 1, st);
+    lev->mis_cd_off.upload(cdoff.data(), nmis + 1, st);
+    lev->mis_tent.alloc(lev->h_mis_off[nmis]);
+    SA_LAUNCH(ctx, k_mis_finalize, (nmis + wpb - 1) / wpb, wpb * 32, 0, L, W, lev->mis_off.p,
+              lev->mis_tent.p, nmis);
+
+    // CSR tentative P
+    DevCsr &P = lev->Ptent;
+    P.rows = lev->ND;
+    P.cols = lev->NDc;
+    DevBuf<int> rowcnt;
+    rowcnt.alloc(lev->ND);
+    P.I.alloc((size_t)lev->ND + 1);
+    const int tb = 256;
+    SA_LAUNCH(ctx, k_ptent_count, (lev->ND + tb - 1) / tb, tb, 0, L, lev->mis_ncd.p,
+              avoid_ess_bdr_dofs, rowcnt.p);
+    dev_exclusive_scan_i32(ctx, rowcnt.p, P.I.p, lev->ND);
+    int nnz = 0;
+    SA_CUDA(cudaMemcpyAsync(&nnz, P.I.p + lev->ND, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SA_CUDA(cudaStreamSynchronize(st));
+    P.nnz = nnz;
+    P.J.alloc(nnz);
+    P.A.alloc(nnz);
+    SA_LAUNCH(ctx, k_ptent_fill, (lev->ND + tb - 1) / tb, tb, 0, L, lev->mis_ncd.p,
+              lev->mis_cd_off.p, lev->mis_off.p, lev->mis_tent.p, P.I.p, P.J.p, P.A.p);
+    SA_CUDA(cudaStreamSynchronize(st));
+    lev->have_tent = true;
+    lev->have_P = false;
+    lev->have_Ac = false;
+    if (mis_numcoarsedof)
+        std::copy(lev->h_mis_ncd.begin(), lev->h_mis_ncd.end(), mis_numcoarsedof);
+    if (NDc_out)
+        *NDc_out = lev->NDc;
+    SA_API_END
+}
+
+extern "C" int sa_gpu_get_mis_tent(sa_gpu_level *lev, double *mis_tent)
+{
+    SA_API_BEGIN
+    if (!lev->have_tent)
+        SA_FAIL("sa_gpu_get_mis_tent: no tentative prolongator");
+    lev->mis_tent.download(mis_tent, lev->h_mis_off[lev->num_mises], lev->ctx->stream);
+    SA_CUDA(cudaStreamSynchronize(lev->ctx->stream));
+    SA_API_END
+}
+
+extern "C" int sa_gpu_coarse_elmats(sa_gpu_level *finer, sa_gpu_level *coarse)
+{
+    SA_API_BEGIN
+    sa_gpu_ctx *ctx = finer->ctx;
+    cudaStream_t st = ctx->stream;
+    if (!finer->have_tent)
+        SA_FAIL("sa_gpu_coarse_elmats: finer level has no tentative prolongator");
+    if (coarse->NE != finer->nparts)
+        SA_FAIL("sa_gpu_coarse_elmats: coarse elements must be the finer AEs");
+    const int nparts = finer->nparts;
+    // coarse dof -> finer MIS
+    std::vector<int> cdof_mis(std::max(1, finer->NDc));
+    {
+        int cd = 0;
+        for (int mis = 0; mis < finer->num_mises; ++mis)
+            for (int k = 0; k < finer->h_mis_ncd[mis]; ++k)
+                cdof_mis[cd++] = mis;
+    }
+    DevBuf<int> d_cdof_mis;
+    d_cdof_mis.upload(cdof_mis.data(), cdof_mis.size(), st);
+    coarse->h_elmat_off.assign((size_t)nparts + 1, 0);
+    int64_t max_scratch = 1;
+    for (int e = 0; e < nparts; ++e)
+    {
+        const int64_t nc = coarse->h_e2d_I[e + 1] - coarse->h_e2d_I[e];
+        const int64_t n = finer->h_AE2d_I[e + 1] - finer->h_AE2d_I[e];
+        coarse->h_elmat_off[e + 1] = coarse->h_elmat_off[e] + nc * nc;
+        max_scratch = std::max(max_scratch, n * n + n * nc);
+    }
+    int max_mis = 1;
+    for (int mis = 0; mis < finer->num_mises; ++mis)
+        max_mis = std::max(max_mis, finer->h_mis2d_I[mis + 1] - finer->h_mis2d_I[mis]);
+    coarse->elmat_off.upload(coarse->h_elmat_off.data(), (size_t)nparts + 1, st);
+    coarse->elmat.alloc(coarse->h_elmat_off[nparts]);
+    // bounded scratch: persistent blocks
+    const size_t scratch_budget = (size_t)1 << 28; // 2 GB of doubles
+    int blocks = std::min(nparts, ctx->num_sms * 4);
+    blocks = (int)std::max<size_t>(1, std::min<size_t>(blocks, scratch_budget / (size_t)max_scratch));
+    DevBuf<double> scratch;
+    scratch.alloc((size_t)blocks * max_scratch);
+    CoarseElmatArgs C;
+    C.ce2d_I = coarse->e2d_I.p;
+    C.ce2d_J = coarse->e2d_J.p;
+    C.cdof_mis = d_cdof_mis.p;
+    C.cdoff = finer->mis_cd_off.p;
+    C.mis_off = finer->mis_off.p;
+    C.mis_tent = finer->mis_tent.p;
+    C.out_off = coarse->elmat_off.p;
+    C.out = coarse->elmat.p;
+    C.scratch = scratch.p;
+    C.scratch_stride = max_scratch;
+    C.max_mis = max_mis;
+    LevelTables L = finer->tables();
+    const size_t smem = (size_t)max_mis * (sizeof(double) + sizeof(int)) + 16;
+    if (smem > ctx->smem_optin)
+        SA_FAIL("sa_gpu_coarse_elmats: MIS of %d dofs exceeds the shared buffers", max_mis);
+    SA_CUDA(cudaFuncSetAttribute(k_coarse_elmat, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)ctx->smem_optin));
+    SA_LAUNCH(ctx, k_coarse_elmat, blocks, 256, smem, L, C, nparts);
+    SA_CUDA(cudaStreamSynchronize(st));
+    coarse->have_elmat = true;
+    SA_API_END
+}
+
+extern "C" int sa_gpu_get_coarse_elmats(sa_gpu_level *coarse, double *celmat)
+{
+    SA_API_BEGIN
+    if (!coarse->have_elmat)
+        SA_FAIL("sa_gpu_get_coarse_elmats: no element matrices");
+    coarse->elmat.download(celmat, coarse->h_elmat_off[coarse->NE], coarse->ctx->stream);
+    SA_CUDA(cudaStreamSynchronize(coarse->ctx->stream));
+    SA_API_END
+}

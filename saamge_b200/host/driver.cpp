@@ -131,8 +131,9 @@ extern "C" void sa_drv_hier_destroy(void *hier)
         return;
     if (H->impl && H->impl_free)
         H->impl_free(H->impl);
-    for (size_t l = 1; l < H->rels.size(); ++l)
-        agg_free_partitioning(H->rels[l]);
+    if (H->owns_rels)
+        for (size_t l = 1; l < H->rels.size(); ++l)
+            agg_free_partitioning(H->rels[l]);
     delete H;
 }
 

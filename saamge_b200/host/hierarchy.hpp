@@ -29,6 +29,7 @@ struct sa_hierarchy_t
     sa_problem_t *prob = NULL;
     sa_drv_params_t params;
     std::vector<agg_partitioning_relations_t *> rels; // rels[0] borrowed from prob
+    bool owns_rels = true;                            // rels[1..] freed with the handle
     std::vector<sa_level_results_t> levels;           // one per coarsening
     sa_pcg_results_t pcg;
     std::map<std::string, double> times;

@@ -1,0 +1,774 @@
+// Hierarchy builders (tg_ / ml_ / interp_) on top of the CUDA library's C ABI
+// (see saamge.hpp).  Control flow follows amg/src/ml.cpp:111-236, 361-472 and
+// amg/src/tg.cpp:402-540, 979-1014; all arithmetic happens in sa_gpu_* calls.
+#include <chrono>
+#include <cmath>
+#include <cstring>
+
+#include "hierarchy.hpp"
+#include "saamge.hpp"
+
+namespace saamge
+{
+
+static double now_s()
+{
+    return std::chrono::duration<double>(
+               std::chrono::steady_clock::now().time_since_epoch())
+        .count();
+}
+
+static sa_gpu_ctx *g_ctx = NULL;
+
+sa_gpu_ctx *proc_gpu_init(int device)
+{
+    if (!g_ctx)
+        sa_gpu_check(sa_gpu_ctx_create(device, &g_ctx), "sa_gpu_ctx_create");
+    return g_ctx;
+}
+
+sa_gpu_ctx *proc_gpu_ctx()
+{
+    if (!g_ctx)
+        proc_gpu_init(0);
+    return g_ctx;
+}
+
+void proc_gpu_finalize()
+{
+    if (g_ctx)
+        sa_gpu_ctx_destroy(g_ctx);
+    g_ctx = NULL;
+}
+
+void sa_gpu_check(int rc, const char *what)
+{
+    if (rc)
+    {
+        // the reference's failure mode: message + abort (amg/inc/common.hpp:635-647)
+        std::fprintf(stderr, "ASSERT: %s failed: %s\n", what, sa_gpu_last_error());
+        std::abort();
+    }
+}
+
+/* ------------------------------------------------------------------ providers */
+
+ElementMatrixStandardGeometric::ElementMatrixStandardGeometric(
+    const agg_partitioning_relations_t &agg_part_rels,
+    const SparseMatrix &assembled_processor_matrix, const double *blocks,
+    const int64_t *offsets)
+    : ElementMatrixProvider(agg_part_rels), A_(assembled_processor_matrix), blocks_(blocks),
+      offsets_(offsets)
+{
+    is_geometric = true;
+}
+
+Matrix *ElementMatrixStandardGeometric::GetMatrix(int elno, bool &free_matr) const
+{
+    const int ne = agg_part_rels.elem_to_dof->RowSize(elno);
+    DenseMatrix *elmat = new DenseMatrix(ne, ne);
+    std::memcpy(elmat->Data(), blocks_ + offsets_[elno], sizeof(double) * ne * ne);
+    free_matr = true;
+    return elmat;
+}
+
+// single-AE assembly through the same device code path the batched stage uses
+static SparseMatrix *build_AE_stiff_on_device(const agg_partitioning_relations_t &rels,
+                                              const ElementMatrixProvider *emp, int elno);
+
+SparseMatrix *ElementMatrixStandardGeometric::BuildAEStiff(int elno) const
+{
+    return build_AE_stiff_on_device(agg_part_rels, this, elno);
+}
+
+ElementMatrixDenseArray::ElementMatrixDenseArray(const agg_partitioning_relations_t &agg_part_rels,
+                                                 const double *blocks, const int64_t *offsets)
+    : ElementMatrixProvider(agg_part_rels), blocks_(blocks), offsets_(offsets)
+{
+    is_geometric = false;
+}
+
+Matrix *ElementMatrixDenseArray::GetMatrix(int elno, bool &free_matr) const
+{
+    const int ne = agg_part_rels.elem_to_dof->RowSize(elno);
+    DenseMatrix *elmat = new DenseMatrix(ne, ne);
+    std::memcpy(elmat->Data(), blocks_ + offsets_[elno], sizeof(double) * ne * ne);
+    free_matr = true;
+    return elmat;
+}
+
+SparseMatrix *ElementMatrixDenseArray::BuildAEStiff(int elno) const
+{
+    return build_AE_stiff_on_device(agg_part_rels, this, elno);
+}
+
+ElementMatrixParallelCoarse::ElementMatrixParallelCoarse(
+    const agg_partitioning_relations_t &agg_part_rels, levels_level_t *level)
+    : ElementMatrixProvider(agg_part_rels), level(level)
+{
+    is_geometric = false;
+}
+
+Matrix *ElementMatrixParallelCoarse::GetMatrix(int elno, bool &free_matr) const
+{
+    (void)elno;
+    (void)free_matr;
+    // the blocks exist only on the device of the coarse level; read them back with
+    // sa_gpu_get_coarse_elmats (tg_download_results does).
+    std::fprintf(stderr, "ASSERT: ElementMatrixParallelCoarse::GetMatrix: element matrices are "
+                         "device resident; use tg_download_results\n");
+    std::abort();
+    return NULL;
+}
+
+SparseMatrix *ElementMatrixParallelCoarse::BuildAEStiff(int elno) const
+{
+    (void)elno;
+    std::fprintf(stderr, "ASSERT: ElementMatrixParallelCoarse::BuildAEStiff: use the level's "
+                         "sa_gpu_build_AE_stiff\n");
+    std::abort();
+    return NULL;
+}
+
+static void fill_desc(sa_gpu_level_desc &d, const agg_partitioning_relations_t &r)
+{
+    std::memset(&d, 0, sizeof d);
+    d.ND = r.ND;
+    d.NE = r.elem_to_dof->Size();
+    d.nparts = r.nparts;
+    d.num_mises = r.num_mises;
+    d.elem_to_dof_I = r.elem_to_dof->GetI();
+    d.elem_to_dof_J = r.elem_to_dof->GetJ();
+    d.dof_to_elem_I = r.dof_to_elem->GetI();
+    d.dof_to_elem_J = r.dof_to_elem->GetJ();
+    d.AE_to_elem_I = r.AE_to_elem->GetI();
+    d.AE_to_elem_J = r.AE_to_elem->GetJ();
+    d.AE_to_dof_I = r.AE_to_dof->GetI();
+    d.AE_to_dof_J = r.AE_to_dof->GetJ();
+    d.dof_to_AE_I = r.dof_to_AE->GetI();
+    d.dof_to_AE_J = r.dof_to_AE->GetJ();
+    d.dof_id_inAE = r.dof_id_inAE;
+    d.partitioning = r.partitioning;
+    d.agg_flags = r.agg_flags;
+    d.mis_to_dof_I = r.mis_to_dof->GetI();
+    d.mis_to_dof_J = r.mis_to_dof->GetJ();
+    d.mis_to_AE_I = r.mis_to_AE->GetI();
+    d.mis_to_AE_J = r.mis_to_AE->GetJ();
+    d.AE_to_mis_I = r.AE_to_mis->GetI();
+    d.AE_to_mis_J = r.AE_to_mis->GetJ();
+    d.mises = r.mises;
+    d.mis_coarsedofoffsets = r.mis_coarsedofoffsets;
+}
+
+static SparseMatrix *build_AE_stiff_on_device(const agg_partitioning_relations_t &rels,
+                                              const ElementMatrixProvider *emp, int elno)
+{
+    sa_gpu_level_desc d;
+    fill_desc(d, rels);
+    const SparseMatrix *A = emp->AssembledMatrix();
+    if (A)
+    {
+        d.A_I = A->GetI();
+        d.A_J = A->GetJ();
+        d.A_data = A->GetData();
+        d.assemble_with_global = 1;
+    }
+    else
+    {
+        // the stage needs some operator only in with_global mode; give it an empty one
+        static const int zeroI[1] = {0};
+        (void)zeroI;
+    }
+    d.elmat = emp->DenseBlocks();
+    d.elmat_off = emp->DenseBlockOffsets();
+    sa_gpu_level *lev = NULL;
+    std::vector<int> emptyI;
+    if (!A)
+    {
+        emptyI.assign((size_t)rels.ND + 1, 0);
+        d.A_I = emptyI.data();
+        d.A_J = emptyI.data();
+        static const double zero = 0.;
+        d.A_data = &zero;
+    }
+    sa_gpu_check(sa_gpu_level_create(proc_gpu_ctx(), &d, NULL, &lev), "sa_gpu_level_create");
+    const int n = rels.AE_to_dof->RowSize(elno);
+    std::vector<double> dense((size_t)n * n);
+    sa_gpu_check(sa_gpu_build_AE_stiff(lev, elno, dense.data()), "sa_gpu_build_AE_stiff");
+    sa_gpu_level_destroy(lev);
+    SparseMatrix *S = new SparseMatrix;
+    S->h = S->w = n;
+    S->I.assign((size_t)n + 1, 0);
+    for (int i = 0; i < n; ++i)
+    {
+        for (int j = 0; j < n; ++j)
+            if (dense[(size_t)j * n + i] != 0.)
+            {
+                S->J.push_back(j);
+                S->A.push_back(dense[(size_t)j * n + i]);
+            }
+        S->I[i + 1] = (int)S->J.size();
+    }
+    return S;
+}
+
+/* ---------------------------------------------------------------- parameters */
+
+MultilevelParameters::MultilevelParameters(int coarsenings, int *nparts_arr_arg,
+                                           int first_nu_pro, int nu_pro_arg, int nu_relax_arg,
+                                           double first_theta, double theta_arg,
+                                           int polynomial_coarse_space_arg,
+                                           bool use_correct_nullspace, bool use_arpack,
+                                           bool do_aggregates)
+    : coarse_partitioner(NULL), coarse_partitioner_data(NULL), testmesh_inject(false),
+      num_coarsenings(coarsenings), use_correct_nullspace(use_correct_nullspace),
+      use_arpack(use_arpack), do_aggregates(do_aggregates), avoid_ess_bdr_dofs(true),
+      coarse_direct(false), smooth_drop_tol(0.0)
+{
+    // amg/src/ml.cpp:54-89
+    nparts_arr = new int[num_coarsenings];
+    nu_pro = new int[num_coarsenings];
+    nu_relax = new int[num_coarsenings];
+    theta = new double[num_coarsenings];
+    polynomial_coarse_space = new int[num_coarsenings];
+    nparts_arr[0] = nparts_arr_arg[0];
+    nu_pro[0] = first_nu_pro;
+    nu_relax[0] = nu_relax_arg;
+    theta[0] = first_theta;
+    polynomial_coarse_space[0] = polynomial_coarse_space_arg;
+    for (int i = 1; i < num_coarsenings; ++i)
+    {
+        nparts_arr[i] = nparts_arr_arg[i];
+        nu_pro[i] = nu_pro_arg;
+        nu_relax[i] = nu_relax_arg;
+        theta[i] = theta_arg;
+        polynomial_coarse_space[i] = polynomial_coarse_space_arg;
+    }
+}
+
+MultilevelParameters::~MultilevelParameters()
+{
+    delete[] nparts_arr;
+    delete[] nu_pro;
+    delete[] nu_relax;
+    delete[] theta;
+    delete[] polynomial_coarse_space;
+}
+
+// amg/src/smpr.cpp:266-280
+double *smpr_sa_poly_roots(int &nu, int *degree)
+{
+    SA_ASSERT(nu >= 0);
+    const double denom = (double)(2 * nu + 1);
+    double *roots = new double[(*degree = nu) > 0 ? nu : 1];
+    for (int i = 1; i <= nu; ++i)
+    {
+        const double sin_val = sin(((double)i * M_PI) / denom);
+        roots[i - 1] = sin_val * sin_val;
+    }
+    return roots;
+}
+
+// amg/src/smpr.cpp:282-306
+double *smpr_sas_poly_roots(int &nu, int *degree)
+{
+    SA_ASSERT(nu > 0);
+    const int twonu = 2 * nu;
+    const double denom = (double)(2 * nu + 1);
+    double *roots = new double[*degree = twonu + nu + 1];
+    for (int i = 0; i <= twonu; ++i)
+    {
+        const double val = cos(((double)i * M_PI) / denom);
+        roots[i] = val * val;
+    }
+    for (int i = 1; i <= nu; ++i)
+    {
+        const double val = sin(((double)i * M_PI) / denom);
+        roots[i + twonu] = val * val;
+    }
+    return roots;
+}
+
+/* -------------------------------------------------------------------- two-grid */
+
+// amg/src/tg.cpp:402-430 + interp_init_data (amg/src/interp.cpp:231-277) +
+// smpr_init_poly_data (amg/src/smpr.cpp:359-423)
+tg_data_t *tg_init_data(const SparseMatrix *A, const agg_partitioning_relations_t &agg_part_rels,
+                        int nu_pro, int nu_relax, double theta, bool smooth_interp,
+                        double smooth_drop_tol, bool use_arpack)
+{
+    (void)A;
+    tg_data_t *tg_data = new tg_data_t;
+    std::memset(tg_data, 0, sizeof(*tg_data));
+    tg_data->theta = theta;
+    interp_data_t *id = new interp_data_t;
+    std::memset(id, 0, sizeof(*id));
+    id->nparts = agg_part_rels.nparts;
+    SA_ASSERT(nu_pro >= 0);
+    id->nu_pro = nu_pro;
+    id->interp_smoother_roots = smpr_sa_poly_roots(id->nu_pro, &id->interp_smoother_degree);
+    id->times_apply_smoother = 1;
+    id->use_arpack = use_arpack;
+    id->scaling_P = false;
+    id->drop_tol = smooth_drop_tol;
+    tg_data->interp_data = id;
+    smpr_poly_data_t *pd = new smpr_poly_data_t;
+    std::memset(pd, 0, sizeof(*pd));
+    SA_ASSERT(nu_relax > 0);
+    pd->nu = nu_relax;
+    pd->roots = smpr_sas_poly_roots(pd->nu, &pd->degree);
+    pd->weightfirst = 1.;
+    tg_data->poly_data = pd;
+    tg_data->smooth_interp = smooth_interp;
+    tg_data->tag = -1;
+    tg_data->doing_spectral = false;
+    tg_data->polynomial_coarse_space = -1;
+    return tg_data;
+}
+
+// the AE loop of amg/src/interp.cpp:387-556 as one batched device stage
+void interp_compute_vectors(const agg_partitioning_relations_t &agg_part_rels,
+                            const interp_data_t &interp_data, tg_data_t &tg_data, double &theta)
+{
+    sa_gpu_check(sa_gpu_local_spectral(tg_data.gpu, theta, 0, agg_part_rels.nparts,
+                                       interp_data.testmesh_inject ? 1 : 0),
+                 "sa_gpu_local_spectral");
+    // theta averaging of amg/src/interp.cpp:571-589 is the identity when all_eigens == false
+}
+
+// amg/src/interp.cpp:728-759
+void interp_sparse_tent_assemble(const agg_partitioning_relations_t &agg_part_rels,
+                                 interp_data_t &interp_data, tg_data_t &tg_data,
+                                 bool avoid_ess_bdr_dofs)
+{
+    delete[] interp_data.mis_numcoarsedof;
+    interp_data.mis_numcoarsedof = new int[agg_part_rels.num_mises > 0 ? agg_part_rels.num_mises : 1];
+    int NDc = 0;
+    sa_gpu_check(sa_gpu_tentative_P(tg_data.gpu, avoid_ess_bdr_dofs ? 1 : 0,
+                                    interp_data.mis_numcoarsedof, &NDc),
+                 "sa_gpu_tentative_P");
+    interp_data.num_mises = agg_part_rels.num_mises;
+    interp_data.coarse_truedof_offset = 0;
+}
+
+// amg/src/tg.cpp:502-540 (spectral branch) + tg_assemble_and_smooth (:432-473)
+void tg_build_hierarchy(const SparseMatrix *Ag, tg_data_t &tg_data,
+                        const agg_partitioning_relations_t &agg_part_rels,
+                        ElementMatrixProvider *elem_data, bool avoid_ess_bdr_dofs,
+                        tg_data_t *finer)
+{
+    SA_ASSERT(tg_data.polynomial_coarse_space == -1 && tg_data.theta > 0.0);
+    tg_data.elem_data = elem_data;
+    tg_data.doing_spectral = true;
+
+    sa_gpu_level_desc d;
+    fill_desc(d, agg_part_rels);
+    if (Ag)
+    {
+        d.A_I = Ag->GetI();
+        d.A_J = Ag->GetJ();
+        d.A_data = Ag->GetData();
+    }
+    d.elmat = elem_data->DenseBlocks();
+    d.elmat_off = elem_data->DenseBlockOffsets();
+    d.assemble_with_global = elem_data->AssembledMatrix() ? 1 : 0;
+    if (tg_data.gpu)
+        sa_gpu_level_destroy(tg_data.gpu);
+    tg_data.gpu = NULL;
+    sa_gpu_check(sa_gpu_level_create(proc_gpu_ctx(), &d, finer ? finer->gpu : NULL, &tg_data.gpu),
+                 "sa_gpu_level_create");
+    if (!d.elmat)
+    {
+        // ElementMatrixParallelCoarse: P_e^T A_AE P_e of every finer AE, on the device
+        SA_ASSERT(finer && finer->gpu);
+        sa_gpu_check(sa_gpu_coarse_elmats(finer->gpu, tg_data.gpu), "sa_gpu_coarse_elmats");
+    }
+    // smpr_update_Dinv_neg (tg_init_data -> smpr_init_poly_data in the reference)
+    sa_gpu_check(sa_gpu_build_Dinv_neg(tg_data.gpu), "sa_gpu_build_Dinv_neg");
+
+    // interp_sparse_tent_build (amg/src/interp.cpp:694-726)
+    interp_compute_vectors(agg_part_rels, *tg_data.interp_data, tg_data, tg_data.theta);
+    interp_sparse_tent_assemble(agg_part_rels, *tg_data.interp_data, tg_data, avoid_ess_bdr_dofs);
+    // tg_smooth_interp (amg/inc/tg.hpp:678-693)
+    interp_data_t &id = *tg_data.interp_data;
+    sa_gpu_check(sa_gpu_smooth_P(tg_data.gpu, tg_data.smooth_interp ? id.interp_smoother_degree : 0,
+                                 id.interp_smoother_roots),
+                 "sa_gpu_smooth_P");
+    tg_data.have_Ac = false;
+}
+
+// amg/src/tg.cpp:917-932
+tg_data_t *tg_produce_data(const SparseMatrix &Ag,
+                           const agg_partitioning_relations_t &agg_part_rels, int nu_pro,
+                           int nu_relax, ElementMatrixProvider *elem_data, double theta,
+                           bool smooth_interp, int polynomial_coarse_arg, bool use_arpack,
+                           bool avoid_ess_bdr_dofs)
+{
+    tg_data_t *tg_data =
+        tg_init_data(&Ag, agg_part_rels, nu_pro, nu_relax, theta, smooth_interp, 0.0, use_arpack);
+    tg_data->polynomial_coarse_space = polynomial_coarse_arg;
+    tg_build_hierarchy(&Ag, *tg_data, agg_part_rels, elem_data, avoid_ess_bdr_dofs);
+    return tg_data;
+}
+
+// amg/src/tg.cpp:979-1014; the coarsest solver is created by ml_impose_cycle
+void tg_update_coarse_operator(tg_data_t *tg_data, bool perform_solve_init, bool coarse_direct)
+{
+    (void)perform_solve_init;
+    (void)coarse_direct;
+    SA_ASSERT(tg_data && tg_data->gpu);
+    sa_gpu_check(sa_gpu_rap(tg_data->gpu), "sa_gpu_rap");
+    tg_data->have_Ac = true;
+}
+
+void tg_free_data(tg_data_t *tg_data)
+{
+    if (!tg_data)
+        return;
+    if (tg_data->poly_data)
+    {
+        delete[] tg_data->poly_data->roots;
+        delete tg_data->poly_data;
+    }
+    if (tg_data->interp_data)
+    {
+        delete[] tg_data->interp_data->interp_smoother_roots;
+        delete[] tg_data->interp_data->mis_numcoarsedof;
+        delete tg_data->interp_data;
+    }
+    sa_gpu_level_destroy(tg_data->gpu);
+    delete tg_data->elem_data; // tg_data takes ownership (amg/src/tg.cpp:518,946)
+    delete tg_data;
+}
+
+/* ------------------------------------------------------------------ multilevel */
+
+static void levels_list_push_coarse_data(levels_list_t &list,
+                                         agg_partitioning_relations_t *agg_part_rels,
+                                         tg_data_t *tg_data)
+{
+    levels_level_t *lev = new levels_level_t;
+    lev->finer = list.coarsest;
+    lev->coarser = NULL;
+    lev->agg_part_rels = agg_part_rels;
+    lev->tg_data = tg_data;
+    if (list.coarsest)
+        list.coarsest->coarser = lev;
+    else
+        list.finest = lev;
+    list.coarsest = lev;
+    list.num_levels++;
+}
+
+levels_level_t *levels_list_get_level(const levels_list_t &list, int i)
+{
+    levels_level_t *l = list.finest;
+    while (l && i-- > 0)
+        l = l->coarser;
+    return l;
+}
+
+// amg/src/ml.cpp:111-236
+void ml_produce_hierarchy_from_level(int coarsenings, int starting_level, ml_data_t &ml_data,
+                                     const MultilevelParameters &mlp)
+{
+    SA_ASSERT(1 <= ml_data.levels_list.num_levels);
+    agg_partitioning_relations_t *agg_part_rels = ml_data.levels_list.coarsest->agg_part_rels;
+    tg_data_t *tg_data = ml_data.levels_list.coarsest->tg_data;
+    for (int i = starting_level; i < coarsenings; ++i)
+    {
+        SA_ASSERT(tg_data->have_Ac);
+        int nparts = mlp.get_nparts(i);
+        int *partitioning = NULL;
+        if (mlp.coarse_partitioner)
+            partitioning = mlp.coarse_partitioner(i, agg_part_rels->nparts, &nparts,
+                                                  mlp.coarse_partitioner_data);
+        agg_part_rels = agg_create_partitioning_coarse(
+            *agg_part_rels, tg_data->interp_data->mis_numcoarsedof, &nparts,
+            mlp.get_avoid_ess_bdr_dofs(), partitioning);
+        tg_data_t *finer_tg = tg_data;
+        tg_data = tg_init_data(NULL, *agg_part_rels, mlp.get_nu_pro(i), mlp.get_nu_relax(i),
+                               mlp.get_theta(i), mlp.get_smooth_interp(i),
+                               mlp.get_smooth_drop_tol(), mlp.get_use_arpack());
+        tg_data->use_w_cycle = false;
+        tg_data->polynomial_coarse_space = mlp.get_polynomial_coarse_space(i);
+        ElementMatrixProvider *emp =
+            new ElementMatrixParallelCoarse(*agg_part_rels, ml_data.levels_list.coarsest);
+        tg_build_hierarchy(NULL, *tg_data, *agg_part_rels, emp, mlp.get_avoid_ess_bdr_dofs(),
+                           finer_tg);
+        tg_update_coarse_operator(tg_data, i + 1 == coarsenings, mlp.get_coarse_direct());
+        levels_list_push_coarse_data(ml_data.levels_list, agg_part_rels, tg_data);
+    }
+    ml_impose_cycle(ml_data, false);
+}
+
+// amg/src/ml.cpp:361-377: chain the levels; coarsest level gets the exact solver
+void ml_impose_cycle(ml_data_t &ml_data, bool Wcycle)
+{
+    SA_ASSERT(!Wcycle);
+    std::vector<sa_gpu_level *> levels;
+    int i = 0;
+    for (levels_level_t *level = ml_data.levels_list.finest; level; level = level->coarser)
+    {
+        level->tg_data->tag = i++;
+        levels.push_back(level->tg_data->gpu);
+    }
+    if (ml_data.gpu_solver)
+        sa_gpu_solver_destroy(ml_data.gpu_solver);
+    ml_data.gpu_solver = NULL;
+    sa_gpu_check(sa_gpu_solver_create(proc_gpu_ctx(), levels.data(), (int)levels.size(),
+                                      ml_data.nu_relax, &ml_data.gpu_solver),
+                 "sa_gpu_solver_create");
+}
+
+// amg/src/ml.cpp:379-472
+ml_data_t *ml_produce_data(const SparseMatrix &Ag, agg_partitioning_relations_t *agg_part_rels,
+                           ElementMatrixProvider *elem_data_finest,
+                           const MultilevelParameters &mlp)
+{
+    SA_ASSERT(elem_data_finest);
+    ml_data_t *ml_data = new ml_data_t;
+    std::memset(ml_data, 0, sizeof(*ml_data));
+    SA_ASSERT(mlp.get_num_coarsenings() > 0);
+    ml_data->nu_relax = mlp.get_nu_relax(0);
+    tg_data_t *tg_data =
+        tg_init_data(&Ag, *agg_part_rels, mlp.get_nu_pro(0), mlp.get_nu_relax(0), mlp.get_theta(0),
+                     mlp.get_smooth_interp(0), mlp.get_smooth_drop_tol(), mlp.get_use_arpack());
+    tg_data->use_w_cycle = false;
+    tg_data->polynomial_coarse_space = mlp.get_polynomial_coarse_space(0);
+    tg_data->interp_data->testmesh_inject = mlp.testmesh_inject;
+    tg_build_hierarchy(&Ag, *tg_data, *agg_part_rels, elem_data_finest,
+                       mlp.get_avoid_ess_bdr_dofs());
+    tg_update_coarse_operator(tg_data, 1 >= mlp.get_num_coarsenings(), mlp.get_coarse_direct());
+    levels_list_push_coarse_data(ml_data->levels_list, agg_part_rels, tg_data);
+    ml_produce_hierarchy_from_level(mlp.get_num_coarsenings(), 1, *ml_data, mlp);
+    return ml_data;
+}
+
+// amg/src/ml.cpp:474-486: the finest agg_part_rels belongs to the caller
+void ml_free_data(ml_data_t *ml_data)
+{
+    if (!ml_data)
+        return;
+    if (ml_data->gpu_solver)
+        sa_gpu_solver_destroy(ml_data->gpu_solver);
+    // free coarse to fine: a level's operator aliases the finer level's Ac
+    levels_level_t *level = ml_data->levels_list.coarsest;
+    while (level)
+    {
+        levels_level_t *finer = level->finer;
+        tg_free_data(level->tg_data);
+        if (finer)
+            agg_free_partitioning(level->agg_part_rels);
+        delete level;
+        level = finer;
+    }
+    delete ml_data;
+}
+
+void VCycleSolver::Mult(const Vector &b, Vector &x) const
+{
+    x.resize(b.size());
+    sa_gpu_check(sa_gpu_vcycle(ml_data->gpu_solver, b.data(), x.data()), "sa_gpu_vcycle");
+}
+
+int kalchev_pcg(ml_data_t &ml_data, const Vector &b, Vector &x, int print_iter,
+                int max_num_iter, double RTOLERANCE, double ATOLERANCE,
+                std::vector<double> *brr_history)
+{
+    int iters = 0, hl = 0;
+    std::vector<double> hist((size_t)max_num_iter + 2);
+    sa_gpu_check(sa_gpu_pcg(ml_data.gpu_solver, b.data(), x.data(), max_num_iter, RTOLERANCE,
+                            ATOLERANCE, &iters, hist.data(), (int)hist.size(), &hl),
+                 "sa_gpu_pcg");
+    if (print_iter)
+        for (int i = 0; i < hl; ++i)
+            std::printf("PCG Iteration: %d, (B r, r) = %g\n", i, hist[i]);
+    if (brr_history)
+        brr_history->assign(hist.begin(), hist.begin() + hl);
+    return iters;
+}
+
+void tg_download_results(const tg_data_t &tg_data, const agg_partitioning_relations_t &rels,
+                         tg_data_t *coarser, sa_level_results_t &R)
+{
+    sa_gpu_level *g = tg_data.gpu;
+    R.nparts = rels.nparts;
+    R.num_mises = rels.num_mises;
+    R.ND = rels.ND;
+    R.ae_m.resize(rels.nparts);
+    sa_gpu_check(sa_gpu_get_spectral_counts(g, R.ae_m.data()), "sa_gpu_get_spectral_counts");
+    R.ae_eval_off.assign((size_t)rels.nparts + 1, 0);
+    R.ae_evect_off.assign((size_t)rels.nparts + 1, 0);
+    const bool inject = tg_data.interp_data->testmesh_inject;
+    for (int i = 0; i < rels.nparts; ++i)
+    {
+        const int n = rels.AE_to_dof->RowSize(i);
+        const int nev = R.ae_m[i] - ((inject && i == 0) ? 1 : 0);
+        R.ae_eval_off[i + 1] = R.ae_eval_off[i] + nev;
+        R.ae_evect_off[i + 1] = R.ae_evect_off[i] + (int64_t)n * R.ae_m[i];
+    }
+    R.evals.resize(R.ae_eval_off[rels.nparts]);
+    R.evects.resize(R.ae_evect_off[rels.nparts]);
+    R.ae_D.resize(rels.AE_to_dof->Size_of_connections());
+    sa_gpu_check(sa_gpu_get_spectral(g, R.evals.data(), R.evects.data(), R.ae_D.data()),
+                 "sa_gpu_get_spectral");
+    R.mis_numcoarsedof.assign(tg_data.interp_data->mis_numcoarsedof,
+                              tg_data.interp_data->mis_numcoarsedof + rels.num_mises);
+    R.mis_off.assign((size_t)rels.num_mises + 1, 0);
+    for (int mis = 0; mis < rels.num_mises; ++mis)
+        R.mis_off[mis + 1] =
+            R.mis_off[mis] + (int64_t)rels.mises_size[mis] * R.mis_numcoarsedof[mis];
+    R.mis_tent.resize(R.mis_off[rels.num_mises]);
+    sa_gpu_check(sa_gpu_get_mis_tent(g, R.mis_tent.data()), "sa_gpu_get_mis_tent");
+    struct
+    {
+        int which;
+        SparseMatrix *M;
+    } mats[3] = {{SA_GPU_MAT_PTENT, &R.tent_interp}, {SA_GPU_MAT_P, &R.interp},
+                 {SA_GPU_MAT_AC, &R.Ac}};
+    for (int k = 0; k < 3; ++k)
+    {
+        int rows, cols, nnz;
+        sa_gpu_check(sa_gpu_get_csr_sizes(g, mats[k].which, &rows, &cols, &nnz),
+                     "sa_gpu_get_csr_sizes");
+        SparseMatrix &M = *mats[k].M;
+        M.h = rows;
+        M.w = cols;
+        M.I.resize((size_t)rows + 1);
+        M.J.resize(nnz);
+        M.A.resize(nnz);
+        sa_gpu_check(sa_gpu_get_csr(g, mats[k].which, M.I.data(), M.J.data(), M.A.data()),
+                     "sa_gpu_get_csr");
+    }
+    R.NDc = R.Ac.h;
+    R.Dinv_neg.resize(rels.ND);
+    sa_gpu_check(sa_gpu_get_Dinv_neg(g, R.Dinv_neg.data()), "sa_gpu_get_Dinv_neg");
+    R.celmat_off.clear();
+    R.celmat.clear();
+    if (coarser && coarser->gpu)
+    {
+        // sizes follow the coarse elem_to_dof rows; the coarse level knows them
+        int rows, cols, nnz;
+        (void)cols;
+        (void)nnz;
+        (void)rows;
+    }
+}
+
+} // namespace saamge
+
+/* ------------------------------------------------------ driver entry points */
+
+using namespace saamge;
+
+struct product_impl_t
+{
+    ml_data_t *ml = NULL;
+    int64_t launches0 = 0;
+};
+
+static void product_impl_free(void *p)
+{
+    product_impl_t *pi = (product_impl_t *)p;
+    ml_free_data(pi->ml);
+    delete pi;
+}
+
+struct block_partitioner_data_t
+{
+    const sa_problem_t *prob;
+    const sa_drv_params_t *p;
+};
+
+static int *block_coarse_partitioner(int level, int num_elem, int *nparts, void *data)
+{
+    block_partitioner_data_t *d = (block_partitioner_data_t *)data;
+    return sa_block_coarse_partitioning(*d->prob, *d->p, level, num_elem, nparts);
+}
+
+extern "C" void *sa_drv_ml_build(void *prob_, const sa_drv_params_t *p, int device)
+{
+    sa_problem_t *prob = (sa_problem_t *)prob_;
+    SA_ASSERT(prob && prob->rels);
+    proc_gpu_init(device);
+    sa_hierarchy_t *H = new sa_hierarchy_t;
+    H->prob = prob;
+    H->params = *p;
+    product_impl_t *pi = new product_impl_t;
+    H->impl = pi;
+    H->impl_free = product_impl_free;
+    H->owns_rels = false; // coarse relations belong to ml_data (ml_free_data)
+    const fem_problem_t &f = *prob->fem;
+    std::vector<int> nparts_arr = sa_target_nparts(f.NE, *p);
+    const double t0 = now_s();
+    std::vector<int64_t> offsets((size_t)f.NE + 1);
+    for (int e = 0; e <= f.NE; ++e)
+        offsets[e] = (int64_t)e * f.ne * f.ne;
+    // the provider is owned by tg_data (amg/src/tg.cpp:518,946); offsets must outlive
+    // tg_build_hierarchy only (data is copied to the device there)
+    ElementMatrixProvider *emp =
+        new ElementMatrixStandardGeometric(*prob->rels, f.A, f.elmat.data(), offsets.data());
+    MultilevelParameters mlp(p->num_levels - 1, nparts_arr.data(), p->first_nu_pro, p->nu_pro,
+                             p->nu_relax, p->first_theta, p->theta, -1, false, false, false);
+    mlp.set_coarse_direct(true);
+    mlp.testmesh_inject = p->testmesh_inject != 0;
+    block_partitioner_data_t bpd = {prob, p};
+    if (p->partition_kind == 1)
+        mlp.set_coarse_partitioner(block_coarse_partitioner, &bpd);
+    pi->ml = ml_produce_data(f.A, prob->rels, emp, mlp);
+    sa_gpu_ctx_sync(proc_gpu_ctx());
+    H->times["setup"] = now_s() - t0;
+    for (levels_level_t *l = pi->ml->levels_list.finest; l; l = l->coarser)
+        H->rels.push_back(l->agg_part_rels);
+    return H;
+}
+
+extern "C" int sa_drv_ml_download(void *hier)
+{
+    sa_hierarchy_t *H = (sa_hierarchy_t *)hier;
+    product_impl_t *pi = (product_impl_t *)H->impl;
+    H->levels.clear();
+    H->levels.resize(pi->ml->levels_list.num_levels);
+    int i = 0;
+    for (levels_level_t *l = pi->ml->levels_list.finest; l; l = l->coarser, ++i)
+    {
+        tg_download_results(*l->tg_data, *l->agg_part_rels, l->coarser ? l->coarser->tg_data : NULL,
+                            H->levels[i]);
+        if (l->coarser)
+        {
+            // coarse element matrices of this level's AEs live on the coarser level
+            const agg_partitioning_relations_t &cr = *l->coarser->agg_part_rels;
+            sa_level_results_t &R = H->levels[i];
+            R.celmat_off.assign((size_t)l->agg_part_rels->nparts + 1, 0);
+            for (int e = 0; e < l->agg_part_rels->nparts; ++e)
+            {
+                const int64_t nc = cr.elem_to_dof->RowSize(e);
+                R.celmat_off[e + 1] = R.celmat_off[e] + nc * nc;
+            }
+            R.celmat.resize(R.celmat_off[l->agg_part_rels->nparts]);
+            sa_gpu_check(sa_gpu_get_coarse_elmats(l->coarser->tg_data->gpu, R.celmat.data()),
+                         "sa_gpu_get_coarse_elmats");
+        }
+    }
+    return 0;
+}
+
+extern "C" int sa_drv_ml_pcg(void *hier, int maxiter, double rtol, double atol)
+{
+    sa_hierarchy_t *H = (sa_hierarchy_t *)hier;
+    product_impl_t *pi = (product_impl_t *)H->impl;
+    const fem_problem_t &f = *H->prob->fem;
+    H->pcg.x.assign(f.b.size(), 0.);
+    H->pcg.brr.clear();
+    const double t0 = now_s();
+    H->pcg.iterations = kalchev_pcg(*pi->ml, f.b, H->pcg.x, 0, maxiter, rtol, atol, &H->pcg.brr);
+    H->times["pcg"] = now_s() - t0;
+    Vector r(f.b.size());
+    SpMult(f.A, H->pcg.x.data(), r.data());
+    double s = 0.;
+    for (size_t i = 0; i < f.b.size(); ++i)
+        s += (f.b[i] - r[i]) * (f.b[i] - r[i]);
+    H->pcg.final_res_norm = std::sqrt(s);
+    return H->pcg.iterations;
+}

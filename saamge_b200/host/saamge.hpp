@@ -1,0 +1,272 @@
+// Host-side mirror of the reference's hierarchy-building interface for the hot
+// path: same names, argument meaning and ownership rules as the tg_ / ml_ / interp_
+// entry points of SAAMGE, on the MFEM-free types of sa_types.hpp.  Every function
+// hands its work to the CUDA library through the C ABI of include/saamge_b200.h;
+// there is no CPU implementation behind these calls (they fail if no GPU is present).
+//
+//   reference header            what is mirrored here
+//   amg/inc/elmat.hpp:53-170    ElementMatrixProvider + StandardGeometric / DenseArray / ParallelCoarse
+//   amg/inc/interp.hpp:54-100   interp_data_t
+//   amg/inc/smpr.hpp:89-108     smpr_poly_data_t, smpr_sa_poly_roots, smpr_sas_poly_roots
+//   amg/inc/tg_data.hpp:47-83   tg_data_t
+//   amg/inc/tg.hpp:428-610      tg_init_data, tg_build_hierarchy, tg_produce_data,
+//                               tg_update_coarse_operator, tg_free_data, tg_pcg_run
+//   amg/inc/levels.hpp:47-64    levels_level_t, levels_list_t
+//   amg/inc/ml.hpp:59-196       MultilevelParameters, ml_data_t, ml_produce_data,
+//                               ml_produce_hierarchy_from_level, ml_impose_cycle, ml_free_data
+//   amg/inc/solve.hpp:129-181   VCycleSolver
+#ifndef SAAMGE_B200_SAAMGE_HPP
+#define SAAMGE_B200_SAAMGE_HPP
+
+#include "../../include/saamge_b200.h"
+#include "aggregates.hpp"
+#include "elmat.hpp"
+#include "level_results.hpp"
+#include "sa_types.hpp"
+
+namespace saamge
+{
+
+/* ---- device context (plays the role of proc_init / PROC_COMM, amg/inc/process.hpp:94-98) ---- */
+sa_gpu_ctx *proc_gpu_init(int device);
+sa_gpu_ctx *proc_gpu_ctx();
+void proc_gpu_finalize();
+/// SA_ASSERT-style abort with the CUDA library's message when rc != 0
+void sa_gpu_check(int rc, const char *what);
+
+/* ---- element-matrix providers ---- */
+class ElementMatrixStandardGeometric : public ElementMatrixProvider
+{
+public:
+    /// \a assembled_processor_matrix: BC-eliminated matrix; \a blocks: dense element
+    /// matrices (what bf->ComputeElementMatrix returns), block e at blocks[offsets[e]]
+    ElementMatrixStandardGeometric(const agg_partitioning_relations_t &agg_part_rels,
+                                   const SparseMatrix &assembled_processor_matrix,
+                                   const double *blocks, const int64_t *offsets);
+    virtual Matrix *GetMatrix(int elno, bool &free_matr) const;
+    virtual SparseMatrix *BuildAEStiff(int elno) const;
+    virtual const double *DenseBlocks() const { return blocks_; }
+    virtual const int64_t *DenseBlockOffsets() const { return offsets_; }
+    virtual const SparseMatrix *AssembledMatrix() const { return &A_; }
+
+private:
+    const SparseMatrix &A_;
+    const double *blocks_;
+    const int64_t *offsets_;
+};
+
+class ElementMatrixDenseArray : public ElementMatrixProvider
+{
+public:
+    ElementMatrixDenseArray(const agg_partitioning_relations_t &agg_part_rels,
+                            const double *blocks, const int64_t *offsets);
+    virtual Matrix *GetMatrix(int elno, bool &free_matr) const;
+    virtual SparseMatrix *BuildAEStiff(int elno) const;
+    virtual const double *DenseBlocks() const { return blocks_; }
+    virtual const int64_t *DenseBlockOffsets() const { return offsets_; }
+
+private:
+    const double *blocks_;
+    const int64_t *offsets_;
+};
+
+struct levels_level_struct;
+
+/// Coarse "element" matrices P_e^T A_AE(e) P_e of the finer level's AEs; they are
+/// computed and kept on the device (sa_gpu_coarse_elmats).
+class ElementMatrixParallelCoarse : public ElementMatrixProvider
+{
+public:
+    ElementMatrixParallelCoarse(const agg_partitioning_relations_t &agg_part_rels,
+                                struct levels_level_struct *level);
+    virtual Matrix *GetMatrix(int elno, bool &free_matr) const;
+    virtual SparseMatrix *BuildAEStiff(int elno) const;
+    struct levels_level_struct *finer_level() const { return level; }
+
+private:
+    struct levels_level_struct *level;
+    mutable std::vector<double> cache_; // read-back of the device blocks, on demand
+};
+
+/* ---- data ---- */
+typedef struct
+{
+    int nparts;
+    int nu_pro;
+    int interp_smoother_degree;
+    double *interp_smoother_roots;
+    int times_apply_smoother;
+    bool use_arpack; /*!< accepted for API compatibility; the device path is always direct */
+    bool scaling_P;  /*!< not supported on the device path (CorrectNullspace is out of scope) */
+    int *mis_numcoarsedof;
+    int coarse_truedof_offset;
+    int num_mises;
+    double drop_tol;
+    bool testmesh_inject;
+    // cut_evects_arr / rhs_matrices_arr / AEs_stiffm / mis_tent_interps of the reference
+    // live on the device; interp_download() copies them into a flat host record
+} interp_data_t;
+
+typedef struct
+{
+    int nu;
+    int degree;
+    const double *roots;
+    double weightfirst;
+    int degree2;
+    const double *roots2;
+    double param;
+} smpr_poly_data_t;
+
+double *smpr_sa_poly_roots(int &nu, int *degree);
+double *smpr_sas_poly_roots(int &nu, int *degree);
+
+class VCycleSolver;
+
+typedef struct
+{
+    interp_data_t *interp_data;
+    sa_gpu_level *gpu; /*!< device-resident Ac, interp, restr, tent_interp, Dinv_neg */
+    bool smooth_interp;
+    double theta;
+    VCycleSolver *coarse_solver;
+    smpr_poly_data_t *poly_data;
+    bool use_w_cycle;
+    int polynomial_coarse_space;
+    bool doing_spectral;
+    int tag;
+    ElementMatrixProvider *elem_data;
+    bool have_Ac;
+} tg_data_t;
+
+typedef struct levels_level_struct
+{
+    struct levels_level_struct *finer;
+    agg_partitioning_relations_t *agg_part_rels;
+    tg_data_t *tg_data;
+    struct levels_level_struct *coarser;
+} levels_level_t;
+
+typedef struct
+{
+    int num_levels;
+    levels_level_t *finest;
+    levels_level_t *coarsest;
+} levels_list_t;
+
+class MultilevelParameters
+{
+public:
+    MultilevelParameters(int coarsenings, int *nparts_arr, int first_nu_pro, int nu_pro,
+                         int nu_relax, double first_theta, double theta,
+                         int polynomial_coarse_space, bool use_correct_nullspace,
+                         bool use_arpack, bool do_aggregates);
+    ~MultilevelParameters();
+    int get_num_coarsenings() const { return num_coarsenings; }
+    int get_nu_pro(int j) const { return nu_pro[j]; }
+    int get_nu_relax(int j) const { return nu_relax[j]; }
+    double get_theta(int j) const { return theta[j]; }
+    bool get_smooth_interp(int j) const { return (nu_pro[j] > 0); }
+    int get_polynomial_coarse_space(int j) const { return polynomial_coarse_space[j]; }
+    bool get_use_correct_nullspace() const { return use_correct_nullspace; }
+    bool get_use_arpack() const { return use_arpack; }
+    bool get_do_aggregates() const { return do_aggregates; }
+    int get_nparts(int j) const { return nparts_arr[j]; }
+    bool get_avoid_ess_bdr_dofs() const { return avoid_ess_bdr_dofs; }
+    double get_smooth_drop_tol() const { return smooth_drop_tol; }
+    bool get_coarse_direct() const { return coarse_direct; }
+    void set_coarse_direct(bool cd) { coarse_direct = cd; }
+    /* fixtures: fixed coarse partitions instead of METIS (cf. the hard-coded
+       partitions of the mltest fixture, amg/src/aggregates.cpp:1777-1794) */
+    typedef int *(*coarse_partition_ft)(int level, int num_elem, int *nparts, void *data);
+    void set_coarse_partitioner(coarse_partition_ft f, void *data)
+    {
+        coarse_partitioner = f;
+        coarse_partitioner_data = data;
+    }
+    coarse_partition_ft coarse_partitioner;
+    void *coarse_partitioner_data;
+    bool testmesh_inject;
+
+private:
+    int num_coarsenings;
+    int *nparts_arr;
+    int *nu_pro;
+    int *nu_relax;
+    double *theta;
+    int *polynomial_coarse_space;
+    bool use_correct_nullspace;
+    bool use_arpack;
+    bool do_aggregates;
+    bool avoid_ess_bdr_dofs;
+    bool coarse_direct;
+    double smooth_drop_tol;
+};
+
+typedef struct
+{
+    levels_list_t levels_list;
+    sa_gpu_solver *gpu_solver; /*!< V-cycle chain on the device (ml_impose_cycle) */
+    int nu_relax;
+} ml_data_t;
+
+/* ---- two-grid entry points ---- */
+tg_data_t *tg_init_data(const SparseMatrix *A, const agg_partitioning_relations_t &agg_part_rels,
+                        int nu_pro, int nu_relax, double theta, bool smooth_interp,
+                        double smooth_drop_tol, bool use_arpack);
+/// \a Ag == NULL: the operator is the coarse operator the finer level left on the
+/// device.  \a finer: finer level's tg_data (NULL on the finest level).
+void tg_build_hierarchy(const SparseMatrix *Ag, tg_data_t &tg_data,
+                        const agg_partitioning_relations_t &agg_part_rels,
+                        ElementMatrixProvider *elem_data, bool avoid_ess_bdr_dofs,
+                        tg_data_t *finer = NULL);
+tg_data_t *tg_produce_data(const SparseMatrix &Ag,
+                           const agg_partitioning_relations_t &agg_part_rels, int nu_pro,
+                           int nu_relax, ElementMatrixProvider *elem_data, double theta,
+                           bool smooth_interp, int polynomial_coarse_arg, bool use_arpack,
+                           bool avoid_ess_bdr_dofs);
+void tg_update_coarse_operator(tg_data_t *tg_data, bool perform_solve_init, bool coarse_direct);
+void tg_free_data(tg_data_t *tg_data);
+
+/* the stages tg_build_hierarchy runs, exposed like in the reference */
+void interp_compute_vectors(const agg_partitioning_relations_t &agg_part_rels,
+                            const interp_data_t &interp_data, tg_data_t &tg_data, double &theta);
+void interp_sparse_tent_assemble(const agg_partitioning_relations_t &agg_part_rels,
+                                 interp_data_t &interp_data, tg_data_t &tg_data,
+                                 bool avoid_ess_bdr_dofs);
+
+/* ---- multilevel entry points ---- */
+ml_data_t *ml_produce_data(const SparseMatrix &Ag, agg_partitioning_relations_t *agg_part_rels,
+                           ElementMatrixProvider *elem_data_finest,
+                           const MultilevelParameters &mlp);
+void ml_produce_hierarchy_from_level(int coarsenings, int starting_level, ml_data_t &ml_data,
+                                     const MultilevelParameters &mlp);
+void ml_impose_cycle(ml_data_t &ml_data, bool Wcycle);
+void ml_free_data(ml_data_t *ml_data);
+levels_level_t *levels_list_get_level(const levels_list_t &list, int i);
+
+/* ---- solve ---- */
+class VCycleSolver
+{
+public:
+    VCycleSolver(ml_data_t *ml_data) : ml_data(ml_data) {}
+    /// one V-cycle from x = 0 (amg/src/solve.cpp:309-323)
+    void Mult(const Vector &b, Vector &x) const;
+
+private:
+    ml_data_t *ml_data;
+};
+
+/// kalchev_pcg (amg/src/mfem_addons.cpp:106-248) with the hierarchy's V-cycle as B.
+/// Returns the iteration count (negative on failure).
+int kalchev_pcg(ml_data_t &ml_data, const Vector &b, Vector &x, int print_iter,
+                int max_num_iter, double RTOLERANCE, double ATOLERANCE,
+                std::vector<double> *brr_history = NULL);
+
+/// Copies one level's device results into the flat host record (tests, file dumps).
+void tg_download_results(const tg_data_t &tg_data, const agg_partitioning_relations_t &rels,
+                         tg_data_t *coarser, sa_level_results_t &R);
+
+} // namespace saamge
+
+#endif

@@ -1,0 +1,45 @@
+"""Loader for the CPU oracle (oracle/liboracle.so) -- test infrastructure only."""
+import ctypes
+import glob
+import os
+
+import saamge_b200 as sab
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_LIB = os.path.join(ROOT, "oracle", "liboracle.so")
+_orc = None
+
+
+def lapack_path():
+    import scipy
+
+    pats = os.path.join(os.path.dirname(scipy.__file__), "..", "scipy.libs", "libscipy_openblas*.so")
+    libs = glob.glob(pats)
+    if not libs:
+        raise RuntimeError("scipy's bundled OpenBLAS not found")
+    return os.path.abspath(libs[0])
+
+
+def oracle(num_threads=0):
+    global _orc
+    if _orc is None:
+        sab.host_lib()
+        o = ctypes.CDLL(ORACLE_LIB)
+        o.sa_orc_init.argtypes = [ctypes.c_char_p, ctypes.c_int]
+        o.sa_orc_ml_build.restype = ctypes.c_void_p
+        o.sa_orc_ml_build.argtypes = [ctypes.c_void_p, ctypes.POINTER(sab.Params)]
+        o.sa_orc_ml_pcg.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double]
+        o.sa_orc_time_local_spectral.restype = ctypes.c_double
+        o.sa_orc_time_local_spectral.argtypes = [ctypes.c_void_p, ctypes.POINTER(sab.Params), ctypes.c_int, ctypes.c_int]
+        o.sa_orc_check_mises.argtypes = [ctypes.c_void_p]
+        o.sa_orc_init(lapack_path().encode(), num_threads)
+        _orc = o
+    return _orc
+
+
+def orc_build(problem, params):
+    return sab.Hierarchy(oracle().sa_orc_ml_build(problem.handle, ctypes.byref(params)))
+
+
+def orc_pcg(hier, maxiter=1000, rtol=1e-12, atol=0.0):
+    return oracle().sa_orc_ml_pcg(hier.handle, maxiter, rtol, atol)

@@ -1,0 +1,231 @@
+"""Parity metrics between two hierarchies (normally: B200 path vs CPU oracle).
+
+Gauge freedom.  Eigenvectors are defined up to sign (rotation inside multiple
+eigenvalues) and the SVD basis of every MIS up to an orthogonal k x k matrix Q_mis.
+What both implementations must agree on is therefore: integer maps and sparsity
+patterns (bit-exact), eigenvalues, the eigen*spaces* per AE, the column *space* of
+the tentative prolongator per MIS, and every operator after the change of coarse
+basis Q = blockdiag(Q_mis):  P_g = S P_o Q,  Ac_g = Q^T Ac_o Q, where S is the
+(diagonal, +-1) basis change of the previous level (identity on the finest level).
+Tolerances are the ones BASELINE.json's north_star states.
+"""
+import numpy as np
+import scipy.sparse as sp
+
+MAPS = [
+    "partitioning",
+    "elem_to_dof.I",
+    "elem_to_dof.J",
+    "AE_to_elem.I",
+    "AE_to_elem.J",
+    "AE_to_dof.I",
+    "AE_to_dof.J",
+    "dof_to_AE.I",
+    "dof_to_AE.J",
+    "dof_id_inAE",
+    "agg_flags",
+    "mises",
+    "mises_size",
+    "mis_to_dof.I",
+    "mis_to_dof.J",
+    "mis_to_AE.I",
+    "mis_to_AE.J",
+    "AE_to_mis.I",
+    "AE_to_mis.J",
+]
+
+
+def _pattern(M, drop=1e-13):
+    M = M.tocsr().copy()
+    M.data[np.abs(M.data) <= drop] = 0.0
+    M.eliminate_zeros()
+    M.sort_indices()
+    return M.indptr.copy(), M.indices.copy()
+
+
+def compare_level(Hg, Ho, level, S_prev=None, check_celmat=True):
+    """Returns (metrics dict, S for the next level or None if the gauge is not diagonal)."""
+    m = {}
+    # ---- integer maps: bit-exact
+    bad = [k for k in MAPS if not np.array_equal(Hg.get(k, level), Ho.get(k, level))]
+    m["maps_mismatch"] = bad
+    AEI = Ho.get("AE_to_dof.I", level)
+    AEJ = Ho.get("AE_to_dof.J", level)
+    nparts = len(AEI) - 1
+    ND = int(Ho.scalar("ND", level))
+    if S_prev is None:
+        S_prev = np.ones(ND)
+
+    # ---- per-AE spectral data
+    mg, mo = Hg.get("ae_m", level), Ho.get("ae_m", level)
+    m["ae_m_mismatch"] = int(np.sum(mg != mo))
+    Dg, Do = Hg.get("ae_D", level), Ho.get("ae_D", level)
+    m["D_relerr"] = float(np.max(np.abs(Dg - Do) / np.abs(Do))) if len(Do) else 0.0
+    eg, eo = Hg.get("evals", level), Ho.get("evals", level)
+    if len(eg) == len(eo):
+        m["eval_err"] = float(np.max(np.abs(eg - eo) / np.maximum(np.abs(eo), 1.0))) if len(eo) else 0.0
+    else:
+        m["eval_err"] = float("inf")
+    og, oo = Hg.get("ae_evect_off", level), Ho.get("ae_evect_off", level)
+    Zg, Zo = Hg.get("evects", level), Ho.get("evects", level)
+    worst = 0.0
+    dnorm_worst = 0.0
+    if m["ae_m_mismatch"] == 0:
+        for i in range(nparts):
+            n = AEI[i + 1] - AEI[i]
+            k = mo[i]
+            if k == 0:
+                continue
+            dofs = AEJ[AEI[i] : AEI[i + 1]]
+            s = S_prev[dofs]
+            D = Do[AEI[i] : AEI[i + 1]]
+            A = Zg[og[i] : og[i + 1]].reshape(k, n).T * s[:, None]
+            B = Zo[oo[i] : oo[i + 1]].reshape(k, n).T
+            # D-orthonormalise both (they are D-orthonormal up to roundoff / injected vector)
+            sq = np.sqrt(D)[:, None]
+            Qa, _ = np.linalg.qr(A * sq)
+            Qb, _ = np.linalg.qr(B * sq)
+            sin = np.linalg.norm(Qa - Qb @ (Qb.T @ Qa), 2)
+            worst = max(worst, sin)
+            # normalisation z^T D z = 1 of the GPU vectors (skip an injected all-ones column)
+            nd = np.abs(np.sum(A * A * D[:, None], axis=0) - 1.0)
+            if i == 0 and len(nd) and np.allclose(np.abs(A[:, -1]), 1.0):
+                nd = nd[:-1]
+            if len(nd):
+                dnorm_worst = max(dnorm_worst, float(nd.max()))
+    else:
+        worst = float("inf")
+    m["eigenspace_sin"] = float(worst)
+    m["evect_Dnorm_err"] = float(dnorm_worst)
+
+    # ---- per-MIS blocks
+    kg, ko = Hg.get("mis_numcoarsedof", level), Ho.get("mis_numcoarsedof", level)
+    m["mis_ncd_mismatch"] = int(np.sum(kg != ko))
+    m["NDc"] = int(ko.sum())
+    S_next = None
+    if m["mis_ncd_mismatch"] == 0:
+        misI = Ho.get("mis_to_dof.I", level)
+        misJ = Ho.get("mis_to_dof.J", level)
+        offg, offo = Hg.get("mis_off", level), Ho.get("mis_off", level)
+        Tg, To = Hg.get("mis_tent", level), Ho.get("mis_tent", level)
+        nmis = len(ko)
+        worst = 0.0
+        orth = 0.0
+        rows, cols, vals = [], [], []
+        col0 = 0
+        diag_gauge = True
+        for mis in range(nmis):
+            k = ko[mis]
+            s = misI[mis + 1] - misI[mis]
+            if k == 0:
+                continue
+            sg = S_prev[misJ[misI[mis] : misI[mis + 1]]]
+            Ug = Tg[offg[mis] : offg[mis + 1]].reshape(k, s).T * sg[:, None]
+            Uo = To[offo[mis] : offo[mis + 1]].reshape(k, s).T
+            Q = Uo.T @ Ug
+            worst = max(worst, np.linalg.norm(Ug - Uo @ Q, 2))
+            orth = max(orth, np.linalg.norm(Ug.T @ Ug - np.eye(k), 2))
+            if np.max(np.abs(np.abs(Q) - np.eye(k))) > 1e-6:
+                diag_gauge = False
+            for a in range(k):
+                for b in range(k):
+                    rows.append(col0 + a)
+                    cols.append(col0 + b)
+                    vals.append(Q[a, b])
+            col0 += k
+        m["mis_space_sin"] = float(worst)
+        m["mis_orth_err"] = float(orth)
+        m["gauge_is_signs"] = bool(diag_gauge)
+        NDc = col0
+        Q = sp.csr_matrix((vals, (rows, cols)), shape=(NDc, NDc))
+        Sd = sp.diags(S_prev)
+        # ---- tentative and final prolongator
+        for name in ("tent_interp", "interp"):
+            Pg, Po = Hg.csr(name, level), Ho.csr(name, level)
+            pg, po = _pattern(Pg), _pattern(Po)
+            m[name + "_pattern_equal"] = bool(
+                np.array_equal(pg[0], po[0]) and np.array_equal(pg[1], po[1])
+            )
+            diff = (Pg - Sd @ Po @ Q).tocsr()
+            scale = max(1e-300, np.abs(Po.data).max())
+            m[name + "_err"] = float(np.abs(diff.data).max() / scale) if diff.nnz else 0.0
+        # ---- coarse operator
+        Ag, Ao = Hg.csr("Ac", level), Ho.csr("Ac", level)
+        pg, po = _pattern(Ag), _pattern(Ao)
+        m["Ac_pattern_equal"] = bool(np.array_equal(pg[0], po[0]) and np.array_equal(pg[1], po[1]))
+        diff = (Ag - Q.T @ Ao @ Q).tocsr()
+        m["Ac_err"] = float(np.abs(diff.data).max() / np.abs(Ao.data).max()) if diff.nnz else 0.0
+        m["Ac_nnz"] = int(Ao.nnz)
+        # relative error entry by entry on entries that are not tiny
+        A2 = (Q.T @ Ao @ Q).tocsr()
+        big = np.abs(A2.data) > 1e-8 * np.abs(Ao.data).max()
+        if big.any():
+            Agd = Ag.tocsr()
+            r, c = A2.nonzero()
+            ref = np.asarray(A2[r, c]).ravel()
+            got = np.asarray(Agd[r, c]).ravel()
+            sel = np.abs(ref) > 1e-8 * np.abs(Ao.data).max()
+            m["Ac_entry_relerr"] = float(np.max(np.abs(got[sel] - ref[sel]) / np.abs(ref[sel])))
+        # ---- Dinv_neg
+        dg, do = Hg.get("Dinv_neg", level), Ho.get("Dinv_neg", level)
+        m["Dinv_relerr"] = float(np.max(np.abs(dg - do) / np.abs(do)))
+        if diag_gauge:
+            S_next = np.asarray(Q.diagonal()).copy()
+            S_next = np.where(S_next >= 0, 1.0, -1.0)
+        # ---- coarse element matrices (exist when a coarser level was built)
+        cg = Hg.get("celmat", level)
+        co = Ho.get("celmat", level)
+        if check_celmat and len(co) and len(cg) == len(co):
+            offs = Ho.get("celmat_off", level)
+            ceI = Ho.get("elem_to_dof.I", level + 1)
+            ceJ = Ho.get("elem_to_dof.J", level + 1)
+            Qd = Q.toarray() if NDc <= 4000 else None
+            worst = 0.0
+            scale = np.abs(co).max()
+            for e in range(nparts):
+                cd = ceJ[ceI[e] : ceI[e + 1]]
+                nc = len(cd)
+                if nc == 0:
+                    continue
+                Mg = cg[offs[e] : offs[e + 1]].reshape(nc, nc).T
+                Mo = co[offs[e] : offs[e + 1]].reshape(nc, nc).T
+                Qe = Qd[np.ix_(cd, cd)] if Qd is not None else Q[cd][:, cd].toarray()
+                worst = max(worst, np.abs(Mg - Qe.T @ Mo @ Qe).max() / scale)
+            m["celmat_err"] = float(worst)
+        elif len(co) != len(cg):
+            m["celmat_err"] = float("inf")
+    return m, S_next
+
+
+def compare_hierarchies(Hg, Ho):
+    out = []
+    S = None
+    nl = int(Ho.scalar("num_coarsenings", 0))
+    for l in range(nl):
+        m, S = compare_level(Hg, Ho, l, S)
+        out.append(m)
+        if S is None and l + 1 < nl:
+            m["note"] = "gauge not diagonal: coarser levels not comparable entry-wise"
+            break
+    return out
+
+
+def assert_level_ok(m, level, eig_tol=1e-10, space_tol=1e-8, ac_tol=1e-9):
+    assert m["maps_mismatch"] == [], (level, m["maps_mismatch"])
+    assert m["ae_m_mismatch"] == 0, (level, "ae_m", m["ae_m_mismatch"])
+    assert m["D_relerr"] <= 1e-11, (level, "D", m["D_relerr"])
+    assert m["eval_err"] <= eig_tol, (level, "eval", m["eval_err"])
+    assert m["eigenspace_sin"] <= space_tol, (level, "eigenspace", m["eigenspace_sin"])
+    assert m["evect_Dnorm_err"] <= 1e-10, (level, "Dnorm", m["evect_Dnorm_err"])
+    assert m["mis_ncd_mismatch"] == 0, (level, "mis_ncd", m["mis_ncd_mismatch"])
+    assert m["mis_space_sin"] <= space_tol, (level, "mis_space", m["mis_space_sin"])
+    assert m["mis_orth_err"] <= 1e-10, (level, "mis_orth", m["mis_orth_err"])
+    assert m["tent_interp_pattern_equal"], (level, "tent pattern")
+    assert m["interp_pattern_equal"], (level, "interp pattern")
+    assert m["Ac_pattern_equal"], (level, "Ac pattern")
+    assert m["tent_interp_err"] <= space_tol, (level, "tent", m["tent_interp_err"])
+    assert m["interp_err"] <= space_tol, (level, "interp", m["interp_err"])
+    assert m["Ac_err"] <= ac_tol, (level, "Ac", m["Ac_err"])
+    assert m["Dinv_relerr"] <= 1e-12, (level, "Dinv", m["Dinv_relerr"])
+    if "celmat_err" in m:
+        assert m["celmat_err"] <= ac_tol, (level, "celmat", m["celmat_err"])
