@@ -19,6 +19,7 @@
 #ifndef SAAMGE_B200_H
 #define SAAMGE_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -42,6 +43,11 @@ int64_t sa_gpu_ctx_launch_count(sa_gpu_ctx *ctx);
    begin==0 to record the end event, synchronise and return elapsed ms (CUDA events
    on the context's stream) */
 double sa_gpu_ctx_timer(sa_gpu_ctx *ctx, int begin);
+
+/* per-stage device timings (CUDA events around each kernel group).  enable: 1/0/-1
+   (-1 = unchanged; also switched on by the environment variable SA_GPU_PROFILE=1);
+   buf receives "name milliseconds" lines accumulated so far and the table is reset */
+int sa_gpu_ctx_profile(sa_gpu_ctx *ctx, int enable, char *buf, int buflen);
 
 /* ---- one level: the integer data contract agg_partitioning_relations_t
  *      (amg/inc/aggregates.hpp:120-179) + operator + element matrices ---- */
@@ -181,6 +187,14 @@ int sa_gpu_solver_upload(sa_gpu_solver *solver, const double *b, const double *x
 int sa_gpu_pcg_resident(sa_gpu_solver *solver, int maxiter, double rtol, double atol,
                         int *iters);
 int sa_gpu_solver_download(sa_gpu_solver *solver, double *x);
+
+/* page-lock / unlock a caller-owned host buffer so that the copies made by
+   sa_gpu_level_create run at full PCIe speed (optional) */
+int sa_gpu_host_register(const void *p, size_t bytes);
+int sa_gpu_host_unregister(const void *p);
+/* cycle counters of the four phases of the assemble+tridiagonalise kernel summed over
+   thread blocks since the last call (diagnostics) */
+int sa_gpu_debug_phase_clocks(double *out4);
 
 /* ---- micro-benchmarks used by bench.py for the roofline denominators ---- */
 /* runs `reps` SpMVs y = A x on device-resident vectors; returns ms per SpMV */

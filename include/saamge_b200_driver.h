@@ -69,6 +69,17 @@ int sa_drv_get(void *obj, const char *name, int level, const void **ptr, int64_t
  * "time.<stage>" in seconds, ...).  Returns NaN for unknown names. */
 double sa_drv_get_scalar(void *obj, const char *name, int level);
 
+/* ---- bench driver (bench.py): local spectral stage of the finest level ---- */
+void *sa_drv_bench_create(void *prob, const sa_drv_params_t *p, int device);
+void sa_drv_bench_destroy(void *bench);
+/* mode 0: inputs resident on the device, returns device milliseconds (CUDA events);
+   mode 1: end to end from host buffers (H2D of all inputs + compute + D2H of results) */
+double sa_drv_bench_step(void *bench, int mode, int ae_begin, int ae_end);
+/* "h2d_bytes", "d2h_bytes", "launches", "flops", "bytes", "sum_m", "pinned", "phase.N" */
+double sa_drv_bench_scalar(void *bench, const char *name);
+/* device stage profile of the process-wide context (see sa_gpu_ctx_profile) */
+int sa_drv_gpu_profile(int enable, char *buf, int buflen);
+
 #ifdef __cplusplus
 }
 #endif

@@ -171,6 +171,10 @@ class Hierarchy:
     def scalar(self, name, level=0):
         return host_lib().sa_drv_get_scalar(self.handle, name.encode(), level)
 
+    def times(self):
+        keys = bytes(self.get("time_keys").astype(np.uint8)).decode().split("\n")
+        return {k: self.scalar("time." + k) for k in keys if k}
+
     def csr(self, name, level=0):
         import scipy.sparse as sp
 

@@ -37,6 +37,10 @@ extern "C" int sa_gpu_ctx_create(int device, sa_gpu_ctx **out)
     SA_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     SA_CUDA(cudaEventCreate(&ctx->ev0));
     SA_CUDA(cudaEventCreate(&ctx->ev1));
+    SA_CUDA(cudaEventCreate(&ctx->pev0));
+    SA_CUDA(cudaEventCreate(&ctx->pev1));
+    const char *pe = getenv("SA_GPU_PROFILE");
+    ctx->profile = pe && pe[0] == '1';
     *out = ctx;
     SA_API_END
 }
@@ -53,6 +57,28 @@ extern "C" void sa_gpu_ctx_destroy(sa_gpu_ctx *ctx)
     if (ctx->stream)
         cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+extern "C" int sa_gpu_ctx_profile(sa_gpu_ctx *ctx, int enable, char *buf, int buflen)
+{
+    // enable: 1/0 switches profiling, -1 leaves it; the accumulated "name ms" lines are
+    // written to buf (if given) and the table is cleared
+    if (buf && buflen > 0)
+    {
+        std::string out;
+        char line[160];
+        for (size_t i = 0; i < ctx->prof.size(); ++i)
+        {
+            snprintf(line, sizeof line, "%s %.6f\n", ctx->prof[i].first.c_str(),
+                     ctx->prof[i].second);
+            out += line;
+        }
+        snprintf(buf, buflen, "%s", out.c_str());
+        ctx->prof.clear();
+    }
+    if (enable >= 0)
+        ctx->profile = enable != 0;
+    return 0;
 }
 
 extern "C" void *sa_gpu_ctx_stream(sa_gpu_ctx *ctx) { return (void *)ctx->stream; }
@@ -379,4 +405,31 @@ extern "C" double sa_gpu_bench_fp64_peak(sa_gpu_ctx *ctx)
     {
         return -1.;
     }
+}
+
+/* pinned host memory helpers for callers that stage large inputs (bench e2e path) */
+extern "C" int sa_gpu_host_register(const void *p, size_t bytes)
+{
+    if (!p || !bytes)
+        return 1;
+    cudaError_t e = cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess)
+    {
+        cudaGetLastError();
+        return 1;
+    }
+    return 0;
+}
+
+extern "C" int sa_gpu_host_unregister(const void *p)
+{
+    if (!p)
+        return 1;
+    cudaError_t e = cudaHostUnregister(const_cast<void *>(p));
+    if (e != cudaSuccess)
+    {
+        cudaGetLastError();
+        return 1;
+    }
+    return 0;
 }

@@ -62,6 +62,10 @@ __device__ __forceinline__ double block_sum(double v, double *sbuf)
     return sbuf[32];
 }
 
+// cycle counters of the phases of k_assemble_tridiag, summed over blocks
+// (assembly, D + scaling, tridiagonalisation, copy-out); read by sa_gpu_debug_phase_clocks
+__device__ unsigned long long g_phase_clk[4];
+
 // One block per slot of the list.  tile_in_smem: tile lives in dynamic shared
 // memory (n <= nmax_smem), otherwise directly in the V block of the AE.
 __global__ void k_assemble_tridiag(LevelTables L, ChunkDev C, const int *slot_list, int nslots,
@@ -83,7 +87,11 @@ __global__ void k_assemble_tridiag(LevelTables L, ChunkDev C, const int *slot_li
     double *dd = C.d + C.doff[slot], *ee = C.e + C.doff[slot], *tt = C.tau + C.doff[slot],
            *sinv = C.sinv + C.doff[slot];
 
+    long long tc0 = clock64();
     sa_dev_assemble_AE(L, part, T, ld);
+    long long tc1 = clock64();
+    if (threadIdx.x == 0)
+        atomicAdd(&g_phase_clk[0], (unsigned long long)(tc1 - tc0));
 
     // weighted-l1 diagonal D_ii = sum_j |a_ij| sqrt(a_ii / a_jj)  (amg/src/mbox.cpp:913-949)
     int bad = 0;
@@ -128,6 +136,9 @@ __global__ void k_assemble_tridiag(LevelTables L, ChunkDev C, const int *slot_li
     }
     __syncthreads();
 
+    tc0 = clock64();
+    if (threadIdx.x == 0)
+        atomicAdd(&g_phase_clk[1], (unsigned long long)(tc0 - tc1));
     // Householder tridiagonalisation, lower triangle convention of dsytd2:
     // H(k) annihilates A(k+2:n-1, k); reflector stored below the subdiagonal.
     for (int k = 0; k < n - 1; ++k)
@@ -196,6 +207,9 @@ __global__ void k_assemble_tridiag(LevelTables L, ChunkDev C, const int *slot_li
         tt[n - 1] = 0.;
     }
     __syncthreads();
+    tc1 = clock64();
+    if (threadIdx.x == 0)
+        atomicAdd(&g_phase_clk[2], (unsigned long long)(tc1 - tc0));
     if (tile_in_smem)
     {
         // only the reflectors (strictly below the subdiagonal) are needed later
@@ -634,6 +648,7 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         });
         DevBuf<int> d_order;
         d_order.upload(order.data(), ns, st);
+        ProfScope *pa = new ProfScope(ctx, "eig.assemble_tridiag");
         const int bucket_edges[] = {32, 48, 64, 80, 96, 112, 128, 144, 160, nmax_smem};
         int pos = 0;
         // large (global-memory tile) bucket first
@@ -672,6 +687,7 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
             pos += cnt;
         }
 
+        delete pa;
         // counts
         DevBuf<int> d_nev, d_mtot;
         DevBuf<double> d_glo, d_ghi, d_tn;
@@ -680,8 +696,11 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         d_glo.alloc(ns);
         d_ghi.alloc(ns);
         d_tn.alloc(ns);
-        SA_LAUNCH(ctx, k_count, (ns + 127) / 128, 128, 0, C, lev->AE2d_I.p, ns, theta,
-                  inject_ones_ae0, d_nev.p, d_mtot.p, d_glo.p, d_ghi.p, d_tn.p);
+        {
+            ProfScope ps(ctx, "eig.count");
+            SA_LAUNCH(ctx, k_count, (ns + 127) / 128, 128, 0, C, lev->AE2d_I.p, ns, theta,
+                      inject_ones_ae0, d_nev.p, d_mtot.p, d_glo.p, d_ghi.p, d_tn.p);
+        }
         PieceResult *pr = new PieceResult;
         pieces.push_back(pr);
         pr->a0 = a0;
@@ -721,8 +740,12 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         d_evect_off.upload(pr->evect_off.data(), ns + 1, st);
         pr->evals.alloc(nev_total);
         pr->evects.alloc(pr->evect_off[ns]);
-        SA_LAUNCH(ctx, k_bisect, (nev_total + 127) / 128, 128, 0, C, lev->AE2d_I.p, d_ev_slot.p,
-                  d_ev_idx.p, nev_total, d_glo.p, d_ghi.p, d_tn.p, d_eval_off.p, pr->evals.p);
+        {
+            ProfScope ps(ctx, "eig.bisect");
+            SA_LAUNCH(ctx, k_bisect, (nev_total + 127) / 128, 128, 0, C, lev->AE2d_I.p,
+                      d_ev_slot.p, d_ev_idx.p, nev_total, d_glo.p, d_ghi.p, d_tn.p, d_eval_off.p,
+                      pr->evals.p);
+        }
         // inverse iteration
         {
             // resident warps bounded by workspace: 4 double + 1 int arrays of 32*nmax
@@ -736,11 +759,17 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
             DevBuf<int> ws_i;
             ws_d.alloc((size_t)blocks * wpb * 4 * 32 * nmax);
             ws_i.alloc((size_t)blocks * wpb * 32 * nmax);
-            SA_LAUNCH(ctx, k_inverse_iter, blocks, wpb * 32, 0, C, lev->AE2d_I.p, ns, d_nev.p,
-                      d_eval_off.p, pr->evals.p, d_evect_off.p, pr->evects.p, d_tn.p, ws_d.p,
-                      ws_i.p, nmax);
-            SA_LAUNCH(ctx, k_back_transform, ns, 128, 0, C, lev->AE2d_I.p, d_nev.p, d_mtot.p,
-                      d_evect_off.p, pr->evects.p);
+            {
+                ProfScope ps(ctx, "eig.inverse_iter");
+                SA_LAUNCH(ctx, k_inverse_iter, blocks, wpb * 32, 0, C, lev->AE2d_I.p, ns, d_nev.p,
+                          d_eval_off.p, pr->evals.p, d_evect_off.p, pr->evects.p, d_tn.p, ws_d.p,
+                          ws_i.p, nmax);
+            }
+            {
+                ProfScope ps(ctx, "eig.back_transform");
+                SA_LAUNCH(ctx, k_back_transform, ns, 128, 0, C, lev->AE2d_I.p, d_nev.p, d_mtot.p,
+                          d_evect_off.p, pr->evects.p);
+            }
             SA_CUDA(cudaStreamSynchronize(st)); // workspace freed at scope exit
         }
         a0 = a1;
@@ -797,6 +826,17 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
     }
     lev->have_spectral = true;
     SA_API_END
+}
+
+extern "C" int sa_gpu_debug_phase_clocks(double *out4)
+{
+    unsigned long long h[4] = {0, 0, 0, 0}, z[4] = {0, 0, 0, 0};
+    if (cudaMemcpyFromSymbol(h, g_phase_clk, sizeof h) != cudaSuccess)
+        return 1;
+    cudaMemcpyToSymbol(g_phase_clk, z, sizeof z);
+    for (int i = 0; i < 4; ++i)
+        out4[i] = (double)h[i];
+    return 0;
 }
 
 extern "C" int sa_gpu_get_spectral_counts(sa_gpu_level *lev, int *ae_m)

@@ -119,6 +119,43 @@ struct sa_gpu_ctx
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t launches = 0;
+    // optional per-stage device timing (SA_GPU_PROFILE=1): name -> accumulated ms
+    bool profile = false;
+    cudaEvent_t pev0 = nullptr, pev1 = nullptr;
+    std::vector<std::pair<std::string, double>> prof;
+    void prof_add(const std::string &name, double ms)
+    {
+        for (size_t i = 0; i < prof.size(); ++i)
+            if (prof[i].first == name)
+            {
+                prof[i].second += ms;
+                return;
+            }
+        prof.push_back(std::make_pair(name, ms));
+    }
+};
+
+/* scope timer: CUDA events on the context's stream, active only when profiling */
+struct ProfScope
+{
+    sa_gpu_ctx *ctx;
+    std::string name;
+    ProfScope(sa_gpu_ctx *c, const char *n) : ctx(c), name(n)
+    {
+        if (ctx->profile)
+            cudaEventRecord(ctx->pev0, ctx->stream);
+    }
+    ~ProfScope()
+    {
+        if (ctx->profile)
+        {
+            cudaEventRecord(ctx->pev1, ctx->stream);
+            cudaEventSynchronize(ctx->pev1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ctx->pev0, ctx->pev1);
+            ctx->prof_add(name, ms);
+        }
+    }
 };
 
 #define SA_LAUNCH(ctx, kernel, grid, block, smem, ...)                             \

@@ -522,10 +522,11 @@ void dev_spgemm(sa_gpu_ctx *ctx, const DevCsr &A, const DevCsr &B, DevCsr &C)
             }
         lists[b].push_back(r);
     }
+    // static shared (s_cnt) counts against the opt-in limit
     SA_CUDA(cudaFuncSetAttribute(k_spgemm_rows<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)ctx->smem_optin));
+                                 (int)ctx->smem_optin - 1024));
     SA_CUDA(cudaFuncSetAttribute(k_spgemm_rows<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)ctx->smem_optin));
+                                 (int)ctx->smem_optin - 1024));
     DevBuf<int> d_list[nbins];
     for (int b = 0; b < nbins; ++b)
         d_list[b].upload(lists[b].data(), lists[b].size(), st);

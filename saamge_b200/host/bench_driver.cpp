@@ -1,0 +1,196 @@
+// Bench driver: times the local spectral stage (a2-a7) of the finest level through the
+// C ABI, either with inputs already resident on the device ("value") or end to end
+// from host buffers with the H2D / D2H copies inside the timed region ("e2e").
+// Used by bench.py only; see include/saamge_b200_driver.h.
+#include <cmath>
+#include <cstring>
+#include <string>
+
+#include "hierarchy.hpp"
+#include "saamge.hpp"
+
+extern "C" {
+int sa_gpu_host_register(const void *p, size_t bytes);
+int sa_gpu_host_unregister(const void *p);
+int sa_gpu_debug_phase_clocks(double *out4);
+}
+
+using namespace saamge;
+
+struct sa_bench_t
+{
+    sa_problem_t *prob = NULL;
+    sa_drv_params_t p;
+    sa_gpu_ctx *ctx = NULL;
+    sa_gpu_level *lev = NULL; // resident level
+    sa_gpu_level_desc desc;
+    std::vector<int64_t> offsets;
+    std::vector<int> ae_m;
+    std::vector<double> evals, evects;
+    double h2d_bytes = 0., d2h_bytes = 0.;
+    bool pinned = false;
+};
+
+static double desc_bytes(const sa_gpu_level_desc &d)
+{
+    double b = 0.;
+    b += 4. * (d.NE + 1 + d.elem_to_dof_I[d.NE]);
+    b += 4. * (d.ND + 1 + d.dof_to_elem_I[d.ND]);
+    b += 4. * (d.nparts + 1 + d.AE_to_elem_I[d.nparts]);
+    b += 4. * (d.nparts + 1 + d.AE_to_dof_I[d.nparts]);
+    b += 4. * (d.ND + 1 + 2. * d.dof_to_AE_I[d.ND]);
+    b += 4. * d.NE + 1. * d.ND;
+    b += 4. * (d.num_mises + 1 + d.mis_to_dof_I[d.num_mises]);
+    b += 4. * (d.num_mises + 1 + d.mis_to_AE_I[d.num_mises]);
+    b += 4. * (d.nparts + 1 + d.AE_to_mis_I[d.nparts]);
+    b += 4. * d.ND;
+    if (d.A_I)
+        b += 4. * (d.ND + 1) + 12. * d.A_I[d.ND];
+    if (d.elmat)
+        b += 8. * (d.NE + 1) + 8. * d.elmat_off[d.NE];
+    return b;
+}
+
+extern "C" void *sa_drv_bench_create(void *prob_, const sa_drv_params_t *p, int device)
+{
+    sa_problem_t *prob = (sa_problem_t *)prob_;
+    SA_ASSERT(prob && prob->rels);
+    sa_bench_t *B = new sa_bench_t;
+    B->prob = prob;
+    B->p = *p;
+    B->ctx = proc_gpu_init(device);
+    const fem_problem_t &f = *prob->fem;
+    const agg_partitioning_relations_t &r = *prob->rels;
+    B->offsets.resize((size_t)f.NE + 1);
+    for (int e = 0; e <= f.NE; ++e)
+        B->offsets[e] = (int64_t)e * f.ne * f.ne;
+    sa_gpu_level_desc &d = B->desc;
+    std::memset(&d, 0, sizeof d);
+    d.ND = r.ND;
+    d.NE = r.elem_to_dof->Size();
+    d.nparts = r.nparts;
+    d.num_mises = r.num_mises;
+    d.elem_to_dof_I = r.elem_to_dof->GetI();
+    d.elem_to_dof_J = r.elem_to_dof->GetJ();
+    d.dof_to_elem_I = r.dof_to_elem->GetI();
+    d.dof_to_elem_J = r.dof_to_elem->GetJ();
+    d.AE_to_elem_I = r.AE_to_elem->GetI();
+    d.AE_to_elem_J = r.AE_to_elem->GetJ();
+    d.AE_to_dof_I = r.AE_to_dof->GetI();
+    d.AE_to_dof_J = r.AE_to_dof->GetJ();
+    d.dof_to_AE_I = r.dof_to_AE->GetI();
+    d.dof_to_AE_J = r.dof_to_AE->GetJ();
+    d.dof_id_inAE = r.dof_id_inAE;
+    d.partitioning = r.partitioning;
+    d.agg_flags = r.agg_flags;
+    d.mis_to_dof_I = r.mis_to_dof->GetI();
+    d.mis_to_dof_J = r.mis_to_dof->GetJ();
+    d.mis_to_AE_I = r.mis_to_AE->GetI();
+    d.mis_to_AE_J = r.mis_to_AE->GetJ();
+    d.AE_to_mis_I = r.AE_to_mis->GetI();
+    d.AE_to_mis_J = r.AE_to_mis->GetJ();
+    d.mises = r.mises;
+    d.A_I = f.A.GetI();
+    d.A_J = f.A.GetJ();
+    d.A_data = f.A.GetData();
+    d.elmat = f.elmat.data();
+    d.elmat_off = B->offsets.data();
+    d.assemble_with_global = 1;
+    B->h2d_bytes = desc_bytes(d);
+    // pin the large host arrays so the e2e copies run at full PCIe speed
+    B->pinned = 0 == sa_gpu_host_register(f.elmat.data(), f.elmat.size() * sizeof(double));
+    sa_gpu_host_register(f.A.GetData(), f.A.A.size() * sizeof(double));
+    sa_gpu_host_register(f.A.GetJ(), f.A.J.size() * sizeof(int));
+    sa_gpu_check(sa_gpu_level_create(B->ctx, &d, NULL, &B->lev), "sa_gpu_level_create");
+    B->ae_m.resize(r.nparts);
+    return B;
+}
+
+extern "C" void sa_drv_bench_destroy(void *b_)
+{
+    sa_bench_t *B = (sa_bench_t *)b_;
+    if (!B)
+        return;
+    const fem_problem_t &f = *B->prob->fem;
+    sa_gpu_host_unregister(f.elmat.data());
+    sa_gpu_host_unregister(f.A.GetData());
+    sa_gpu_host_unregister(f.A.GetJ());
+    sa_gpu_level_destroy(B->lev);
+    delete B;
+}
+
+/* mode 0: device-resident inputs, AEs [ae_begin, ae_end); returns device ms
+   mode 1: end to end from host buffers: upload, compute, read back m / lambda / vectors */
+extern "C" double sa_drv_bench_step(void *b_, int mode, int ae_begin, int ae_end)
+{
+    sa_bench_t *B = (sa_bench_t *)b_;
+    const double theta = B->p.first_theta;
+    if (mode == 0)
+    {
+        sa_gpu_ctx_timer(B->ctx, 1);
+        sa_gpu_check(sa_gpu_local_spectral(B->lev, theta, ae_begin, ae_end, 0),
+                     "sa_gpu_local_spectral");
+        return sa_gpu_ctx_timer(B->ctx, 0);
+    }
+    sa_gpu_ctx_timer(B->ctx, 1);
+    sa_gpu_level *lev = NULL;
+    sa_gpu_check(sa_gpu_level_create(B->ctx, &B->desc, NULL, &lev), "sa_gpu_level_create");
+    sa_gpu_check(sa_gpu_local_spectral(lev, theta, ae_begin, ae_end, 0), "sa_gpu_local_spectral");
+    sa_gpu_check(sa_gpu_get_spectral_counts(lev, B->ae_m.data()), "sa_gpu_get_spectral_counts");
+    const agg_partitioning_relations_t &r = *B->prob->rels;
+    size_t ne = 0, nv = 0;
+    for (int i = 0; i < r.nparts; ++i)
+    {
+        ne += B->ae_m[i];
+        nv += (size_t)B->ae_m[i] * r.AE_to_dof->RowSize(i);
+    }
+    B->evals.resize(ne);
+    B->evects.resize(nv);
+    sa_gpu_check(sa_gpu_get_spectral(lev, B->evals.data(), B->evects.data(), NULL),
+                 "sa_gpu_get_spectral");
+    const double ms = sa_gpu_ctx_timer(B->ctx, 0);
+    B->d2h_bytes = 8. * (ne + nv) + 4. * r.nparts;
+    sa_gpu_level_destroy(lev);
+    return ms;
+}
+
+extern "C" double sa_drv_bench_scalar(void *b_, const char *name_)
+{
+    sa_bench_t *B = (sa_bench_t *)b_;
+    const std::string name(name_);
+    const agg_partitioning_relations_t &r = *B->prob->rels;
+    if (name == "h2d_bytes") return B->h2d_bytes;
+    if (name == "d2h_bytes") return B->d2h_bytes;
+    if (name == "pinned") return B->pinned ? 1. : 0.;
+    if (name == "launches") return (double)sa_gpu_ctx_launch_count(B->ctx);
+    if (name == "flops" || name == "bytes" || name == "sum_m")
+    {
+        // algorithmic work of the eigen stage:
+        //   F = 4/3 n^3 + 2 n^2 m + 3 n^2 ; bytes = 8 n^2 + 8 n m + 8 m
+        sa_gpu_check(sa_gpu_get_spectral_counts(B->lev, B->ae_m.data()),
+                     "sa_gpu_get_spectral_counts");
+        double F = 0., Bt = 0., M = 0.;
+        for (int i = 0; i < r.nparts; ++i)
+        {
+            const double n = r.AE_to_dof->RowSize(i), m = B->ae_m[i];
+            F += 4. / 3. * n * n * n + 2. * n * n * m + 3. * n * n;
+            Bt += 8. * n * n + 8. * n * m + 8. * m;
+            M += m;
+        }
+        return name == "flops" ? F : (name == "bytes" ? Bt : M);
+    }
+    if (name.compare(0, 6, "phase.") == 0)
+    {
+        static double clk[4] = {0, 0, 0, 0};
+        const int idx = name[6] - '0';
+        if (idx == 0)
+            sa_gpu_debug_phase_clocks(clk);
+        return (idx >= 0 && idx < 4) ? clk[idx] : NAN;
+    }
+    return NAN;
+}
+
+extern "C" int sa_drv_gpu_profile(int enable, char *buf, int buflen)
+{
+    return sa_gpu_ctx_profile(proc_gpu_ctx(), enable, buf, buflen);
+}

@@ -238,6 +238,16 @@ extern "C" int sa_drv_get(void *obj, const char *name_, int level, const void **
         return 3;
     sa_hierarchy_t *H = (sa_hierarchy_t *)obj;
     if (name == "pcg.brr") RET_VEC(H->pcg.brr);
+    if (name == "time_keys")
+    {
+        // newline separated list of timer names
+        static thread_local std::string keys;
+        keys.clear();
+        for (std::map<std::string, double>::const_iterator it = H->times.begin();
+             it != H->times.end(); ++it)
+            keys += it->first + "\n";
+        RET_ARR(keys.data(), keys.size(), char);
+    }
     if (name == "pcg.x") RET_VEC(H->pcg.x);
     if (level < 0)
         return 4;

@@ -4,6 +4,9 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <string>
+#include <utility>
+#include <vector>
 
 #include "hierarchy.hpp"
 #include "saamge.hpp"
@@ -19,6 +22,22 @@ static double now_s()
 }
 
 static sa_gpu_ctx *g_ctx = NULL;
+
+// wall-clock log of the device stages (every sa_gpu_* stage call returns synchronised)
+static std::vector<std::pair<std::string, double>> g_stage_log;
+static int g_stage_level = 0;
+struct StageTimer
+{
+    std::string name;
+    double t0;
+    StageTimer(const char *n) : name(n), t0(now_s()) {}
+    ~StageTimer()
+    {
+        char key[96];
+        std::snprintf(key, sizeof key, "l%d.%s", g_stage_level, name.c_str());
+        g_stage_log.push_back(std::make_pair(std::string(key), now_s() - t0));
+    }
+};
 
 sa_gpu_ctx *proc_gpu_init(int device)
 {
@@ -330,6 +349,7 @@ tg_data_t *tg_init_data(const SparseMatrix *A, const agg_partitioning_relations_
 void interp_compute_vectors(const agg_partitioning_relations_t &agg_part_rels,
                             const interp_data_t &interp_data, tg_data_t &tg_data, double &theta)
 {
+    StageTimer tm("local_spectral");
     sa_gpu_check(sa_gpu_local_spectral(tg_data.gpu, theta, 0, agg_part_rels.nparts,
                                        interp_data.testmesh_inject ? 1 : 0),
                  "sa_gpu_local_spectral");
@@ -344,6 +364,7 @@ void interp_sparse_tent_assemble(const agg_partitioning_relations_t &agg_part_re
     delete[] interp_data.mis_numcoarsedof;
     interp_data.mis_numcoarsedof = new int[agg_part_rels.num_mises > 0 ? agg_part_rels.num_mises : 1];
     int NDc = 0;
+    StageTimer tm("tentative");
     sa_gpu_check(sa_gpu_tentative_P(tg_data.gpu, avoid_ess_bdr_dofs ? 1 : 0,
                                     interp_data.mis_numcoarsedof, &NDc),
                  "sa_gpu_tentative_P");
@@ -375,22 +396,31 @@ void tg_build_hierarchy(const SparseMatrix *Ag, tg_data_t &tg_data,
     if (tg_data.gpu)
         sa_gpu_level_destroy(tg_data.gpu);
     tg_data.gpu = NULL;
-    sa_gpu_check(sa_gpu_level_create(proc_gpu_ctx(), &d, finer ? finer->gpu : NULL, &tg_data.gpu),
-                 "sa_gpu_level_create");
+    {
+        StageTimer tm("upload");
+        sa_gpu_check(sa_gpu_level_create(proc_gpu_ctx(), &d, finer ? finer->gpu : NULL,
+                                         &tg_data.gpu),
+                     "sa_gpu_level_create");
+    }
     if (!d.elmat)
     {
         // ElementMatrixParallelCoarse: P_e^T A_AE P_e of every finer AE, on the device
         SA_ASSERT(finer && finer->gpu);
+        StageTimer tm("coarse_elmats");
         sa_gpu_check(sa_gpu_coarse_elmats(finer->gpu, tg_data.gpu), "sa_gpu_coarse_elmats");
     }
-    // smpr_update_Dinv_neg (tg_init_data -> smpr_init_poly_data in the reference)
-    sa_gpu_check(sa_gpu_build_Dinv_neg(tg_data.gpu), "sa_gpu_build_Dinv_neg");
+    {
+        // smpr_update_Dinv_neg (tg_init_data -> smpr_init_poly_data in the reference)
+        StageTimer tm("Dinv_neg");
+        sa_gpu_check(sa_gpu_build_Dinv_neg(tg_data.gpu), "sa_gpu_build_Dinv_neg");
+    }
 
     // interp_sparse_tent_build (amg/src/interp.cpp:694-726)
     interp_compute_vectors(agg_part_rels, *tg_data.interp_data, tg_data, tg_data.theta);
     interp_sparse_tent_assemble(agg_part_rels, *tg_data.interp_data, tg_data, avoid_ess_bdr_dofs);
     // tg_smooth_interp (amg/inc/tg.hpp:678-693)
     interp_data_t &id = *tg_data.interp_data;
+    StageTimer tm("smooth_P");
     sa_gpu_check(sa_gpu_smooth_P(tg_data.gpu, tg_data.smooth_interp ? id.interp_smoother_degree : 0,
                                  id.interp_smoother_roots),
                  "sa_gpu_smooth_P");
@@ -417,6 +447,7 @@ void tg_update_coarse_operator(tg_data_t *tg_data, bool perform_solve_init, bool
     (void)perform_solve_init;
     (void)coarse_direct;
     SA_ASSERT(tg_data && tg_data->gpu);
+    StageTimer tm("rap");
     sa_gpu_check(sa_gpu_rap(tg_data->gpu), "sa_gpu_rap");
     tg_data->have_Ac = true;
 }
@@ -478,14 +509,17 @@ void ml_produce_hierarchy_from_level(int coarsenings, int starting_level, ml_dat
     for (int i = starting_level; i < coarsenings; ++i)
     {
         SA_ASSERT(tg_data->have_Ac);
+        g_stage_level = i;
         int nparts = mlp.get_nparts(i);
         int *partitioning = NULL;
+        StageTimer *ttopo = new StageTimer("topology");
         if (mlp.coarse_partitioner)
             partitioning = mlp.coarse_partitioner(i, agg_part_rels->nparts, &nparts,
                                                   mlp.coarse_partitioner_data);
         agg_part_rels = agg_create_partitioning_coarse(
             *agg_part_rels, tg_data->interp_data->mis_numcoarsedof, &nparts,
             mlp.get_avoid_ess_bdr_dofs(), partitioning);
+        delete ttopo;
         tg_data_t *finer_tg = tg_data;
         tg_data = tg_init_data(NULL, *agg_part_rels, mlp.get_nu_pro(i), mlp.get_nu_relax(i),
                                mlp.get_theta(i), mlp.get_smooth_interp(i),
@@ -516,6 +550,7 @@ void ml_impose_cycle(ml_data_t &ml_data, bool Wcycle)
     if (ml_data.gpu_solver)
         sa_gpu_solver_destroy(ml_data.gpu_solver);
     ml_data.gpu_solver = NULL;
+    StageTimer tm("solver_create");
     sa_gpu_check(sa_gpu_solver_create(proc_gpu_ctx(), levels.data(), (int)levels.size(),
                                       ml_data.nu_relax, &ml_data.gpu_solver),
                  "sa_gpu_solver_create");
@@ -530,6 +565,8 @@ ml_data_t *ml_produce_data(const SparseMatrix &Ag, agg_partitioning_relations_t 
     ml_data_t *ml_data = new ml_data_t;
     std::memset(ml_data, 0, sizeof(*ml_data));
     SA_ASSERT(mlp.get_num_coarsenings() > 0);
+    g_stage_level = 0;
+    g_stage_log.clear();
     ml_data->nu_relax = mlp.get_nu_relax(0);
     tg_data_t *tg_data =
         tg_init_data(&Ag, *agg_part_rels, mlp.get_nu_pro(0), mlp.get_nu_relax(0), mlp.get_theta(0),
@@ -719,6 +756,8 @@ extern "C" void *sa_drv_ml_build(void *prob_, const sa_drv_params_t *p, int devi
     pi->ml = ml_produce_data(f.A, prob->rels, emp, mlp);
     sa_gpu_ctx_sync(proc_gpu_ctx());
     H->times["setup"] = now_s() - t0;
+    for (size_t i = 0; i < g_stage_log.size(); ++i)
+        H->times[g_stage_log[i].first] += g_stage_log[i].second;
     for (levels_level_t *l = pi->ml->levels_list.finest; l; l = l->coarser)
         H->rels.push_back(l->agg_part_rels);
     return H;

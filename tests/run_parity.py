@@ -37,6 +37,8 @@ def main():
         print("gpu build %.3fs" % (time.time() - t), flush=True)
         itg = sab.ml_pcg(Hg)
         sab.ml_download(Hg)
+        print("gpu times", {k: round(v, 4) for k, v in Hg.times().items()})
+        print("orc times", {k: round(v, 4) for k, v in Ho.times().items()})
     print("pcg iters gpu", itg, "oracle", ito)
     print("brr gpu", Hg.get("pcg.brr")[:8], "\nbrr orc", Ho.get("pcg.brr")[:8])
     print("final res gpu", Hg.scalar("pcg.final_res_norm"), "orc", Ho.scalar("pcg.final_res_norm"))
