@@ -40,6 +40,12 @@ void sa_drv_default_params(sa_drv_params_t *p);
 /* ---- problem (input producer) ---- */
 void *sa_drv_problem_create(int dim, int nx, int ny, int nz, int order, int coef_kind,
                             double contrast, uint64_t seed);
+/* ess_mask: essential sides, bit 0: x=0, 1: x=1, 2: y=0, 3: y=1, 4: z=0, 5: z=1 */
+void *sa_drv_problem_create_ex(int dim, int nx, int ny, int nz, int order, int coef_kind,
+                               double contrast, uint64_t seed, int ess_mask);
+/* fixtures: explicit partitions (finest level / coarsening `level` >= 1) */
+int sa_drv_problem_partition_array(void *prob, const int *part, int nparts);
+void sa_drv_problem_set_coarse_partition(void *prob, int level, const int *part, int n);
 void sa_drv_problem_destroy(void *prob);
 /* Fine-level partition + relations; returns number of AEs. */
 int sa_drv_problem_partition(void *prob, const sa_drv_params_t *p);

@@ -1238,10 +1238,8 @@ extern "C" void *sa_orc_ml_build(void *prob_, const sa_drv_params_t *p)
             oracle_level_t *F = ml->levels[i - 1];
             const double t0 = now_s();
             int nparts = nparts_arr[i];
-            int *partitioning = NULL;
-            if (p->partition_kind == 1)
-                partitioning = sa_block_coarse_partitioning(*prob, *p, i, F->agg_part_rels->nparts,
-                                                            &nparts);
+            int *partitioning = sa_prescribed_coarse_partitioning(
+                *prob, *p, i, F->agg_part_rels->nparts, &nparts);
             agg_partitioning_relations_t *rels = agg_create_partitioning_coarse(
                 *F->agg_part_rels, F->mis_numcoarsedof.data(), &nparts, avoid, partitioning);
             H->rels.push_back(rels);

@@ -50,6 +50,28 @@ int *sa_block_coarse_partitioning(const sa_problem_t &prob, const sa_drv_params_
                                              nparts);
 }
 
+int *sa_prescribed_coarse_partitioning(const sa_problem_t &prob, const sa_drv_params_t &p,
+                                       int level, int num_elem, int *nparts)
+{
+    std::map<int, std::vector<int>>::const_iterator it = prob.coarse_partitions.find(level);
+    if (it != prob.coarse_partitions.end())
+    {
+        SA_ASSERT((int)it->second.size() == num_elem);
+        int *out = new int[num_elem];
+        int mx = 0;
+        for (int i = 0; i < num_elem; ++i)
+        {
+            out[i] = it->second[i];
+            mx = std::max(mx, out[i] + 1);
+        }
+        *nparts = mx;
+        return out;
+    }
+    if (p.partition_kind == 1)
+        return sa_block_coarse_partitioning(prob, p, level, num_elem, nparts);
+    return NULL;
+}
+
 } // namespace saamge
 
 extern "C" void sa_drv_default_params(sa_drv_params_t *p)
@@ -79,6 +101,37 @@ extern "C" void *sa_drv_problem_create(int dim, int nx, int ny, int nz, int orde
     prob->fem = fem_generate_structured(dim, nx, ny, nz, order, coef_kind, contrast, seed);
     prob->times["fem"] = now_s() - t0;
     return prob;
+}
+
+extern "C" void *sa_drv_problem_create_ex(int dim, int nx, int ny, int nz, int order,
+                                          int coef_kind, double contrast, uint64_t seed,
+                                          int ess_mask)
+{
+    sa_problem_t *prob = new sa_problem_t;
+    prob->fem =
+        fem_generate_structured_ex(dim, nx, ny, nz, order, coef_kind, contrast, seed, ess_mask);
+    return prob;
+}
+
+extern "C" int sa_drv_problem_partition_array(void *prob_, const int *part, int nparts)
+{
+    sa_problem_t *prob = (sa_problem_t *)prob_;
+    SA_ASSERT(prob && prob->fem && !prob->rels);
+    const fem_problem_t &f = *prob->fem;
+    prob->target_nparts0 = nparts;
+    int *partitioning = new int[f.NE];
+    std::memcpy(partitioning, part, sizeof(int) * f.NE);
+    Table *elem_to_dof = new Table(f.elem_to_dof);
+    Table *elem_to_elem = new Table(f.elem_to_elem);
+    prob->rels = agg_create_partitioning_fine(f.NE, elem_to_dof, elem_to_elem, partitioning,
+                                              f.bdr_dofs.data(), &nparts, true);
+    return nparts;
+}
+
+extern "C" void sa_drv_problem_set_coarse_partition(void *prob_, int level, const int *part, int n)
+{
+    sa_problem_t *prob = (sa_problem_t *)prob_;
+    prob->coarse_partitions[level].assign(part, part + n);
 }
 
 extern "C" void sa_drv_problem_destroy(void *prob_)

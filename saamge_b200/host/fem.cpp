@@ -106,6 +106,13 @@ fem_problem_t *fem_generate_structured(int dim, int nx, int ny, int nz,
                                        int order, int coef_kind,
                                        double contrast, uint64_t seed)
 {
+    return fem_generate_structured_ex(dim, nx, ny, nz, order, coef_kind, contrast, seed, 63);
+}
+
+fem_problem_t *fem_generate_structured_ex(int dim, int nx, int ny, int nz, int order,
+                                          int coef_kind, double contrast, uint64_t seed,
+                                          int ess_mask)
+{
     SA_ASSERT(dim == 2 || dim == 3);
     SA_ASSERT(order == 1 || order == 2);
     if (dim == 2)
@@ -216,6 +223,24 @@ fem_problem_t *fem_generate_structured(int dim, int nx, int ny, int nz,
         }
     }
 
+    else if (coef_kind == FEM_COEF_MLTEST)
+    {
+        const double d = 10.;
+        for (int e = 0; e < NE; ++e)
+        {
+            const int ex = e % nx, ey = (e / nx) % ny, ez = e / (nx * ny);
+            const double x0 = (ex + 0.5) / nx, x1 = (ey + 0.5) / ny, x2 = (ez + 0.5) / nz;
+            const int c0 = (int)std::ceil(x0 * d) & 1, c1 = (int)std::ceil(x1 * d) & 1,
+                      c2 = (int)std::ceil(x2 * d) & 1;
+            bool hi;
+            if (dim == 2)
+                hi = (c0 == c1);
+            else
+                hi = (c2 && c0 == c1) || (!c2 && c0 != c1);
+            fp->coef[e] = hi ? 1e6 : 1e0;
+        }
+    }
+
     // reference element matrix for a cell hx x hy x hz
     const double hx = 1. / nx, hy = 1. / ny, hz = (dim == 3) ? 1. / nz : 1.;
     double M1[9], S1[9], L1[3];
@@ -263,9 +288,10 @@ fem_problem_t *fem_generate_structured(int dim, int nx, int ny, int nz,
     for (int d = 0; d < ND; ++d)
     {
         const int ix = d % gx, iy = (d / gx) % gy, iz = d / (gx * gy);
-        bool on = ix == 0 || ix == gx - 1 || iy == 0 || iy == gy - 1;
+        bool on = (ix == 0 && (ess_mask & 1)) || (ix == gx - 1 && (ess_mask & 2)) ||
+                  (iy == 0 && (ess_mask & 4)) || (iy == gy - 1 && (ess_mask & 8));
         if (dim == 3)
-            on = on || iz == 0 || iz == gz - 1;
+            on = on || (iz == 0 && (ess_mask & 16)) || (iz == gz - 1 && (ess_mask & 32));
         if (on)
             fp->bdr_dofs[d] = 0x02; // AGG_ON_ESS_DOMAIN_BORDER_FLAG
     }

@@ -17,7 +17,9 @@ enum fem_coef_kind
 {
     FEM_COEF_CONSTANT = 0,  // k == 1 (Poisson; BASELINE config C1)
     FEM_COEF_LOGNORMAL = 1, // exp(s*g), g smoothed Gaussian, max/min = contrast
-    FEM_COEF_CHECKER = 2    // checkerboard 1 / contrast on 4^d blocks
+    FEM_COEF_CHECKER = 2,   // checkerboard 1 / contrast on 4^d blocks
+    FEM_COEF_MLTEST = 3     // checkboard_coef of the mltest driver evaluated at element
+                            // centres (amg/test/mltest/mltest.cpp:156-175): 1e6 / 1
 };
 
 struct fem_problem_t
@@ -40,6 +42,11 @@ struct fem_problem_t
 fem_problem_t *fem_generate_structured(int dim, int nx, int ny, int nz,
                                        int order, int coef_kind,
                                        double contrast, uint64_t seed);
+/// Same with a choice of essential sides: bit 0: x=0, 1: x=1, 2: y=0, 3: y=1, 4: z=0,
+/// 5: z=1 (the mltest fixture marks only x=0, amg/test/mltest/mltest.cpp:476-479).
+fem_problem_t *fem_generate_structured_ex(int dim, int nx, int ny, int nz, int order,
+                                          int coef_kind, double contrast, uint64_t seed,
+                                          int ess_mask);
 
 } // namespace saamge
 

@@ -20,6 +20,8 @@ struct sa_problem_t
     fem_problem_t *fem = NULL;
     agg_partitioning_relations_t *rels = NULL; // finest relations (owned)
     int target_nparts0 = 0;                    // requested number of AEs on the finest level
+    // explicit coarse partitions (fixtures): coarsening index -> element -> AE
+    std::map<int, std::vector<int>> coarse_partitions;
     std::map<std::string, double> times;
 };
 
@@ -57,6 +59,9 @@ static inline std::vector<int> sa_target_nparts(int NE, const sa_drv_params_t &p
 /// blocks (the fine AEs themselves form a regular grid).  Returns new int[].
 int *sa_block_coarse_partitioning(const sa_problem_t &prob, const sa_drv_params_t &p,
                                   int level, int num_elem, int *nparts);
+/// Fixture / block partition of coarsening \a level if one is prescribed, else NULL (METIS).
+int *sa_prescribed_coarse_partitioning(const sa_problem_t &prob, const sa_drv_params_t &p,
+                                       int level, int num_elem, int *nparts);
 
 } // namespace saamge
 

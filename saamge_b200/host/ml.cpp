@@ -721,7 +721,7 @@ struct block_partitioner_data_t
 static int *block_coarse_partitioner(int level, int num_elem, int *nparts, void *data)
 {
     block_partitioner_data_t *d = (block_partitioner_data_t *)data;
-    return sa_block_coarse_partitioning(*d->prob, *d->p, level, num_elem, nparts);
+    return sa_prescribed_coarse_partitioning(*d->prob, *d->p, level, num_elem, nparts);
 }
 
 extern "C" void *sa_drv_ml_build(void *prob_, const sa_drv_params_t *p, int device)
@@ -751,7 +751,7 @@ extern "C" void *sa_drv_ml_build(void *prob_, const sa_drv_params_t *p, int devi
     mlp.set_coarse_direct(true);
     mlp.testmesh_inject = p->testmesh_inject != 0;
     block_partitioner_data_t bpd = {prob, p};
-    if (p->partition_kind == 1)
+    if (p->partition_kind == 1 || !prob->coarse_partitions.empty())
         mlp.set_coarse_partitioner(block_coarse_partitioner, &bpd);
     pi->ml = ml_produce_data(f.A, prob->rels, emp, mlp);
     sa_gpu_ctx_sync(proc_gpu_ctx());
