@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 spectral-AMGe hot path.
+
+Metric (BASELINE.json): agglomerate eigensolves/sec (+ setup & PCG solve time) on the
+128^3 hex diffusion problem with a synthetic SPE10-like lognormal coefficient.
+
+A "step" is one pass of the local spectral stage (SURVEY.md section 8a rows a2-a7:
+assemble every AE matrix, weighted-l1 D, eigenpairs of A z = lambda D z with
+lambda <= theta) over all ~40k agglomerates of the finest level.
+  value : AEs / s with all inputs resident in HBM (CUDA events on the library's stream)
+  e2e   : the same stage through the C ABI from HOST buffers: H2D of every input
+          (element blocks, operator, tables) + compute + D2H of m / lambda / vectors
+Extra keys: roofline (dominant kernel), roofline_spmv, cpu_baseline (the CPU oracle on
+the box's host cores, bounded sample), full-hierarchy setup and PCG solve times.
+
+Multi-GPU (torchrun, one rank per GPU): every rank owns one 128^3 subdomain (its own
+coefficient seed) -> weak scaling, no data-path collective in the stage; times are
+max-reduced over ranks.
+
+--impl reference : the reference's CPU path (the oracle port: same algorithm, same
+LAPACK dsygvx calls) on all host cores, bounded sample per step; rank 0 only.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # name: (n, levels, first_elems_per_agg, elems_per_agg, METIS tile)
+    "c3_128": dict(n=128, levels=4, fepa=52, epa=64, tile=32,
+                   desc="3D diffusion 128^3 hex Q1, lognormal coefficient 1e6 contrast, ~40k METIS AEs (BASELINE configs[2])"),
+    "c2_64": dict(n=64, levels=3, fepa=52, epa=64, tile=32,
+                  desc="3D diffusion 64^3 hex Q1, lognormal coefficient 1e6 contrast, 3-level (BASELINE configs[1])"),
+    "small_32": dict(n=32, levels=3, fepa=52, epa=64, tile=32, desc="32^3 smoke workload"),
+}
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                    capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[1]))
+                mx.append(float(s[2]))
+                for nm, v in zip(names, s[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def make_problem(sab, wl, seed):
+    w = WORKLOADS[wl]
+    p = sab.default_params(num_levels=w["levels"], first_elems_per_agg=w["fepa"], elems_per_agg=w["epa"],
+                           partition_kind=2, block=(w["tile"],) * 3)
+    pr = sab.Problem(3, w["n"], coef_kind=1, contrast=1e6, seed=seed)
+    nae = pr.partition(p)
+    return pr, p, nae
+
+
+def cpu_sample(ou, pr, p, nae, target_s, threads):
+    """Times the oracle's local spectral stage on a bounded AE sample (~target_s seconds)."""
+    o = ou.oracle(threads)
+    cores = o.sa_orc_num_threads()
+    n0 = min(nae, max(2 * cores, 16))
+    t0 = o.sa_orc_time_local_spectral(pr.handle, ctypes.byref(p), 0, n0)
+    rate = n0 / max(t0, 1e-9)
+    ns = int(min(nae, max(n0, rate * target_s)))
+    t = o.sa_orc_time_local_spectral(pr.handle, ctypes.byref(p), 0, ns)
+    return ns, t, cores
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port on all host cores; rank 0 only."""
+    if rank != 0:
+        return
+    import oracle_util as ou
+    import saamge_b200 as sab
+
+    pr, p, nae = make_problem(sab, args.workload, 12345)
+    threads = os.cpu_count() or 1
+    per_step_s = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    ns, t, cores = cpu_sample(ou, pr, p, nae, per_step_s, threads)  # calibration + warm-up
+    for _ in range(max(0, args.warmup - 1)):
+        ou.oracle().sa_orc_time_local_spectral(pr.handle, ctypes.byref(p), 0, ns)
+    tot = 0.0
+    for _ in range(args.steps):
+        tot += ou.oracle().sa_orc_time_local_spectral(pr.handle, ctypes.byref(p), 0, ns)
+    value = ns * args.steps / tot
+    w = WORKLOADS[args.workload]
+    line = {
+        "impl": "reference", "metric": "agglomerate eigensolves/sec", "value": value, "unit": "AE/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "description": w["desc"], "n_AE_total": nae,
+                   "sample_AEs_per_step": ns, "theta": 0.003},
+        "cpu_baseline": {"value": value, "unit": "AE/s", "cores": cores, "kind": "port",
+                         "sample": "first %d of %d AEs per step (assemble + D + dsygvx), OpenMP over AEs, OpenBLAS 1 thread" % (ns, nae)},
+        "e2e": {"value": value, "unit": "AE/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3_128", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-hierarchy", action="store_true", help="skip the full setup + PCG extras")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import saamge_b200 as sab
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    h = sab.host_lib()
+    h.sa_drv_gpu_profile.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
+    w = WORKLOADS[args.workload]
+    t0 = time.time()
+    pr, p, nae = make_problem(sab, args.workload, 12345 + rank)  # one subdomain per rank
+    t_inputs = time.time() - t0
+    B = h.sa_drv_bench_create(pr.handle, ctypes.byref(p), local_rank)
+
+    # ---- device-resident steps ("value")
+    for _ in range(args.warmup):
+        h.sa_drv_bench_step(B, 0, 0, nae)
+    launches0 = h.sa_drv_bench_scalar(B, b"launches")
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    ms_local = 0.0
+    for _ in range(args.steps):
+        ms_local += h.sa_drv_bench_step(B, 0, 0, nae)
+    barrier()
+    sampler.stop_flag = True
+    launches = int(h.sa_drv_bench_scalar(B, b"launches") - launches0)
+    ms_total = max_over_ranks(ms_local)
+    nae_all = sum_over_ranks(float(nae))
+    value = nae_all * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end from host buffers
+    e2e_steps = min(args.steps, 3)
+    h.sa_drv_bench_step(B, 1, 0, nae)
+    barrier()
+    ms_e2e = 0.0
+    for _ in range(e2e_steps):
+        ms_e2e += h.sa_drv_bench_step(B, 1, 0, nae)
+    barrier()
+    ms_e2e = max_over_ranks(ms_e2e)
+    e2e_value = nae_all * e2e_steps / (ms_e2e * 1e-3)
+    h2d = h.sa_drv_bench_scalar(B, b"h2d_bytes")
+    d2h = h.sa_drv_bench_scalar(B, b"d2h_bytes")
+
+    # ---- roofline of the dominant kernel (assemble + tridiagonalise), profiled steps
+    h.sa_drv_gpu_profile(1, None, 0)
+    prof_steps = 2
+    for _ in range(prof_steps):
+        h.sa_drv_bench_step(B, 0, 0, nae)
+    buf = ctypes.create_string_buffer(8192)
+    h.sa_drv_gpu_profile(0, buf, 8192)
+    prof = {}
+    for ln in buf.value.decode().splitlines():
+        k, v = ln.split()
+        prof[k] = float(v) / prof_steps
+    flops = h.sa_drv_bench_scalar(B, b"flops")
+    abytes = h.sa_drv_bench_scalar(B, b"bytes")
+    gl = sab.gpu_lib()
+    ctxp = ctypes.c_void_p(h.sa_drv_ctx()) if hasattr(h, "sa_drv_ctx") else None
+    fp64_peak = None
+    if ctxp:
+        fp64_peak = gl.sa_gpu_bench_fp64_peak(ctxp)
+    kern_ms = prof.get("eig.assemble_tridiag", float("nan"))
+    achieved = flops / (kern_ms * 1e-3) / 1e12
+    roofline = {
+        "kernel": "k_assemble_tridiag (assemble + weighted-l1 scaling + Householder tridiagonalisation)",
+        "bound": "tensor", "bound_detail": "FP64 FMA pipe (no FP64 tcgen05 path; DMMA unused at n~125)",
+        "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+        "frac": (achieved / fp64_peak) if fp64_peak else None,
+        "peak_source": "measured in this run: dependent-free DFMA loop (sa_gpu_bench_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
+        "algorithmic_flops_per_step": flops, "algorithmic_bytes_per_step": abytes,
+        "kernel_ms_per_step": kern_ms, "stage_ms": prof, "traffic": None,
+    }
+
+    line = {
+        "metric": "agglomerate eigensolves/sec", "value": value, "unit": "AE/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "description": w["desc"], "n_AE_per_gpu": nae,
+                   "theta": 0.003, "partition": "METIS k-way on a %d^3 tile, replicated" % w["tile"],
+                   "l2": "inputs larger than L2 (element blocks + operator = %.2f GB per step)" % (h2d / 1e9),
+                   "host_inputs_s": t_inputs},
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e_value, "unit": "AE/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / e2e_steps, "pinned": bool(h.sa_drv_bench_scalar(B, b"pinned"))},
+        "gpu_launches": launches,
+        "roofline": roofline,
+    }
+    h.sa_drv_bench_destroy(B)
+
+    # ---- extras on rank 0: full hierarchy (setup + PCG), SpMV / smoother roofline, CPU sample
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        if not args.no_hierarchy:
+            t0 = time.time()
+            H = sab.ml_build(pr, p, local_rank)
+            setup_s = time.time() - t0
+            t0 = time.time()
+            its = sab.ml_pcg(H, 1000, 1e-12, 0.0)
+            pcg_s = time.time() - t0
+            line["hierarchy"] = {"levels": w["levels"], "setup_s": setup_s, "pcg_s": pcg_s, "pcg_iterations": its,
+                                 "final_residual": H.scalar("pcg.final_res_norm"),
+                                 "stage_s": {k: round(v, 4) for k, v in H.times().items()},
+                                 "dofs": [int(H.scalar("ND", l)) for l in range(w["levels"] - 1)]}
+            if hasattr(h, "sa_drv_ml_spmv_bench"):
+                h.sa_drv_ml_spmv_bench.restype = ctypes.c_double
+                h.sa_drv_ml_spmv_bench.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+                nnz = pr.scalar("nnz")
+                nd = pr.scalar("ND")
+                ms = h.sa_drv_ml_spmv_bench(H.handle, 0, 50)
+                ms2 = h.sa_drv_ml_spmv_bench(H.handle, 1, 50)
+                b_spmv = 12.0 * nnz + 20.0 * nd
+                b_sm = b_spmv + 24.0 * nd
+                pk = peaks["hbm_gbs"]
+                line["roofline_spmv"] = {"bound": "hbm", "achieved": b_spmv / (ms * 1e-3) / 1e9, "peak": pk,
+                                         "unit": "GB/s", "frac": b_spmv / (ms * 1e-3) / 1e9 / pk, "traffic": None,
+                                         "ms": ms, "peak_source": peak_src, "algorithmic_bytes": b_spmv}
+                line["roofline_smoother"] = {"bound": "hbm", "achieved": b_sm / (ms2 * 1e-3) / 1e9, "peak": pk,
+                                             "unit": "GB/s", "frac": b_sm / (ms2 * 1e-3) / 1e9 / pk,
+                                             "traffic": None, "ms": ms2, "algorithmic_bytes": b_sm}
+            H.close()
+        if world == 1 and not args.no_cpu:
+            import oracle_util as ou
+
+            ns, t, cores = cpu_sample(ou, pr, p, nae, args.cpu_seconds, os.cpu_count() or 1)
+            line["cpu_baseline"] = {"value": ns / t, "unit": "AE/s", "cores": cores, "kind": "port",
+                                    "sample": "first %d of %d AEs (assemble + D + LAPACK dsygvx), %.1f s, OpenMP over AEs" % (ns, nae, t)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

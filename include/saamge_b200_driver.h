@@ -85,6 +85,10 @@ double sa_drv_bench_step(void *bench, int mode, int ae_begin, int ae_end);
 double sa_drv_bench_scalar(void *bench, const char *name);
 /* device stage profile of the process-wide context (see sa_gpu_ctx_profile) */
 int sa_drv_gpu_profile(int enable, char *buf, int buflen);
+/* the process-wide sa_gpu_ctx */
+void *sa_drv_ctx(void);
+/* kind 0: SpMV with the finest operator, 1: fused smoother step; ms per call */
+double sa_drv_ml_spmv_bench(void *hier, int kind, int reps);
 
 #ifdef __cplusplus
 }

@@ -194,3 +194,19 @@ extern "C" int sa_drv_gpu_profile(int enable, char *buf, int buflen)
 {
     return sa_gpu_ctx_profile(proc_gpu_ctx(), enable, buf, buflen);
 }
+
+extern "C" void *sa_drv_ctx(void) { return proc_gpu_ctx(); }
+
+/* kind 0: SpMV with the finest operator, kind 1: fused polynomial-smoother step;
+   returns milliseconds per call (device-resident vectors, CUDA events) */
+extern "C" double sa_drv_ml_spmv_bench(void *hier, int kind, int reps)
+{
+    sa_hierarchy_t *H = (sa_hierarchy_t *)hier;
+    struct impl_t
+    {
+        ml_data_t *ml;
+    };
+    ml_data_t *ml = ((impl_t *)H->impl)->ml;
+    sa_gpu_level *lev = ml->levels_list.finest->tg_data->gpu;
+    return kind == 0 ? sa_gpu_bench_spmv(lev, SA_GPU_MAT_A, reps) : sa_gpu_bench_smoother(lev, reps);
+}

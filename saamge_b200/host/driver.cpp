@@ -162,6 +162,45 @@ extern "C" int sa_drv_problem_partition(void *prob_, const sa_drv_params_t *p)
     if (p->partition_kind == 1)
         partitioning = part_generate_partitioning_blocks(f.dim, f.nx, f.ny, f.nz, p->block[0],
                                                          p->block[1], p->block[2], &nparts);
+    else if (p->partition_kind == 2)
+    {
+        // METIS on one tile of block[0]^dim elements, replicated over the grid (the
+        // toolkit's METIS needs minutes for 128^3 elements / 40k parts; a tile keeps the
+        // irregular METIS agglomerate shapes at a fraction of the cost)
+        const int t = std::max(1, p->block[0]);
+        SA_ASSERT(f.nx % t == 0 && f.ny % t == 0 && (f.dim == 2 || f.nz % t == 0));
+        const int tz = (f.dim == 3) ? t : 1;
+        const int tn = t * t * tz;
+        Table g;
+        g.nrows = g.ncols = tn;
+        g.I.assign((size_t)tn + 1, 0);
+        for (int e = 0; e < tn; ++e)
+        {
+            const int ex = e % t, ey = (e / t) % t, ez = e / (t * t);
+            if (f.dim == 3 && ez > 0) g.J.push_back(e - t * t);
+            if (ey > 0) g.J.push_back(e - t);
+            if (ex > 0) g.J.push_back(e - 1);
+            if (ex < t - 1) g.J.push_back(e + 1);
+            if (ey < t - 1) g.J.push_back(e + t);
+            if (f.dim == 3 && ez < tz - 1) g.J.push_back(e + t * t);
+            g.I[e + 1] = (int)g.J.size();
+        }
+        int tparts = std::max(1, tn / p->first_elems_per_agg);
+        const double tm = now_s();
+        int *tp = part_generate_partitioning_unweighted(g, &tparts);
+        prob->times["metis"] = now_s() - tm;
+        partitioning = new int[f.NE];
+        const int gx = f.nx / t, gy = f.ny / t;
+        for (int e = 0; e < f.NE; ++e)
+        {
+            const int ex = e % f.nx, ey = (e / f.nx) % f.ny, ez = e / (f.nx * f.ny);
+            const int tile = (ex / t) + gx * ((ey / t) + gy * (ez / t));
+            const int loc = (ex % t) + t * ((ey % t) + t * (ez % t));
+            partitioning[e] = tile * tparts + tp[loc];
+        }
+        delete[] tp;
+        nparts = tparts * gx * gy * ((f.dim == 3) ? f.nz / t : 1);
+    }
     // the relations take ownership of the tables (amg/inc/aggregates.hpp:353-369)
     Table *elem_to_dof = new Table(f.elem_to_dof);
     Table *elem_to_elem = new Table(f.elem_to_elem);
