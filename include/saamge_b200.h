@@ -194,7 +194,7 @@ int sa_gpu_host_register(const void *p, size_t bytes);
 int sa_gpu_host_unregister(const void *p);
 /* cycle counters of the four phases of the assemble+tridiagonalise kernel summed over
    thread blocks since the last call (diagnostics) */
-int sa_gpu_debug_phase_clocks(double *out4);
+int sa_gpu_debug_phase_clocks(double *out8);
 
 /* ---- micro-benchmarks used by bench.py for the roofline denominators ---- */
 /* runs `reps` SpMVs y = A x on device-resident vectors; returns ms per SpMV */

@@ -1,7 +1,8 @@
 // Device-side assembly of one AE's dense local matrix, executed cooperatively by
-// one thread block.  One thread owns one row of the tile, so every entry is summed
-// by a single thread in ascending element order: deterministic, no atomics, and
-// the same summation order as the CPU path.
+// one thread block.  One warp owns one row of the tile at a time and its lanes own
+// distinct entries of that row, so every entry is summed by a single thread in
+// ascending element order: deterministic, no atomics, and the same summation order
+// as the CPU path.
 //   mode with_global = 1: agg_build_AE_stiffm_with_global + agg_assemble_value
 //                         (amg/src/aggregates.cpp:855-945, 68-184)
 //   mode with_global = 0: agg_build_AE_stiffm (amg/src/aggregates.cpp:959-1086)
@@ -56,38 +57,42 @@ __device__ __forceinline__ double sa_dev_assemble_value(const LevelTables &L, in
 
 /// Fills the n x n column-major tile T (leading dimension ld) with the matrix of AE
 /// `part`.  All threads of the block must call; ends with __syncthreads().
-static __device__ void sa_dev_assemble_AE(const LevelTables &L, int part, double *T, int ld)
+/// T may live in shared or global memory.
+template <class TP>
+static __device__ void sa_dev_assemble_AE(const LevelTables &L, int part, TP T, int ld)
 {
     const int rb = L.AE2d_I[part];
     const int n = L.AE2d_I[part + 1] - rb;
     const int *dofs = L.AE2d_J + rb;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (int64_t q = threadIdx.x; q < (int64_t)n * ld; q += blockDim.x)
         T[q] = 0.;
     __syncthreads();
     if (L.with_global)
     {
-        for (int i = threadIdx.x; i < n; i += blockDim.x)
+        for (int i = wid; i < n; i += nw)
         {
             const int glob_dof = dofs[i];
             const char fi = L.agg_flags[glob_dof];
             const int ab = L.A_I[glob_dof], ae = L.A_I[glob_dof + 1];
-            for (int p = ab; p < ae; ++p)
+            for (int p = ab + lane; p < ae; p += 32)
             {
                 const int glob_neigh = L.A_J[p];
                 const int local_neigh = sa_dev_map_id_glob_to_AE(L, glob_neigh, part);
                 if (local_neigh < 0)
                     continue;
                 const char fj = L.agg_flags[glob_neigh];
-                const bool both_iface = (fi & SA_AGG_BETWEEN_AES_FLAG) && (fj & SA_AGG_BETWEEN_AES_FLAG);
+                const bool both_iface =
+                    (fi & SA_AGG_BETWEEN_AES_FLAG) && (fj & SA_AGG_BETWEEN_AES_FLAG);
                 const bool ess = (fi & SA_AGG_ON_ESS_DOMAIN_BORDER_FLAG) ||
                                  (fj & SA_AGG_ON_ESS_DOMAIN_BORDER_FLAG);
                 // bdr_cond_imposed = assemble_ess_diag = true (amg/src/elmat.cpp:51-52)
                 if (both_iface && !(ess && !(glob_neigh == glob_dof)))
                 {
                     // the reference assembles (i, j) for i <= j and mirrors the value
-                    const double value = (i <= local_neigh)
-                                             ? sa_dev_assemble_value(L, glob_dof, glob_neigh, part)
-                                             : sa_dev_assemble_value(L, glob_neigh, glob_dof, part);
+                    const double value =
+                        (i <= local_neigh) ? sa_dev_assemble_value(L, glob_dof, glob_neigh, part)
+                                           : sa_dev_assemble_value(L, glob_neigh, glob_dof, part);
                     T[i + (int64_t)ld * local_neigh] = value;
                 }
                 else
@@ -97,7 +102,9 @@ static __device__ void sa_dev_assemble_AE(const LevelTables &L, int part, double
     }
     else
     {
-        for (int i = threadIdx.x; i < n; i += blockDim.x)
+        // elements of a row are visited one after the other (ascending); the lanes take
+        // the element's columns, which map to distinct tile entries
+        for (int i = wid; i < n; i += nw)
         {
             const int g = dofs[i];
             const int bi = L.d2e_I[g], ei = L.d2e_I[g + 1];
@@ -116,7 +123,7 @@ static __device__ void sa_dev_assemble_AE(const LevelTables &L, int part, double
                         break;
                     }
                 const double *Ke = L.elmat + L.elmat_off[elem];
-                for (int j = 0; j < sz; ++j)
+                for (int j = lane; j < sz; j += 32)
                 {
                     const double el = Ke[(int64_t)j * sz + k];
                     if (0. != el)
@@ -125,6 +132,7 @@ static __device__ void sa_dev_assemble_AE(const LevelTables &L, int part, double
                         T[i + (int64_t)ld * local_j] += el;
                     }
                 }
+                __syncwarp();
             }
         }
     }

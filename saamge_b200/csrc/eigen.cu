@@ -64,7 +64,7 @@ __device__ __forceinline__ double block_sum(double v, double *sbuf)
 
 // cycle counters of the phases of k_assemble_tridiag, summed over blocks
 // (assembly, D + scaling, tridiagonalisation, copy-out); read by sa_gpu_debug_phase_clocks
-__device__ unsigned long long g_phase_clk[4];
+__device__ unsigned long long g_phase_clk[8];
 
 // One block per slot of the list.  tile_in_smem: tile lives in dynamic shared
 // memory (n <= nmax_smem), otherwise directly in the V block of the AE.
@@ -216,6 +216,355 @@ __global__ void k_assemble_tridiag(LevelTables L, ChunkDev C, const int *slot_li
         for (int64_t q = threadIdx.x; q < (int64_t)n * n; q += blockDim.x)
             Vout[q] = T[q];
     }
+}
+
+// Shared-memory variant, 2-D thread mapping.  Work of a Householder step on the
+// trailing r x r block is spread over all threads: thread (a, c) owns row k+1+a and
+// the columns j == c (mod ncls), with ncls = blockDim / roundup32(r) growing as the
+// block shrinks so that every warp stays busy.  Reductions go through per-warp slots
+// summed in a fixed order (deterministic, no atomics); 4 block barriers per step.
+// Shared layout (doubles): [slots 32][v n][w n][dg n][psum blockDim][tile n*n].
+__global__ void __launch_bounds__(512, 1)
+k_at_smem(LevelTables L, ChunkDev C, const int *slot_list, double *ae_D)
+{
+    extern __shared__ double sm[];
+    const int slot = slot_list[blockIdx.x];
+    const int part = C.ae_of_slot[slot];
+    const int rb = L.AE2d_I[part];
+    const int n = L.AE2d_I[part + 1] - rb;
+    const int NT = blockDim.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    double *slots_n = sm;       // 16: partial norms of the next column
+    double *slots_p = sm + 16;  // 16: partial p.v
+    double *v = sm + 32;
+    double *w = v + n;
+    double *dg = w + n;
+    double *psum = dg + n;
+    double *T = psum + NT;
+    const int ld = n;
+    double *dd = C.d + C.doff[slot], *ee = C.e + C.doff[slot], *tt = C.tau + C.doff[slot],
+           *sinv = C.sinv + C.doff[slot];
+    double *Vout = C.V + C.voff[slot];
+
+    long long tc0 = clock64();
+    sa_dev_assemble_AE(L, part, T, ld);
+    long long tc1 = clock64();
+    if (tid == 0)
+        atomicAdd(&g_phase_clk[0], (unsigned long long)(tc1 - tc0));
+
+    // weighted-l1 diagonal D_ii = sum_j |a_ij| sqrt(a_ii / a_jj)  (amg/src/mbox.cpp:913-949),
+    // evaluated as sqrt(a_ii) * sum_j |a_ij| / sqrt(a_jj)
+    int bad = 0;
+    for (int i = tid; i < n; i += NT)
+    {
+        const double a = T[i + ld * i];
+        if (!(a > 0.))
+            bad = 1;
+        dg[i] = a;
+        w[i] = rsqrt(a);
+    }
+    __syncthreads();
+    {
+        const int rpad = (n + 31) & ~31;
+        const int ncls = max(1, NT / rpad);
+        for (int a0 = 0; a0 < n; a0 += (ncls == 1 ? NT : rpad))
+        {
+            // rows a0 .. ; when ncls == 1 (n > NT/2) rows are simply strided over threads
+            const int a = (ncls == 1) ? tid : tid % rpad;
+            const int c = (ncls == 1) ? 0 : tid / rpad;
+            const int i = a0 + a;
+            double s = 0.;
+            if (i < n && c < ncls)
+                for (int j = c; j < n; j += ncls)
+                    s += fabs(T[i + ld * j]) * w[j];
+            psum[tid] = s;
+            __syncthreads();
+            if (i < n && c == 0)
+            {
+                double t = s;
+                for (int cc = 1; cc < ncls; ++cc)
+                    t += psum[cc * rpad + a];
+                const double sum = sqrt(dg[i]) * t;
+                ae_D[rb + i] = sum;
+                const double si = 1. / sqrt(sum);
+                v[i] = si; // scaling vector kept in v for the moment
+                sinv[i] = si;
+                if (!(sum > 0.) || !isfinite(sum))
+                    bad = 1;
+            }
+            __syncthreads();
+        }
+    }
+    if (__syncthreads_or(bad))
+    {
+        if (tid == 0)
+            C.status[slot] = 1;
+        return;
+    }
+    // A^ = D^-1/2 A D^-1/2
+    for (int q = tid; q < n * n; q += NT)
+    {
+        const int i = q % n, j = q / n;
+        T[q] *= v[i] * v[j];
+    }
+    __syncthreads();
+    long long tc2 = clock64();
+    if (tid == 0)
+        atomicAdd(&g_phase_clk[1], (unsigned long long)(tc2 - tc1));
+
+    // ---- Householder tridiagonalisation (lower), see k_assemble_tridiag for the recurrences
+    // norm of the first column below the subdiagonal
+    {
+        double part2 = 0.;
+        for (int i = 2 + tid; i < n; i += NT)
+        {
+            const double x = T[i];
+            part2 += x * x;
+        }
+        for (int o = 16; o > 0; o >>= 1)
+            part2 += __shfl_xor_sync(0xffffffffu, part2, o);
+        if (lane == 0)
+            slots_n[wid] = part2;
+    }
+    __syncthreads();
+    int nslots_n = NT >> 5; // number of valid norm slots for the coming step
+    long long ph0 = 0, ph1 = 0, ph2 = 0, ph3 = 0;
+    int cur_rpad = -1, ncls = 1, my_a = tid, my_c = 0;
+    for (int k = 0; k < n - 1; ++k)
+    {
+        long long q0 = clock64();
+        const int r = n - k - 1;
+        const int rpad = (r + 31) & ~31;
+        if (rpad != cur_rpad)
+        {
+            // thread -> (row a, column class c); changes only every 32 steps
+            cur_rpad = rpad;
+            ncls = max(1, NT / rpad);
+            my_a = tid % rpad;
+            my_c = tid / rpad;
+        }
+        double xnorm2 = 0.;
+        for (int s = 0; s < nslots_n; ++s)
+            xnorm2 += slots_n[s];
+        const double alpha = T[(k + 1) + ld * k];
+        double tau = 0., beta = alpha, scal = 0.;
+        if (xnorm2 > 0.)
+        {
+            // beta = -sign(alpha) ||x||, tau = 1 - alpha / beta, scal = 1 / (alpha - beta)
+            const double nx2 = alpha * alpha + xnorm2;
+            const double rinv = rsqrt(nx2);
+            const double nx = nx2 * rinv;
+            beta = -copysign(nx, alpha);
+            tau = 1. + alpha * copysign(rinv, alpha);
+            scal = 1. / (alpha - beta);
+        }
+        for (int a = tid; a < r; a += NT)
+        {
+            const int i = k + 1 + a;
+            const double vi = (a == 0) ? 1. : T[i + ld * k] * scal;
+            v[i] = vi;
+            if (a > 0)
+                T[i + ld * k] = vi; // keep the reflector in place
+        }
+        if (tid == 0)
+        {
+            dd[k] = T[k + ld * k];
+            ee[k] = beta;
+            tt[k] = tau;
+        }
+        __syncthreads(); // (1) v visible, slots_n consumed
+        long long q1 = clock64();
+        ph0 += q1 - q0;
+        const int nrw = (min(r, NT) + 31) >> 5; // warps that own rows
+        if (tau != 0.)
+        {
+            // p = tau * A22 v (partial sums per column class)
+            double pv = 0.;
+            if (ncls > 1)
+            {
+                const int a = my_a, c = my_c;
+                double s = 0.;
+                if (a < r && c < ncls)
+                {
+                    const double *__restrict__ Tp = T + (k + 1 + a) + ld * (k + 1 + c);
+                    const double *__restrict__ vp = v + (k + 1 + c);
+                    const int cnt = (r - c + ncls - 1) / ncls;
+                    const int stT = ld * ncls;
+                    double s1 = 0., s2 = 0., s3 = 0.;
+                    int q = 0;
+                    for (; q + 4 <= cnt; q += 4)
+                    {
+                        s += Tp[0] * vp[0];
+                        s1 += Tp[stT] * vp[ncls];
+                        s2 += Tp[2 * stT] * vp[2 * ncls];
+                        s3 += Tp[3 * stT] * vp[3 * ncls];
+                        Tp += 4 * stT;
+                        vp += 4 * ncls;
+                    }
+                    for (; q < cnt; ++q)
+                    {
+                        s += Tp[0] * vp[0];
+                        Tp += stT;
+                        vp += ncls;
+                    }
+                    s += s1 + s2 + s3;
+                }
+                psum[tid] = s;
+                __syncthreads(); // (2)
+                {
+                    long long q2 = clock64();
+                    ph1 += q2 - q1;
+                    q1 = q2;
+                }
+                if (tid < r)
+                {
+                    double t = psum[tid];
+#pragma unroll 4
+                    for (int cc = 1; cc < ncls; ++cc)
+                        t += psum[cc * rpad + tid];
+                    t *= tau;
+                    w[k + 1 + tid] = t;
+                    pv = t * v[k + 1 + tid];
+                }
+            }
+            else
+            {
+                for (int a = tid; a < r; a += NT)
+                {
+                    const int i = k + 1 + a;
+                    double s = 0.;
+                    for (int j = k + 1; j < n; ++j)
+                        s += T[i + ld * j] * v[j];
+                    s *= tau;
+                    w[i] = s;
+                    pv += s * v[i];
+                }
+            }
+            for (int o = 16; o > 0; o >>= 1)
+                pv += __shfl_xor_sync(0xffffffffu, pv, o);
+            if (lane == 0)
+                slots_p[wid] = pv;
+            __syncthreads(); // (3) w (= p) and the p.v slots visible
+            {
+                long long q2 = clock64();
+                ph2 += q2 - q1;
+                q1 = q2;
+            }
+            double pvs = 0.;
+            for (int s = 0; s < nrw; ++s)
+                pvs += slots_p[s];
+            const double alpha2 = -0.5 * tau * pvs;
+            // A22 -= v w^T + w v^T with w = p + alpha2 v formed on the fly; the class that
+            // owns column k+1 also accumulates the norm needed by the next step
+            double nrm = 0.;
+            if (ncls > 1)
+            {
+                const int a = my_a, c = my_c;
+                if (a < r && c < ncls)
+                {
+                    const int i = k + 1 + a;
+                    const double vi = v[i], wi = w[i] + alpha2 * vi;
+                    double *Tp = T + i + ld * (k + 1 + c);
+                    const double *vp = v + (k + 1 + c);
+                    const double *wp = w + (k + 1 + c);
+                    const int cnt = (r - c + ncls - 1) / ncls;
+                    const int stT = ld * ncls;
+                    int q = 0;
+                    if (c == 0 && cnt > 0)
+                    {
+                        // column k+1: also feeds the norm of the next Householder vector
+                        const double vj = vp[0], wj = wp[0] + alpha2 * vj;
+                        const double t = Tp[0] - (vi * wj + wi * vj);
+                        Tp[0] = t;
+                        if (a >= 2)
+                            nrm = t * t;
+                        Tp += stT;
+                        vp += ncls;
+                        wp += ncls;
+                        q = 1;
+                    }
+                    for (; q + 4 <= cnt; q += 4)
+                    {
+                        const double v0 = vp[0], v1 = vp[ncls], v2 = vp[2 * ncls], v3 = vp[3 * ncls];
+                        const double w0 = wp[0] + alpha2 * v0, w1 = wp[ncls] + alpha2 * v1,
+                                     w2 = wp[2 * ncls] + alpha2 * v2, w3 = wp[3 * ncls] + alpha2 * v3;
+                        const double t0 = Tp[0], t1 = Tp[stT], t2 = Tp[2 * stT], t3 = Tp[3 * stT];
+                        Tp[0] = t0 - (vi * w0 + wi * v0);
+                        Tp[stT] = t1 - (vi * w1 + wi * v1);
+                        Tp[2 * stT] = t2 - (vi * w2 + wi * v2);
+                        Tp[3 * stT] = t3 - (vi * w3 + wi * v3);
+                        Tp += 4 * stT;
+                        vp += 4 * ncls;
+                        wp += 4 * ncls;
+                    }
+                    for (; q < cnt; ++q)
+                    {
+                        const double vj = vp[0], wj = wp[0] + alpha2 * vj;
+                        Tp[0] = Tp[0] - (vi * wj + wi * vj);
+                        Tp += stT;
+                        vp += ncls;
+                        wp += ncls;
+                    }
+                }
+            }
+            else
+            {
+                for (int a = tid; a < r; a += NT)
+                {
+                    const int i = k + 1 + a;
+                    const double vi = v[i], wi = w[i] + alpha2 * vi;
+                    for (int j = k + 1; j < n; ++j)
+                    {
+                        const double vj = v[j], wj = w[j] + alpha2 * vj;
+                        const double t = T[i + ld * j] - (vi * wj + wi * vj);
+                        T[i + ld * j] = t;
+                        if (j == k + 1 && a >= 2)
+                            nrm += t * t;
+                    }
+                }
+            }
+            for (int o = 16; o > 0; o >>= 1)
+                nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+            if (lane == 0)
+                slots_n[wid] = nrm;
+        }
+        else
+        {
+            // H = I: only the norm of the next column is needed
+            double nrm = 0.;
+            for (int a = 2 + tid; a < r; a += NT)
+            {
+                const double x = T[(k + 1 + a) + ld * (k + 1)];
+                nrm += x * x;
+            }
+            for (int o = 16; o > 0; o >>= 1)
+                nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+            if (lane == 0)
+                slots_n[wid] = nrm;
+        }
+        nslots_n = nrw;
+        __syncthreads(); // (4) trailing block and norm slots complete
+        ph3 += clock64() - q1;
+    }
+    if (tid == 0)
+    {
+        atomicAdd(&g_phase_clk[4], (unsigned long long)ph0);
+        atomicAdd(&g_phase_clk[5], (unsigned long long)ph1);
+        atomicAdd(&g_phase_clk[6], (unsigned long long)ph2);
+        atomicAdd(&g_phase_clk[7], (unsigned long long)ph3);
+    }
+    if (tid == 0)
+    {
+        dd[n - 1] = T[(n - 1) + ld * (n - 1)];
+        ee[n - 1] = 0.;
+        tt[n - 1] = 0.;
+    }
+    long long tc3 = clock64();
+    if (tid == 0)
+        atomicAdd(&g_phase_clk[2], (unsigned long long)(tc3 - tc2));
+    // only the reflectors (strictly below the subdiagonal) are needed later
+    for (int q = tid; q < n * n; q += NT)
+        Vout[q] = T[q];
 }
 
 // one thread per slot: number of eigenvalues in (-1, theta] and search bounds
@@ -564,7 +913,7 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         // n*n + 3n + 40 doubles must fit
         const size_t cap = ctx->smem_optin / sizeof(double);
         int n = 1;
-        while ((size_t)(n + 1) * (n + 1) + 3 * (size_t)(n + 1) + 40 <= cap)
+        while ((size_t)(n + 1) * (n + 1) + 3 * (size_t)(n + 1) + 32 + 512 <= cap)
             ++n;
         nmax_smem = n;
     }
@@ -677,13 +1026,12 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
             if (!cnt)
                 continue;
             const int nb = AI[a0 + order[pos] + 1] - AI[a0 + order[pos]];
-            const size_t smem = ((size_t)nb * nb + 3 * (size_t)nb + 40) * sizeof(double);
-            SA_CUDA(cudaFuncSetAttribute(k_assemble_tridiag,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+            const int threads = nb <= 64 ? 256 : 512;
+            const size_t smem =
+                ((size_t)nb * nb + 3 * (size_t)nb + 32 + (size_t)threads) * sizeof(double);
+            SA_CUDA(cudaFuncSetAttribute(k_at_smem, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)ctx->smem_optin));
-            const int threads = nb <= 64 ? 64 : (nb <= 128 ? 128 : 192);
-            SA_LAUNCH(ctx, k_assemble_tridiag, cnt, threads, smem, L, C, d_order.p + pos, cnt, 1,
-                      lev->ae_D.p);
+            SA_LAUNCH(ctx, k_at_smem, cnt, threads, smem, L, C, d_order.p + pos, lev->ae_D.p);
             pos += cnt;
         }
 
@@ -828,14 +1176,14 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
     SA_API_END
 }
 
-extern "C" int sa_gpu_debug_phase_clocks(double *out4)
+extern "C" int sa_gpu_debug_phase_clocks(double *out8)
 {
-    unsigned long long h[4] = {0, 0, 0, 0}, z[4] = {0, 0, 0, 0};
+    unsigned long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0}, z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (cudaMemcpyFromSymbol(h, g_phase_clk, sizeof h) != cudaSuccess)
         return 1;
     cudaMemcpyToSymbol(g_phase_clk, z, sizeof z);
-    for (int i = 0; i < 4; ++i)
-        out4[i] = (double)h[i];
+    for (int i = 0; i < 8; ++i)
+        out8[i] = (double)h[i];
     return 0;
 }
 

@@ -12,7 +12,7 @@
 extern "C" {
 int sa_gpu_host_register(const void *p, size_t bytes);
 int sa_gpu_host_unregister(const void *p);
-int sa_gpu_debug_phase_clocks(double *out4);
+int sa_gpu_debug_phase_clocks(double *out8);
 }
 
 using namespace saamge;
@@ -181,11 +181,11 @@ extern "C" double sa_drv_bench_scalar(void *b_, const char *name_)
     }
     if (name.compare(0, 6, "phase.") == 0)
     {
-        static double clk[4] = {0, 0, 0, 0};
+        static double clk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         const int idx = name[6] - '0';
         if (idx == 0)
             sa_gpu_debug_phase_clocks(clk);
-        return (idx >= 0 && idx < 4) ? clk[idx] : NAN;
+        return (idx >= 0 && idx < 8) ? clk[idx] : NAN;
     }
     return NAN;
 }

@@ -12,7 +12,7 @@ h.sa_drv_gpu_profile(1,None,0)
 for it in range(3):
     ms=h.sa_drv_bench_step(B,0,0,na)
     buf=ctypes.create_string_buffer(4096); h.sa_drv_gpu_profile(-1,buf,4096)
-    ph=[h.sa_drv_bench_scalar(B,b"phase.%d"%i) for i in range(4)]
+    ph=[h.sa_drv_bench_scalar(B,b"phase.%d"%i) for i in range(8)]
     print("resident step %.3f ms -> %.0f AE/s"%(ms, na/ms*1e3), buf.value.decode().replace("\n","; "), "phase Mcycles", [round(x/1e6,1) for x in ph])
 h.sa_drv_gpu_profile(0,None,0)
 for it in range(2):
