@@ -6,6 +6,8 @@
 #include "sa_gpu_internal.cuh"
 
 static thread_local char g_err[1024] = "";
+cudaStream_t g_sa_alloc_stream = nullptr;
+bool g_sa_alloc_async = false;
 
 void sa_gpu_set_error(const char *fmt, ...)
 {
@@ -39,6 +41,23 @@ extern "C" int sa_gpu_ctx_create(int device, sa_gpu_ctx **out)
     SA_CUDA(cudaEventCreate(&ctx->ev1));
     SA_CUDA(cudaEventCreate(&ctx->pev0));
     SA_CUDA(cudaEventCreate(&ctx->pev1));
+    // stream-ordered allocator that never returns memory to the driver between calls
+    {
+        int supported = 0;
+        cudaDeviceGetAttribute(&supported, cudaDevAttrMemoryPoolsSupported, device);
+        const char *na = getenv("SA_GPU_NO_ASYNC_ALLOC");
+        if (supported && !(na && na[0] == '1') && !g_sa_alloc_async)
+        {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
+            {
+                unsigned long long thr = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+                g_sa_alloc_stream = ctx->stream;
+                g_sa_alloc_async = true;
+            }
+        }
+    }
     const char *pe = getenv("SA_GPU_PROFILE");
     ctx->profile = pe && pe[0] == '1';
     *out = ctx;
@@ -54,6 +73,12 @@ extern "C" void sa_gpu_ctx_destroy(sa_gpu_ctx *ctx)
         cudaEventDestroy(ctx->ev0);
     if (ctx->ev1)
         cudaEventDestroy(ctx->ev1);
+    if (ctx->stream == g_sa_alloc_stream)
+    {
+        // buffers that outlive the context fall back to synchronous frees on the null stream
+        cudaStreamSynchronize(ctx->stream);
+        g_sa_alloc_stream = nullptr;
+    }
     if (ctx->stream)
         cudaStreamDestroy(ctx->stream);
     delete ctx;

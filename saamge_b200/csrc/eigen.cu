@@ -964,19 +964,22 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
             dofftot += n;
             nmax = std::max(nmax, n);
         }
-        DevBuf<int> d_ae, d_doff, d_status;
-        DevBuf<int64_t> d_voff;
-        DevBuf<double> d_V, d_d, d_e, d_tau, d_sinv;
+        // work arrays are cached in the level (grow only): cudaMalloc/cudaFree of the
+        // multi-GB reflector block would otherwise dominate the stage
+        SpectralWs &WS = lev->sws;
+        DevBuf<int> &d_ae = WS.ae, &d_doff = WS.doff, &d_status = WS.status;
+        DevBuf<int64_t> &d_voff = WS.voff;
+        DevBuf<double> &d_V = WS.V, &d_d = WS.d, &d_e = WS.e, &d_tau = WS.tau, &d_sinv = WS.sinv;
         d_ae.upload(h_ae.data(), ns, st);
         d_doff.upload(h_doff.data(), ns, st);
         d_voff.upload(h_voff.data(), ns, st);
-        d_status.alloc(ns);
-        d_status.zero(st);
-        d_V.alloc(vo);
-        d_d.alloc(dofftot);
-        d_e.alloc(dofftot);
-        d_tau.alloc(dofftot);
-        d_sinv.alloc(dofftot);
+        d_status.ensure(ns);
+        SA_CUDA(cudaMemsetAsync(d_status.p, 0, (size_t)ns * sizeof(int), st));
+        d_V.ensure(vo);
+        d_d.ensure(dofftot);
+        d_e.ensure(dofftot);
+        d_tau.ensure(dofftot);
+        d_sinv.ensure(dofftot);
         ChunkDev C;
         C.ae_of_slot = d_ae.p;
         C.voff = d_voff.p;
@@ -995,7 +998,7 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
             return (AI[a0 + x + 1] - AI[a0 + x]) > (AI[a0 + y + 1] - AI[a0 + y]);
         });
-        DevBuf<int> d_order;
+        DevBuf<int> &d_order = WS.order;
         d_order.upload(order.data(), ns, st);
         ProfScope *pa = new ProfScope(ctx, "eig.assemble_tridiag");
         const int bucket_edges[] = {32, 48, 64, 80, 96, 112, 128, 144, 160, nmax_smem};
@@ -1037,13 +1040,13 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
 
         delete pa;
         // counts
-        DevBuf<int> d_nev, d_mtot;
-        DevBuf<double> d_glo, d_ghi, d_tn;
-        d_nev.alloc(ns);
-        d_mtot.alloc(ns);
-        d_glo.alloc(ns);
-        d_ghi.alloc(ns);
-        d_tn.alloc(ns);
+        DevBuf<int> &d_nev = WS.nev, &d_mtot = WS.mtot;
+        DevBuf<double> &d_glo = WS.glo, &d_ghi = WS.ghi, &d_tn = WS.tn;
+        d_nev.ensure(ns);
+        d_mtot.ensure(ns);
+        d_glo.ensure(ns);
+        d_ghi.ensure(ns);
+        d_tn.ensure(ns);
         {
             ProfScope ps(ctx, "eig.count");
             SA_LAUNCH(ctx, k_count, (ns + 127) / 128, 128, 0, C, lev->AE2d_I.p, ns, theta,
@@ -1080,8 +1083,8 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
             }
         }
         const int nev_total = (int)pr->eval_off[ns];
-        DevBuf<int> d_ev_slot, d_ev_idx;
-        DevBuf<int64_t> d_eval_off, d_evect_off;
+        DevBuf<int> &d_ev_slot = WS.ev_slot, &d_ev_idx = WS.ev_idx;
+        DevBuf<int64_t> &d_eval_off = WS.eval_off, &d_evect_off = WS.evect_off;
         d_ev_slot.upload(ev_slot.data(), nev_total, st);
         d_ev_idx.upload(ev_idx.data(), nev_total, st);
         d_eval_off.upload(pr->eval_off.data(), ns + 1, st);
@@ -1103,10 +1106,10 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
             warps = std::max<size_t>(1, std::min(warps, ws_budget / per_warp));
             const int wpb = 4;
             const int blocks = (int)((warps + wpb - 1) / wpb);
-            DevBuf<double> ws_d;
-            DevBuf<int> ws_i;
-            ws_d.alloc((size_t)blocks * wpb * 4 * 32 * nmax);
-            ws_i.alloc((size_t)blocks * wpb * 32 * nmax);
+            DevBuf<double> &ws_d = WS.ws_d;
+            DevBuf<int> &ws_i = WS.ws_i;
+            ws_d.ensure((size_t)blocks * wpb * 4 * 32 * nmax);
+            ws_i.ensure((size_t)blocks * wpb * 32 * nmax);
             {
                 ProfScope ps(ctx, "eig.inverse_iter");
                 SA_LAUNCH(ctx, k_inverse_iter, blocks, wpb * 32, 0, C, lev->AE2d_I.p, ns, d_nev.p,
@@ -1140,8 +1143,8 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
     }
     // (re)allocate the flat arrays; a partial range keeps nothing outside it, so
     // sharded callers use sa_gpu_set_spectral for the other ranges afterwards
-    lev->evals.alloc(lev->h_eval_off[nparts]);
-    lev->evects.alloc(lev->h_evect_off[nparts]);
+    lev->evals.ensure(lev->h_eval_off[nparts]);
+    lev->evects.ensure(lev->h_evect_off[nparts]);
     for (size_t p = 0; p < pieces.size(); ++p)
     {
         PieceResult *pr = pieces[p];

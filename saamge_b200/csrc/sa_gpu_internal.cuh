@@ -45,6 +45,12 @@ void sa_gpu_set_error(const char *fmt, ...);
     }                                                                              \
     return 0;
 
+/* stream used for stream-ordered allocation (set by sa_gpu_ctx_create; one context per
+   process is the expected use).  With a pool release threshold of "never", cudaMallocAsync /
+   cudaFreeAsync recycle device memory without the cost of cudaMalloc / cudaFree. */
+extern cudaStream_t g_sa_alloc_stream;
+extern bool g_sa_alloc_async;
+
 template <class T> struct DevBuf
 {
     T *p = nullptr;
@@ -53,10 +59,16 @@ template <class T> struct DevBuf
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { release(); }
+    bool async_owned = false;
     void release()
     {
         if (p)
-            cudaFree(p);
+        {
+            if (async_owned)
+                cudaFreeAsync(p, g_sa_alloc_stream);
+            else
+                cudaFree(p);
+        }
         p = nullptr;
         n = 0;
     }
@@ -64,7 +76,17 @@ template <class T> struct DevBuf
     {
         release();
         n = count;
-        SA_CUDA(cudaMalloc((void **)&p, (count ? count : 1) * sizeof(T)));
+        if (g_sa_alloc_async)
+        {
+            SA_CUDA(cudaMallocAsync((void **)&p, (count ? count : 1) * sizeof(T),
+                                    g_sa_alloc_stream));
+            async_owned = true;
+        }
+        else
+        {
+            SA_CUDA(cudaMalloc((void **)&p, (count ? count : 1) * sizeof(T)));
+            async_owned = false;
+        }
     }
     void ensure(size_t count)
     {
@@ -92,6 +114,7 @@ template <class T> struct DevBuf
     {
         std::swap(p, o.p);
         std::swap(n, o.n);
+        std::swap(async_owned, o.async_owned);
     }
 };
 
@@ -187,6 +210,14 @@ struct LevelTables
     int with_global;
 };
 
+/* grow-only work arrays of the local spectral stage, cached per level */
+struct SpectralWs
+{
+    DevBuf<int> ae, doff, status, order, nev, mtot, ev_slot, ev_idx, ws_i;
+    DevBuf<int64_t> voff, eval_off, evect_off;
+    DevBuf<double> V, d, e, tau, sinv, glo, ghi, tn, ws_d;
+};
+
 struct sa_gpu_level
 {
     sa_gpu_ctx *ctx = nullptr;
@@ -219,6 +250,7 @@ struct sa_gpu_level
     DevBuf<int64_t> evect_off, eval_off;
     DevBuf<double> evals, evects, ae_D;  // ae_D offsets = AE2d_I
     double max_residual = 0.;
+    SpectralWs sws;
     // tentative P
     bool have_tent = false;
     int avoid_ess = 1;
