@@ -55,18 +55,52 @@ __device__ __forceinline__ double sa_dev_assemble_value(const LevelTables &L, in
     return value;
 }
 
+/// Tile addressing: full column-major square, or lower triangle packed by columns
+/// (entry (i,j), i >= j, at T[cjm[j] + i] with cjm[j] = j*n - j*(j-1)/2 - j).
+struct FullTile
+{
+    double *T;
+    int ld;
+    __device__ __forceinline__ bool has(int, int) const { return true; }
+    __device__ __forceinline__ double &at(int i, int j) const { return T[i + (int64_t)ld * j]; }
+    __device__ __forceinline__ int64_t size(int n) const { return (int64_t)n * ld; }
+};
+struct PackedTile
+{
+    double *T;
+    const int *cjm;
+    __device__ __forceinline__ bool has(int i, int j) const { return i >= j; }
+    __device__ __forceinline__ double &at(int i, int j) const { return T[cjm[j] + i]; }
+    __device__ __forceinline__ int64_t size(int n) const { return (int64_t)n * (n + 1) / 2; }
+};
+
+template <class Tile>
+static __device__ void sa_dev_assemble_AE_tile(const LevelTables &L, int part, Tile tile);
+
 /// Fills the n x n column-major tile T (leading dimension ld) with the matrix of AE
 /// `part`.  All threads of the block must call; ends with __syncthreads().
 /// T may live in shared or global memory.
 template <class TP>
 static __device__ void sa_dev_assemble_AE(const LevelTables &L, int part, TP T, int ld)
 {
+    FullTile ft;
+    ft.T = T;
+    ft.ld = ld;
+    sa_dev_assemble_AE_tile(L, part, ft);
+}
+
+template <class Tile>
+static __device__ void sa_dev_assemble_AE_tile(const LevelTables &L, int part, Tile tile)
+{
     const int rb = L.AE2d_I[part];
     const int n = L.AE2d_I[part + 1] - rb;
     const int *dofs = L.AE2d_J + rb;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int64_t q = threadIdx.x; q < (int64_t)n * ld; q += blockDim.x)
-        T[q] = 0.;
+    {
+        const int64_t tot = tile.size(n);
+        for (int64_t q = threadIdx.x; q < tot; q += blockDim.x)
+            tile.T[q] = 0.;
+    }
     __syncthreads();
     if (L.with_global)
     {
@@ -79,7 +113,7 @@ static __device__ void sa_dev_assemble_AE(const LevelTables &L, int part, TP T, 
             {
                 const int glob_neigh = L.A_J[p];
                 const int local_neigh = sa_dev_map_id_glob_to_AE(L, glob_neigh, part);
-                if (local_neigh < 0)
+                if (local_neigh < 0 || !tile.has(i, local_neigh))
                     continue;
                 const char fj = L.agg_flags[glob_neigh];
                 const bool both_iface =
@@ -93,10 +127,10 @@ static __device__ void sa_dev_assemble_AE(const LevelTables &L, int part, TP T, 
                     const double value =
                         (i <= local_neigh) ? sa_dev_assemble_value(L, glob_dof, glob_neigh, part)
                                            : sa_dev_assemble_value(L, glob_neigh, glob_dof, part);
-                    T[i + (int64_t)ld * local_neigh] = value;
+                    tile.at(i, local_neigh) = value;
                 }
                 else
-                    T[i + (int64_t)ld * local_neigh] = L.A_data[p];
+                    tile.at(i, local_neigh) = L.A_data[p];
             }
         }
     }
@@ -129,7 +163,8 @@ static __device__ void sa_dev_assemble_AE(const LevelTables &L, int part, TP T, 
                     if (0. != el)
                     {
                         const int local_j = sa_dev_map_id_glob_to_AE(L, L.e2d_J[eb + j], part);
-                        T[i + (int64_t)ld * local_j] += el;
+                        if (tile.has(i, local_j))
+                            tile.at(i, local_j) += el;
                     }
                 }
                 __syncwarp();

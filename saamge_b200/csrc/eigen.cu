@@ -567,6 +567,8 @@ k_at_smem(LevelTables L, ChunkDev C, const int *slot_list, double *ae_D)
         Vout[q] = T[q];
 }
 
+#include "eigen_packed.cuh"
+
 // one thread per slot: number of eigenvalues in (-1, theta] and search bounds
 __global__ void k_count(ChunkDev C, const int *AE2d_I, int nslots, double theta, int inject_ae0,
                         int *nev, int *m_total, double *glo, double *ghi, double *tnorm_out)
@@ -790,8 +792,9 @@ __global__ void k_inverse_iter(ChunkDev C, const int *AE2d_I, int nslots, const 
 }
 
 // grid.x = slots; each warp of the block handles vectors w, w + nwarps, ...
+// nmax_packed: AEs with n <= nmax_packed keep their reflectors as a packed lower triangle
 __global__ void k_back_transform(ChunkDev C, const int *AE2d_I, const int *nev, const int *m_total,
-                                 const int64_t *evect_off_slot, double *evects)
+                                 const int64_t *evect_off_slot, double *evects, int nmax_packed)
 {
     const int slot = blockIdx.x;
     const int m = nev[slot];
@@ -810,7 +813,10 @@ __global__ void k_back_transform(ChunkDev C, const int *AE2d_I, const int *nev, 
             const double t = tau[k];
             if (t == 0.)
                 continue;
-            const double *vk = V + (int64_t)n * k;
+            // column k of the reflector block: full layout V[i + n k], packed V[cjm(k) + i]
+            const double *vk = (n <= nmax_packed)
+                                   ? V + ((int64_t)k * n - ((int64_t)k * (k - 1)) / 2 - k)
+                                   : V + (int64_t)n * k;
             double s = 0.;
             for (int i = k + 1 + lane; i < n; i += 32)
                 s += ((i == k + 1) ? 1. : vk[i]) * z[i];
@@ -908,15 +914,32 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
 
     // chunks of consecutive AEs bounded by the reflector storage budget
     const size_t budget_doubles = (size_t)3 << 30; // 24 GB of reflectors per chunk
+    // largest n whose packed lower triangle (+ vectors) fits the shared memory of one block
     int nmax_smem = 0;
+    auto packed_smem_doubles = [](size_t n) {
+        return n * (n + 1) / 2 + 3 * n + (n + 1) / 2 + 32 + 256;
+    };
     {
-        // n*n + 3n + 40 doubles must fit
+        const size_t cap = (ctx->smem_optin - 1024) / sizeof(double);
+        int n = 1;
+        while (packed_smem_doubles((size_t)n + 1) <= cap)
+            ++n;
+        nmax_smem = n;
+    }
+    static int use_square = getenv("SA_GPU_SQUARE_TILE") ? atoi(getenv("SA_GPU_SQUARE_TILE")) : 0;
+    if (use_square)
+    {
         const size_t cap = ctx->smem_optin / sizeof(double);
         int n = 1;
         while ((size_t)(n + 1) * (n + 1) + 3 * (size_t)(n + 1) + 32 + 512 <= cap)
             ++n;
         nmax_smem = n;
     }
+    // reflector block of an AE: packed triangle when it goes through the shared-memory
+    // kernel, full square otherwise
+    auto vsize = [&](size_t n) -> size_t {
+        return (!use_square && (int)n <= nmax_smem) ? n * (n + 1) / 2 : n * n;
+    };
 
     struct PieceResult
     {
@@ -944,9 +967,9 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         while (a1 < ae_end)
         {
             const size_t n = AI[a1 + 1] - AI[a1];
-            if (a1 > a0 && vtot + n * n > budget_doubles)
+            if (a1 > a0 && vtot + vsize(n) > budget_doubles)
                 break;
-            vtot += n * n;
+            vtot += vsize(n);
             ++a1;
         }
         const int ns = a1 - a0;
@@ -960,7 +983,7 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
             h_ae[s] = a0 + s;
             h_voff[s] = vo;
             h_doff[s] = dofftot;
-            vo += (int64_t)n * n;
+            vo += (int64_t)vsize((size_t)n);
             dofftot += n;
             nmax = std::max(nmax, n);
         }
@@ -1001,7 +1024,8 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         DevBuf<int> &d_order = WS.order;
         d_order.upload(order.data(), ns, st);
         ProfScope *pa = new ProfScope(ctx, "eig.assemble_tridiag");
-        const int bucket_edges[] = {32, 48, 64, 80, 96, 112, 128, 144, 160, nmax_smem};
+        const int bucket_edges[] = {32,  48,  64,  80,  96,  104, 112, 120, 128, 136,
+                                    144, 152, 160, 176, 192, 208, 224, nmax_smem};
         int pos = 0;
         // large (global-memory tile) bucket first
         {
@@ -1029,12 +1053,26 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
             if (!cnt)
                 continue;
             const int nb = AI[a0 + order[pos] + 1] - AI[a0 + order[pos]];
-            const int threads = nb <= 64 ? 256 : 512;
-            const size_t smem =
-                ((size_t)nb * nb + 3 * (size_t)nb + 32 + (size_t)threads) * sizeof(double);
-            SA_CUDA(cudaFuncSetAttribute(k_at_smem, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)ctx->smem_optin));
-            SA_LAUNCH(ctx, k_at_smem, cnt, threads, smem, L, C, d_order.p + pos, lev->ae_D.p);
+            if (use_square)
+            {
+                static int thr_env =
+                    getenv("SA_GPU_AT_THREADS") ? atoi(getenv("SA_GPU_AT_THREADS")) : 0;
+                const int threads = thr_env ? thr_env : (nb <= 64 ? 256 : 512);
+                const size_t smem =
+                    ((size_t)nb * nb + 3 * (size_t)nb + 32 + (size_t)threads) * sizeof(double);
+                SA_CUDA(cudaFuncSetAttribute(k_at_smem,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)ctx->smem_optin));
+                SA_LAUNCH(ctx, k_at_smem, cnt, threads, smem, L, C, d_order.p + pos, lev->ae_D.p);
+            }
+            else
+            {
+                const size_t smem = packed_smem_doubles((size_t)nb) * sizeof(double);
+                SA_CUDA(cudaFuncSetAttribute(k_at_packed,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)ctx->smem_optin - 1024));
+                SA_LAUNCH(ctx, k_at_packed, cnt, 256, smem, L, C, d_order.p + pos, lev->ae_D.p);
+            }
             pos += cnt;
         }
 
@@ -1119,7 +1157,7 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
             {
                 ProfScope ps(ctx, "eig.back_transform");
                 SA_LAUNCH(ctx, k_back_transform, ns, 128, 0, C, lev->AE2d_I.p, d_nev.p, d_mtot.p,
-                          d_evect_off.p, pr->evects.p);
+                          d_evect_off.p, pr->evects.p, use_square ? 0 : nmax_smem);
             }
             SA_CUDA(cudaStreamSynchronize(st)); // workspace freed at scope exit
         }
