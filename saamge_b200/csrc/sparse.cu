@@ -132,13 +132,37 @@ __global__ void k_spmv(int rows, const int *__restrict__ I, const int *__restric
     const int sub = t % TPR;
     const bool valid = row < rows;
     double s = 0.;
+    // epilogue operands are fetched up front so their latency overlaps the matrix stream
+    double br = 0., dr = 0., xr = 0.;
+    if (valid)
+    {
+        if (MODE == 1 || MODE == 3 || MODE == 4)
+            br = b[row];
+        if (MODE == 3 || MODE == 4)
+            dr = dinv[row];
+        if (MODE == 3)
+            xr = x[row];
+        if (MODE == 2)
+            xr = y[row];
+    }
     if (MODE != 4)
     {
         if (valid)
         {
+            // matrix entries are streamed (evict-first) so that x stays cached
             const int e = I[row + 1];
-            for (int p = I[row] + sub; p < e; p += TPR)
-                s += A[p] * x[J[p]];
+            int p = I[row] + sub;
+            double s1 = 0.;
+            for (; p + TPR < e; p += 2 * TPR)
+            {
+                const int j0 = __ldcs(J + p), j1 = __ldcs(J + p + TPR);
+                const double a0 = __ldcs(A + p), a1 = __ldcs(A + p + TPR);
+                s += a0 * x[j0];
+                s1 += a1 * x[j1];
+            }
+            if (p < e)
+                s += __ldcs(A + p) * x[__ldcs(J + p)];
+            s += s1;
         }
 #pragma unroll
         for (int o = TPR >> 1; o > 0; o >>= 1)
@@ -149,20 +173,20 @@ __global__ void k_spmv(int rows, const int *__restrict__ I, const int *__restric
         if (MODE == 0)
             y[row] = s;
         else if (MODE == 1)
-            y[row] = b[row] - s;
+            y[row] = br - s;
         else if (MODE == 2)
-            y[row] += s;
+            y[row] = xr + s;
         else if (MODE == 3)
         {
-            double tmp = -1. * b[row];
+            double tmp = -1. * br;
             tmp += s;
-            tmp *= dinv[row];
-            y[row] = x[row] + mult * tmp;
+            tmp *= dr;
+            y[row] = xr + mult * tmp;
         }
         else
         {
-            double tmp = -1. * b[row];
-            tmp *= dinv[row];
+            double tmp = -1. * br;
+            tmp *= dr;
             y[row] = mult * tmp;
         }
     }
@@ -183,13 +207,24 @@ void launch_spmv(sa_gpu_ctx *ctx, const DevCsr &A, const double *x, const double
         SA_LAUNCH(ctx, kern, (unsigned)((threads + tb - 1) / tb), tb, 0,               \
                   A.rows, A.I.p, A.J.p, A.A.p, x, b, dinv, mult, y);                   \
     }
-    if (avg <= 3.)
+    static int tpr_env = getenv("SA_GPU_SPMV_TPR") ? atoi(getenv("SA_GPU_SPMV_TPR")) : 0;
+    if (tpr_env == 2)
         SA_SPMV_CASE(2)
-    else if (avg <= 6.)
+    else if (tpr_env == 4)
         SA_SPMV_CASE(4)
-    else if (avg <= 40.)
+    else if (tpr_env == 8)
         SA_SPMV_CASE(8)
-    else if (avg <= 96.)
+    else if (tpr_env == 16)
+        SA_SPMV_CASE(16)
+    else if (tpr_env == 32)
+        SA_SPMV_CASE(32)
+    else if (avg <= 4.)
+        SA_SPMV_CASE(2)
+    else if (avg <= 48.)
+        SA_SPMV_CASE(4)
+    else if (avg <= 128.)
+        SA_SPMV_CASE(8)
+    else if (avg <= 384.)
         SA_SPMV_CASE(16)
     else
         SA_SPMV_CASE(32)
