@@ -117,6 +117,29 @@ class Level:
         check(self.lib.sa_gpu_get_spectral(self.h, _dp(ev), _dp(Z), _dp(D)), "get_spectral")
         return m, ev, Z, D
 
+    def set_spectral(self, m, evals, evects, D):
+        m = np.ascontiguousarray(m, dtype=np.int32)
+        evals = np.ascontiguousarray(evals, dtype=np.float64)
+        evects = np.ascontiguousarray(evects, dtype=np.float64)
+        D = np.ascontiguousarray(D, dtype=np.float64)
+        check(self.lib.sa_gpu_set_spectral(self.h, 0, self.nparts, _ip(m), _dp(evals), _dp(evects), _dp(D)),
+              "set_spectral")
+
+    def local_spectral_sharded(self, theta, dist, group=None):
+        """Local spectral stage sharded over the ranks of `dist` (contiguous AE ranges
+        balanced on n^3), results all-gathered and installed on every rank."""
+        from . import sharding
+
+        n = self.ae_sizes()
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        a, b = sharding.shard_ranges(n, world)[rank]
+        self.local_spectral(theta, a, b)
+        m, ev, Z, D = self.spectral()
+        do = np.concatenate([[0], np.cumsum(n)])
+        full = sharding.allgather_spectral((m[a:b], ev, Z, D[do[a]:do[b]]), dist, group)
+        self.set_spectral(*full)
+        return a, b
+
     def build_AE_stiff(self, part):
         n = int(self.ae_sizes()[part])
         out = np.zeros(n * n)
