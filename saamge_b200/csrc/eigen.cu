@@ -69,7 +69,8 @@ __device__ unsigned long long g_phase_clk[8];
 // One block per slot of the list.  tile_in_smem: tile lives in dynamic shared
 // memory (n <= nmax_smem), otherwise directly in the V block of the AE.
 __global__ void k_assemble_tridiag(LevelTables L, ChunkDev C, const int *slot_list, int nslots,
-                                   int tile_in_smem, double *ae_D)
+                                   int tile_in_smem, double *ae_D, double *tile_base,
+                                   int64_t tile_stride, int stop_after_scale)
 {
     extern __shared__ double sm[];
     const int slot = slot_list[blockIdx.x];
@@ -82,7 +83,8 @@ __global__ void k_assemble_tridiag(LevelTables L, ChunkDev C, const int *slot_li
     double *v = sm + 40;
     double *w = v + n;
     double *dg = w + n;
-    double *T = tile_in_smem ? (dg + n) : Vout;
+    double *T = tile_in_smem ? (dg + n)
+                             : (tile_base ? tile_base + (int64_t)blockIdx.x * tile_stride : Vout);
     const int ld = n;
     double *dd = C.d + C.doff[slot], *ee = C.e + C.doff[slot], *tt = C.tau + C.doff[slot],
            *sinv = C.sinv + C.doff[slot];
@@ -139,6 +141,8 @@ __global__ void k_assemble_tridiag(LevelTables L, ChunkDev C, const int *slot_li
     tc0 = clock64();
     if (threadIdx.x == 0)
         atomicAdd(&g_phase_clk[1], (unsigned long long)(tc0 - tc1));
+    if (stop_after_scale)
+        return;
     // Householder tridiagonalisation, lower triangle convention of dsytd2:
     // H(k) annihilates A(k+2:n-1, k); reflector stored below the subdiagonal.
     for (int k = 0; k < n - 1; ++k)
@@ -568,6 +572,7 @@ k_at_smem(LevelTables L, ChunkDev C, const int *slot_list, double *ae_D)
 }
 
 #include "eigen_packed.cuh"
+#include "eigen_large.cuh"
 
 // one thread per slot: number of eigenvalues in (-1, theta] and search bounds
 __global__ void k_count(ChunkDev C, const int *AE2d_I, int nslots, double theta, int inject_ae0,
@@ -937,9 +942,7 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
     }
     // reflector block of an AE: packed triangle when it goes through the shared-memory
     // kernel, full square otherwise
-    auto vsize = [&](size_t n) -> size_t {
-        return (!use_square && (int)n <= nmax_smem) ? n * (n + 1) / 2 : n * n;
-    };
+    auto vsize = [&](size_t n) -> size_t { return !use_square ? n * (n + 1) / 2 : n * n; };
 
     struct PieceResult
     {
@@ -1032,7 +1035,7 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
             int cnt = 0;
             while (pos + cnt < ns && (AI[a0 + order[pos + cnt] + 1] - AI[a0 + order[pos + cnt]]) > nmax_smem)
                 ++cnt;
-            if (cnt)
+            if (cnt && use_square)
             {
                 const int nb = AI[a0 + order[pos] + 1] - AI[a0 + order[pos]];
                 const size_t smem = (size_t)(3 * nb + 40) * sizeof(double);
@@ -1040,7 +1043,64 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)ctx->smem_optin));
                 SA_LAUNCH(ctx, k_assemble_tridiag, cnt, 512, smem, L, C, d_order.p + pos, cnt, 0,
-                          lev->ae_D.p);
+                          lev->ae_D.p, (double *)nullptr, (int64_t)0, 0);
+            }
+            else if (cnt)
+            {
+                // groups of thread blocks per matrix, cooperative launches of B matrices
+                SA_CUDA(cudaFuncSetAttribute(k_assemble_tridiag,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)ctx->smem_optin));
+                SA_CUDA(cudaFuncSetAttribute(k_tridiag_coop,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)ctx->smem_optin));
+                int done = 0;
+                while (done < cnt)
+                {
+                    const int nb = AI[a0 + order[pos + done] + 1] - AI[a0 + order[pos + done]];
+                    const size_t smem_c = ((size_t)3 * nb + 64 + 16 * 32) * sizeof(double);
+                    if (smem_c > ctx->smem_optin)
+                        SA_FAIL("sa_gpu_local_spectral: AE with %d dofs exceeds the supported "
+                                "size of the large-matrix eigensolver", nb);
+                    static int gdiv = getenv("SA_GPU_COOP_DIV") ? atoi(getenv("SA_GPU_COOP_DIV")) : 180;
+                    int G = std::max(2, std::min(ctx->num_sms, nb / gdiv));
+                    int B = std::max(1, std::min(cnt - done, ctx->num_sms / G));
+                    if (B == cnt - done)
+                        G = std::max(2, ctx->num_sms / B);
+                    G = std::min(G, std::max(1, (nb + 31) / 32));
+                    const int64_t tstride = (int64_t)nb * nb;
+                    WS.Twork.ensure((size_t)B * tstride);
+                    WS.pbuf.ensure((size_t)B * 2 * nb + (size_t)B * 4);
+                    WS.counters.ensure(B);
+                    SA_CUDA(cudaMemsetAsync(WS.pbuf.p, 0,
+                                            ((size_t)B * 2 * nb + (size_t)B * 4) * sizeof(double), st));
+                    SA_CUDA(cudaMemsetAsync(WS.counters.p, 0, (size_t)B * sizeof(unsigned int), st));
+                    const size_t smem_a = (size_t)(3 * nb + 40) * sizeof(double);
+                    SA_LAUNCH(ctx, k_assemble_tridiag, B, 512, smem_a, L, C, d_order.p + pos + done,
+                              B, 0, lev->ae_D.p, WS.Twork.p, tstride, 1);
+                    std::vector<CoopMatrix> hm(B);
+                    for (int b = 0; b < B; ++b)
+                    {
+                        hm[b].slot = order[pos + done + b];
+                        hm[b].T = WS.Twork.p + (int64_t)b * tstride;
+                        hm[b].pbuf = WS.pbuf.p + (int64_t)b * 2 * nb;
+                        hm[b].pvacc = WS.pbuf.p + (int64_t)B * 2 * nb + (int64_t)b * 4;
+                        hm[b].counter = WS.counters.p + b;
+                    }
+                    WS.coopmats.ensure((size_t)B * sizeof(CoopMatrix));
+                    SA_CUDA(cudaMemcpyAsync(WS.coopmats.p, hm.data(), (size_t)B * sizeof(CoopMatrix),
+                                            cudaMemcpyHostToDevice, st));
+                    SA_CUDA(cudaStreamSynchronize(st)); // hm goes out of scope
+                    const CoopMatrix *dm = (const CoopMatrix *)WS.coopmats.p;
+                    void *args[] = {(void *)&L, (void *)&C, (void *)&dm, (void *)&G};
+                    SA_CUDA(cudaLaunchCooperativeKernel((const void *)k_tridiag_coop, dim3(B * G),
+                                                        dim3(512), args, smem_c, st));
+                    ctx->launches++;
+                    done += B;
+                }
+            }
+            if (cnt)
+            {
                 pos += cnt;
             }
         }
@@ -1157,7 +1217,7 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
             {
                 ProfScope ps(ctx, "eig.back_transform");
                 SA_LAUNCH(ctx, k_back_transform, ns, 128, 0, C, lev->AE2d_I.p, d_nev.p, d_mtot.p,
-                          d_evect_off.p, pr->evects.p, use_square ? 0 : nmax_smem);
+                          d_evect_off.p, pr->evects.p, use_square ? 0 : 0x7fffffff);
             }
             SA_CUDA(cudaStreamSynchronize(st)); // workspace freed at scope exit
         }

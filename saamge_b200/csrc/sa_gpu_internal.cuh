@@ -216,6 +216,10 @@ struct SpectralWs
     DevBuf<int> ae, doff, status, order, nev, mtot, ev_slot, ev_idx, ws_i;
     DevBuf<int64_t> voff, eval_off, evect_off;
     DevBuf<double> V, d, e, tau, sinv, glo, ghi, tn, ws_d;
+    // large-matrix (cooperative) path
+    DevBuf<double> Twork, pbuf;
+    DevBuf<unsigned int> counters;
+    DevBuf<char> coopmats;
 };
 
 struct sa_gpu_level
