@@ -285,17 +285,30 @@ def main():
     }
     h.sa_drv_bench_destroy(B)
 
-    # ---- extras on rank 0: full hierarchy (setup + PCG), SpMV / smoother roofline, CPU sample
-    if rank == 0:
+    # ---- extras: full hierarchy (setup + PCG), SpMV / smoother roofline, CPU sample.
+    # With several ranks the AE loop of every level is sharded over the GPUs (one common
+    # problem, per-AE results all-gathered over NCCL); the solve runs on rank 0.
+    if world > 1 and not args.no_hierarchy:
+        pr.close()
+        pr, p, nae = make_problem(sab, args.workload, 12345)
+        sab.enable_sharding(dist)
+        barrier()
+    if rank == 0 or (world > 1 and not args.no_hierarchy):
         peaks, peak_src = measured_peaks()
         if not args.no_hierarchy:
             t0 = time.time()
             H = sab.ml_build(pr, p, local_rank)
+            barrier()
             setup_s = time.time() - t0
+            if rank != 0:
+                H.close()
+                dist.destroy_process_group()
+                return
             t0 = time.time()
             its = sab.ml_pcg(H, 1000, 1e-12, 0.0)
             pcg_s = time.time() - t0
-            line["hierarchy"] = {"levels": w["levels"], "setup_s": setup_s, "pcg_s": pcg_s, "pcg_iterations": its,
+            line["hierarchy"] = {"levels": w["levels"], "setup_s": setup_s, "setup_sharded_over_gpus": world,
+                                 "pcg_s": pcg_s, "pcg_gpus": 1, "pcg_iterations": its,
                                  "final_residual": H.scalar("pcg.final_res_norm"),
                                  "stage_s": {k: round(v, 4) for k, v in H.times().items()},
                                  "dofs": [int(H.scalar("ND", l)) for l in range(w["levels"] - 1)]}

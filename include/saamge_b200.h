@@ -105,6 +105,8 @@ void sa_gpu_level_destroy(sa_gpu_level *level);
  * (amg/src/interp.cpp:510-524).  Results stay on the device. */
 int sa_gpu_local_spectral(sa_gpu_level *level, double theta, int ae_begin, int ae_end,
                           int inject_ones_ae0);
+/* sizes (dofs) of the AEs of the level, nparts ints */
+int sa_gpu_get_AE_sizes(sa_gpu_level *level, int *ae_n);
 /* number of accepted vectors per AE (cut_evects_arr[i]->Width()), nparts ints */
 int sa_gpu_get_spectral_counts(sa_gpu_level *level, int *ae_m);
 /* evals: sum(m_i) doubles (AE-major, ascending per AE; an injected vector has no

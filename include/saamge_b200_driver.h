@@ -62,6 +62,12 @@ int sa_drv_ml_pcg(void *hier, int maxiter, double rtol, double atol);
 int sa_drv_ml_download(void *hier);
 void sa_drv_hier_destroy(void *hier);
 
+/* ---- multi-GPU: shard the AE loop of every level over `world` ranks; `exchange` is
+ * called with the device level after the rank computed AEs [begin, end) and must
+ * all-gather the per-AE results (sa_gpu_get_spectral -> collective -> sa_gpu_set_spectral) */
+typedef void (*sa_drv_exchange_ft)(void *gpu_level, int begin, int end, int nparts);
+void sa_drv_set_sharding(int rank, int world, sa_drv_exchange_ft exchange);
+
 /* ---- generic read access (problem, relations, hierarchy records) ----
  * obj   : problem or hierarchy handle
  * name  : e.g. "A.I", "elem_to_dof.J", "AE_to_dof.I", "mises", "evals", "evects",

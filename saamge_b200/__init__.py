@@ -194,6 +194,54 @@ class Hierarchy:
             self.handle = None
 
 
+_exchange_keepalive = []
+
+
+def enable_sharding(dist, group=None):
+    """Shard the AE loop of every level over the ranks of `dist` (torch.distributed, NCCL on
+    GPUs): each rank computes its AE range, the per-AE results are all-gathered."""
+    from . import sharding
+
+    h = host_lib()
+    g = gpu_lib()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    CB = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int)
+    ip = ctypes.POINTER(ctypes.c_int)
+    dp = ctypes.POINTER(ctypes.c_double)
+
+    def exchange(level, a, b, nparts):
+        lev = ctypes.c_void_p(level)
+        n = np.zeros(nparts, dtype=np.int32)
+        m = np.zeros(nparts, dtype=np.int32)
+        g.sa_gpu_get_AE_sizes(lev, n.ctypes.data_as(ip))
+        g.sa_gpu_get_spectral_counts(lev, m.ctypes.data_as(ip))
+        m[:a] = 0
+        m[b:] = 0
+        ev = np.zeros(int(m.sum()))
+        Z = np.zeros(int((m.astype(np.int64) * n).sum()))
+        D = np.zeros(int(n.sum()))
+        rc = g.sa_gpu_get_spectral(lev, ev.ctypes.data_as(dp), Z.ctypes.data_as(dp), D.ctypes.data_as(dp))
+        assert rc == 0, g.sa_gpu_last_error()
+        do = np.concatenate([[0], np.cumsum(n.astype(np.int64))])
+        full = sharding.allgather_spectral((m[a:b], ev, Z, D[do[a]:do[b]]), dist, group)
+        fm, fev, fZ, fD = [np.ascontiguousarray(x) for x in full]
+        rc = g.sa_gpu_set_spectral(lev, 0, nparts, fm.astype(np.int32).ctypes.data_as(ip), fev.ctypes.data_as(dp),
+                                   fZ.ctypes.data_as(dp), fD.ctypes.data_as(dp))
+        assert rc == 0, g.sa_gpu_last_error()
+
+    cb = CB(exchange)
+    _exchange_keepalive.append(cb)
+    h.sa_drv_set_sharding.argtypes = [ctypes.c_int, ctypes.c_int, CB]
+    h.sa_drv_set_sharding(rank, world, cb)
+
+
+def disable_sharding():
+    h = host_lib()
+    CB = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int)
+    h.sa_drv_set_sharding.argtypes = [ctypes.c_int, ctypes.c_int, CB]
+    h.sa_drv_set_sharding(0, 1, CB())
+
+
 def ml_build(problem, params, device=0):
     """ml_produce_data through the B200 path; returns a Hierarchy."""
     h = host_lib().sa_drv_ml_build(problem.handle, ctypes.byref(params), device)

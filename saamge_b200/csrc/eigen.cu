@@ -1288,6 +1288,13 @@ extern "C" int sa_gpu_debug_phase_clocks(double *out8)
     return 0;
 }
 
+extern "C" int sa_gpu_get_AE_sizes(sa_gpu_level *lev, int *ae_n)
+{
+    for (int i = 0; i < lev->nparts; ++i)
+        ae_n[i] = lev->h_AE2d_I[i + 1] - lev->h_AE2d_I[i];
+    return 0;
+}
+
 extern "C" int sa_gpu_get_spectral_counts(sa_gpu_level *lev, int *ae_m)
 {
     SA_API_BEGIN

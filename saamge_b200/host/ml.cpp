@@ -3,6 +3,7 @@
 // amg/src/tg.cpp:402-540, 979-1014; all arithmetic happens in sa_gpu_* calls.
 #include <chrono>
 #include <cmath>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <utility>
@@ -346,10 +347,57 @@ tg_data_t *tg_init_data(const SparseMatrix *A, const agg_partitioning_relations_
 }
 
 // the AE loop of amg/src/interp.cpp:387-556 as one batched device stage
+/* AE sharding over ranks (one process per GPU): the rank computes a contiguous AE range
+   balanced on n^3 and an exchange callback (NCCL all-gather, installed by the launcher)
+   completes the set on every rank -- how the reference spreads its AE loop over MPI ranks
+   (amg/src/interp.cpp:387). */
+static int g_shard_rank = 0, g_shard_world = 1;
+static sa_spectral_exchange_ft g_shard_exchange = NULL;
+
+void sa_set_sharding(int rank, int world, sa_spectral_exchange_ft exchange)
+{
+    g_shard_rank = rank;
+    g_shard_world = world;
+    g_shard_exchange = exchange;
+}
+
+void sa_shard_range(const agg_partitioning_relations_t &rels, int rank, int world, int *begin,
+                    int *end)
+{
+    const int nparts = rels.nparts;
+    std::vector<double> cost((size_t)nparts + 1, 0.);
+    for (int i = 0; i < nparts; ++i)
+    {
+        const double n = rels.AE_to_dof->RowSize(i);
+        cost[i + 1] = cost[i] + n * n * n;
+    }
+    auto bound = [&](int r) {
+        if (r <= 0)
+            return 0;
+        if (r >= world)
+            return nparts;
+        const double target = cost[nparts] * r / world;
+        int b = (int)(std::lower_bound(cost.begin() + 1, cost.end(), target) - (cost.begin() + 1)) + 1;
+        return std::min(b, nparts);
+    };
+    *begin = bound(rank);
+    *end = std::max(*begin, bound(rank + 1));
+}
+
 void interp_compute_vectors(const agg_partitioning_relations_t &agg_part_rels,
                             const interp_data_t &interp_data, tg_data_t &tg_data, double &theta)
 {
     StageTimer tm("local_spectral");
+    if (g_shard_world > 1 && g_shard_exchange)
+    {
+        int a = 0, b = 0;
+        sa_shard_range(agg_part_rels, g_shard_rank, g_shard_world, &a, &b);
+        sa_gpu_check(sa_gpu_local_spectral(tg_data.gpu, theta, a, b,
+                                           (interp_data.testmesh_inject && a == 0) ? 1 : 0),
+                     "sa_gpu_local_spectral");
+        g_shard_exchange(tg_data.gpu, a, b, agg_part_rels.nparts);
+        return;
+    }
     sa_gpu_check(sa_gpu_local_spectral(tg_data.gpu, theta, 0, agg_part_rels.nparts,
                                        interp_data.testmesh_inject ? 1 : 0),
                  "sa_gpu_local_spectral");
@@ -694,6 +742,11 @@ void tg_download_results(const tg_data_t &tg_data, const agg_partitioning_relati
 }
 
 } // namespace saamge
+
+extern "C" void sa_drv_set_sharding(int rank, int world, sa_drv_exchange_ft cb)
+{
+    saamge::sa_set_sharding(rank, world, (saamge::sa_spectral_exchange_ft)cb);
+}
 
 /* ------------------------------------------------------ driver entry points */
 

@@ -34,6 +34,14 @@ void proc_gpu_finalize();
 /// SA_ASSERT-style abort with the CUDA library's message when rc != 0
 void sa_gpu_check(int rc, const char *what);
 
+/* ---- multi-GPU: AE sharding of the local spectral stage ---- */
+/// Called after this rank computed AEs [begin, end): must leave the complete set of
+/// per-AE results on the level (sa_gpu_get_spectral / all-gather / sa_gpu_set_spectral).
+typedef void (*sa_spectral_exchange_ft)(sa_gpu_level *level, int begin, int end, int nparts);
+void sa_set_sharding(int rank, int world, sa_spectral_exchange_ft exchange);
+void sa_shard_range(const agg_partitioning_relations_t &rels, int rank, int world, int *begin,
+                    int *end);
+
 /* ---- element-matrix providers ---- */
 class ElementMatrixStandardGeometric : public ElementMatrixProvider
 {
