@@ -198,6 +198,26 @@ int sa_gpu_host_unregister(const void *p);
    thread blocks since the last call (diagnostics) */
 int sa_gpu_debug_phase_clocks(double *out8);
 
+/* ---- device-pointer entry points (row-partitioned multi-GPU solve: the caller owns the
+ *      vectors on the device, e.g. torch tensors, and drives the halo exchange) ----
+ * Device addresses of a level's CSR matrix (valid while the level lives). */
+int sa_gpu_level_dev_csr(sa_gpu_level *level, int which, const int **I, const int **J,
+                         const double **A, int *rows, int *cols, int *nnz);
+int sa_gpu_level_dev_dinv(sa_gpu_level *level, const double **dinv_neg);
+/* Rows [row0, row0+nrows) of a device CSR matrix applied to x (indexed by global column) on
+ * the context's stream.  I_row0 = I + row0; b, dinv, y, xrow are already offset to row0.
+ * mode 0: y = A x, 1: y = b - A x, 2: y += A x,
+ *      3: y = xrow + mult * dinv .* (A x - b)  (one smpr_compute_poly step),
+ *      4: y = mult * dinv .* (-b)              (first step from x = 0) */
+int sa_gpu_dev_spmv(sa_gpu_ctx *ctx, int mode, int nrows, double avg_nnz_per_row,
+                    const int *I_row0, const int *J, const double *A, const double *x,
+                    const double *xrow, const double *b, const double *dinv, double mult,
+                    double *y);
+/* dense exact coarsest solve of a solver on device vectors: x = Ac^-1 b */
+int sa_gpu_solver_dev_coarse(sa_gpu_solver *solver, const double *b, double *x);
+/* polynomial degree, roots (at most cap entries) and coarsest size of a solver */
+int sa_gpu_solver_info(sa_gpu_solver *solver, int *degree, double *roots, int cap, int *nc);
+
 /* ---- micro-benchmarks used by bench.py for the roofline denominators ---- */
 /* runs `reps` SpMVs y = A x on device-resident vectors; returns ms per SpMV */
 double sa_gpu_bench_spmv(sa_gpu_level *level, int which, int reps);

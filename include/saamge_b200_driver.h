@@ -93,6 +93,9 @@ double sa_drv_bench_scalar(void *bench, const char *name);
 int sa_drv_gpu_profile(int enable, char *buf, int buflen);
 /* the process-wide sa_gpu_ctx */
 void *sa_drv_ctx(void);
+/* device handles of a hierarchy built by sa_drv_ml_build (sa_gpu_level*, sa_gpu_solver*) */
+void *sa_drv_ml_gpu_level(void *hier, int level);
+void *sa_drv_ml_gpu_solver(void *hier);
 /* kind 0: SpMV with the finest operator, 1: fused smoother step; ms per call */
 double sa_drv_ml_spmv_bench(void *hier, int kind, int reps);
 

@@ -458,3 +458,40 @@ extern "C" int sa_gpu_host_unregister(const void *p)
     }
     return 0;
 }
+
+/* ---- device-pointer entry points for row-partitioned (multi-GPU) solves ---- */
+
+extern "C" int sa_gpu_level_dev_csr(sa_gpu_level *lev, int which, const int **I, const int **J,
+                                    const double **A, int *rows, int *cols, int *nnz)
+{
+    SA_API_BEGIN
+    DevCsr *M = pick(lev, which);
+    if (!M)
+        SA_FAIL("sa_gpu_level_dev_csr: matrix %d not available", which);
+    *I = M->I.p;
+    *J = M->J.p;
+    *A = M->A.p;
+    *rows = M->rows;
+    *cols = M->cols;
+    *nnz = M->nnz;
+    SA_API_END
+}
+
+extern "C" int sa_gpu_level_dev_dinv(sa_gpu_level *lev, const double **dinv)
+{
+    SA_API_BEGIN
+    if (!lev->have_Dinv)
+        SA_FAIL("sa_gpu_level_dev_dinv: not built");
+    *dinv = lev->Dinv_neg.p;
+    SA_API_END
+}
+
+extern "C" int sa_gpu_dev_spmv(sa_gpu_ctx *ctx, int mode, int nrows, double avg_nnz_per_row,
+                               const int *I_row0, const int *J, const double *A, const double *x,
+                               const double *xrow, const double *b, const double *dinv,
+                               double mult, double *y)
+{
+    SA_API_BEGIN
+    dev_spmv_rows(ctx, mode, nrows, avg_nnz_per_row, I_row0, J, A, x, xrow, b, dinv, mult, y);
+    SA_API_END
+}

@@ -285,6 +285,9 @@ void dev_spmv_add(sa_gpu_ctx *ctx, const DevCsr &A, const double *x, double *y);
 /* xout = xin + mult * dinv_neg .* (A xin - b);  first==1: xin == 0 (skips the SpMV) */
 void dev_smoother_step(sa_gpu_ctx *ctx, const DevCsr &A, const double *dinv_neg, const double *b,
                        const double *xin, double *xout, double mult, int xin_is_zero);
+void dev_spmv_rows(sa_gpu_ctx *ctx, int mode, int nrows, double avg, const int *I_row0,
+                   const int *J, const double *A, const double *x, const double *xrow,
+                   const double *b, const double *dinv, double mult, double *y);
 void dev_exclusive_scan_i32(sa_gpu_ctx *ctx, const int *in, int *out, int n); // out has n+1
 void dev_exclusive_scan_i64(sa_gpu_ctx *ctx, const int64_t *in, int64_t *out, int n);
 

@@ -465,3 +465,21 @@ extern "C" int sa_gpu_solver_download(sa_gpu_solver *S, double *x)
     SA_CUDA(cudaStreamSynchronize(S->ctx->stream));
     SA_API_END
 }
+
+extern "C" int sa_gpu_solver_dev_coarse(sa_gpu_solver *S, const double *b, double *x)
+{
+    SA_API_BEGIN
+    if (S->nc)
+        SA_LAUNCH(S->ctx, k_dense_symv, (S->nc + 7) / 8, 256, 0, S->nc, S->Ainv.p, b, x);
+    SA_API_END
+}
+
+extern "C" int sa_gpu_solver_info(sa_gpu_solver *S, int *degree, double *roots, int cap, int *nc)
+{
+    SA_API_BEGIN
+    *degree = S->degree;
+    for (int i = 0; i < S->degree && i < cap; ++i)
+        roots[i] = S->roots[i];
+    *nc = S->nc;
+    SA_API_END
+}

@@ -125,8 +125,10 @@ template <int TPR, int MODE>
 __global__ void k_spmv(int rows, const int *__restrict__ I, const int *__restrict__ J,
                        const double *__restrict__ A, const double *__restrict__ x,
                        const double *__restrict__ b, const double *__restrict__ dinv, double mult,
-                       double *__restrict__ y)
+                       double *__restrict__ y, const double *__restrict__ xrow)
 {
+    // I, b, dinv, y and xrow are indexed by the LOCAL row (they may point into the middle
+    // of the global arrays: row-partitioned use); x is indexed by the global column
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int row = t / TPR;
     const int sub = t % TPR;
@@ -141,7 +143,7 @@ __global__ void k_spmv(int rows, const int *__restrict__ I, const int *__restric
         if (MODE == 3 || MODE == 4)
             dr = dinv[row];
         if (MODE == 3)
-            xr = x[row];
+            xr = xrow[row];
         if (MODE == 2)
             xr = y[row];
     }
@@ -193,19 +195,19 @@ __global__ void k_spmv(int rows, const int *__restrict__ I, const int *__restric
 }
 
 template <int MODE>
-void launch_spmv(sa_gpu_ctx *ctx, const DevCsr &A, const double *x, const double *b,
-                 const double *dinv, double mult, double *y)
+void launch_spmv_raw(sa_gpu_ctx *ctx, int rows, double avg, const int *I, const int *J,
+                     const double *Aval, const double *x, const double *xrow, const double *b,
+                     const double *dinv, double mult, double *y)
 {
-    if (A.rows == 0)
+    if (rows == 0)
         return;
-    const double avg = (double)A.nnz / std::max(1, A.rows);
     const int tb = 256;
 #define SA_SPMV_CASE(TPR)                                                              \
     {                                                                                  \
-        const long long threads = (long long)A.rows * TPR;                             \
+        const long long threads = (long long)rows * TPR;                               \
         auto kern = k_spmv<TPR, MODE>;                                                 \
-        SA_LAUNCH(ctx, kern, (unsigned)((threads + tb - 1) / tb), tb, 0,               \
-                  A.rows, A.I.p, A.J.p, A.A.p, x, b, dinv, mult, y);                   \
+        SA_LAUNCH(ctx, kern, (unsigned)((threads + tb - 1) / tb), tb, 0, rows, I, J,   \
+                  Aval, x, b, dinv, mult, y, xrow);                                    \
     }
     static int tpr_env = getenv("SA_GPU_SPMV_TPR") ? atoi(getenv("SA_GPU_SPMV_TPR")) : 0;
     if (tpr_env == 2)
@@ -229,6 +231,40 @@ void launch_spmv(sa_gpu_ctx *ctx, const DevCsr &A, const double *x, const double
     else
         SA_SPMV_CASE(32)
 #undef SA_SPMV_CASE
+}
+
+template <int MODE>
+void launch_spmv(sa_gpu_ctx *ctx, const DevCsr &A, const double *x, const double *b,
+                 const double *dinv, double mult, double *y)
+{
+    launch_spmv_raw<MODE>(ctx, A.rows, (double)A.nnz / std::max(1, A.rows), A.I.p, A.J.p, A.A.p,
+                          x, x, b, dinv, mult, y);
+}
+
+/* device-pointer entry: rows [row0, row0 + nrows) of a CSR matrix whose arrays live on the
+   device; I_row0 = I + row0 (absolute offsets), b / dinv / y / xrow already offset */
+void dev_spmv_rows_impl(sa_gpu_ctx *ctx, int mode, int nrows, double avg, const int *I_row0,
+                        const int *J, const double *A, const double *x, const double *xrow,
+                        const double *b, const double *dinv, double mult, double *y)
+{
+    switch (mode)
+    {
+    case 0:
+        launch_spmv_raw<0>(ctx, nrows, avg, I_row0, J, A, x, xrow, b, dinv, mult, y);
+        break;
+    case 1:
+        launch_spmv_raw<1>(ctx, nrows, avg, I_row0, J, A, x, xrow, b, dinv, mult, y);
+        break;
+    case 2:
+        launch_spmv_raw<2>(ctx, nrows, avg, I_row0, J, A, x, xrow, b, dinv, mult, y);
+        break;
+    case 3:
+        launch_spmv_raw<3>(ctx, nrows, avg, I_row0, J, A, x, xrow, b, dinv, mult, y);
+        break;
+    default:
+        launch_spmv_raw<4>(ctx, nrows, avg, I_row0, J, A, x, xrow, b, dinv, mult, y);
+        break;
+    }
 }
 
 /* -------------------------------------------------------------- Dinv_neg */
@@ -451,6 +487,13 @@ __global__ void k_scale_rows_add_identity(int rows, const int *I, const int *J, 
 }
 
 } // namespace
+
+void dev_spmv_rows(sa_gpu_ctx *ctx, int mode, int nrows, double avg, const int *I_row0,
+                   const int *J, const double *A, const double *x, const double *xrow,
+                   const double *b, const double *dinv, double mult, double *y)
+{
+    dev_spmv_rows_impl(ctx, mode, nrows, avg, I_row0, J, A, x, xrow, b, dinv, mult, y);
+}
 
 void dev_exclusive_scan_i32(sa_gpu_ctx *ctx, const int *in, int *out, int n)
 {

@@ -210,3 +210,27 @@ extern "C" double sa_drv_ml_spmv_bench(void *hier, int kind, int reps)
     sa_gpu_level *lev = ml->levels_list.finest->tg_data->gpu;
     return kind == 0 ? sa_gpu_bench_spmv(lev, SA_GPU_MAT_A, reps) : sa_gpu_bench_smoother(lev, reps);
 }
+
+/* device handles of a built hierarchy (for the row-partitioned multi-GPU solve driven from
+   Python: saamge_b200/dist_solve.py) */
+extern "C" void *sa_drv_ml_gpu_level(void *hier, int level)
+{
+    sa_hierarchy_t *H = (sa_hierarchy_t *)hier;
+    struct impl_t
+    {
+        ml_data_t *ml;
+    };
+    ml_data_t *ml = ((impl_t *)H->impl)->ml;
+    levels_level_t *l = levels_list_get_level(ml->levels_list, level);
+    return l ? (void *)l->tg_data->gpu : NULL;
+}
+
+extern "C" void *sa_drv_ml_gpu_solver(void *hier)
+{
+    sa_hierarchy_t *H = (sa_hierarchy_t *)hier;
+    struct impl_t
+    {
+        ml_data_t *ml;
+    };
+    return (void *)((impl_t *)H->impl)->ml->gpu_solver;
+}

@@ -398,6 +398,7 @@ extern "C" double sa_drv_get_scalar(void *obj, const char *name_, int level)
         times = &H->times;
         if (name == "num_levels") return (double)H->rels.size() + 1. - (H->rels.size() > H->levels.size() ? 1. : 0.);
         if (name == "num_coarsenings") return (double)H->levels.size();
+        if (name == "num_rels") return (double)H->rels.size();
         if (name == "pcg.iterations") return H->pcg.iterations;
         if (name == "pcg.final_res_norm") return H->pcg.final_res_norm;
         if (level >= 0 && level < (int)H->rels.size())

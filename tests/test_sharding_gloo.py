@@ -58,3 +58,31 @@ def test_allgather_spectral_world2():
     for pp in procs:
         pp.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_halo_plan_is_consistent():
+    """Every piece a rank plans to receive is planned as a send by its owner and lies in the
+    owner's range; together the pieces cover the needed range outside the own rows."""
+    from saamge_b200.dist_solve import _ranges, halo_plan
+
+    rng = np.random.default_rng(1)
+    for world in (2, 3, 8):
+        n = 1000
+        part = _ranges(n, world)
+        need = []
+        for q in range(world):
+            lo = max(0, part[q] - int(rng.integers(0, 300)))
+            hi = min(n, part[q + 1] + int(rng.integers(0, 300)))
+            need.append((lo, hi))
+        plans = [halo_plan(need, part, q) for q in range(world)]
+        for me in range(world):
+            sends, recvs = plans[me]
+            covered = np.zeros(n, dtype=bool)
+            covered[part[me]:part[me + 1]] = True
+            for q, lo, hi in recvs:
+                assert part[q] <= lo < hi <= part[q + 1]
+                assert (me, lo, hi) in plans[q][0]
+                covered[lo:hi] = True
+            assert covered[need[me][0]:need[me][1]].all()
+            for q, lo, hi in sends:
+                assert (me, lo, hi) in plans[q][1]
