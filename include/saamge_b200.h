@@ -87,12 +87,27 @@ typedef struct
     /* (coarse levels) finer MIS -> first coarse dof, finer num_mises+1 entries;
        needed by sa_gpu_coarse_elmats */
     const int *mis_coarsedofoffsets;
+    /* 1: pipelined upload.  sa_gpu_level_create returns while the large arrays (operator,
+          element blocks) are still being copied, in slabs, on a separate copy stream;
+          sa_gpu_local_spectral starts on the first agglomerates as soon as the slabs they
+          read have arrived.  The caller keeps every host array of this description valid
+          and unmodified until the first call that uses the level returns (or until
+          sa_gpu_level_upload_wait).  Host arrays should be pinned (sa_gpu_host_register);
+          pageable memory works but does not overlap.
+       0: all copies are complete when sa_gpu_level_create returns. */
+    int async_upload;
 } sa_gpu_level_desc;
+
+/* sizeof(sa_gpu_level_desc) as compiled into the library (lets FFI bindings that mirror
+   the struct by hand check their layout). */
+size_t sa_gpu_level_desc_size(void);
 
 /* Copies the description to the device.  \a finer may be NULL (finest level). */
 int sa_gpu_level_create(sa_gpu_ctx *ctx, const sa_gpu_level_desc *desc, sa_gpu_level *finer,
                         sa_gpu_level **level);
 void sa_gpu_level_destroy(sa_gpu_level *level);
+/* Blocks until a pipelined upload (desc.async_upload) has finished; no-op otherwise. */
+int sa_gpu_level_upload_wait(sa_gpu_level *level);
 
 /* ---- setup: local spectral stage ---- */
 

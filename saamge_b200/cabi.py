@@ -30,6 +30,7 @@ class LevelDesc(ctypes.Structure):
         ("elmat", _d), ("elmat_off", _l),
         ("assemble_with_global", ctypes.c_int),
         ("mis_coarsedofoffsets", _i),
+        ("async_upload", ctypes.c_int),
     ]
 
 
@@ -61,7 +62,7 @@ class Context:
 class Level:
     """Finest level built from a saamge_b200.Problem (relations must exist)."""
 
-    def __init__(self, ctx, problem, with_global=True, give_operator=True):
+    def __init__(self, ctx, problem, with_global=True, give_operator=True, async_upload=False):
         self.ctx, self.lib = ctx, ctx.lib
         g = problem.get
         self.keep = {}
@@ -94,6 +95,8 @@ class Level:
         d.elmat = _dp(self.elmat)
         d.elmat_off = self.elmat_off.ctypes.data_as(_l)
         d.assemble_with_global = 1 if with_global else 0
+        # pipelined upload: the numpy arrays in self.keep / self.elmat stay alive with the object
+        d.async_upload = 1 if async_upload else 0
         self.desc = d
         self.nparts, self.ND, self.num_mises = d.nparts, d.ND, d.num_mises
         self.h = ctypes.c_void_p()

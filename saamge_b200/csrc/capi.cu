@@ -1,6 +1,7 @@
 // Context / level lifetime, read-back and micro-benchmark entry points of the C ABI
 // (include/saamge_b200.h).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 
 #include "sa_gpu_internal.cuh"
@@ -19,6 +20,8 @@ void sa_gpu_set_error(const char *fmt, ...)
 
 extern "C" const char *sa_gpu_last_error(void) { return g_err; }
 
+extern "C" size_t sa_gpu_level_desc_size(void) { return sizeof(sa_gpu_level_desc); }
+
 extern "C" int sa_gpu_ctx_create(int device, sa_gpu_ctx **out)
 {
     SA_API_BEGIN
@@ -36,7 +39,15 @@ extern "C" int sa_gpu_ctx_create(int device, sa_gpu_ctx **out)
     SA_CUDA(cudaGetDeviceProperties(&prop, device));
     ctx->num_sms = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    ctx->smem_per_sm = prop.sharedMemPerMultiprocessor;
     SA_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    SA_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    SA_CUDA(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+    for (int i = 0; i < sa_gpu_ctx::NAUX; ++i)
+    {
+        SA_CUDA(cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking));
+        SA_CUDA(cudaEventCreateWithFlags(&ctx->join_ev[i], cudaEventDisableTiming));
+    }
     SA_CUDA(cudaEventCreate(&ctx->ev0));
     SA_CUDA(cudaEventCreate(&ctx->ev1));
     SA_CUDA(cudaEventCreate(&ctx->pev0));
@@ -79,6 +90,17 @@ extern "C" void sa_gpu_ctx_destroy(sa_gpu_ctx *ctx)
         cudaStreamSynchronize(ctx->stream);
         g_sa_alloc_stream = nullptr;
     }
+    if (ctx->copy_stream)
+        cudaStreamDestroy(ctx->copy_stream);
+    for (int i = 0; i < sa_gpu_ctx::NAUX; ++i)
+    {
+        if (ctx->aux[i])
+            cudaStreamDestroy(ctx->aux[i]);
+        if (ctx->join_ev[i])
+            cudaEventDestroy(ctx->join_ev[i]);
+    }
+    if (ctx->fork_ev)
+        cudaEventDestroy(ctx->fork_ev);
     if (ctx->stream)
         cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -138,6 +160,60 @@ static void upload_table(DevBuf<int> &dI, DevBuf<int> &dJ, const int *I, const i
     dJ.upload(J, (size_t)I[rows], st);
 }
 
+void sa_level_wait_slab(sa_gpu_level *lev, int slab)
+{
+    PendingUpload &P = lev->pending;
+    if (!P.active || P.ev.empty())
+        return;
+    slab = std::max(0, std::min(slab, (int)P.ev.size() - 1));
+    SA_CUDA(cudaStreamWaitEvent(lev->ctx->stream, P.ev[slab], 0));
+}
+
+static void level_host_copies_from(sa_gpu_level *L, const sa_gpu_level_desc *d)
+{
+    L->h_mis2d_I.assign(d->mis_to_dof_I, d->mis_to_dof_I + d->num_mises + 1);
+    L->h_mis2AE_I.assign(d->mis_to_AE_I, d->mis_to_AE_I + d->num_mises + 1);
+    L->h_mis2AE_J.assign(d->mis_to_AE_J, d->mis_to_AE_J + d->mis_to_AE_I[d->num_mises]);
+    L->h_e2d_I.assign(d->elem_to_dof_I, d->elem_to_dof_I + d->NE + 1);
+    if (d->elmat)
+        L->h_elmat_off.assign(d->elmat_off, d->elmat_off + d->NE + 1);
+}
+
+void sa_level_host_copies(sa_gpu_level *lev)
+{
+    PendingUpload &P = lev->pending;
+    if (P.host_copies_done)
+        return;
+    level_host_copies_from(lev, &P.desc);
+    P.host_copies_done = true;
+}
+
+void sa_level_ready(sa_gpu_level *lev)
+{
+    PendingUpload &P = lev->pending;
+    sa_level_host_copies(lev);
+    if (!P.active)
+        return;
+    // the host arrays are the caller's again once this returns: block the host, not just
+    // the stream
+    if (!P.ev.empty())
+    {
+        cudaStreamWaitEvent(lev->ctx->stream, P.ev.back(), 0);
+        cudaEventSynchronize(P.ev.back());
+    }
+    for (size_t i = 0; i < P.ev.size(); ++i)
+        cudaEventDestroy(P.ev[i]);
+    P.ev.clear();
+    P.active = false;
+}
+
+extern "C" int sa_gpu_level_upload_wait(sa_gpu_level *lev)
+{
+    SA_API_BEGIN
+    sa_level_ready(lev);
+    SA_API_END
+}
+
 extern "C" int sa_gpu_level_create(sa_gpu_ctx *ctx, const sa_gpu_level_desc *d,
                                    sa_gpu_level *finer, sa_gpu_level **out)
 {
@@ -148,7 +224,14 @@ extern "C" int sa_gpu_level_create(sa_gpu_ctx *ctx, const sa_gpu_level_desc *d,
     struct Guard
     {
         sa_gpu_level *l;
-        ~Guard() { delete l; }
+        ~Guard()
+        {
+            if (l)
+            {
+                sa_level_ready(l);
+                delete l;
+            }
+        }
     } g{L};
     L->ctx = ctx;
     L->finer = finer;
@@ -157,33 +240,16 @@ extern "C" int sa_gpu_level_create(sa_gpu_ctx *ctx, const sa_gpu_level_desc *d,
     L->nparts = d->nparts;
     L->num_mises = d->num_mises;
     L->with_global = d->assemble_with_global;
-    upload_table(L->e2d_I, L->e2d_J, d->elem_to_dof_I, d->elem_to_dof_J, d->NE, st);
-    upload_table(L->d2e_I, L->d2e_J, d->dof_to_elem_I, d->dof_to_elem_J, d->ND, st);
-    upload_table(L->AE2e_I, L->AE2e_J, d->AE_to_elem_I, d->AE_to_elem_J, d->nparts, st);
-    upload_table(L->AE2d_I, L->AE2d_J, d->AE_to_dof_I, d->AE_to_dof_J, d->nparts, st);
-    upload_table(L->d2AE_I, L->d2AE_J, d->dof_to_AE_I, d->dof_to_AE_J, d->ND, st);
-    L->dof_id_inAE.upload(d->dof_id_inAE, (size_t)d->dof_to_AE_I[d->ND], st);
-    L->partitioning.upload(d->partitioning, d->NE, st);
-    L->agg_flags.upload(d->agg_flags, d->ND, st);
-    upload_table(L->mis2d_I, L->mis2d_J, d->mis_to_dof_I, d->mis_to_dof_J, d->num_mises, st);
-    upload_table(L->mis2AE_I, L->mis2AE_J, d->mis_to_AE_I, d->mis_to_AE_J, d->num_mises, st);
-    upload_table(L->AE2mis_I, L->AE2mis_J, d->AE_to_mis_I, d->AE_to_mis_J, d->nparts, st);
-    L->mises.upload(d->mises, d->ND, st);
-    L->h_AE2d_I.assign(d->AE_to_dof_I, d->AE_to_dof_I + d->nparts + 1);
-    L->h_mis2d_I.assign(d->mis_to_dof_I, d->mis_to_dof_I + d->num_mises + 1);
-    L->h_mis2AE_I.assign(d->mis_to_AE_I, d->mis_to_AE_I + d->num_mises + 1);
-    L->h_mis2AE_J.assign(d->mis_to_AE_J, d->mis_to_AE_J + d->mis_to_AE_I[d->num_mises]);
-    L->h_e2d_I.assign(d->elem_to_dof_I, d->elem_to_dof_I + d->NE + 1);
-    if (d->A_I)
-    {
-        L->A_own.rows = L->A_own.cols = d->ND;
-        L->A_own.nnz = d->A_I[d->ND];
-        L->A_own.I.upload(d->A_I, (size_t)d->ND + 1, st);
-        L->A_own.J.upload(d->A_J, L->A_own.nnz, st);
-        L->A_own.A.upload(d->A_data, L->A_own.nnz, st);
-        L->A = &L->A_own;
-    }
-    else
+    const bool dbg = getenv("SA_GPU_PIPE_DEBUG") != NULL;
+    const auto t_in = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (dbg)
+            fprintf(stderr, "[level_create] %s at %.2f ms\n", what,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_in)
+                        .count());
+    };
+    const bool async = d->async_upload != 0 && (d->A_I || d->elmat);
+    if (!d->A_I)
     {
         if (!finer || !finer->have_Ac)
             SA_FAIL("sa_gpu_level_create: no operator given and the finer level has no Ac");
@@ -192,17 +258,146 @@ extern "C" int sa_gpu_level_create(sa_gpu_ctx *ctx, const sa_gpu_level_desc *d,
                     finer->Ac.rows, d->ND);
         L->A = &finer->Ac;
     }
+    else
+    {
+        L->A_own.rows = L->A_own.cols = d->ND;
+        L->A_own.nnz = d->A_I[d->ND];
+        L->A = &L->A_own;
+    }
+    const size_t nnz = d->A_I ? (size_t)d->A_I[d->ND] : 0;
+    const size_t nel = d->elmat ? (size_t)d->elmat_off[d->NE] : 0;
+    L->have_elmat = d->elmat != NULL;
+
+    // every host -> device copy of the level: {device buffer, source, bytes}; the buffers
+    // are allocated first (main-stream order), the copies follow on one stream
+    struct Copy
+    {
+        void *dst;
+        const void *src;
+        size_t bytes;
+    };
+    std::vector<Copy> small, big;
+    auto reg_i = [&](DevBuf<int> &b, const int *src, size_t count, std::vector<Copy> &list) {
+        b.ensure(count);
+        b.n = count;
+        if (count)
+            list.push_back(Copy{b.p, src, count * sizeof(int)});
+    };
+    auto reg_table = [&](DevBuf<int> &dI, DevBuf<int> &dJ, const int *I, const int *J, int rows) {
+        reg_i(dI, I, (size_t)rows + 1, small);
+        reg_i(dJ, J, (size_t)I[rows], small);
+    };
+    reg_table(L->e2d_I, L->e2d_J, d->elem_to_dof_I, d->elem_to_dof_J, d->NE);
+    reg_table(L->d2e_I, L->d2e_J, d->dof_to_elem_I, d->dof_to_elem_J, d->ND);
+    reg_table(L->AE2e_I, L->AE2e_J, d->AE_to_elem_I, d->AE_to_elem_J, d->nparts);
+    reg_table(L->AE2d_I, L->AE2d_J, d->AE_to_dof_I, d->AE_to_dof_J, d->nparts);
+    reg_table(L->d2AE_I, L->d2AE_J, d->dof_to_AE_I, d->dof_to_AE_J, d->ND);
+    reg_i(L->dof_id_inAE, d->dof_id_inAE, (size_t)d->dof_to_AE_I[d->ND], small);
+    reg_i(L->partitioning, d->partitioning, d->NE, small);
+    L->agg_flags.ensure(d->ND);
+    L->agg_flags.n = d->ND;
+    if (d->ND)
+        small.push_back(Copy{L->agg_flags.p, d->agg_flags, (size_t)d->ND});
+    reg_table(L->mis2d_I, L->mis2d_J, d->mis_to_dof_I, d->mis_to_dof_J, d->num_mises);
+    reg_table(L->mis2AE_I, L->mis2AE_J, d->mis_to_AE_I, d->mis_to_AE_J, d->num_mises);
+    reg_table(L->AE2mis_I, L->AE2mis_J, d->AE_to_mis_I, d->AE_to_mis_J, d->nparts);
+    reg_i(L->mises, d->mises, d->ND, small);
+    if (d->A_I)
+    {
+        reg_i(L->A_own.I, d->A_I, (size_t)d->ND + 1, small);
+        reg_i(L->A_own.J, d->A_J, nnz, big);
+        L->A_own.A.ensure(nnz);
+        L->A_own.A.n = nnz;
+        if (nnz)
+            big.push_back(Copy{L->A_own.A.p, d->A_data, nnz * sizeof(double)});
+    }
     if (d->elmat)
     {
-        L->h_elmat_off.assign(d->elmat_off, d->elmat_off + d->NE + 1);
-        L->elmat_off.upload(d->elmat_off, (size_t)d->NE + 1, st);
-        L->elmat.upload(d->elmat, (size_t)d->elmat_off[d->NE], st);
-        L->have_elmat = true;
+        L->elmat_off.ensure((size_t)d->NE + 1);
+        L->elmat_off.n = (size_t)d->NE + 1;
+        small.push_back(Copy{L->elmat_off.p, d->elmat_off, ((size_t)d->NE + 1) * sizeof(int64_t)});
+        L->elmat.ensure(nel);
+        L->elmat.n = nel;
+        if (nel)
+            big.push_back(Copy{L->elmat.p, d->elmat, nel * sizeof(double)});
     }
+    auto issue = [&](const std::vector<Copy> &list, cudaStream_t s) {
+        for (size_t i = 0; i < list.size(); ++i)
+            SA_CUDA(cudaMemcpyAsync(list[i].dst, list[i].src, list[i].bytes, cudaMemcpyHostToDevice,
+                                    s));
+    };
+    if (!async)
+    {
+        issue(small, st);
+        issue(big, st);
+    }
+    else
+    {
+        // Pipelined upload on the copy stream: the tables first, then the operator and the
+        // element blocks in S slabs (equal row / element ranges, interleaved), one event per
+        // slab.  The main stream only waits for the tables; the local spectral stage waits
+        // slab by slab.
+        const int S = 16;
+        cudaStream_t cs = ctx->copy_stream;
+        cudaEvent_t ea; // the buffers were allocated in main-stream order
+        SA_CUDA(cudaEventCreateWithFlags(&ea, cudaEventDisableTiming));
+        SA_CUDA(cudaEventRecord(ea, st));
+        SA_CUDA(cudaStreamWaitEvent(cs, ea, 0));
+        issue(small, cs);
+        SA_CUDA(cudaEventRecord(ea, cs));
+        SA_CUDA(cudaStreamWaitEvent(st, ea, 0));
+        SA_CUDA(cudaEventDestroy(ea));
+        const int rows_per = (d->ND + S - 1) / S, elems_per = (d->NE + S - 1) / S;
+        PendingUpload &P = L->pending;
+        P.active = true;
+        for (int sl = 0; sl < S; ++sl)
+        {
+            if (d->A_I)
+            {
+                const int r0 = std::min(d->ND, sl * rows_per), r1 = std::min(d->ND, r0 + rows_per);
+                const size_t k0 = d->A_I[r0], k1 = d->A_I[r1];
+                if (k1 > k0)
+                {
+                    SA_CUDA(cudaMemcpyAsync(L->A_own.J.p + k0, d->A_J + k0, (k1 - k0) * sizeof(int),
+                                            cudaMemcpyHostToDevice, cs));
+                    SA_CUDA(cudaMemcpyAsync(L->A_own.A.p + k0, d->A_data + k0,
+                                            (k1 - k0) * sizeof(double), cudaMemcpyHostToDevice, cs));
+                }
+            }
+            if (d->elmat)
+            {
+                const int e0 = std::min(d->NE, sl * elems_per), e1 = std::min(d->NE, e0 + elems_per);
+                const size_t k0 = d->elmat_off[e0], k1 = d->elmat_off[e1];
+                if (k1 > k0)
+                    SA_CUDA(cudaMemcpyAsync(L->elmat.p + k0, d->elmat + k0,
+                                            (k1 - k0) * sizeof(double), cudaMemcpyHostToDevice, cs));
+            }
+            cudaEvent_t ev;
+            SA_CUDA(cudaEventCreateWithFlags(&ev, dbg ? cudaEventDefault : cudaEventDisableTiming));
+            P.ev.push_back(ev);
+            SA_CUDA(cudaEventRecord(ev, cs));
+        }
+    }
+    lap("copies issued");
+    // host copies of the small index arrays
+    L->h_AE2d_I.assign(d->AE_to_dof_I, d->AE_to_dof_I + d->nparts + 1);
+    if (async)
+    {
+        PendingUpload &P = L->pending;
+        P.desc = *d;
+        P.host_copies_done = false; // deferred: sa_level_host_copies
+        P.rows_per = std::max(1, (d->ND + (int)P.ev.size() - 1) / (int)P.ev.size());
+        P.elems_per = std::max(1, (d->NE + (int)P.ev.size() - 1) / (int)P.ev.size());
+    }
+    else
+        level_host_copies_from(L, d);
     if (d->mis_coarsedofoffsets && finer)
         L->h_mis_coarsedofoffsets.assign(d->mis_coarsedofoffsets,
                                          d->mis_coarsedofoffsets + finer->num_mises + 1);
-    SA_CUDA(cudaStreamSynchronize(st));
+    // synchronous mode: the host arrays are the caller's again on return
+    if (!async)
+        SA_CUDA(cudaStreamSynchronize(st));
+    lap("return");
     g.l = nullptr;
     *out = L;
     SA_API_END
@@ -213,6 +408,7 @@ extern "C" void sa_gpu_level_destroy(sa_gpu_level *level)
     if (!level)
         return;
     cudaSetDevice(level->ctx->device);
+    sa_level_ready(level);
     delete level;
 }
 
@@ -249,6 +445,7 @@ extern "C" int sa_gpu_get_csr_sizes(sa_gpu_level *lev, int which, int *rows, int
 extern "C" int sa_gpu_get_csr(sa_gpu_level *lev, int which, int *I, int *J, double *data)
 {
     SA_API_BEGIN
+    sa_level_ready(lev);
     DevCsr *M = pick(lev, which);
     if (!M)
         SA_FAIL("sa_gpu_get_csr: matrix %d not available", which);
@@ -276,6 +473,7 @@ extern "C" int sa_gpu_get_Dinv_neg(sa_gpu_level *lev, double *dinv_neg)
 extern "C" int sa_gpu_spmv(sa_gpu_level *lev, int which, const double *x, double *y)
 {
     SA_API_BEGIN
+    sa_level_ready(lev);
     DevCsr *M = pick(lev, which);
     if (!M)
         SA_FAIL("sa_gpu_spmv: matrix %d not available", which);
@@ -292,6 +490,7 @@ extern "C" int sa_gpu_poly_smooth(sa_gpu_level *lev, const double *b, double *x,
                                   const double *roots)
 {
     SA_API_BEGIN
+    sa_level_ready(lev);
     if (!lev->have_Dinv)
         SA_FAIL("sa_gpu_poly_smooth: sa_gpu_build_Dinv_neg has not been called");
     cudaStream_t st = lev->ctx->stream;
@@ -321,6 +520,7 @@ __global__ void k_fill(double *x, int n, double v)
 
 extern "C" double sa_gpu_bench_spmv(sa_gpu_level *lev, int which, int reps)
 {
+    sa_level_ready(lev);
     try
     {
         DevCsr *M = pick(lev, which);
@@ -349,6 +549,7 @@ extern "C" double sa_gpu_bench_spmv(sa_gpu_level *lev, int which, int reps)
 
 extern "C" double sa_gpu_bench_smoother(sa_gpu_level *lev, int reps)
 {
+    sa_level_ready(lev);
     try
     {
         if (!lev->have_Dinv || !lev->A)
@@ -465,6 +666,7 @@ extern "C" int sa_gpu_level_dev_csr(sa_gpu_level *lev, int which, const int **I,
                                     const double **A, int *rows, int *cols, int *nnz)
 {
     SA_API_BEGIN
+    sa_level_ready(lev);
     DevCsr *M = pick(lev, which);
     if (!M)
         SA_FAIL("sa_gpu_level_dev_csr: matrix %d not available", which);
@@ -480,6 +682,7 @@ extern "C" int sa_gpu_level_dev_csr(sa_gpu_level *lev, int which, const int **I,
 extern "C" int sa_gpu_level_dev_dinv(sa_gpu_level *lev, const double **dinv)
 {
     SA_API_BEGIN
+    sa_level_ready(lev);
     if (!lev->have_Dinv)
         SA_FAIL("sa_gpu_level_dev_dinv: not built");
     *dinv = lev->Dinv_neg.p;

@@ -894,6 +894,43 @@ LevelTables sa_gpu_level::tables() const
     return T;
 }
 
+__global__ void k_stage_copy(int *dst, const int *src, size_t nwords)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords;
+         i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
+/* host array -> device buffer through the pinned staging area (see HostStage); the caller
+   resets stage.used only after a synchronisation of the main stream */
+template <class T>
+static void staged_upload(sa_gpu_ctx *ctx, HostStage &hs, DevBuf<T> &dst, const T *src, size_t count)
+{
+    static_assert(sizeof(T) % 4 == 0, "word copies");
+    dst.ensure(count);
+    dst.n = count;
+    if (!count)
+        return;
+    const size_t bytes = (count * sizeof(T) + 15) & ~(size_t)15;
+    if (hs.used + bytes > hs.cap)
+    {
+        // pending staged copies read the old area
+        SA_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (hs.p)
+            SA_CUDA(cudaFreeHost(hs.p));
+        hs.p = nullptr;
+        hs.cap = std::max<size_t>(2 * (hs.used + bytes), (size_t)1 << 20);
+        hs.used = 0;
+        SA_CUDA(cudaMallocHost((void **)&hs.p, hs.cap));
+    }
+    char *h = hs.p + hs.used;
+    hs.used += bytes;
+    std::memcpy(h, src, count * sizeof(T));
+    const size_t nwords = count * sizeof(T) / 4;
+    const int blocks = (int)std::min<size_t>((nwords + 255) / 256, (size_t)ctx->num_sms * 4);
+    SA_LAUNCH(ctx, k_stage_copy, blocks, 256, 0, (int *)dst.p, (const int *)h, nwords);
+}
+
 extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_begin, int ae_end,
                                      int inject_ones_ae0)
 {
@@ -962,12 +999,74 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         }
     } guard{pieces};
 
+    // Pipelined upload (desc.async_upload): split the range into pieces of consecutive AEs;
+    // a piece starts as soon as the slabs its AEs read are on the device.  Worth it only
+    // when the first piece does not already need (nearly) everything.
+    // Pieces grow (1/8, 3/8, 1/2 of the range): a small first piece starts early, later
+    // ones are large enough to keep the per-piece overhead (launch tails, two host
+    // synchronisations) small while their slabs arrive behind the running piece.
+    std::vector<int> piece_ends; // ascending, last == ae_end
+    if (lev->pending.active && ae_end - ae_begin >= 64)
+    {
+        const int len = ae_end - ae_begin;
+        const int e0 = ae_begin + len / 8, e1 = ae_begin + len / 2;
+        if (lev->pending.need(ae_begin, e0) + 2 < (int)lev->pending.ev.size())
+        {
+            piece_ends.push_back(e0);
+            piece_ends.push_back(e1);
+        }
+    }
+    piece_ends.push_back(ae_end);
+
+    // Size the cached work arrays for the largest piece up front: growing them piece by
+    // piece would make the stream-ordered allocator map new memory in the middle of the
+    // pipeline (and leave odd-sized holes behind for the next call).
+    int range_nmax = 1;
+    for (int i = ae_begin; i < ae_end; ++i)
+        range_nmax = std::max(range_nmax, AI[i + 1] - AI[i]);
+    if (piece_ends.size() > 1)
+    {
+        size_t max_v = 0, max_d = 0, max_ns = 0;
+        for (size_t pi = 0; pi < piece_ends.size(); ++pi)
+        {
+            const int b0 = pi ? piece_ends[pi - 1] : ae_begin, b1 = piece_ends[pi];
+            size_t v = 0;
+            for (int i = b0; i < b1; ++i)
+                v += vsize((size_t)(AI[i + 1] - AI[i]));
+            max_v = std::max(max_v, std::min(v, budget_doubles));
+            max_d = std::max(max_d, (size_t)(AI[b1] - AI[b0]));
+            max_ns = std::max(max_ns, (size_t)(b1 - b0));
+        }
+        SpectralWs &WS = lev->sws;
+        WS.V.ensure(max_v);
+        WS.d.ensure(max_d);
+        WS.e.ensure(max_d);
+        WS.tau.ensure(max_d);
+        WS.sinv.ensure(max_d);
+        WS.ae.ensure(max_ns);
+        WS.doff.ensure(max_ns);
+        WS.voff.ensure(max_ns);
+        WS.status.ensure(max_ns);
+        WS.order.ensure(max_ns);
+        WS.nev.ensure(max_ns);
+        WS.mtot.ensure(max_ns);
+        WS.glo.ensure(max_ns);
+        WS.ghi.ensure(max_ns);
+        WS.tn.ensure(max_ns);
+        WS.eval_off.ensure(max_ns + 1);
+        WS.evect_off.ensure(max_ns + 1);
+    }
+
+    const bool pipe_debug = getenv("SA_GPU_PIPE_DEBUG") != NULL && lev->pending.active;
+    std::vector<cudaEvent_t> dbg_ev;
+    std::vector<int> dbg_need;
     int a0 = ae_begin;
     while (a0 < ae_end)
     {
         size_t vtot = 0;
         int a1 = a0;
-        while (a1 < ae_end)
+        const int piece_end = *std::upper_bound(piece_ends.begin(), piece_ends.end(), a0);
+        while (a1 < piece_end)
         {
             const size_t n = AI[a1 + 1] - AI[a1];
             if (a1 > a0 && vtot + vsize(n) > budget_doubles)
@@ -996,9 +1095,10 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         DevBuf<int> &d_ae = WS.ae, &d_doff = WS.doff, &d_status = WS.status;
         DevBuf<int64_t> &d_voff = WS.voff;
         DevBuf<double> &d_V = WS.V, &d_d = WS.d, &d_e = WS.e, &d_tau = WS.tau, &d_sinv = WS.sinv;
-        d_ae.upload(h_ae.data(), ns, st);
-        d_doff.upload(h_doff.data(), ns, st);
-        d_voff.upload(h_voff.data(), ns, st);
+        ctx->stage.used = 0; // the previous chunk ended with a stream synchronisation
+        staged_upload(ctx, ctx->stage, d_ae, h_ae.data(), ns);
+        staged_upload(ctx, ctx->stage, d_doff, h_doff.data(), ns);
+        staged_upload(ctx, ctx->stage, d_voff, h_voff.data(), ns);
         d_status.ensure(ns);
         SA_CUDA(cudaMemsetAsync(d_status.p, 0, (size_t)ns * sizeof(int), st));
         d_V.ensure(vo);
@@ -1025,10 +1125,43 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
             return (AI[a0 + x + 1] - AI[a0 + x]) > (AI[a0 + y + 1] - AI[a0 + y]);
         });
         DevBuf<int> &d_order = WS.order;
-        d_order.upload(order.data(), ns, st);
+        staged_upload(ctx, ctx->stage, d_order, order.data(), ns);
+        if (lev->pending.active)
+        {
+            const int need = lev->pending.need(a0, a1);
+            if (pipe_debug)
+            {
+                cudaEvent_t e;
+                cudaEventCreate(&e);
+                cudaEventRecord(e, st);
+                dbg_ev.push_back(e);
+                dbg_need.push_back(need);
+            }
+            sa_level_wait_slab(lev, need);
+            if (pipe_debug)
+            {
+                cudaEvent_t e;
+                cudaEventCreate(&e);
+                cudaEventRecord(e, st);
+                dbg_ev.push_back(e);
+            }
+        }
         ProfScope *pa = new ProfScope(ctx, "eig.assemble_tridiag");
-        const int bucket_edges[] = {32,  48,  64,  80,  96,  104, 112, 120, 128, 136,
-                                    144, 152, 160, 176, 192, 208, 224, nmax_smem};
+        // one launch per occupancy class: the packed tile of the class's largest n decides
+        // how many blocks are resident per SM (3, 2 or 1; the launch bounds cap it at 3), so
+        // finer size classes would only add launch tails
+        std::vector<int> bucket_edges;
+        for (int c = 3; c >= 1; --c)
+        {
+            const size_t cap = (ctx->smem_per_sm / c - 1024) / sizeof(double);
+            int n = 1;
+            while (n < nmax_smem && packed_smem_doubles((size_t)n + 1) <= cap)
+                ++n;
+            if (bucket_edges.empty() || n > bucket_edges.back())
+                bucket_edges.push_back(n);
+        }
+        if (bucket_edges.back() < nmax_smem)
+            bucket_edges.push_back(nmax_smem);
         int pos = 0;
         // large (global-memory tile) bucket first
         {
@@ -1104,7 +1237,12 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
                 pos += cnt;
             }
         }
-        for (int b = (int)(sizeof(bucket_edges) / sizeof(int)) - 1; b >= 0 && pos < ns; --b)
+        // the occupancy classes are independent: one side stream each (fork / join on the
+        // main stream), so a class with few blocks does not leave the GPU idle
+        SA_CUDA(cudaEventRecord(ctx->fork_ev, st));
+        bool used_aux[sa_gpu_ctx::NAUX] = {false, false, false};
+        int nlaunch = 0;
+        for (int b = (int)bucket_edges.size() - 1; b >= 0 && pos < ns; --b)
         {
             const int lo_edge = (b == 0) ? 0 : std::min(bucket_edges[b - 1], nmax_smem);
             int cnt = 0;
@@ -1113,6 +1251,13 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
             if (!cnt)
                 continue;
             const int nb = AI[a0 + order[pos] + 1] - AI[a0 + order[pos]];
+            const int ai = nlaunch++ % sa_gpu_ctx::NAUX;
+            cudaStream_t sb = ctx->aux[ai];
+            if (!used_aux[ai])
+            {
+                SA_CUDA(cudaStreamWaitEvent(sb, ctx->fork_ev, 0));
+                used_aux[ai] = true;
+            }
             if (use_square)
             {
                 static int thr_env =
@@ -1123,7 +1268,7 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
                 SA_CUDA(cudaFuncSetAttribute(k_at_smem,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)ctx->smem_optin));
-                SA_LAUNCH(ctx, k_at_smem, cnt, threads, smem, L, C, d_order.p + pos, lev->ae_D.p);
+                k_at_smem<<<cnt, threads, smem, sb>>>(L, C, d_order.p + pos, lev->ae_D.p);
             }
             else
             {
@@ -1131,12 +1276,22 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
                 SA_CUDA(cudaFuncSetAttribute(k_at_packed,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)ctx->smem_optin - 1024));
-                SA_LAUNCH(ctx, k_at_packed, cnt, 256, smem, L, C, d_order.p + pos, lev->ae_D.p);
+                k_at_packed<<<cnt, 256, smem, sb>>>(L, C, d_order.p + pos, lev->ae_D.p);
             }
+            ctx->launches++;
+            SA_CUDA(cudaGetLastError());
             pos += cnt;
         }
+        for (int i = 0; i < sa_gpu_ctx::NAUX; ++i)
+            if (used_aux[i])
+            {
+                SA_CUDA(cudaEventRecord(ctx->join_ev[i], ctx->aux[i]));
+                SA_CUDA(cudaStreamWaitEvent(st, ctx->join_ev[i], 0));
+            }
 
         delete pa;
+        if (a1 == ae_end)
+            sa_level_host_copies(lev); // deferred host work, hidden behind the longest queue
         // counts
         DevBuf<int> &d_nev = WS.nev, &d_mtot = WS.mtot;
         DevBuf<double> &d_glo = WS.glo, &d_ghi = WS.ghi, &d_tn = WS.tn;
@@ -1183,10 +1338,10 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         const int nev_total = (int)pr->eval_off[ns];
         DevBuf<int> &d_ev_slot = WS.ev_slot, &d_ev_idx = WS.ev_idx;
         DevBuf<int64_t> &d_eval_off = WS.eval_off, &d_evect_off = WS.evect_off;
-        d_ev_slot.upload(ev_slot.data(), nev_total, st);
-        d_ev_idx.upload(ev_idx.data(), nev_total, st);
-        d_eval_off.upload(pr->eval_off.data(), ns + 1, st);
-        d_evect_off.upload(pr->evect_off.data(), ns + 1, st);
+        staged_upload(ctx, ctx->stage, d_ev_slot, ev_slot.data(), nev_total);
+        staged_upload(ctx, ctx->stage, d_ev_idx, ev_idx.data(), nev_total);
+        staged_upload(ctx, ctx->stage, d_eval_off, pr->eval_off.data(), ns + 1);
+        staged_upload(ctx, ctx->stage, d_evect_off, pr->evect_off.data(), ns + 1);
         pr->evals.alloc(nev_total);
         pr->evects.alloc(pr->evect_off[ns]);
         {
@@ -1198,6 +1353,7 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         // inverse iteration
         {
             // resident warps bounded by workspace: 4 double + 1 int arrays of 32*nmax
+            nmax = range_nmax; // one workspace size for all chunks of the call
             const size_t per_warp = (size_t)32 * nmax * (4 * sizeof(double) + sizeof(int));
             size_t warps = std::min<size_t>((size_t)ctx->num_sms * 16, (size_t)ns);
             const size_t ws_budget = (size_t)4 << 30;
@@ -1224,6 +1380,37 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         a0 = a1;
     }
 
+    if (pipe_debug && !dbg_ev.empty())
+    {
+        // timeline relative to the first piece reaching its wait: slab arrival, piece
+        // (queued, released) times
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        cudaEventSynchronize(e);
+        cudaEventSynchronize(lev->pending.ev.back());
+        float ms;
+        fprintf(stderr, "[pipe] slabs:");
+        for (size_t i = 0; i < lev->pending.ev.size(); ++i)
+        {
+            cudaEventElapsedTime(&ms, dbg_ev[0], lev->pending.ev[i]);
+            fprintf(stderr, " %.1f", ms);
+        }
+        fprintf(stderr, "\n[pipe] pieces (need: queued released):");
+        for (size_t i = 0; i + 1 < dbg_ev.size(); i += 2)
+        {
+            float m0, m1;
+            cudaEventElapsedTime(&m0, dbg_ev[0], dbg_ev[i]);
+            cudaEventElapsedTime(&m1, dbg_ev[0], dbg_ev[i + 1]);
+            fprintf(stderr, " %d: %.1f %.1f;", dbg_need[i / 2], m0, m1);
+        }
+        cudaEventElapsedTime(&ms, dbg_ev[0], e);
+        fprintf(stderr, "\n[pipe] end %.1f\n", ms);
+        for (size_t i = 0; i < dbg_ev.size(); ++i)
+            cudaEventDestroy(dbg_ev[i]);
+        cudaEventDestroy(e);
+    }
+    sa_level_ready(lev); // a pipelined upload is complete from here on
     // merge the pieces into the level's flat arrays (range [ae_begin, ae_end) only)
     for (size_t p = 0; p < pieces.size(); ++p)
         for (int s = 0; s < pieces[p]->a1 - pieces[p]->a0; ++s)
@@ -1361,6 +1548,7 @@ extern "C" int sa_gpu_set_spectral(sa_gpu_level *lev, int ae_begin, int ae_end, 
 extern "C" int sa_gpu_build_AE_stiff(sa_gpu_level *lev, int part, double *dense_out)
 {
     SA_API_BEGIN
+    sa_level_ready(lev);
     if (part < 0 || part >= lev->nparts)
         SA_FAIL("sa_gpu_build_AE_stiff: bad AE index %d", part);
     if (!lev->have_elmat)

@@ -159,22 +159,24 @@ k_tridiag_coop(LevelTables L, ChunkDev C, const CoopMatrix *mats, int G)
                     const double vi = v[i], wi = w[i];
                     double *Tp = T + i + (int64_t)n * j0;
                     int j = j0;
+                    const int64_t ln = n;
                     if (pending)
                     {
-                        for (; j + 4 <= j1; j += 4, Tp += 4 * (int64_t)n)
+                        for (; j + 8 <= j1; j += 8, Tp += 8 * ln)
                         {
-                            double t0 = Tp[0], t1 = Tp[n], t2 = Tp[2 * (int64_t)n], t3 = Tp[3 * (int64_t)n];
-                            t0 -= vi * w[j] + wi * v[j];
-                            t1 -= vi * w[j + 1] + wi * v[j + 1];
-                            t2 -= vi * w[j + 2] + wi * v[j + 2];
-                            t3 -= vi * w[j + 3] + wi * v[j + 3];
-                            Tp[0] = t0;
-                            Tp[n] = t1;
-                            Tp[2 * (int64_t)n] = t2;
-                            Tp[3 * (int64_t)n] = t3;
-                            acc += t0 * vn[j] + t1 * vn[j + 1] + t2 * vn[j + 2] + t3 * vn[j + 3];
+                            double t[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u)
+                                t[u] = Tp[u * ln];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u)
+                            {
+                                t[u] -= vi * w[j + u] + wi * v[j + u];
+                                Tp[u * ln] = t[u];
+                                acc += t[u] * vn[j + u];
+                            }
                         }
-                        for (; j < j1; ++j, Tp += n)
+                        for (; j < j1; ++j, Tp += ln)
                         {
                             const double t0 = Tp[0] - (vi * w[j] + wi * v[j]);
                             Tp[0] = t0;
@@ -183,10 +185,17 @@ k_tridiag_coop(LevelTables L, ChunkDev C, const CoopMatrix *mats, int G)
                     }
                     else
                     {
-                        for (; j + 4 <= j1; j += 4, Tp += 4 * (int64_t)n)
-                            acc += Tp[0] * vn[j] + Tp[n] * vn[j + 1] + Tp[2 * (int64_t)n] * vn[j + 2] +
-                                   Tp[3 * (int64_t)n] * vn[j + 3];
-                        for (; j < j1; ++j, Tp += n)
+                        for (; j + 8 <= j1; j += 8, Tp += 8 * ln)
+                        {
+                            double t[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u)
+                                t[u] = Tp[u * ln];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u)
+                                acc += t[u] * vn[j + u];
+                        }
+                        for (; j < j1; ++j, Tp += ln)
                             acc += Tp[0] * vn[j];
                     }
                 }

@@ -54,7 +54,8 @@ extern bool g_sa_alloc_async;
 template <class T> struct DevBuf
 {
     T *p = nullptr;
-    size_t n = 0;
+    size_t n = 0;   // elements in use
+    size_t cap = 0; // elements allocated (grow-only until release)
     DevBuf() {}
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
@@ -71,11 +72,13 @@ template <class T> struct DevBuf
         }
         p = nullptr;
         n = 0;
+        cap = 0;
     }
     void alloc(size_t count)
     {
         release();
         n = count;
+        cap = count;
         if (g_sa_alloc_async)
         {
             SA_CUDA(cudaMallocAsync((void **)&p, (count ? count : 1) * sizeof(T),
@@ -90,8 +93,10 @@ template <class T> struct DevBuf
     }
     void ensure(size_t count)
     {
-        if (count > n || !p)
+        if (count > cap || !p)
             alloc(count);
+        else if (count > n)
+            n = count;
     }
     void upload(const T *h, size_t count, cudaStream_t s)
     {
@@ -114,6 +119,7 @@ template <class T> struct DevBuf
     {
         std::swap(p, o.p);
         std::swap(n, o.n);
+        std::swap(cap, o.cap);
         std::swap(async_owned, o.async_owned);
     }
 };
@@ -134,12 +140,37 @@ struct DevCsr
     }
 };
 
+/* Pinned, device-visible host staging area for the small per-chunk index arrays of the
+   local spectral stage.  A kernel on the main stream pulls the data over PCIe, so these
+   uploads do not queue behind a pipelined bulk upload in the copy engine's FIFO. */
+struct HostStage
+{
+    char *p = nullptr;
+    size_t cap = 0, used = 0;
+    HostStage() {}
+    HostStage(const HostStage &) = delete;
+    HostStage &operator=(const HostStage &) = delete;
+    ~HostStage()
+    {
+        if (p)
+            cudaFreeHost(p);
+    }
+};
+
 struct sa_gpu_ctx
 {
     int device = 0;
     int num_sms = 148;
     size_t smem_optin = 0;
+    size_t smem_per_sm = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr; // pipelined uploads (desc.async_upload)
+    // side streams + fork/join events: independent launches of one stage (the occupancy
+    // classes of the eigen stage) run side by side so their tails overlap
+    static const int NAUX = 3;
+    HostStage stage; // see HostStage
+    cudaStream_t aux[NAUX] = {nullptr, nullptr, nullptr};
+    cudaEvent_t fork_ev = nullptr, join_ev[NAUX] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t launches = 0;
     // optional per-stage device timing (SA_GPU_PROFILE=1): name -> accumulated ms
@@ -222,8 +253,41 @@ struct SpectralWs
     DevBuf<char> coopmats;
 };
 
+/* pipelined upload of a level: the operator and the element blocks travel in slabs on the
+   context's copy stream; slab s is complete when ev[s] has fired.  ae_need[i] is the first
+   slab index after which every row / element block AE i reads is on the device. */
+struct PendingUpload
+{
+    bool active = false;
+    std::vector<cudaEvent_t> ev;
+    // the caller keeps the host arrays valid while the upload is pending (API contract), so
+    // the level's host-side copies of the index arrays are deferred until the GPU is busy
+    sa_gpu_level_desc desc;
+    bool host_copies_done = true;
+    int rows_per = 1, elems_per = 1;
+    /* first slab after which everything AEs [a0, a1) read is on the device */
+    int need(int a0, int a1) const
+    {
+        int me = -1, md = -1;
+        if (desc.elmat)
+            for (int k = desc.AE_to_elem_I[a0]; k < desc.AE_to_elem_I[a1]; ++k)
+                me = me > desc.AE_to_elem_J[k] ? me : desc.AE_to_elem_J[k];
+        if (desc.A_I)
+            for (int k = desc.AE_to_dof_I[a0]; k < desc.AE_to_dof_I[a1]; ++k)
+                md = md > desc.AE_to_dof_J[k] ? md : desc.AE_to_dof_J[k];
+        int s = 0;
+        if (me >= 0)
+            s = me / elems_per;
+        if (md >= 0 && md / rows_per > s)
+            s = md / rows_per;
+        const int S = (int)ev.size();
+        return s < S - 1 ? s : S - 1;
+    }
+};
+
 struct sa_gpu_level
 {
+    PendingUpload pending;
     sa_gpu_ctx *ctx = nullptr;
     sa_gpu_level *finer = nullptr;
     int ND = 0, NE = 0, nparts = 0, num_mises = 0;
@@ -273,6 +337,13 @@ struct sa_gpu_level
 
     LevelTables tables() const;
 };
+
+/* capi.cu: make the context's stream wait for a pending pipelined upload (all of it) */
+void sa_level_ready(sa_gpu_level *lev);
+/* ... or only for slabs [0, slab] (used by the local spectral stage between AE pieces) */
+void sa_level_wait_slab(sa_gpu_level *lev, int slab);
+/* deferred host-side copies of a pipelined level (no-op when done) */
+void sa_level_host_copies(sa_gpu_level *lev);
 
 /* ---- sparse.cu ---- */
 void dev_csr_transpose(sa_gpu_ctx *ctx, const DevCsr &A, DevCsr &At);

@@ -253,6 +253,8 @@ extern "C" int sa_gpu_solver_create(sa_gpu_ctx *ctx, sa_gpu_level **levels, int 
     SA_API_BEGIN
     if (nlevels < 1 || nu_relax < 1)
         SA_FAIL("sa_gpu_solver_create: bad arguments");
+    for (int l = 0; l < nlevels; ++l)
+        sa_level_ready(levels[l]);
     sa_gpu_solver *S = new sa_gpu_solver;
     S->ctx = ctx;
     struct Guard

@@ -710,6 +710,7 @@ void dev_spgemm(sa_gpu_ctx *ctx, const DevCsr &A, const DevCsr &B, DevCsr &C)
 extern "C" int sa_gpu_build_Dinv_neg(sa_gpu_level *lev)
 {
     SA_API_BEGIN
+    sa_level_ready(lev);
     sa_gpu_ctx *ctx = lev->ctx;
     if (!lev->A)
         SA_FAIL("sa_gpu_build_Dinv_neg: level has no operator");
@@ -738,6 +739,7 @@ extern "C" int sa_gpu_build_Dinv_neg(sa_gpu_level *lev)
 extern "C" int sa_gpu_smooth_P(sa_gpu_level *lev, int degree, const double *roots)
 {
     SA_API_BEGIN
+    sa_level_ready(lev);
     sa_gpu_ctx *ctx = lev->ctx;
     cudaStream_t st = ctx->stream;
     if (!lev->have_tent)
@@ -790,6 +792,7 @@ extern "C" int sa_gpu_smooth_P(sa_gpu_level *lev, int degree, const double *root
 extern "C" int sa_gpu_rap(sa_gpu_level *lev)
 {
     SA_API_BEGIN
+    sa_level_ready(lev);
     sa_gpu_ctx *ctx = lev->ctx;
     if (!lev->have_P)
         SA_FAIL("sa_gpu_rap: no prolongator (call sa_gpu_smooth_P)");

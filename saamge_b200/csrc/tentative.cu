@@ -364,6 +364,7 @@ extern "C" int sa_gpu_tentative_P(sa_gpu_level *lev, int avoid_ess_bdr_dofs,
                                   int *mis_numcoarsedof, int *NDc_out)
 {
     SA_API_BEGIN
+    sa_level_ready(lev);
     sa_gpu_ctx *ctx = lev->ctx;
     cudaStream_t st = ctx->stream;
     if (!lev->have_spectral)
@@ -466,6 +467,7 @@ extern "C" int sa_gpu_get_mis_tent(sa_gpu_level *lev, double *mis_tent)
 extern "C" int sa_gpu_coarse_elmats(sa_gpu_level *finer, sa_gpu_level *coarse)
 {
     SA_API_BEGIN
+    sa_level_ready(finer);
     sa_gpu_ctx *ctx = finer->ctx;
     cudaStream_t st = ctx->stream;
     if (!finer->have_tent)

@@ -2,7 +2,9 @@
 // C ABI, either with inputs already resident on the device ("value") or end to end
 // from host buffers with the H2D / D2H copies inside the timed region ("e2e").
 // Used by bench.py only; see include/saamge_b200_driver.h.
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -29,7 +31,19 @@ struct sa_bench_t
     std::vector<double> evals, evects;
     double h2d_bytes = 0., d2h_bytes = 0.;
     bool pinned = false;
+    std::vector<const void *> registered;
+    double e2e_phase_ms[3] = {0., 0., 0.}; // upload, compute, read back (last mode-1 step)
 };
+
+static bool pin(sa_bench_t *B, const void *p, size_t bytes)
+{
+    if (!p || bytes == 0)
+        return true;
+    if (sa_gpu_host_register(p, bytes) != 0)
+        return false;
+    B->registered.push_back(p);
+    return true;
+}
 
 static double desc_bytes(const sa_gpu_level_desc &d)
 {
@@ -98,9 +112,27 @@ extern "C" void *sa_drv_bench_create(void *prob_, const sa_drv_params_t *p, int 
     d.assemble_with_global = 1;
     B->h2d_bytes = desc_bytes(d);
     // pin the large host arrays so the e2e copies run at full PCIe speed
-    B->pinned = 0 == sa_gpu_host_register(f.elmat.data(), f.elmat.size() * sizeof(double));
-    sa_gpu_host_register(f.A.GetData(), f.A.A.size() * sizeof(double));
-    sa_gpu_host_register(f.A.GetJ(), f.A.J.size() * sizeof(int));
+    // (every array the level upload reads: element blocks, operator, relation tables)
+    bool ok = pin(B, f.elmat.data(), f.elmat.size() * sizeof(double));
+    ok = pin(B, f.A.GetData(), f.A.A.size() * sizeof(double)) && ok;
+    ok = pin(B, f.A.GetJ(), f.A.J.size() * sizeof(int)) && ok;
+    ok = pin(B, f.A.GetI(), ((size_t)d.ND + 1) * sizeof(int)) && ok;
+    ok = pin(B, B->offsets.data(), B->offsets.size() * sizeof(int64_t)) && ok;
+    const struct { const int *I, *J; int n; } tabs[] = {
+        {d.elem_to_dof_I, d.elem_to_dof_J, d.NE},   {d.dof_to_elem_I, d.dof_to_elem_J, d.ND},
+        {d.AE_to_elem_I, d.AE_to_elem_J, d.nparts}, {d.AE_to_dof_I, d.AE_to_dof_J, d.nparts},
+        {d.dof_to_AE_I, d.dof_to_AE_J, d.ND},       {d.mis_to_dof_I, d.mis_to_dof_J, d.num_mises},
+        {d.mis_to_AE_I, d.mis_to_AE_J, d.num_mises}, {d.AE_to_mis_I, d.AE_to_mis_J, d.nparts}};
+    for (const auto &t : tabs)
+    {
+        ok = pin(B, t.I, ((size_t)t.n + 1) * sizeof(int)) && ok;
+        ok = pin(B, t.J, (size_t)t.I[t.n] * sizeof(int)) && ok;
+    }
+    ok = pin(B, d.dof_id_inAE, (size_t)d.dof_to_AE_I[d.ND] * sizeof(int)) && ok;
+    ok = pin(B, d.partitioning, (size_t)d.NE * sizeof(int)) && ok;
+    ok = pin(B, d.agg_flags, (size_t)d.ND) && ok;
+    ok = pin(B, d.mises, (size_t)d.ND * sizeof(int)) && ok;
+    B->pinned = ok;
     sa_gpu_check(sa_gpu_level_create(B->ctx, &d, NULL, &B->lev), "sa_gpu_level_create");
     B->ae_m.resize(r.nparts);
     return B;
@@ -111,10 +143,8 @@ extern "C" void sa_drv_bench_destroy(void *b_)
     sa_bench_t *B = (sa_bench_t *)b_;
     if (!B)
         return;
-    const fem_problem_t &f = *B->prob->fem;
-    sa_gpu_host_unregister(f.elmat.data());
-    sa_gpu_host_unregister(f.A.GetData());
-    sa_gpu_host_unregister(f.A.GetJ());
+    for (const void *p : B->registered)
+        sa_gpu_host_unregister(p);
     sa_gpu_level_destroy(B->lev);
     delete B;
 }
@@ -132,10 +162,35 @@ extern "C" double sa_drv_bench_step(void *b_, int mode, int ae_begin, int ae_end
                      "sa_gpu_local_spectral");
         return sa_gpu_ctx_timer(B->ctx, 0);
     }
+    // SA_BENCH_BREAKDOWN=1 synchronises between the three phases to time them separately
+    // (diagnostic only: it removes the overlap the normal path has)
+    static const bool breakdown = getenv("SA_BENCH_BREAKDOWN") != NULL;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [&](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double, std::milli>(now() - t0).count();
+    };
     sa_gpu_ctx_timer(B->ctx, 1);
+    auto t0 = now();
     sa_gpu_level *lev = NULL;
-    sa_gpu_check(sa_gpu_level_create(B->ctx, &B->desc, NULL, &lev), "sa_gpu_level_create");
+    // pipelined upload: the eigen stage starts on the first AEs while the rest of the
+    // operator / element blocks is still in flight (SA_BENCH_SYNC_UPLOAD=1 turns it off)
+    static const bool sync_upload = getenv("SA_BENCH_SYNC_UPLOAD") != NULL;
+    sa_gpu_level_desc desc = B->desc;
+    desc.async_upload = (breakdown || sync_upload) ? 0 : 1;
+    sa_gpu_check(sa_gpu_level_create(B->ctx, &desc, NULL, &lev), "sa_gpu_level_create");
+    if (breakdown)
+    {
+        sa_gpu_ctx_sync(B->ctx);
+        B->e2e_phase_ms[0] = ms_since(t0);
+        t0 = now();
+    }
     sa_gpu_check(sa_gpu_local_spectral(lev, theta, ae_begin, ae_end, 0), "sa_gpu_local_spectral");
+    if (breakdown)
+    {
+        sa_gpu_ctx_sync(B->ctx);
+        B->e2e_phase_ms[1] = ms_since(t0);
+        t0 = now();
+    }
     sa_gpu_check(sa_gpu_get_spectral_counts(lev, B->ae_m.data()), "sa_gpu_get_spectral_counts");
     const agg_partitioning_relations_t &r = *B->prob->rels;
     size_t ne = 0, nv = 0;
@@ -148,6 +203,8 @@ extern "C" double sa_drv_bench_step(void *b_, int mode, int ae_begin, int ae_end
     B->evects.resize(nv);
     sa_gpu_check(sa_gpu_get_spectral(lev, B->evals.data(), B->evects.data(), NULL),
                  "sa_gpu_get_spectral");
+    if (breakdown)
+        B->e2e_phase_ms[2] = ms_since(t0);
     const double ms = sa_gpu_ctx_timer(B->ctx, 0);
     B->d2h_bytes = 8. * (ne + nv) + 4. * r.nparts;
     sa_gpu_level_destroy(lev);
@@ -162,6 +219,9 @@ extern "C" double sa_drv_bench_scalar(void *b_, const char *name_)
     if (name == "h2d_bytes") return B->h2d_bytes;
     if (name == "d2h_bytes") return B->d2h_bytes;
     if (name == "pinned") return B->pinned ? 1. : 0.;
+    if (name == "e2e.upload_ms") return B->e2e_phase_ms[0];
+    if (name == "e2e.compute_ms") return B->e2e_phase_ms[1];
+    if (name == "e2e.readback_ms") return B->e2e_phase_ms[2];
     if (name == "launches") return (double)sa_gpu_ctx_launch_count(B->ctx);
     if (name == "flops" || name == "bytes" || name == "sum_m")
     {

@@ -25,6 +25,14 @@ def test_gpu_abi_symbols():
     assert missing == []
 
 
+def test_level_desc_layout_matches_ctypes_mirror():
+    from saamge_b200 import cabi
+
+    lib = sab.gpu_lib()
+    lib.sa_gpu_level_desc_size.restype = ctypes.c_size_t
+    assert lib.sa_gpu_level_desc_size() == ctypes.sizeof(cabi.LevelDesc)
+
+
 def test_driver_abi_symbols():
     lib = sab.host_lib()
     names = declared("saamge_b200_driver.h", "sa_drv_")

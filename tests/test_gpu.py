@@ -4,6 +4,8 @@ properties at larger sizes.  Tolerances are the north star's: maps/patterns bit-
 (patterns up to numerical zeros, see parity._pattern_mismatch), eigenvalues 1e-10,
 eigenspaces 1e-8 (sine of the largest principal angle), coarse operator 1e-9, PCG
 iterations +-1."""
+import ctypes
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -242,6 +244,35 @@ def test_abi_sparse_kernels(ctx):
     assert np.linalg.norm(A @ xs - pr.get("b")) <= 1e-5 * np.linalg.norm(pr.get("b"))
     S.close()
     lev.close()
+    pr.close()
+
+
+def test_abi_pipelined_upload_is_bit_identical(ctx):
+    """desc.async_upload: the eigen stage starts on the first AEs while later slabs of the
+    operator / element blocks are still in flight; results must not depend on it."""
+    pr, p = _problem(n=16, blk=4)
+    ref = cabi.Level(ctx, pr)
+    ref.local_spectral(0.003)
+    m0, ev0, Z0, D0 = ref.spectral()
+    for first_call in ("spectral", "spmv", "wait"):
+        lev = cabi.Level(ctx, pr, async_upload=True)
+        if first_call == "spmv":  # any other entry point waits for the whole upload
+            x = np.ones(lev.ND)
+            assert np.array_equal(lev.spmv(0, x), ref.spmv(0, x))
+        elif first_call == "wait":
+            assert lev.lib.sa_gpu_level_upload_wait(lev.h) == 0
+        lev.local_spectral(0.003)
+        m1, ev1, Z1, D1 = lev.spectral()
+        assert np.array_equal(m0, m1) and np.array_equal(ev0, ev1)
+        assert np.array_equal(Z0, Z1) and np.array_equal(D0, D1)
+        lev.close()
+    # partial AE range on a pipelined level (the sharded path)
+    lev = cabi.Level(ctx, pr, async_upload=True)
+    h = lev.nparts // 2
+    check = lev.lib.sa_gpu_local_spectral(lev.h, ctypes.c_double(0.003), h, lev.nparts, 0)
+    assert check == 0
+    lev.close()
+    ref.close()
     pr.close()
 
 
