@@ -25,36 +25,6 @@ __device__ __forceinline__ int sa_dev_map_id_glob_to_AE(const LevelTables &L, in
     return -1;
 }
 
-/// agg_assemble_value (amg/src/aggregates.cpp:68-184): sum over the elements of
-/// AE `part` containing both dofs of the element-matrix entry (di, dj).
-__device__ __forceinline__ double sa_dev_assemble_value(const LevelTables &L, int di, int dj,
-                                                        int part)
-{
-    double value = 0.;
-    const int bi = L.d2e_I[di], ei = L.d2e_I[di + 1];
-    for (int p = bi; p < ei; ++p)
-    {
-        const int elno = L.d2e_J[p];
-        if (L.partitioning[elno] != part)
-            continue;
-        const int eb = L.e2d_I[elno];
-        const int ndofs = L.e2d_I[elno + 1] - eb;
-        int dii = -1, djj = -1;
-        for (int k = 0; k < ndofs; ++k)
-        {
-            const int g = L.e2d_J[eb + k];
-            if (g == di)
-                dii = k;
-            if (g == dj)
-                djj = k;
-        }
-        if (djj < 0)
-            continue; // element does not contain dj
-        value += L.elmat[L.elmat_off[elno] + (int64_t)djj * ndofs + dii];
-    }
-    return value;
-}
-
 /// Tile addressing: full column-major square, or lower triangle packed by columns
 /// (entry (i,j), i >= j, at T[cjm[j] + i] with cjm[j] = j*n - j*(j-1)/2 - j).
 struct FullTile
@@ -108,6 +78,11 @@ static __device__ void sa_dev_assemble_AE_tile(const LevelTables &L, int part, T
         {
             const int glob_dof = dofs[i];
             const char fi = L.agg_flags[glob_dof];
+            // (1) entries taken from the global operator: lanes own the row's nonzeros.
+            //     Entries that the reference re-assembles from the AE's elements (both dofs on
+            //     an AE interface, and not an off-diagonal touching an essential dof --
+            //     bdr_cond_imposed = assemble_ess_diag = true, amg/src/elmat.cpp:51-52) stay
+            //     zero here and are summed in (2).
             const int ab = L.A_I[glob_dof], ae = L.A_I[glob_dof + 1];
             for (int p = ab + lane; p < ae; p += 32)
             {
@@ -120,17 +95,49 @@ static __device__ void sa_dev_assemble_AE_tile(const LevelTables &L, int part, T
                     (fi & SA_AGG_BETWEEN_AES_FLAG) && (fj & SA_AGG_BETWEEN_AES_FLAG);
                 const bool ess = (fi & SA_AGG_ON_ESS_DOMAIN_BORDER_FLAG) ||
                                  (fj & SA_AGG_ON_ESS_DOMAIN_BORDER_FLAG);
-                // bdr_cond_imposed = assemble_ess_diag = true (amg/src/elmat.cpp:51-52)
-                if (both_iface && !(ess && !(glob_neigh == glob_dof)))
-                {
-                    // the reference assembles (i, j) for i <= j and mirrors the value
-                    const double value =
-                        (i <= local_neigh) ? sa_dev_assemble_value(L, glob_dof, glob_neigh, part)
-                                           : sa_dev_assemble_value(L, glob_neigh, glob_dof, part);
-                    tile.at(i, local_neigh) = value;
-                }
-                else
+                if (!(both_iface && !(ess && !(glob_neigh == glob_dof))))
                     tile.at(i, local_neigh) = L.A_data[p];
+            }
+            if (!(fi & SA_AGG_BETWEEN_AES_FLAG))
+                continue;
+            __syncwarp();
+            // (2) agg_assemble_value for the whole row at once: the AE's elements containing
+            //     the row dof, ascending (the order of the reference's sum); the lanes take
+            //     the element's columns, which are distinct tile entries.  The reference
+            //     evaluates the (smaller local id, larger local id) entry and mirrors it.
+            const int bi = L.d2e_I[glob_dof], ei = L.d2e_I[glob_dof + 1];
+            for (int p = bi; p < ei; ++p)
+            {
+                const int elem = L.d2e_J[p];
+                if (L.partitioning[elem] != part)
+                    continue;
+                const int eb = L.e2d_I[elem];
+                const int sz = L.e2d_I[elem + 1] - eb;
+                int k = -1;
+                for (int q = 0; q < sz; ++q)
+                    if (L.e2d_J[eb + q] == glob_dof)
+                    {
+                        k = q;
+                        break;
+                    }
+                const double *Ke = L.elmat + L.elmat_off[elem];
+                for (int j = lane; j < sz; j += 32)
+                {
+                    const int gj = L.e2d_J[eb + j];
+                    const char fj = L.agg_flags[gj];
+                    if (!(fj & SA_AGG_BETWEEN_AES_FLAG))
+                        continue;
+                    const bool ess = (fi & SA_AGG_ON_ESS_DOMAIN_BORDER_FLAG) ||
+                                     (fj & SA_AGG_ON_ESS_DOMAIN_BORDER_FLAG);
+                    if (ess && gj != glob_dof)
+                        continue;
+                    const int local_j = sa_dev_map_id_glob_to_AE(L, gj, part);
+                    if (!tile.has(i, local_j))
+                        continue;
+                    tile.at(i, local_j) += (i <= local_j) ? Ke[(int64_t)j * sz + k]
+                                                          : Ke[(int64_t)k * sz + j];
+                }
+                __syncwarp();
             }
         }
     }
@@ -172,6 +179,245 @@ static __device__ void sa_dev_assemble_AE_tile(const LevelTables &L, int part, T
         }
     }
     __syncthreads();
+}
+
+/// Same result as sa_dev_assemble_AE_tile, for AEs whose index structure fits a scratch area
+/// in shared memory (the fine-level case: a few dozen small elements).  The generic routine
+/// chases d2AE / d2e / e2d through global memory for every entry, one dependent load after
+/// the other; here the AE's structure is staged once:
+///   - open-addressing hash  global dof -> local id           (replaces agg_map_id_glob_to_AE)
+///   - per element of the AE: its dofs as local ids, its block offset
+///   - the AE dofs' flags
+/// and the assembly itself only reads the operator row / the element blocks from global
+/// memory.  Summation order per entry is unchanged (elements ascending).
+/// Returns false (uniformly, nothing written) when the structure does not fit; the caller
+/// then uses the generic routine.  Ends with __syncthreads().
+template <class Tile>
+static __device__ bool sa_dev_assemble_AE_staged(const LevelTables &L, int part, Tile tile,
+                                                 void *scratch, int scratch_bytes)
+{
+    const int rb = L.AE2d_I[part];
+    const int n = L.AE2d_I[part + 1] - rb;
+    const int *dofs = L.AE2d_J + rb;
+    const int eb0 = L.AE2e_I[part];
+    const int ne = L.AE2e_I[part + 1] - eb0;
+    const int *elems = L.AE2e_J + eb0;
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int lane = tid & 31, wid = tid >> 5, nw = NT >> 5;
+    int H = 32, Hlog = 5;
+    while (H < 2 * n)
+    {
+        H <<= 1;
+        ++Hlog;
+    }
+    if (n > 255 || ne > 1024 ||
+        scratch_bytes < 8 * ne + 8 + 4 * H + 8 * ne + 4 + 8 * n + H + n)
+        return false;
+    long long *eoff = (long long *)scratch;       // ne: element block offsets
+    int *hdr = (int *)(eoff + ne);                // [0] total element dofs, [1] largest element
+    int *hkey = hdr + 2;                          // H
+    int *ebase = hkey + H;                        // ne: e2d_I[elem]
+    int *epre = ebase + ne;                       // ne + 1: prefix of the element sizes
+    int *arow = epre + ne + 1;                    // 2 n: operator row begin / end of each dof
+    unsigned char *hval = (unsigned char *)(arow + 2 * n); // H
+    unsigned char *flg = hval + H;                // n
+    unsigned char *eloc = flg + n;                // total element dofs
+    if (tid < 2)
+        hdr[tid] = 0;
+    for (int q = tid; q < H; q += NT)
+        hkey[q] = -1;
+    __syncthreads();
+    for (int s = tid; s < ne; s += NT)
+    {
+        const int e = elems[s];
+        const int b = L.e2d_I[e];
+        const int sz = L.e2d_I[e + 1] - b;
+        ebase[s] = b;
+        epre[s + 1] = sz;
+        eoff[s] = L.elmat_off[e];
+        atomicAdd(&hdr[0], sz);
+        atomicMax(&hdr[1], sz);
+    }
+    for (int i = tid; i < n; i += NT)
+    {
+        const int key = dofs[i];
+        flg[i] = (unsigned char)L.agg_flags[key];
+        if (L.with_global)
+        {
+            arow[2 * i] = L.A_I[key];
+            arow[2 * i + 1] = L.A_I[key + 1];
+        }
+        unsigned int slot = ((unsigned int)key * 0x9E3779B1u) >> (32 - Hlog);
+        while (true)
+        {
+            const int old = atomicCAS(&hkey[slot], -1, key);
+            if (old == -1)
+            {
+                hval[slot] = (unsigned char)i;
+                break;
+            }
+            slot = (slot + 1) & (H - 1);
+        }
+    }
+    __syncthreads();
+    const int tot = hdr[0], maxsz = hdr[1];
+    const int fixed = (int)((unsigned char *)eloc - (unsigned char *)scratch);
+    if (maxsz > 32 || fixed + tot > scratch_bytes)
+    {
+        __syncthreads();
+        return false;
+    }
+    if (tid == 0)
+    {
+        epre[0] = 0;
+        for (int s = 0; s < ne; ++s)
+            epre[s + 1] += epre[s];
+    }
+    {
+        const int64_t tsz = tile.size(n);
+        for (int64_t q = tid; q < tsz; q += NT)
+            tile.T[q] = 0.;
+    }
+    __syncthreads();
+    auto lookup = [&](int key) -> int {
+        unsigned int slot = ((unsigned int)key * 0x9E3779B1u) >> (32 - Hlog);
+        while (true)
+        {
+            const int k = hkey[slot];
+            if (k == key)
+                return (int)hval[slot];
+            if (k == -1)
+                return -1;
+            slot = (slot + 1) & (H - 1);
+        }
+    };
+    for (int s = wid; s < ne; s += nw)
+    {
+        const int sz = epre[s + 1] - epre[s];
+        if (lane < sz)
+            eloc[epre[s] + lane] = (unsigned char)lookup(L.e2d_J[ebase[s] + lane]);
+    }
+    __syncthreads();
+    int gsz = 1;
+    while (gsz < maxsz)
+        gsz <<= 1;
+    const int G = 32 / gsz; // elements scanned per warp step
+    const bool wg = L.with_global != 0;
+    for (int i = wid; i < n; i += nw)
+    {
+        const unsigned char fi = flg[i];
+        if (wg)
+        {
+            // entries copied from the global operator (see sa_dev_assemble_AE_tile)
+            const int ab = arow[2 * i], ae = arow[2 * i + 1];
+            for (int p = ab + lane; p < ae; p += 32)
+            {
+                const int gj = L.A_J[p];
+                const double aval = L.A_data[p]; // issued together with the index load
+                const int lj = lookup(gj);
+                if (lj < 0 || !tile.has(i, lj))
+                    continue;
+                const unsigned char fj = flg[lj];
+                const bool both_iface =
+                    (fi & SA_AGG_BETWEEN_AES_FLAG) && (fj & SA_AGG_BETWEEN_AES_FLAG);
+                const bool ess = ((fi | fj) & SA_AGG_ON_ESS_DOMAIN_BORDER_FLAG) != 0;
+                if (!(both_iface && !(ess && lj != i)))
+                    tile.at(i, lj) = aval;
+            }
+            if (!(fi & SA_AGG_BETWEEN_AES_FLAG))
+                continue;
+            __syncwarp();
+        }
+        // the AE's elements containing dof i, ascending: collect up to NB hits (element slot,
+        // position of dof i in it), fetch their block entries together, then add in order
+        const int NB = 8;
+        int nh = 0;
+        int my_hit = 0; // lane h keeps hit h as (slot << 8 | k): no dynamically indexed arrays
+        auto flush = [&]() {
+            double val[NB];
+            int ljs[NB];
+#pragma unroll
+            for (int h = 0; h < NB; ++h)
+            {
+                val[h] = 0.;
+                ljs[h] = -1;
+                const int packed = __shfl_sync(0xffffffffu, my_hit, h);
+                if (h < nh)
+                {
+                    const int hs = packed >> 8, k = packed & 255;
+                    const int sz = epre[hs + 1] - epre[hs];
+                    if (lane < sz)
+                    {
+                        const int j = lane;
+                        const int lj = eloc[epre[hs] + j];
+                        if (tile.has(i, lj))
+                        {
+                            const double *Ke = L.elmat + eoff[hs];
+                            if (wg)
+                            {
+                                const unsigned char fj = flg[lj];
+                                const bool ess =
+                                    ((fi | fj) & SA_AGG_ON_ESS_DOMAIN_BORDER_FLAG) != 0;
+                                if ((fj & SA_AGG_BETWEEN_AES_FLAG) && !(ess && lj != i))
+                                {
+                                    val[h] = (i <= lj) ? Ke[(int64_t)j * sz + k]
+                                                       : Ke[(int64_t)k * sz + j];
+                                    ljs[h] = lj;
+                                }
+                            }
+                            else
+                            {
+                                val[h] = Ke[(int64_t)j * sz + k];
+                                if (0. != val[h])
+                                    ljs[h] = lj;
+                            }
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < NB; ++h)
+            {
+                if (h < nh)
+                {
+                    if (ljs[h] >= 0)
+                        tile.at(i, ljs[h]) += val[h];
+                    __syncwarp();
+                }
+            }
+            nh = 0;
+        };
+        const bool uniform = tot == ne * gsz; // all elements have gsz dofs
+        for (int s0 = 0; s0 < ne; s0 += G)
+        {
+            bool hit = false;
+            if (uniform)
+            {
+                const int idx = s0 * gsz + lane;
+                hit = idx < tot && eloc[idx] == i;
+            }
+            else
+            {
+                const int s = s0 + lane / gsz, q = lane % gsz;
+                if (s < ne && q < epre[s + 1] - epre[s])
+                    hit = eloc[epre[s] + q] == i;
+            }
+            unsigned int ballot = __ballot_sync(0xffffffffu, hit);
+            while (ballot)
+            {
+                const int b = __ffs(ballot) - 1;
+                ballot &= ballot - 1;
+                if (lane == nh)
+                    my_hit = ((s0 + b / gsz) << 8) | (b % gsz);
+                if (++nh == NB)
+                    flush();
+            }
+        }
+        if (nh)
+            flush();
+    }
+    __syncthreads();
+    return true;
 }
 
 #endif

@@ -686,112 +686,137 @@ __global__ void k_bisect(ChunkDev C, const int *AE2d_I, const int *ev_slot, cons
     evals[eval_off_slot[slot] + j] = 0.5 * (lo + hi);
 }
 
-// one warp per slot; lanes = eigenvalues (blocks of 32).  ws: per-warp workspace
-// of 4 double arrays + 1 int array, each 32*nmax entries, interleaved by lane.
-__global__ void k_inverse_iter(ChunkDev C, const int *AE2d_I, int nslots, const int *nev,
-                               const int64_t *eval_off_slot, const double *evals,
-                               const int64_t *evect_off_slot, double *evects,
-                               const double *tnorm, double *ws_d, int *ws_i, int nmax)
+// Inverse iteration (dstein), three kernels per sweep so that every lane has work even when
+// an AE contributes a single vector (the usual case at theta = 0.003):
+//   k_invit_setup: one THREAD per eigenvector: perturbed shift + cluster start (dstein),
+//                  pivoted LU of T - shift I, pseudo-random start vector
+//   k_invit_solve: one thread per eigenvector: forward / backward substitution
+//   k_invit_orth:  one WARP per AE: modified Gram-Schmidt inside clusters + normalisation,
+//                  vector by vector; writes Z and feeds the next solve
+// Workspace: 5 double arrays + 1 int array of nmax * NB entries; entry i of eigenvector t at
+// [i * NB + t], so the 32 eigenvectors of a warp walk the recurrences with coalesced accesses.
+struct InvitWs
+{
+    double *u0inv, *u1, *u2, *mult, *x;
+    int *swp;
+    int64_t NB; // stride = eigenvectors per batch (multiple of 32)
+};
+
+__global__ void k_invit_setup(ChunkDev C, const int *AE2d_I, const int *ev_slot, const int *ev_idx,
+                              int64_t t0, int nb, const int64_t *eval_off_slot,
+                              const double *evals, const double *tnorm, InvitWs W, int *gpind_out)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nb)
+        return;
+    const int slot = ev_slot[t0 + t], j = ev_idx[t0 + t];
+    const int part = C.ae_of_slot[slot];
+    const int n = AE2d_I[part + 1] - AE2d_I[part];
+    const double *d = C.d + C.doff[slot];
+    const double *e = C.e + C.doff[slot];
+    const double *lam = evals + eval_off_slot[slot];
+    const double tn = fmax(tnorm[slot], DBL_MIN);
+    const double pivtol = DBL_EPSILON * tn;
+    const double ortol = 1e-3 * tn; // dstein: ORTOL = ODM3 * ONENRM
+    // dstein: separate (nearly) equal eigenvalues so the shifted systems differ
+    int gpind = 0; // first vector of the cluster of j
+    double xprev = lam[0];
+    for (int q = 1; q <= j; ++q)
+    {
+        double x = lam[q];
+        const double pertol = 10. * fabs(DBL_EPSILON * x);
+        if (x - xprev < pertol)
+            x = xprev + pertol;
+        if (fabs(x - xprev) > ortol)
+            gpind = q;
+        xprev = x;
+    }
+    gpind_out[t0 + t] = gpind;
+    sa_tridiag_lu_factor(n, d, e, xprev, pivtol, W.u0inv + t, W.u1 + t, W.u2 + t, W.mult + t,
+                         W.swp + t, W.NB);
+    for (int i = 0; i < n; ++i)
+        W.x[(int64_t)i * W.NB + t] =
+            sa_hash_uniform(((uint64_t)part << 32) ^ ((uint64_t)j << 16) ^ (uint64_t)i);
+}
+
+__global__ void k_invit_solve(ChunkDev C, const int *AE2d_I, const int *ev_slot, int64_t t0, int nb,
+                              InvitWs W)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nb)
+        return;
+    const int part = C.ae_of_slot[ev_slot[t0 + t]];
+    const int n = AE2d_I[part + 1] - AE2d_I[part];
+    sa_tridiag_lu_solve(n, W.u0inv + t, W.u1 + t, W.u2 + t, W.mult + t, W.swp + t, W.NB, W.x + t,
+                        W.NB);
+}
+
+// slots [s0, s1) are the AEs of this batch; their eigenvectors are t = eval_off_slot[slot] +
+// j - t0 in the workspace
+__global__ void k_invit_orth(ChunkDev C, const int *AE2d_I, int s0, int s1, const int *nev,
+                             const int64_t *eval_off_slot, const int64_t *evect_off_slot,
+                             double *evects, const int *gpind_all, int64_t t0, InvitWs W)
 {
     const int lane = threadIdx.x & 31;
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    double *u0inv = ws_d + (size_t)warp_global * 4 * 32 * nmax;
-    double *u1 = u0inv + (size_t)32 * nmax;
-    double *u2 = u1 + (size_t)32 * nmax;
-    double *mult = u2 + (size_t)32 * nmax;
-    int *swp = ws_i + (size_t)warp_global * 32 * nmax;
-
-    for (int slot = warp_global; slot < nslots; slot += nwarps)
+    for (int slot = s0 + warp_global; slot < s1; slot += nwarps)
     {
         const int m = nev[slot];
         if (m <= 0)
             continue;
         const int part = C.ae_of_slot[slot];
         const int n = AE2d_I[part + 1] - AE2d_I[part];
-        const double *d = C.d + C.doff[slot];
-        const double *e = C.e + C.doff[slot];
-        const double *lam = evals + eval_off_slot[slot];
         double *Z = evects + evect_off_slot[slot];
-        const double tn = fmax(tnorm[slot], DBL_MIN);
-        const double pivtol = DBL_EPSILON * tn;
-        const double ortol = 1e-3 * tn; // dstein: ORTOL = ODM3 * ONENRM
-
+        const int64_t tb = eval_off_slot[slot] - t0;
         if (n == 1)
         {
             if (lane == 0)
+            {
                 Z[0] = 1.;
+                W.x[tb] = 1.;
+            }
             continue;
         }
-        for (int jb = 0; jb < m; jb += 32)
+        for (int jj = 0; jj < m; ++jj)
         {
-            const int j = jb + lane;
-            const bool active = j < m;
-            // dstein: separate (nearly) equal eigenvalues so the shifted systems differ
-            double xj = 0.;
-            int gpind = 0; // first vector of the cluster of j
-            if (active)
+            const int gp = gpind_all[t0 + tb + jj];
+            double *zj = Z + (int64_t)n * jj;
+            double *xj = W.x + tb + jj;
+            for (int i = lane; i < n; i += 32)
+                zj[i] = xj[(int64_t)i * W.NB];
+            __syncwarp();
+            for (int q = gp; q < jj; ++q)
             {
-                double xprev = lam[0];
-                for (int q = 1; q <= j; ++q)
-                {
-                    double x = lam[q];
-                    const double pertol = 10. * fabs(DBL_EPSILON * x);
-                    if (x - xprev < pertol)
-                        x = xprev + pertol;
-                    if (fabs(x - xprev) > ortol)
-                        gpind = q;
-                    xprev = x;
-                }
-                xj = xprev;
-                sa_tridiag_lu_factor(n, d, e, xj, pivtol, u0inv + lane, u1 + lane, u2 + lane,
-                                     mult + lane, swp + lane, 32);
-                for (int i = 0; i < n; ++i)
-                    Z[i + (int64_t)n * j] =
-                        sa_hash_uniform(((uint64_t)part << 32) ^ ((uint64_t)j << 16) ^ (uint64_t)i);
+                const double *zq = Z + (int64_t)n * q;
+                double s = 0.;
+                for (int i = lane; i < n; i += 32)
+                    s += zq[i] * zj[i];
+                s = warp_sum(s);
+                for (int i = lane; i < n; i += 32)
+                    zj[i] -= s * zq[i];
+                __syncwarp();
+            }
+            double s = 0., amax = 0.;
+            for (int i = lane; i < n; i += 32)
+                amax = fmax(amax, fabs(zj[i]));
+            for (int o = 16; o > 0; o >>= 1)
+                amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+            const double sc = (amax > 0.) ? 1. / amax : 1.;
+            for (int i = lane; i < n; i += 32)
+            {
+                const double t = zj[i] * sc;
+                s += t * t;
+            }
+            s = warp_sum(s);
+            const double nrm = (s > 0.) ? sc / sqrt(s) : 0.;
+            for (int i = lane; i < n; i += 32)
+            {
+                const double z = zj[i] * nrm;
+                zj[i] = z;
+                xj[(int64_t)i * W.NB] = z;
             }
             __syncwarp();
-            for (int its = 0; its < 3; ++its)
-            {
-                if (active)
-                    sa_tridiag_lu_solve(n, u0inv + lane, u1 + lane, u2 + lane, mult + lane,
-                                        swp + lane, 32, Z + (int64_t)n * j, 1);
-                __syncwarp();
-                // modified Gram-Schmidt inside clusters + normalisation, vector by vector
-                const int jend = min(m, jb + 32);
-                for (int jj = jb; jj < jend; ++jj)
-                {
-                    const int gp = __shfl_sync(0xffffffffu, gpind, jj - jb);
-                    double *zj = Z + (int64_t)n * jj;
-                    for (int q = gp; q < jj; ++q)
-                    {
-                        const double *zq = Z + (int64_t)n * q;
-                        double s = 0.;
-                        for (int i = lane; i < n; i += 32)
-                            s += zq[i] * zj[i];
-                        s = warp_sum(s);
-                        for (int i = lane; i < n; i += 32)
-                            zj[i] -= s * zq[i];
-                        __syncwarp();
-                    }
-                    double s = 0., amax = 0.;
-                    for (int i = lane; i < n; i += 32)
-                        amax = fmax(amax, fabs(zj[i]));
-                    for (int o = 16; o > 0; o >>= 1)
-                        amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-                    const double sc = (amax > 0.) ? 1. / amax : 1.;
-                    for (int i = lane; i < n; i += 32)
-                    {
-                        const double t = zj[i] * sc;
-                        s += t * t;
-                    }
-                    s = warp_sum(s);
-                    const double nrm = (s > 0.) ? sc / sqrt(s) : 0.;
-                    for (int i = lane; i < n; i += 32)
-                        zj[i] *= nrm;
-                    __syncwarp();
-                }
-            }
         }
     }
 }
@@ -1055,6 +1080,12 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         WS.tn.ensure(max_ns);
         WS.eval_off.ensure(max_ns + 1);
         WS.evect_off.ensure(max_ns + 1);
+        // inverse-iteration workspace: a guess of 1.25 vectors per AE (grows if exceeded)
+        const size_t cap = std::max<size_t>(32, (((size_t)4 << 30) / ((size_t)44 * range_nmax)) & ~(size_t)31);
+        WS.invit_NB = std::min(cap, (max_ns + max_ns / 4 + 1024 + 31) & ~(size_t)31);
+        WS.ws_d.ensure(5 * WS.invit_NB * range_nmax);
+        WS.ws_i.ensure(WS.invit_NB * range_nmax);
+        WS.gpind.ensure(WS.invit_NB);
     }
 
     const bool pipe_debug = getenv("SA_GPU_PIPE_DEBUG") != NULL && lev->pending.active;
@@ -1352,23 +1383,61 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         }
         // inverse iteration
         {
-            // resident warps bounded by workspace: 4 double + 1 int arrays of 32*nmax
-            nmax = range_nmax; // one workspace size for all chunks of the call
-            const size_t per_warp = (size_t)32 * nmax * (4 * sizeof(double) + sizeof(int));
-            size_t warps = std::min<size_t>((size_t)ctx->num_sms * 16, (size_t)ns);
+            nmax = range_nmax; // one workspace shape for all chunks of the call
+            // eigenvectors per batch: bounded by the workspace budget (44 bytes per row and
+            // vector); batches end on AE boundaries (clusters are orthogonalised per AE)
             const size_t ws_budget = (size_t)4 << 30;
-            warps = std::max<size_t>(1, std::min(warps, ws_budget / per_warp));
-            const int wpb = 4;
-            const int blocks = (int)((warps + wpb - 1) / wpb);
+            const int64_t cap = std::max<int64_t>(32, (int64_t)(ws_budget / ((size_t)44 * nmax)) & ~(int64_t)31);
+            int64_t NB = std::min<int64_t>(cap, ((int64_t)nev_total + 31) & ~(int64_t)31);
+            NB = std::max<int64_t>(NB, (int64_t)WS.invit_NB); // grow only (see the pipelined pieces)
+            NB = std::min(NB, cap);
+            WS.invit_NB = (size_t)NB;
             DevBuf<double> &ws_d = WS.ws_d;
             DevBuf<int> &ws_i = WS.ws_i;
-            ws_d.ensure((size_t)blocks * wpb * 4 * 32 * nmax);
-            ws_i.ensure((size_t)blocks * wpb * 32 * nmax);
+            ws_d.ensure((size_t)5 * NB * nmax);
+            ws_i.ensure((size_t)NB * nmax);
+            WS.gpind.ensure(std::max(1, nev_total));
+            InvitWs W;
+            W.NB = NB;
+            W.u0inv = ws_d.p;
+            W.u1 = W.u0inv + (size_t)NB * nmax;
+            W.u2 = W.u1 + (size_t)NB * nmax;
+            W.mult = W.u2 + (size_t)NB * nmax;
+            W.x = W.mult + (size_t)NB * nmax;
+            W.swp = ws_i.p;
             {
                 ProfScope ps(ctx, "eig.inverse_iter");
-                SA_LAUNCH(ctx, k_inverse_iter, blocks, wpb * 32, 0, C, lev->AE2d_I.p, ns, d_nev.p,
-                          d_eval_off.p, pr->evals.p, d_evect_off.p, pr->evects.p, d_tn.p, ws_d.p,
-                          ws_i.p, nmax);
+                int s0 = 0;
+                while (s0 < ns)
+                {
+                    int s1 = s0;
+                    int64_t cnt = 0;
+                    while (s1 < ns && (s1 == s0 || cnt + pr->nev[s1] <= NB))
+                        cnt += pr->nev[s1++];
+                    if (cnt > NB)
+                        SA_FAIL("sa_gpu_local_spectral: one AE has %lld eigenvectors, more than "
+                                "the inverse-iteration workspace holds (%lld)",
+                                (long long)cnt, (long long)NB);
+                    const int64_t t0 = pr->eval_off[s0];
+                    const int nb = (int)cnt;
+                    if (nb > 0)
+                    {
+                        const int tb = 128, gb = (nb + tb - 1) / tb;
+                        SA_LAUNCH(ctx, k_invit_setup, gb, tb, 0, C, lev->AE2d_I.p, d_ev_slot.p,
+                                  d_ev_idx.p, t0, nb, d_eval_off.p, pr->evals.p, d_tn.p, W,
+                                  WS.gpind.p);
+                        const int ob = std::min((s1 - s0 + 3) / 4, ctx->num_sms * 16);
+                        for (int its = 0; its < 3; ++its)
+                        {
+                            SA_LAUNCH(ctx, k_invit_solve, gb, tb, 0, C, lev->AE2d_I.p, d_ev_slot.p,
+                                      t0, nb, W);
+                            SA_LAUNCH(ctx, k_invit_orth, ob, 128, 0, C, lev->AE2d_I.p, s0, s1,
+                                      d_nev.p, d_eval_off.p, d_evect_off.p, pr->evects.p,
+                                      WS.gpind.p, t0, W);
+                        }
+                    }
+                    s0 = s1;
+                }
             }
             {
                 ProfScope ps(ctx, "eig.back_transform");

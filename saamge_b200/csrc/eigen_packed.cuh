@@ -78,7 +78,9 @@ k_at_packed(LevelTables L, ChunkDev C, const int *slot_list, double *ae_D)
         PackedTile pt;
         pt.T = T;
         pt.cjm = cjm;
-        sa_dev_assemble_AE_tile(L, part, pt);
+        // the vector / reduction area (v, w, dg, psum) is free until the scaling step
+        if (!sa_dev_assemble_AE_staged(L, part, pt, (void *)v, (3 * n + NT) * (int)sizeof(double)))
+            sa_dev_assemble_AE_tile(L, part, pt);
     }
     long long tc1 = clock64();
     if (tid == 0)
@@ -159,6 +161,7 @@ k_at_packed(LevelTables L, ChunkDev C, const int *slot_list, double *ae_D)
     __syncthreads();
     int nslots_n = NT >> 5;
     int cur_rpad = -1, ncls = 1, my_a = tid, my_c = 0;
+    int cur_rhpad = -1, ncls2 = 1, my_a2 = tid, my_c2 = 0; // row-pair mapping of the update
     for (int k = 0; k < n - 1; ++k)
     {
         const int r = n - k - 1;
@@ -169,6 +172,14 @@ k_at_packed(LevelTables L, ChunkDev C, const int *slot_list, double *ae_D)
             ncls = max(1, NT / rpad);
             my_a = (ncls == 1) ? tid : tid % rpad;
             my_c = (ncls == 1) ? 0 : tid / rpad;
+        }
+        const int rhpad = (((r + 1) >> 1) + 31) & ~31;
+        if (rhpad != cur_rhpad)
+        {
+            cur_rhpad = rhpad;
+            ncls2 = max(1, NT / rhpad);
+            my_a2 = (ncls2 == 1) ? tid : tid % rhpad;
+            my_c2 = (ncls2 == 1) ? 0 : tid / rhpad;
         }
         double xnorm2 = 0.;
         for (int s = 0; s < nslots_n; ++s)
@@ -248,43 +259,56 @@ k_at_packed(LevelTables L, ChunkDev C, const int *slot_list, double *ae_D)
             for (int s = 0; s < nrw; ++s)
                 pvs += slots_p[s];
             const double alpha2 = -0.5 * tau * pvs;
-            // A22 -= v w^T + w v^T (stored triangle only), w = p + alpha2 v on the fly
-            for (int a = my_a; a < r; a += (ncls == 1 ? NT : r))
-            {
-                if (my_c < ncls)
+            // A22 -= v w^T + w v^T (stored triangle only), w = p + alpha2 v on the fly.
+            // Row a of the stored triangle has a + 1 entries: a thread takes the PAIR of rows
+            // (a2, r - 1 - a2), r + 1 entries together, split over ncls2 column classes, so
+            // that every thread (and warp) has the same amount of work before the barrier.
+            auto update_row = [&](int a, int c, int nc) {
+                const int ia = k + 1 + a;
+                const double vi = v[ia], wi = w[ia] + alpha2 * vi;
+                int j = k + 1 + c;
+                if (c == 0)
                 {
-                    const int ia = k + 1 + a;
-                    const double vi = v[ia], wi = w[ia] + alpha2 * vi;
-                    int j = k + 1 + my_c;
-                    if (my_c == 0)
-                    {
-                        // column k+1 also feeds the norm of the next Householder vector
-                        const double vj = v[j], wj = w[j] + alpha2 * vj;
-                        double *e0 = T + cjm[j] + ia;
-                        const double t = *e0 - (vi * wj + wi * vj);
-                        *e0 = t;
-                        if (a >= 2)
-                            nrm += t * t;
-                        j += ncls;
-                    }
-                    for (; j + ncls <= ia; j += 2 * ncls)
-                    {
-                        const double v0 = v[j], v1 = v[j + ncls];
-                        const double w0 = w[j] + alpha2 * v0, w1 = w[j + ncls] + alpha2 * v1;
-                        double *e0 = T + cjm[j] + ia, *e1 = T + cjm[j + ncls] + ia;
-                        const double t0 = *e0, t1 = *e1;
-                        *e0 = t0 - (vi * w0 + wi * v0);
-                        *e1 = t1 - (vi * w1 + wi * v1);
-                    }
-                    if (j <= ia)
-                    {
-                        const double v0 = v[j], w0 = w[j] + alpha2 * v0;
-                        double *e0 = T + cjm[j] + ia;
-                        *e0 = *e0 - (vi * w0 + wi * v0);
-                    }
+                    // column k+1 also feeds the norm of the next Householder vector
+                    const double vj = v[j], wj = w[j] + alpha2 * vj;
+                    double *e0 = T + cjm[j] + ia;
+                    const double t = *e0 - (vi * wj + wi * vj);
+                    *e0 = t;
+                    if (a >= 2)
+                        nrm += t * t;
+                    j += nc;
                 }
-                if (ncls > 1)
-                    break;
+                for (; j + nc <= ia; j += 2 * nc)
+                {
+                    const double v0 = v[j], v1 = v[j + nc];
+                    const double w0 = w[j] + alpha2 * v0, w1 = w[j + nc] + alpha2 * v1;
+                    double *e0 = T + cjm[j] + ia, *e1 = T + cjm[j + nc] + ia;
+                    const double t0 = *e0, t1 = *e1;
+                    *e0 = t0 - (vi * w0 + wi * v0);
+                    *e1 = t1 - (vi * w1 + wi * v1);
+                }
+                if (j <= ia)
+                {
+                    const double v0 = v[j], w0 = w[j] + alpha2 * v0;
+                    double *e0 = T + cjm[j] + ia;
+                    *e0 = *e0 - (vi * w0 + wi * v0);
+                }
+            };
+            const int rh = (r + 1) >> 1;
+            if (ncls2 == 1)
+            {
+                for (int a2 = tid; a2 < rh; a2 += NT)
+                {
+                    update_row(a2, 0, 1);
+                    if (r - 1 - a2 != a2)
+                        update_row(r - 1 - a2, 0, 1);
+                }
+            }
+            else if (my_c2 < ncls2 && my_a2 < rh)
+            {
+                update_row(my_a2, my_c2, ncls2);
+                if (r - 1 - my_a2 != my_a2)
+                    update_row(r - 1 - my_a2, my_c2, ncls2);
             }
         }
         else

@@ -244,7 +244,8 @@ struct LevelTables
 /* grow-only work arrays of the local spectral stage, cached per level */
 struct SpectralWs
 {
-    DevBuf<int> ae, doff, status, order, nev, mtot, ev_slot, ev_idx, ws_i;
+    DevBuf<int> ae, doff, status, order, nev, mtot, ev_slot, ev_idx, ws_i, gpind;
+    size_t invit_NB = 0; // eigenvectors per inverse-iteration batch the workspace holds
     DevBuf<int64_t> voff, eval_off, evect_off;
     DevBuf<double> V, d, e, tau, sinv, glo, ghi, tn, ws_d;
     // large-matrix (cooperative) path

@@ -72,7 +72,7 @@ SA_HD double sa_hash_uniform(uint64_t key)
 ///   mult: multiplier, swp: 1 if rows i and i+1 were interchanged.
 SA_HD void sa_tridiag_lu_factor(int n, const double *d, const double *e, double shift,
                                 double pivtol, double *u0inv, double *u1, double *u2,
-                                double *mult, int *swp, int stride)
+                                double *mult, int *swp, int64_t stride)
 {
     double a = d[0] - shift;          // current diagonal
     double b = (n > 1) ? e[0] : 0.;   // current superdiagonal
@@ -119,8 +119,8 @@ SA_HD void sa_tridiag_lu_factor(int n, const double *d, const double *e, double 
 
 /// Solves (T - shift I) x = x in place with the stored factorisation; x[i * xstride].
 SA_HD void sa_tridiag_lu_solve(int n, const double *u0inv, const double *u1, const double *u2,
-                               const double *mult, const int *swp, int stride, double *x,
-                               int xstride)
+                               const double *mult, const int *swp, int64_t stride, double *x,
+                               int64_t xstride)
 {
     // forward: apply the row interchanges and eliminations to the right-hand side
     double cur = x[0];
