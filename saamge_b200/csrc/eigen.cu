@@ -639,15 +639,25 @@ __global__ void k_count(ChunkDev C, const int *AE2d_I, int nslots, double theta,
     C.tau[C.doff[slot] + n - 1] = (double)cnt_lo;
 }
 
-// one thread per wanted eigenvalue.  ev_slot/ev_idx map the flat eigenvalue index
-// to (slot, j).
+// SA_BISECT_LPE lanes per wanted eigenvalue; ev_slot/ev_idx map the flat eigenvalue index to
+// (slot, j).  Multisection: the lanes of a group evaluate the Sturm count at LPE interior
+// points of the current interval at once, so it shrinks by (LPE + 1)x per sweep (17 sweeps
+// to double precision at LPE = 8 instead of 53 bisection steps).  The stage is bound by the
+// FP64 divisions of the Sturm recurrence: wider groups cost more evaluations in total,
+// narrower ones a longer dependent chain.
+#define SA_BISECT_LPE 8
 __global__ void k_bisect(ChunkDev C, const int *AE2d_I, const int *ev_slot, const int *ev_idx,
                          int nev_total, const double *glo, const double *ghi,
                          const double *tnorm, const int64_t *eval_off_slot, double *evals)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nev_total)
-        return;
+    const int LPE = SA_BISECT_LPE;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % LPE;               // point of the group
+    const int gbase = lane - sub;             // first lane of the group
+    const unsigned int gmask = ((LPE == 32) ? 0xffffffffu : ((1u << LPE) - 1u)) << gbase;
+    const int t0 = (blockIdx.x * blockDim.x + threadIdx.x) / LPE;
+    const bool live = t0 < nev_total;
+    const int t = live ? t0 : nev_total - 1;  // idle groups shadow the last eigenvalue
     const int slot = ev_slot[t];
     const int j = ev_idx[t];
     const int part = C.ae_of_slot[slot];
@@ -657,33 +667,53 @@ __global__ void k_bisect(ChunkDev C, const int *AE2d_I, const int *ev_slot, cons
     const int first = (int)C.tau[C.doff[slot] + n - 1];
     const int target = first + j; // want the eigenvalue with exactly `target` eigenvalues below it
     double e2max = 0.;
-    for (int i = 0; i + 1 < n; ++i)
+    for (int i = sub; i + 1 < n; i += LPE)
         e2max = fmax(e2max, e[i] * e[i]);
+    for (int o = LPE / 2; o > 0; o >>= 1)
+        e2max = fmax(e2max, __shfl_xor_sync(0xffffffffu, e2max, o));
     const double pivmin = DBL_MIN * fmax(1., e2max);
     double lo = glo[slot], hi = ghi[slot];
     const double tn = tnorm[slot];
     const double atol = 2. * DBL_EPSILON * tn + 2. * pivmin;
-    for (int it = 0; it < 200; ++it)
+    bool done = false;
+    for (int it = 0; it < 96; ++it)
     {
-        const double mid = 0.5 * (lo + hi);
-        if (hi - lo <= atol || mid <= lo || mid >= hi)
+        done = done || (hi - lo <= atol);
+        if (__all_sync(0xffffffffu, done))
             break;
+        const double x = lo + (hi - lo) * ((double)(sub + 1) / (double)(LPE + 1));
+        const bool valid = !done && x > lo && x < hi;
         int cnt = 0;
-        double q = d[0] - mid;
+        double q = d[0] - x;
         if (fabs(q) < pivmin) q = -pivmin;
         cnt += (q <= 0.);
         for (int i = 1; i < n; ++i)
         {
-            q = d[i] - (e[i - 1] * e[i - 1]) / q - mid;
+            const double ei = e[i - 1];
+            q = d[i] - (ei * ei) / q - x;
             if (fabs(q) < pivmin) q = -pivmin;
             cnt += (q <= 0.);
         }
-        if (cnt <= target)
-            lo = mid;
-        else
-            hi = mid;
+        const unsigned int mvalid = (__ballot_sync(0xffffffffu, valid) & gmask) >> gbase;
+        const unsigned int mabove =
+            (__ballot_sync(0xffffffffu, valid && cnt > target) & gmask) >> gbase;
+        // first point with the eigenvalue at or below it, last valid point before that
+        const int fa = mabove ? __ffs(mabove) - 1 : LPE;
+        const unsigned int mlower = mvalid & ((1u << fa) - 1u);
+        const double xhi = __shfl_sync(0xffffffffu, x, gbase + (fa % LPE));
+        const double xlo = __shfl_sync(0xffffffffu, x, gbase + (mlower ? 31 - __clz(mlower) : 0));
+        if (!mvalid)
+            done = true; // no representable point strictly inside the interval
+        else if (!done)
+        {
+            if (fa < LPE)
+                hi = xhi;
+            if (mlower)
+                lo = xlo;
+        }
     }
-    evals[eval_off_slot[slot] + j] = 0.5 * (lo + hi);
+    if (live && sub == 0)
+        evals[eval_off_slot[slot] + j] = 0.5 * (lo + hi);
 }
 
 // Inverse iteration (dstein), three kernels per sweep so that every lane has work even when
@@ -983,13 +1013,16 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
     const size_t budget_doubles = (size_t)3 << 30; // 24 GB of reflectors per chunk
     // largest n whose packed lower triangle (+ vectors) fits the shared memory of one block
     int nmax_smem = 0;
-    auto packed_smem_doubles = [](size_t n) {
-        return n * (n + 1) / 2 + 3 * n + (n + 1) / 2 + 32 + 256;
+    auto packed_smem_doubles = [](size_t n, size_t threads) {
+        return n * (n + 1) / 2 + 3 * n + (n + 1) / 2 + 32 + threads;
     };
+    // threads per block by occupancy class (blocks per SM): fewer resident blocks get more
+    // threads each so that the SM keeps 24 (3 x 8, 2 x 12) or 16 warps
+    auto class_threads = [](int c) { return c >= 3 ? 256 : (c == 2 ? 384 : 512); };
     {
         const size_t cap = (ctx->smem_optin - 1024) / sizeof(double);
         int n = 1;
-        while (packed_smem_doubles((size_t)n + 1) <= cap)
+        while (packed_smem_doubles((size_t)n + 1, class_threads(1)) <= cap)
             ++n;
         nmax_smem = n;
     }
@@ -1181,18 +1214,22 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         // one launch per occupancy class: the packed tile of the class's largest n decides
         // how many blocks are resident per SM (3, 2 or 1; the launch bounds cap it at 3), so
         // finer size classes would only add launch tails
-        std::vector<int> bucket_edges;
-        for (int c = 3; c >= 1; --c)
+        std::vector<int> bucket_edges, bucket_class;
+        static const int max_class = getenv("SA_GPU_MAX_CLASS") ? atoi(getenv("SA_GPU_MAX_CLASS")) : 3;
+        for (int c = std::max(1, std::min(3, max_class)); c >= 1; --c)
         {
             const size_t cap = (ctx->smem_per_sm / c - 1024) / sizeof(double);
             int n = 1;
-            while (n < nmax_smem && packed_smem_doubles((size_t)n + 1) <= cap)
+            while (n < nmax_smem && packed_smem_doubles((size_t)n + 1, class_threads(c)) <= cap)
                 ++n;
+            if (c == 1)
+                n = nmax_smem;
             if (bucket_edges.empty() || n > bucket_edges.back())
+            {
                 bucket_edges.push_back(n);
+                bucket_class.push_back(c);
+            }
         }
-        if (bucket_edges.back() < nmax_smem)
-            bucket_edges.push_back(nmax_smem);
         int pos = 0;
         // large (global-memory tile) bucket first
         {
@@ -1303,11 +1340,19 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
             }
             else
             {
-                const size_t smem = packed_smem_doubles((size_t)nb) * sizeof(double);
-                SA_CUDA(cudaFuncSetAttribute(k_at_packed,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)ctx->smem_optin - 1024));
-                k_at_packed<<<cnt, 256, smem, sb>>>(L, C, d_order.p + pos, lev->ae_D.p);
+                const int cls = bucket_class[b], threads = class_threads(cls);
+                const size_t smem = packed_smem_doubles((size_t)nb, threads) * sizeof(double);
+                auto launch = [&](auto kern) {
+                    SA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)ctx->smem_optin - 1024));
+                    kern<<<cnt, threads, smem, sb>>>(L, C, d_order.p + pos, lev->ae_D.p);
+                };
+                if (cls >= 3)
+                    launch(k_at_packed<256, 3>);
+                else if (cls == 2)
+                    launch(k_at_packed<384, 2>);
+                else
+                    launch(k_at_packed<512, 1>);
             }
             ctx->launches++;
             SA_CUDA(cudaGetLastError());
@@ -1377,7 +1422,7 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         pr->evects.alloc(pr->evect_off[ns]);
         {
             ProfScope ps(ctx, "eig.bisect");
-            SA_LAUNCH(ctx, k_bisect, (nev_total + 127) / 128, 128, 0, C, lev->AE2d_I.p,
+            SA_LAUNCH(ctx, k_bisect, (int)(((int64_t)nev_total * SA_BISECT_LPE + 127) / 128), 128, 0, C, lev->AE2d_I.p,
                       d_ev_slot.p, d_ev_idx.p, nev_total, d_glo.p, d_ghi.p, d_tn.p, d_eval_off.p,
                       pr->evals.p);
         }

@@ -1,6 +1,6 @@
 // Included inside eigen.cu's anonymous namespace (after ChunkDev / g_phase_clk).
 //
-// k_at_packed: assemble + weighted-l1 scaling + Householder tridiagonalisation of one AE
+// k_at_packed<max threads, min blocks per SM>: assemble + weighted-l1 scaling + Householder tridiagonalisation of one AE
 // per thread block with the matrix held as a PACKED LOWER TRIANGLE in shared memory
 // (entry (i,j), i >= j, at T[cjm[j] + i]).  Half the footprint of the square tile means
 // 2-3 resident blocks per SM for n ~ 100-150 -- the kernel is bound by the latency of the
@@ -47,7 +47,8 @@ __device__ __forceinline__ double packed_row_dot(const double *T, const int *cjm
     return s0 + s1;
 }
 
-__global__ void __launch_bounds__(256, 3)
+template <int NTMAX, int MINB>
+__global__ void __launch_bounds__(NTMAX, MINB)
 k_at_packed(LevelTables L, ChunkDev C, const int *slot_list, double *ae_D)
 {
     extern __shared__ double sm[];
