@@ -20,18 +20,22 @@ __device__ __forceinline__ double packed_row_dot(const double *T, const int *cjm
     // and column part           i in (ia, n),  i == ia + 1 + c (mod ncls): A(i, ia) x_i
     double s0 = 0., s1 = 0.;
     int j = k0 + c;
+    // column offsets cjm[j] = j (2n - 1 - j) / 2 are computed, not loaded: the kernel is bound
+    // by shared-memory wavefronts (ncu: 73 % of peak), integer issue slots are free
+    const int tn1 = 2 * n - 1;
+#define SA_CJM(jj) ((((jj) * (tn1 - (jj))) >> 1))
     for (; j + ncls <= ia; j += 2 * ncls)
     {
-        const double a0 = T[cjm[j] + ia], a1 = T[cjm[j + ncls] + ia];
+        const double a0 = T[SA_CJM(j) + ia], a1 = T[SA_CJM(j + ncls) + ia];
         s0 += (ABS ? fabs(a0) : a0) * x[j];
         s1 += (ABS ? fabs(a1) : a1) * x[j + ncls];
     }
     if (j <= ia)
     {
-        const double a0 = T[cjm[j] + ia];
+        const double a0 = T[SA_CJM(j) + ia];
         s0 += (ABS ? fabs(a0) : a0) * x[j];
     }
-    const double *col = T + cjm[ia];
+    const double *col = T + SA_CJM(ia);
     int i = ia + 1 + c;
     for (; i + ncls < n; i += 2 * ncls)
     {
@@ -264,6 +268,7 @@ k_at_packed(LevelTables L, ChunkDev C, const int *slot_list, double *ae_D)
             // Row a of the stored triangle has a + 1 entries: a thread takes the PAIR of rows
             // (a2, r - 1 - a2), r + 1 entries together, split over ncls2 column classes, so
             // that every thread (and warp) has the same amount of work before the barrier.
+            const int tn1 = 2 * n - 1;
             auto update_row = [&](int a, int c, int nc) {
                 const int ia = k + 1 + a;
                 const double vi = v[ia], wi = w[ia] + alpha2 * vi;
@@ -272,7 +277,7 @@ k_at_packed(LevelTables L, ChunkDev C, const int *slot_list, double *ae_D)
                 {
                     // column k+1 also feeds the norm of the next Householder vector
                     const double vj = v[j], wj = w[j] + alpha2 * vj;
-                    double *e0 = T + cjm[j] + ia;
+                    double *e0 = T + SA_CJM(j) + ia;
                     const double t = *e0 - (vi * wj + wi * vj);
                     *e0 = t;
                     if (a >= 2)
@@ -283,7 +288,7 @@ k_at_packed(LevelTables L, ChunkDev C, const int *slot_list, double *ae_D)
                 {
                     const double v0 = v[j], v1 = v[j + nc];
                     const double w0 = w[j] + alpha2 * v0, w1 = w[j + nc] + alpha2 * v1;
-                    double *e0 = T + cjm[j] + ia, *e1 = T + cjm[j + nc] + ia;
+                    double *e0 = T + SA_CJM(j) + ia, *e1 = T + SA_CJM(j + nc) + ia;
                     const double t0 = *e0, t1 = *e1;
                     *e0 = t0 - (vi * w0 + wi * v0);
                     *e1 = t1 - (vi * w1 + wi * v1);
@@ -291,7 +296,7 @@ k_at_packed(LevelTables L, ChunkDev C, const int *slot_list, double *ae_D)
                 if (j <= ia)
                 {
                     const double v0 = v[j], w0 = w[j] + alpha2 * v0;
-                    double *e0 = T + cjm[j] + ia;
+                    double *e0 = T + SA_CJM(j) + ia;
                     *e0 = *e0 - (vi * w0 + wi * v0);
                 }
             };
