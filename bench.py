@@ -265,6 +265,13 @@ def main():
     if ctxp:
         fp64_peak = gl.sa_gpu_bench_fp64_peak(ctxp)
     kern_ms = prof.get("eig.assemble_tridiag", float("nan"))
+    traffic = None  # DRAM bytes per step of the dominant kernel, from the committed ncu capture
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if tj.get("workload") == args.workload:
+            traffic = tj["k_at_packed"]["dram_bytes_per_step"]
+    except Exception:
+        traffic = None
     achieved = flops / (kern_ms * 1e-3) / 1e12
     roofline = {
         "kernel": "k_at_packed (assemble + weighted-l1 scaling + Householder tridiagonalisation; "
@@ -274,7 +281,8 @@ def main():
         "frac": (achieved / fp64_peak) if fp64_peak else None,
         "peak_source": "measured in this run: dependent-free DFMA loop (sa_gpu_bench_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
         "algorithmic_flops_per_step": flops, "algorithmic_bytes_per_step": abytes,
-        "kernel_ms_per_step": kern_ms, "stage_ms": prof, "traffic": None,
+        "kernel_ms_per_step": kern_ms, "stage_ms": prof, "traffic": traffic,
+        "traffic_source": "profiles/r01_traffic.json (ncu dram bytes, per step)" if traffic else None,
     }
 
     line = {

@@ -35,8 +35,95 @@ struct sa_gpu_solver
     }
 };
 
+// ---- cuBLAS (plain library TRSM / SYRK of the blocked dense coarsest factorisation), resolved
+// at run time so the library has no link-time dependency on it
+#include <dlfcn.h>
 namespace
 {
+typedef void *cublasHandle_p;
+struct CublasApi
+{
+    void *dl = nullptr;
+    cublasHandle_p h = nullptr;
+    int (*create)(cublasHandle_p *) = nullptr;
+    int (*destroy)(cublasHandle_p) = nullptr;
+    int (*set_stream)(cublasHandle_p, cudaStream_t) = nullptr;
+    // cublasDtrsm_v2(handle, side, uplo, trans, diag, m, n, alpha, A, lda, B, ldb)
+    int (*dtrsm)(cublasHandle_p, int, int, int, int, int, int, const double *, const double *, int,
+                 double *, int) = nullptr;
+    // cublasDsyrk_v2(handle, uplo, trans, n, k, alpha, A, lda, beta, C, ldc)
+    int (*dsyrk)(cublasHandle_p, int, int, int, int, const double *, const double *, int,
+                 const double *, double *, int) = nullptr;
+    bool ok = false;
+    bool load()
+    {
+        if (ok)
+            return true;
+        const char *names[] = {"libcublas.so.12", "libcublas.so", "/usr/local/cuda/lib64/libcublas.so.12"};
+        for (int i = 0; i < 3 && !dl; ++i)
+            dl = dlopen(names[i], RTLD_NOW | RTLD_LOCAL);
+        if (!dl)
+            return false;
+        create = (int (*)(cublasHandle_p *))dlsym(dl, "cublasCreate_v2");
+        destroy = (int (*)(cublasHandle_p))dlsym(dl, "cublasDestroy_v2");
+        set_stream = (int (*)(cublasHandle_p, cudaStream_t))dlsym(dl, "cublasSetStream_v2");
+        dtrsm = (decltype(dtrsm))dlsym(dl, "cublasDtrsm_v2");
+        dsyrk = (decltype(dsyrk))dlsym(dl, "cublasDsyrk_v2");
+        if (!create || !destroy || !set_stream || !dtrsm || !dsyrk)
+            return false;
+        if (create(&h) != 0)
+            return false;
+        ok = true;
+        return true;
+    }
+};
+CublasApi g_cublas;
+// cuBLAS enum values (cublas_api.h): CUBLAS_SIDE_LEFT 0 / RIGHT 1, FILL_MODE_LOWER 0,
+// OP_N 0 / OP_T 1, DIAG_NON_UNIT 0
+enum { CB_LEFT = 0, CB_RIGHT = 1, CB_LOWER = 0, CB_N = 0, CB_T = 1, CB_NON_UNIT = 0 };
+
+// Cholesky of the nb x nb diagonal block at (k0, k0) of the column-major n x n matrix, in
+// shared memory, one block (the panel step of the blocked factorisation)
+__global__ void k_potf2_block(int n, double *A, int k0, int nb, int *info)
+{
+    extern __shared__ double sb[]; // nb x nb, column-major
+    for (int t = threadIdx.x; t < nb * nb; t += blockDim.x)
+        sb[t] = A[(k0 + t % nb) + (int64_t)n * (k0 + t / nb)];
+    __syncthreads();
+    for (int k = 0; k < nb; ++k)
+    {
+        const double a = sb[k + nb * k];
+        if (!(a > 0.))
+        {
+            if (threadIdx.x == 0)
+                atomicCAS(info, 0, k0 + k + 1);
+            return; // uniform: every thread reads the same pivot
+        }
+        const double pv = sqrt(a), inv = 1. / pv;
+        __syncthreads();
+        for (int i = k + threadIdx.x; i < nb; i += blockDim.x)
+            sb[i + nb * k] = (i == k) ? pv : sb[i + nb * k] * inv;
+        __syncthreads();
+        const int rem = nb - k - 1;
+        for (int t = threadIdx.x; t < rem * rem; t += blockDim.x)
+        {
+            const int i = k + 1 + t % rem, j = k + 1 + t / rem;
+            if (i >= j)
+                sb[i + nb * j] -= sb[i + nb * k] * sb[j + nb * k];
+        }
+        __syncthreads();
+    }
+    for (int t = threadIdx.x; t < nb * nb; t += blockDim.x)
+        if (t % nb >= t / nb)
+            A[(k0 + t % nb) + (int64_t)n * (k0 + t / nb)] = sb[t];
+}
+
+__global__ void k_set_identity(int n, double *X)
+{
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < (int64_t)n * n)
+        X[t] = (t % n == t / n) ? 1. : 0.;
+}
 
 __global__ void k_densify(int n, const int *I, const int *J, const double *A, double *D)
 {
@@ -314,9 +401,46 @@ extern "C" int sa_gpu_solver_create(sa_gpu_ctx *ctx, sa_gpu_level **levels, int 
         if (n)
         {
             SA_LAUNCH(ctx, k_densify, (n + 255) / 256, 256, 0, n, Ac.I.p, Ac.J.p, Ac.A.p, Lm.p);
-            SA_LAUNCH(ctx, k_cholesky, 1, 1024, 0, n, Lm.p, info.p);
-            SA_LAUNCH(ctx, k_chol_inverse, (n + 63) / 64, 64, 0, n, Lm.p, X.p);
             const int64_t nn = (int64_t)n * n;
+            static const int blocked_min =
+                getenv("SA_GPU_COARSE_BLOCKED_MIN") ? atoi(getenv("SA_GPU_COARSE_BLOCKED_MIN")) : 768;
+            if (n >= blocked_min && g_cublas.load())
+            {
+                // blocked right-looking Cholesky: own kernel for the diagonal block, library
+                // TRSM / SYRK for the panel and the trailing update; then A^-1 = L^-T L^-1 by
+                // two triangular solves with the identity
+                const int NB = 64;
+                const double one = 1., minus1 = -1.;
+                g_cublas.set_stream(g_cublas.h, st);
+                for (int k0 = 0; k0 < n; k0 += NB)
+                {
+                    const int nb = std::min(NB, n - k0), rem = n - k0 - nb;
+                    SA_LAUNCH(ctx, k_potf2_block, 1, 256, (size_t)nb * nb * sizeof(double), n, Lm.p,
+                              k0, nb, info.p);
+                    if (rem > 0)
+                    {
+                        double *L11 = Lm.p + k0 + (int64_t)n * k0;
+                        double *L21 = Lm.p + (k0 + nb) + (int64_t)n * k0;
+                        double *A22 = Lm.p + (k0 + nb) + (int64_t)n * (k0 + nb);
+                        if (g_cublas.dtrsm(g_cublas.h, CB_RIGHT, CB_LOWER, CB_T, CB_NON_UNIT, rem, nb,
+                                           &one, L11, n, L21, n) != 0 ||
+                            g_cublas.dsyrk(g_cublas.h, CB_LOWER, CB_N, rem, nb, &minus1, L21, n, &one,
+                                           A22, n) != 0)
+                            SA_FAIL("sa_gpu_solver_create: cuBLAS TRSM/SYRK failed");
+                    }
+                }
+                SA_LAUNCH(ctx, k_set_identity, (unsigned)((nn + 255) / 256), 256, 0, n, X.p);
+                if (g_cublas.dtrsm(g_cublas.h, CB_LEFT, CB_LOWER, CB_N, CB_NON_UNIT, n, n, &one, Lm.p, n,
+                                   X.p, n) != 0 ||
+                    g_cublas.dtrsm(g_cublas.h, CB_LEFT, CB_LOWER, CB_T, CB_NON_UNIT, n, n, &one, Lm.p, n,
+                                   X.p, n) != 0)
+                    SA_FAIL("sa_gpu_solver_create: cuBLAS TRSM failed");
+            }
+            else
+            {
+                SA_LAUNCH(ctx, k_cholesky, 1, 1024, 0, n, Lm.p, info.p);
+                SA_LAUNCH(ctx, k_chol_inverse, (n + 63) / 64, 64, 0, n, Lm.p, X.p);
+            }
             SA_LAUNCH(ctx, k_symmetrize, (unsigned)((nn + 255) / 256), 256, 0, n, X.p, S->Ainv.p);
         }
         int h = 0;
