@@ -1263,29 +1263,55 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
                     if (smem_c > ctx->smem_optin)
                         SA_FAIL("sa_gpu_local_spectral: AE with %d dofs exceeds the supported "
                                 "size of the large-matrix eigensolver", nb);
-                    static int gdiv = getenv("SA_GPU_COOP_DIV") ? atoi(getenv("SA_GPU_COOP_DIV")) : 180;
-                    int G = std::max(2, std::min(ctx->num_sms, nb / gdiv));
-                    int B = std::max(1, std::min(cnt - done, ctx->num_sms / G));
+                    static int gdiv = getenv("SA_GPU_COOP_DIV") ? atoi(getenv("SA_GPU_COOP_DIV")) : 300;
+                    // symmetric (lower-triangle) variant by default; SA_GPU_COOP_SYM=0 keeps
+                    // the full-matrix kernel
+                    static const int coop_sym =
+                        getenv("SA_GPU_COOP_SYM") ? atoi(getenv("SA_GPU_COOP_SYM")) : 1;
+                    // the symmetric kernel can run with 256 threads and two blocks per SM (of
+                    // different groups): one block's barrier wait is the other's compute time
+                    static const int sym_threads =
+                        getenv("SA_GPU_COOP_THREADS") ? atoi(getenv("SA_GPU_COOP_THREADS")) : 512;
+                    const int cthreads = coop_sym ? sym_threads : 512, cwarps = cthreads / 32;
+                    int slots = ctx->num_sms; // co-resident blocks of the cooperative launch
+                    {
+                        const size_t one = ((size_t)3 * ((nb + 31) / 32) * 32 + 64 +
+                                            (size_t)cwarps * (16 * 33) + (size_t)cwarps * 8 * 32) *
+                                           sizeof(double);
+                        if (coop_sym && cthreads <= 256 && 2 * (one + 1024) <= ctx->smem_per_sm)
+                            slots = 2 * ctx->num_sms;
+                    }
+                    int G = std::max(2, std::min(slots, nb / gdiv));
+                    int B = std::max(1, std::min(cnt - done, slots / G));
                     if (B == cnt - done)
-                        G = std::max(2, ctx->num_sms / B);
+                        G = std::max(2, slots / B);
                     G = std::min(G, std::max(1, (nb + 31) / 32));
                     const int64_t tstride = (int64_t)nb * nb;
                     WS.Twork.ensure((size_t)B * tstride);
-                    WS.pbuf.ensure((size_t)B * 2 * nb + (size_t)B * 4);
+                    const int NRB = (nb + 31) / 32, QMAX = (NRB + G - 1) / G;
+                    const size_t smem_sym = ((size_t)3 * NRB * 32 + 64 + (size_t)cwarps * (16 * 33) +
+                                             (size_t)cwarps * QMAX * 32) *
+                                            sizeof(double);
+                    const bool use_sym = coop_sym && smem_sym <= ctx->smem_optin;
+                    const size_t pb_per = use_sym ? (size_t)(2 + 2 * G) * nb : (size_t)2 * nb;
+                    WS.pbuf.ensure((size_t)B * pb_per + (size_t)B * 4);
                     WS.counters.ensure(B);
                     SA_CUDA(cudaMemsetAsync(WS.pbuf.p, 0,
-                                            ((size_t)B * 2 * nb + (size_t)B * 4) * sizeof(double), st));
+                                            ((size_t)B * pb_per + (size_t)B * 4) * sizeof(double), st));
                     SA_CUDA(cudaMemsetAsync(WS.counters.p, 0, (size_t)B * sizeof(unsigned int), st));
                     const size_t smem_a = (size_t)(3 * nb + 40) * sizeof(double);
-                    SA_LAUNCH(ctx, k_assemble_tridiag, B, 512, smem_a, L, C, d_order.p + pos + done,
-                              B, 0, lev->ae_D.p, WS.Twork.p, tstride, 1);
+                    {
+                        ProfScope ps(ctx, "eig.large_assemble");
+                        SA_LAUNCH(ctx, k_assemble_tridiag, B, 512, smem_a, L, C,
+                                  d_order.p + pos + done, B, 0, lev->ae_D.p, WS.Twork.p, tstride, 1);
+                    }
                     std::vector<CoopMatrix> hm(B);
                     for (int b = 0; b < B; ++b)
                     {
                         hm[b].slot = order[pos + done + b];
                         hm[b].T = WS.Twork.p + (int64_t)b * tstride;
-                        hm[b].pbuf = WS.pbuf.p + (int64_t)b * 2 * nb;
-                        hm[b].pvacc = WS.pbuf.p + (int64_t)B * 2 * nb + (int64_t)b * 4;
+                        hm[b].pbuf = WS.pbuf.p + (int64_t)b * pb_per;
+                        hm[b].pvacc = WS.pbuf.p + (int64_t)B * pb_per + (int64_t)b * 4;
                         hm[b].counter = WS.counters.p + b;
                     }
                     WS.coopmats.ensure((size_t)B * sizeof(CoopMatrix));
@@ -1293,9 +1319,23 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
                                             cudaMemcpyHostToDevice, st));
                     SA_CUDA(cudaStreamSynchronize(st)); // hm goes out of scope
                     const CoopMatrix *dm = (const CoopMatrix *)WS.coopmats.p;
-                    void *args[] = {(void *)&L, (void *)&C, (void *)&dm, (void *)&G};
-                    SA_CUDA(cudaLaunchCooperativeKernel((const void *)k_tridiag_coop, dim3(B * G),
-                                                        dim3(512), args, smem_c, st));
+                    ProfScope ps(ctx, "eig.large_tridiag");
+                    if (use_sym)
+                    {
+                        int qmax = QMAX;
+                        void *args[] = {(void *)&L, (void *)&C, (void *)&dm, (void *)&G, (void *)&qmax};
+                        SA_CUDA(cudaFuncSetAttribute(k_tridiag_coop_sym,
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int)ctx->smem_optin));
+                        SA_CUDA(cudaLaunchCooperativeKernel((const void *)k_tridiag_coop_sym,
+                                                            dim3(B * G), dim3(cthreads), args, smem_sym, st));
+                    }
+                    else
+                    {
+                        void *args[] = {(void *)&L, (void *)&C, (void *)&dm, (void *)&G};
+                        SA_CUDA(cudaLaunchCooperativeKernel((const void *)k_tridiag_coop, dim3(B * G),
+                                                            dim3(512), args, smem_c, st));
+                    }
                     ctx->launches++;
                     done += B;
                 }

@@ -4,7 +4,11 @@ import saamge_b200 as sab
 n=int(sys.argv[1]); levels=int(sys.argv[2]); epa=int(sys.argv[3]); nupro=int(sys.argv[4]) if len(sys.argv)>4 else 0
 p=sab.default_params(num_levels=levels, first_elems_per_agg=52, elems_per_agg=epa, partition_kind=2, block=(32,32,32), first_nu_pro=nupro, nu_pro=nupro)
 t=time.time(); pr=sab.Problem(3,n,coef_kind=1); na=pr.partition(p); print("host inputs %.1fs AEs %d"%(time.time()-t,na), flush=True)
+import ctypes
+h=sab.host_lib(); h.sa_drv_gpu_profile.argtypes=[ctypes.c_int,ctypes.c_char_p,ctypes.c_int]
 t=time.time(); H=sab.ml_build(pr,p); print("ml_build %.2fs"%(time.time()-t), flush=True)
+buf=ctypes.create_string_buffer(8192); h.sa_drv_gpu_profile(-1,buf,8192); print("PROF", buf.value.decode().replace("\n","; "))
+g=sab.gpu_lib(); clk=(ctypes.c_double*8)(); g.sa_gpu_debug_phase_clocks(clk); print("PHASE Mcycles", [round(x/1e6,1) for x in clk])
 tm=H.times(); print({k:round(v,3) for k,v in tm.items()})
 for l in range(levels-1):
     print("level",l,"ND",H.scalar("ND",l),"nparts",H.scalar("nparts",l),"mises",H.scalar("num_mises",l))
