@@ -134,9 +134,10 @@ __global__ void k_spmv(int rows, const int *__restrict__ I, const int *__restric
     const int sub = t % TPR;
     const bool valid = row < rows;
     double s = 0.;
-    // epilogue operands are fetched up front so their latency overlaps the matrix stream
+    // epilogue operands are fetched up front (by the lane that writes the row) so their
+    // latency overlaps the matrix stream
     double br = 0., dr = 0., xr = 0.;
-    if (valid)
+    if (valid && sub == 0)
     {
         if (MODE == 1 || MODE == 3 || MODE == 4)
             br = b[row];

@@ -109,6 +109,29 @@ def test_atleast_one_fallback_and_tiny_theta():
     pr.close()
 
 
+@pytest.mark.parametrize("env", [
+    {"SA_GPU_COOP_SYM": "0"},        # full-matrix cooperative kernel (k_tridiag_coop)
+    {"SA_GPU_SQUARE_TILE": "1"},     # square shared-memory tile kernel (k_at_smem)
+    {"SA_GPU_NO_ASYNC_ALLOC": "1"},  # plain cudaMalloc instead of the stream-ordered pool
+    {"SA_GPU_COARSE_BLOCKED_MIN": "1"},  # blocked coarsest factorisation even for tiny n
+])
+def test_parity_of_alternative_kernel_paths(env):
+    """The switches are read once per process, so each variant runs in a fresh interpreter:
+    3-level 24^3 (coarse-level AEs take the large-matrix path) against the oracle."""
+    import os
+    import subprocess
+    import sys
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    e = dict(os.environ)
+    e.update(env)
+    out = subprocess.run([sys.executable, os.path.join(here, "run_parity.py"),
+                          "3", "24", "1", "1", "3", "52", "24", "0", "0"],
+                         env=e, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "PARITY OK" in out.stdout, out.stdout[-2000:]
+
+
 # ---------------------------------------------------------------- direct C ABI
 
 
