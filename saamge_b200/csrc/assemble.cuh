@@ -9,6 +9,8 @@
 #ifndef SA_ASSEMBLE_CUH
 #define SA_ASSEMBLE_CUH
 
+#include <algorithm>
+
 #include "sa_gpu_internal.cuh"
 
 #define SA_AGG_BETWEEN_AES_FLAG 0x01
@@ -417,6 +419,128 @@ static __device__ bool sa_dev_assemble_AE_staged(const LevelTables &L, int part,
             flush();
     }
     __syncthreads();
+    return true;
+}
+
+/// Column-wise assembly of LARGE AE matrices (coarse levels: a few thousand dofs, elements
+/// with a hundred dofs or more) straight into a column-major n x n matrix in global memory;
+/// agg_build_AE_stiffm (amg/src/aggregates.cpp:959-1086) only (no operator rows).
+/// grid = (column splits, matrices), one warp per column at a time:
+///   - the block stages an open-addressing hash global dof -> local id in shared memory;
+///   - a column is summed in a shared-memory buffer of n doubles (scatter by local row id),
+///     over the AE's elements containing the column dof in ascending order (deterministic,
+///     the reference's order); the element block column is read contiguously;
+///   - the finished column is written out coalesced.
+/// Shared memory: 2 * H ints (H = power of two >= 2 n) + warps * n doubles.
+/// parts[m]: AE of matrix m; matrix m at Tbase + m * tstride.
+static __global__ void k_assemble_large(LevelTables L, const int *parts, const int *slot_list,
+                                        const int *ae_of_slot, double *Tbase, int64_t tstride,
+                                        int Hlog)
+{
+    extern __shared__ double smem_al[];
+    const int m = blockIdx.y;
+    const int part = parts ? parts[m] : ae_of_slot[slot_list[m]];
+    const int rb = L.AE2d_I[part];
+    const int n = L.AE2d_I[part + 1] - rb;
+    const int *dofs = L.AE2d_J + rb;
+    const int H = 1 << Hlog;
+    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, wid = tid >> 5, NW = NT >> 5;
+    int *hkey = (int *)smem_al;
+    int *hval = hkey + H;
+    double *buf = (double *)(hval + H) + (size_t)wid * n;
+    double *T = Tbase + (int64_t)m * tstride;
+    for (int q = tid; q < H; q += NT)
+        hkey[q] = -1;
+    __syncthreads();
+    for (int i = tid; i < n; i += NT)
+    {
+        const int key = dofs[i];
+        unsigned int slot = ((unsigned int)key * 0x9E3779B1u) >> (32 - Hlog);
+        while (true)
+        {
+            const int old = atomicCAS(&hkey[slot], -1, key);
+            if (old == -1)
+            {
+                hval[slot] = i;
+                break;
+            }
+            slot = (slot + 1) & (H - 1);
+        }
+    }
+    __syncthreads();
+    for (int col = blockIdx.x * NW + wid; col < n; col += gridDim.x * NW)
+    {
+        for (int i = lane; i < n; i += 32)
+            buf[i] = 0.;
+        __syncwarp();
+        const int g = dofs[col];
+        const int bi = L.d2e_I[g], ei = L.d2e_I[g + 1];
+        for (int p = bi; p < ei; ++p)
+        {
+            const int elem = L.d2e_J[p];
+            if (L.partitioning[elem] != part)
+                continue;
+            const int eb = L.e2d_I[elem];
+            const int sz = L.e2d_I[elem + 1] - eb;
+            int kc = -1; // position of the column dof in the element
+            for (int q0 = 0; q0 < sz && kc < 0; q0 += 32)
+            {
+                const bool hit = (q0 + lane < sz) && L.e2d_J[eb + q0 + lane] == g;
+                const unsigned int b = __ballot_sync(0xffffffffu, hit);
+                if (b)
+                    kc = q0 + __ffs(b) - 1;
+            }
+            const double *Kc = L.elmat + L.elmat_off[elem] + (int64_t)kc * sz; // column kc
+            for (int jr = lane; jr < sz; jr += 32)
+            {
+                const double el = Kc[jr];
+                if (0. != el)
+                {
+                    const int key = L.e2d_J[eb + jr];
+                    unsigned int slot = ((unsigned int)key * 0x9E3779B1u) >> (32 - Hlog);
+                    while (hkey[slot] != key)
+                        slot = (slot + 1) & (H - 1);
+                    buf[hval[slot]] += el; // distinct dofs of one element: distinct rows
+                }
+            }
+            __syncwarp();
+        }
+        double *Tc = T + (int64_t)n * col;
+        for (int i = lane; i < n; i += 32)
+            Tc[i] = buf[i];
+        __syncwarp();
+    }
+}
+
+/// Launches k_assemble_large for nmat matrices (largest: nmax dofs) on \a stream; returns false
+/// (nothing launched) when the shared-memory footprint does not fit or the level assembles
+/// with the global operator.
+static inline bool sa_launch_assemble_large(sa_gpu_ctx *ctx, const LevelTables &L, const int *d_parts,
+                                            const int *d_slot_list, const int *d_ae_of_slot,
+                                            int nmat, int nmax, double *Tbase, int64_t tstride,
+                                            cudaStream_t stream)
+{
+    if (L.with_global || nmat <= 0)
+        return false;
+    int Hlog = 5;
+    while ((1 << Hlog) < 2 * nmax)
+        ++Hlog;
+    int NW = 4;
+    auto smem_of = [&](int nw) {
+        return (size_t)2 * ((size_t)1 << Hlog) * sizeof(int) + (size_t)nw * nmax * sizeof(double);
+    };
+    while (NW > 1 && smem_of(NW) > ctx->smem_optin)
+        NW >>= 1;
+    const size_t smem = smem_of(NW);
+    if (smem > ctx->smem_optin)
+        return false;
+    const int nsplit = std::max(1, std::min((nmax + NW - 1) / NW, (2 * ctx->num_sms + nmat - 1) / nmat));
+    SA_CUDA(cudaFuncSetAttribute(k_assemble_large, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+    k_assemble_large<<<dim3(nsplit, nmat), NW * 32, smem, stream>>>(L, d_parts, d_slot_list,
+                                                                     d_ae_of_slot, Tbase, tstride, Hlog);
+    ctx->launches++;
+    SA_CUDA(cudaGetLastError());
     return true;
 }
 

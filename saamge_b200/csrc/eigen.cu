@@ -70,7 +70,7 @@ __device__ unsigned long long g_phase_clk[8];
 // memory (n <= nmax_smem), otherwise directly in the V block of the AE.
 __global__ void k_assemble_tridiag(LevelTables L, ChunkDev C, const int *slot_list, int nslots,
                                    int tile_in_smem, double *ae_D, double *tile_base,
-                                   int64_t tile_stride, int stop_after_scale)
+                                   int64_t tile_stride, int stop_after_scale, int preassembled)
 {
     extern __shared__ double sm[];
     const int slot = slot_list[blockIdx.x];
@@ -90,7 +90,8 @@ __global__ void k_assemble_tridiag(LevelTables L, ChunkDev C, const int *slot_li
            *sinv = C.sinv + C.doff[slot];
 
     long long tc0 = clock64();
-    sa_dev_assemble_AE(L, part, T, ld);
+    if (!preassembled) // (large AEs: k_assemble_large has filled the tile already)
+        sa_dev_assemble_AE(L, part, T, ld);
     long long tc1 = clock64();
     if (threadIdx.x == 0)
         atomicAdd(&g_phase_clk[0], (unsigned long long)(tc1 - tc0));
@@ -1244,7 +1245,7 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)ctx->smem_optin));
                 SA_LAUNCH(ctx, k_assemble_tridiag, cnt, 512, smem, L, C, d_order.p + pos, cnt, 0,
-                          lev->ae_D.p, (double *)nullptr, (int64_t)0, 0);
+                          lev->ae_D.p, (double *)nullptr, (int64_t)0, 0, 0);
             }
             else if (cnt)
             {
@@ -1302,8 +1303,13 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
                     const size_t smem_a = (size_t)(3 * nb + 40) * sizeof(double);
                     {
                         ProfScope ps(ctx, "eig.large_assemble");
+                        // assembly by columns with all SMs, then D + scaling per matrix
+                        const bool pre = sa_launch_assemble_large(
+                            ctx, L, nullptr, d_order.p + pos + done, C.ae_of_slot, B, nb, WS.Twork.p,
+                            tstride, st);
                         SA_LAUNCH(ctx, k_assemble_tridiag, B, 512, smem_a, L, C,
-                                  d_order.p + pos + done, B, 0, lev->ae_D.p, WS.Twork.p, tstride, 1);
+                                  d_order.p + pos + done, B, 0, lev->ae_D.p, WS.Twork.p, tstride, 1,
+                                  pre ? 1 : 0);
                     }
                     std::vector<CoopMatrix> hm(B);
                     for (int b = 0; b < B; ++b)

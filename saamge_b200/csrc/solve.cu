@@ -403,7 +403,7 @@ extern "C" int sa_gpu_solver_create(sa_gpu_ctx *ctx, sa_gpu_level **levels, int 
             SA_LAUNCH(ctx, k_densify, (n + 255) / 256, 256, 0, n, Ac.I.p, Ac.J.p, Ac.A.p, Lm.p);
             const int64_t nn = (int64_t)n * n;
             static const int blocked_min =
-                getenv("SA_GPU_COARSE_BLOCKED_MIN") ? atoi(getenv("SA_GPU_COARSE_BLOCKED_MIN")) : 768;
+                getenv("SA_GPU_COARSE_BLOCKED_MIN") ? atoi(getenv("SA_GPU_COARSE_BLOCKED_MIN")) : 2500;
             if (n >= blocked_min && g_cublas.load())
             {
                 // blocked right-looking Cholesky: own kernel for the diagonal block, library

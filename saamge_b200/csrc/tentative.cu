@@ -291,12 +291,13 @@ struct CoarseElmatArgs
     int max_mis;                // largest MIS size (shared buffers)
 };
 
-__global__ void k_coarse_elmat(LevelTables L, CoarseElmatArgs C, int nparts)
+__global__ void k_coarse_elmat(LevelTables L, CoarseElmatArgs C, int e_begin, int e_end,
+                               int preassembled)
 {
     extern __shared__ double sm[];
     double *ubuf = sm;                              // max_mis
     int *lidbuf = (int *)(sm + C.max_mis);          // max_mis
-    for (int e = blockIdx.x; e < nparts; e += gridDim.x)
+    for (int e = e_begin + blockIdx.x; e < e_end; e += gridDim.x)
     {
         const int n = L.AE2d_I[e + 1] - L.AE2d_I[e];
         const int cb = C.ce2d_I[e];
@@ -305,7 +306,8 @@ __global__ void k_coarse_elmat(LevelTables L, CoarseElmatArgs C, int nparts)
             continue;
         double *T = C.scratch + (int64_t)blockIdx.x * C.scratch_stride;
         double *Wm = T + (int64_t)n * n;
-        sa_dev_assemble_AE(L, e, T, n);
+        if (!preassembled) // (large AEs: k_assemble_large has filled the tile of this block)
+            sa_dev_assemble_AE(L, e, T, n);
         // W = A_AE * P_e, column by column
         for (int lc = 0; lc < nc; ++lc)
         {
@@ -523,7 +525,37 @@ extern "C" int sa_gpu_coarse_elmats(sa_gpu_level *finer, sa_gpu_level *coarse)
         SA_FAIL("sa_gpu_coarse_elmats: MIS of %d dofs exceeds the shared buffers", max_mis);
     SA_CUDA(cudaFuncSetAttribute(k_coarse_elmat, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)ctx->smem_optin));
-    SA_LAUNCH(ctx, k_coarse_elmat, blocks, 256, smem, L, C, nparts);
+    int nmax = 1;
+    for (int e = 0; e < nparts; ++e)
+        nmax = std::max(nmax, finer->h_AE2d_I[e + 1] - finer->h_AE2d_I[e]);
+    bool rounds = false;
+    if (!L.with_global && nmax > 256)
+    {
+        // large AEs: every round assembles `blocks` AE matrices with all SMs (by columns),
+        // then one block per AE forms P_e^T A_AE P_e
+        std::vector<int> iota(nparts);
+        for (int e = 0; e < nparts; ++e)
+            iota[e] = e;
+        DevBuf<int> d_parts;
+        d_parts.upload(iota.data(), nparts, st);
+        rounds = true;
+        for (int e0 = 0; e0 < nparts && rounds; e0 += blocks)
+        {
+            const int cnt = std::min(blocks, nparts - e0);
+            if (!sa_launch_assemble_large(ctx, L, d_parts.p + e0, nullptr, nullptr, cnt, nmax,
+                                          scratch.p, max_scratch, st))
+            {
+                if (e0 != 0)
+                    SA_FAIL("sa_gpu_coarse_elmats: large assembly became unavailable");
+                rounds = false;
+                break;
+            }
+            SA_LAUNCH(ctx, k_coarse_elmat, cnt, 256, smem, L, C, e0, e0 + cnt, 1);
+        }
+        SA_CUDA(cudaStreamSynchronize(st)); // iota / d_parts go out of scope
+    }
+    if (!rounds)
+        SA_LAUNCH(ctx, k_coarse_elmat, blocks, 256, smem, L, C, 0, nparts, 0);
     SA_CUDA(cudaStreamSynchronize(st));
     coarse->have_elmat = true;
     SA_API_END

@@ -1,4 +1,7 @@
 // Partitioning relations on one process (see aggregates.hpp).
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include "aggregates.hpp"
 #include "part.hpp"
 
@@ -8,6 +11,27 @@
 
 namespace saamge
 {
+
+namespace
+{
+// SA_HOST_PROFILE=1: wall-clock laps of the host-side topology construction on stderr
+struct Lap
+{
+    bool on;
+    std::chrono::steady_clock::time_point t;
+    Lap() : on(getenv("SA_HOST_PROFILE") != NULL), t(std::chrono::steady_clock::now()) {}
+    void operator()(const char *what)
+    {
+        if (!on)
+            return;
+        const auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "[host] %-28s %8.1f ms\n", what,
+                std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
+} // namespace
+
 
 void agg_construct_agg_flags(agg_partitioning_relations_t &agg_part_rels,
                              const agg_dof_status_t *bdr_dofs)
@@ -120,10 +144,12 @@ void agg_create_partitioning_tables(agg_partitioning_relations_t *agg_part_rels,
                                     const agg_dof_status_t *bdr_dofs)
 {
     // amg/src/aggregates.cpp:1357-1443
+    Lap lap;
     agg_part_rels->elem_to_dof = elem_to_dof;
     agg_part_rels->dof_to_elem = new Table;
     Transpose(*elem_to_dof, *agg_part_rels->dof_to_elem, elem_to_dof->ncols);
     agg_part_rels->ND = agg_part_rels->dof_to_elem->Size();
+    lap("tables: dof_to_elem");
 
     agg_part_rels->elem_to_AE = new Table;
     TableFromArray(agg_part_rels->partitioning, NE, agg_part_rels->nparts,
@@ -137,9 +163,13 @@ void agg_create_partitioning_tables(agg_partitioning_relations_t *agg_part_rels,
     agg_part_rels->dof_to_AE = new Table;
     Transpose(*agg_part_rels->AE_to_dof, *agg_part_rels->dof_to_AE,
               agg_part_rels->ND);
+    lap("tables: AE tables");
     agg_build_glob_to_AE_id_map(*agg_part_rels);
+    lap("tables: glob_to_AE_id_map");
     agg_produce_mises(*agg_part_rels);
+    lap("tables: produce_mises");
     agg_construct_agg_flags(*agg_part_rels, bdr_dofs);
+    lap("tables: agg_flags");
 }
 
 agg_partitioning_relations_t *
@@ -187,10 +217,12 @@ agg_create_partitioning_coarse(const agg_partitioning_relations_t &fine,
     std::memset(rels->dof_masterproc, 0, sizeof(int) * std::max(1, NDc));
 
     // elem_to_elem = AE_to_elem * elem_to_elem * elem_to_AE (amg/src/aggregates.cpp:1768-1771)
+    Lap lap;
     Table tmptbl;
     rels->elem_to_elem = new Table;
     Mult(*fine.AE_to_elem, *fine.elem_to_elem, tmptbl);
     Mult(tmptbl, *fine.elem_to_AE, *rels->elem_to_elem);
+    lap("coarse: elem_to_elem product");
 
     const int num_elem = fine.nparts;
     if (partitioning)
@@ -215,6 +247,7 @@ agg_create_partitioning_coarse(const agg_partitioning_relations_t &fine,
         rels->partitioning = part_generate_partitioning(graph, weights.data(), nparts);
     }
     rels->nparts = *nparts;
+    lap("coarse: partitioning");
 
     // finedof_to_dof = pattern of the tentative prolongator
     // (amg/src/aggregates.cpp:1445-1479 on one process)
@@ -241,6 +274,7 @@ agg_create_partitioning_coarse(const agg_partitioning_relations_t &fine,
     Table *elem_to_dof = new Table;
     Mult(*fine.AE_to_dof, finedof_to_dof, *elem_to_dof);
     elem_to_dof->ncols = NDc;
+    lap("coarse: elem_to_dof");
 
     agg_create_partitioning_tables(rels, num_elem, elem_to_dof, NULL);
     SA_ASSERT(rels->ND == NDc);
