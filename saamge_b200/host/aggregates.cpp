@@ -193,10 +193,53 @@ agg_create_partitioning_fine(int NE, Table *elem_to_dof, Table *elem_to_elem,
     return agg_part_rels;
 }
 
+static Table *coarse_elem_to_elem_product(const agg_partitioning_relations_t &fine)
+{
+    // elem_to_elem = AE_to_elem * elem_to_elem * elem_to_AE (amg/src/aggregates.cpp:1768-1771)
+    Table tmptbl;
+    Table *e2e = new Table;
+    Mult(*fine.AE_to_elem, *fine.elem_to_elem, tmptbl);
+    Mult(tmptbl, *fine.elem_to_AE, *e2e);
+    return e2e;
+}
+
+static int *coarse_metis_partitioning(const agg_partitioning_relations_t &fine,
+                                      const Table &elem_to_elem, int *nparts)
+{
+    const int num_elem = fine.nparts;
+    std::vector<int> weights(num_elem);
+    for (int i = 0; i < num_elem; ++i)
+        weights[i] = fine.AE_to_dof->RowSize(i);
+    // METIS does not accept self loops; the product has them.
+    Table graph;
+    graph.nrows = graph.ncols = num_elem;
+    graph.I.assign((size_t)num_elem + 1, 0);
+    for (int i = 0; i < num_elem; ++i)
+    {
+        const int *row = elem_to_elem.GetRow(i);
+        for (int k = 0; k < elem_to_elem.RowSize(i); ++k)
+            if (row[k] != i)
+                graph.J.push_back(row[k]);
+        graph.I[i + 1] = (int)graph.J.size();
+    }
+    return part_generate_partitioning(graph, weights.data(), nparts);
+}
+
+agg_coarse_topology_t agg_coarse_topology(const agg_partitioning_relations_t &fine,
+                                          int nparts_target)
+{
+    agg_coarse_topology_t t;
+    t.elem_to_elem = coarse_elem_to_elem_product(fine);
+    t.nparts = nparts_target;
+    t.partitioning = coarse_metis_partitioning(fine, *t.elem_to_elem, &t.nparts);
+    return t;
+}
+
 agg_partitioning_relations_t *
 agg_create_partitioning_coarse(const agg_partitioning_relations_t &fine,
                                const int *mis_numcoarsedof, int *nparts,
-                               bool avoid_ess_bdr_dofs, int *partitioning)
+                               bool avoid_ess_bdr_dofs, int *partitioning,
+                               Table *coarse_elem_to_elem)
 {
     agg_partitioning_relations_t *rels = new agg_partitioning_relations_t;
     std::memset(rels, 0, sizeof(*rels));
@@ -216,36 +259,15 @@ agg_create_partitioning_coarse(const agg_partitioning_relations_t &fine,
     rels->dof_masterproc = new int[std::max(1, NDc)];
     std::memset(rels->dof_masterproc, 0, sizeof(int) * std::max(1, NDc));
 
-    // elem_to_elem = AE_to_elem * elem_to_elem * elem_to_AE (amg/src/aggregates.cpp:1768-1771)
     Lap lap;
-    Table tmptbl;
-    rels->elem_to_elem = new Table;
-    Mult(*fine.AE_to_elem, *fine.elem_to_elem, tmptbl);
-    Mult(tmptbl, *fine.elem_to_AE, *rels->elem_to_elem);
+    rels->elem_to_elem = coarse_elem_to_elem ? coarse_elem_to_elem : coarse_elem_to_elem_product(fine);
     lap("coarse: elem_to_elem product");
 
     const int num_elem = fine.nparts;
     if (partitioning)
         rels->partitioning = partitioning;
     else
-    {
-        std::vector<int> weights(num_elem);
-        for (int i = 0; i < num_elem; ++i)
-            weights[i] = fine.AE_to_dof->RowSize(i);
-        // METIS does not accept self loops; the product above has them.
-        Table graph;
-        graph.nrows = graph.ncols = num_elem;
-        graph.I.assign((size_t)num_elem + 1, 0);
-        for (int i = 0; i < num_elem; ++i)
-        {
-            const int *row = rels->elem_to_elem->GetRow(i);
-            for (int k = 0; k < rels->elem_to_elem->RowSize(i); ++k)
-                if (row[k] != i)
-                    graph.J.push_back(row[k]);
-            graph.I[i + 1] = (int)graph.J.size();
-        }
-        rels->partitioning = part_generate_partitioning(graph, weights.data(), nparts);
-    }
+        rels->partitioning = coarse_metis_partitioning(fine, *rels->elem_to_elem, nparts);
     rels->nparts = *nparts;
     lap("coarse: partitioning");
 

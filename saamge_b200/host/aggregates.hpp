@@ -120,7 +120,21 @@ void agg_create_partitioning_tables(agg_partitioning_relations_t *agg_part_rels,
 agg_partitioning_relations_t *
 agg_create_partitioning_coarse(const agg_partitioning_relations_t &agg_part_rels_fine,
                                const int *mis_numcoarsedof, int *nparts,
-                               bool avoid_ess_bdr_dofs, int *partitioning = NULL);
+                               bool avoid_ess_bdr_dofs, int *partitioning = NULL,
+                               Table *coarse_elem_to_elem = NULL);
+
+/*! The part of agg_create_partitioning_coarse that depends on the fine relations only (not
+    on the spectral results): coarse elem_to_elem and, unless given, the METIS partitioning
+    of the fine AEs.  It can therefore run on a host thread while the GPU works on the fine
+    level; the results are handed to agg_create_partitioning_coarse (which takes ownership). */
+struct agg_coarse_topology_t
+{
+    Table *elem_to_elem;
+    int *partitioning;
+    int nparts;
+};
+agg_coarse_topology_t agg_coarse_topology(const agg_partitioning_relations_t &agg_part_rels_fine,
+                                          int nparts_target);
 
 void agg_free_partitioning(agg_partitioning_relations_t *agg_part_rels);
 
