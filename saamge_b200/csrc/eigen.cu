@@ -1011,7 +1011,10 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
     lev->ae_D.ensure(AI[nparts]);
 
     // chunks of consecutive AEs bounded by the reflector storage budget
-    const size_t budget_doubles = (size_t)3 << 30; // 24 GB of reflectors per chunk
+    // (measured: smaller chunks do not pay -- 128^3 level 1 takes 5.6 s in one 9 GB chunk, 6.0 s in
+    // three, 6.7 s in six: every chunk ends with a partially filled cooperative batch)
+    static const size_t budget_doubles =
+        (size_t)((getenv("SA_GPU_CHUNK_GB") ? atof(getenv("SA_GPU_CHUNK_GB")) : 24.) * (double)((size_t)1 << 27));
     // largest n whose packed lower triangle (+ vectors) fits the shared memory of one block
     int nmax_smem = 0;
     auto packed_smem_doubles = [](size_t n, size_t threads) {

@@ -278,7 +278,7 @@ k_tridiag_coop(LevelTables L, ChunkDev C, const CoopMatrix *mats, int G)
 // no shuffles per entry and no atomics.
 // Ownership / determinism:
 //   - row blocks are dealt to the G blocks of the group in snake order (balanced triangular
-//     work); inside a block, warp w takes the column blocks cb == w (mod warps): the column
+//     work); inside a block, the column blocks are dealt to the warps (snake order): the column
 //     sums of cb are then a single warp's register, written once per step to this block's row
 //     of pcol[G][n];
 //   - row sums go to a per-warp shared array and are added in warp order into prow[n];
@@ -386,8 +386,13 @@ k_tridiag_coop_sym(LevelTables L, ChunkDev C, const CoopMatrix *mats, int G, int
         const int k1 = k + 1;
         const int cb0 = k1 >> 5;
         const int par = k & 1;
-        for (int cb = cb0 + (((wid - cb0) % NW) + NW) % NW; cb < NRB; cb += NW)
+        // column blocks are dealt to the warps in snake order as well: block cb has about
+        // (NRB - cb) / G tiles here, so a plain cyclic deal would load the low warps 1.6x more
+        for (int cblk = cb0 / NW; cblk * NW < NRB; ++cblk)
         {
+            const int cb = cblk * NW + ((cblk & 1) ? (NW - 1 - wid) : wid);
+            if (cb < cb0 || cb >= NRB)
+                continue;
             double colacc = 0.; // lane = column (cb << 5) + lane
             for (int q = 0; q < QMAX; ++q)
             {
