@@ -34,6 +34,8 @@ def oracle(num_threads=0):
         o.sa_orc_check_mises.argtypes = [ctypes.c_void_p]
         o.sa_orc_init(lapack_path().encode(), num_threads)
         _orc = o
+    elif num_threads > 0:
+        _orc.sa_orc_init(lapack_path().encode(), num_threads)  # re-set the OpenMP thread count
     return _orc
 
 
