@@ -383,8 +383,15 @@ def main():
             import oracle_util as ou
 
             ns, t, cores = cpu_sample(ou, pr, p, nae, args.cpu_seconds, os.cpu_count() or 1)
+            if ns == nae and t < 0.5 * args.cpu_seconds:
+                # the whole level is a short sample on this box: repeat it to ~cpu_seconds of work
+                reps = min(8, int(args.cpu_seconds / max(t, 1e-3)))
+                for _ in range(reps):
+                    ns2, t2, _c = cpu_sample(ou, pr, p, nae, args.cpu_seconds, os.cpu_count() or 1)
+                    ns += ns2
+                    t += t2
             line["cpu_baseline"] = {"value": ns / t, "unit": "AE/s", "cores": cores, "kind": "port",
-                                    "sample": "first %d of %d AEs (assemble + D + LAPACK dsygvx), %.1f s, one single-threaded process per core on contiguous AE slices (mpirun -n P analogue)" % (ns, nae, t)}
+                                    "sample": "%d AEs (passes over the first AEs of the %d of the level; assemble + D + LAPACK dsygvx), %.1f s, one single-threaded process per core on contiguous AE slices (mpirun -n P analogue)" % (ns, nae, t)}
             # what ONE reference MPI rank does (SURVEY 8d asks for both numbers)
             ns1, t1, c1 = cpu_sample(ou, pr, p, nae, min(5.0, args.cpu_seconds), 1)
             line["cpu_baseline_1core"] = {"value": ns1 / t1, "unit": "AE/s", "cores": c1, "kind": "port",
