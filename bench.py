@@ -127,23 +127,35 @@ def cpu_sample(ou, pr, p, nae, target_s, procs):
     bounds = [ns * i // procs for i in range(procs + 1)]
     sys.stdout.flush()
     sys.stderr.flush()
+    # fork cost (page tables of a multi-GB parent) stays outside the timed region: the workers
+    # report ready, then are released together
+    ready_r, ready_w = os.pipe()
+    go_r, go_w = os.pipe()
     pids = []
-    t_start = time.time()
     for i in range(procs):
         pid = os.fork()
         if pid == 0:
             rc = 0
             try:
+                os.write(ready_w, b"r")
+                os.read(go_r, 1)
                 o.sa_orc_time_local_spectral(pr.handle, ctypes.byref(p), bounds[i], bounds[i + 1])
             except BaseException:
                 rc = 1
             os._exit(rc)
         pids.append(pid)
+    got = 0
+    while got < procs:
+        got += len(os.read(ready_r, procs - got))
+    t_start = time.time()
+    os.write(go_w, b"g" * procs)
     bad = 0
     for pid in pids:
         _, st = os.waitpid(pid, 0)
         bad += 1 if st != 0 else 0
     wall = time.time() - t_start
+    for fd in (ready_r, ready_w, go_r, go_w):
+        os.close(fd)
     if bad:
         raise RuntimeError("cpu_sample: %d worker processes failed" % bad)
     return ns, wall, procs
