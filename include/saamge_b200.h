@@ -35,6 +35,10 @@ int sa_gpu_ctx_create(int device, sa_gpu_ctx **ctx);
 void sa_gpu_ctx_destroy(sa_gpu_ctx *ctx);
 const char *sa_gpu_last_error(void);
 /* cudaStream_t of the context as an opaque pointer (for event timing in bench.py) */
+/* Hands the unused blocks of the stream-ordered device memory pool back to the driver.  Worth
+   calling between unrelated large jobs in one process: a pool fragmented by many blocks of
+   other sizes can take seconds to serve a fresh multi-GB request. */
+int sa_gpu_ctx_trim_pool(sa_gpu_ctx *ctx);
 void *sa_gpu_ctx_stream(sa_gpu_ctx *ctx);
 int sa_gpu_ctx_sync(sa_gpu_ctx *ctx);
 /* number of kernel launches issued through this context so far */
@@ -106,6 +110,11 @@ size_t sa_gpu_level_desc_size(void);
 int sa_gpu_level_create(sa_gpu_ctx *ctx, const sa_gpu_level_desc *desc, sa_gpu_level *finer,
                         sa_gpu_level **level);
 void sa_gpu_level_destroy(sa_gpu_level *level);
+/* Returns the cached work arrays of the local spectral stage (reflector block, inverse-
+   iteration workspace, ...; they belong to the level's context and are shared by its
+   levels) to the device memory pool.  Results are kept; a later sa_gpu_local_spectral
+   simply allocates them again. */
+int sa_gpu_level_trim(sa_gpu_level *level);
 /* Blocks until a pipelined upload (desc.async_upload) has finished; no-op otherwise. */
 int sa_gpu_level_upload_wait(sa_gpu_level *level);
 

@@ -128,6 +128,17 @@ extern "C" int sa_gpu_ctx_profile(sa_gpu_ctx *ctx, int enable, char *buf, int bu
     return 0;
 }
 
+extern "C" int sa_gpu_ctx_trim_pool(sa_gpu_ctx *ctx)
+{
+    SA_API_BEGIN
+    SA_CUDA(cudaSetDevice(ctx->device));
+    SA_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaMemPool_t pool;
+    if (g_sa_alloc_async && cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess)
+        SA_CUDA(cudaMemPoolTrimTo(pool, 0));
+    SA_API_END
+}
+
 extern "C" void *sa_gpu_ctx_stream(sa_gpu_ctx *ctx) { return (void *)ctx->stream; }
 
 extern "C" int sa_gpu_ctx_sync(sa_gpu_ctx *ctx)
@@ -205,6 +216,21 @@ void sa_level_ready(sa_gpu_level *lev)
         cudaEventDestroy(P.ev[i]);
     P.ev.clear();
     P.active = false;
+}
+
+extern "C" int sa_gpu_level_trim(sa_gpu_level *lev)
+{
+    SA_API_BEGIN
+    sa_level_ready(lev);
+    SA_CUDA(cudaStreamSynchronize(lev->ctx->stream));
+    SpectralWs &W = lev->ctx->sws;
+    W.V.release();
+    W.Twork.release();
+    W.ws_d.release();
+    W.ws_i.release();
+    W.pbuf.release();
+    W.invit_NB = 0;
+    SA_API_END
 }
 
 extern "C" int sa_gpu_level_upload_wait(sa_gpu_level *lev)

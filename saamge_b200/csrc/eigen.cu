@@ -1099,7 +1099,7 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
             max_d = std::max(max_d, (size_t)(AI[b1] - AI[b0]));
             max_ns = std::max(max_ns, (size_t)(b1 - b0));
         }
-        SpectralWs &WS = lev->sws;
+        SpectralWs &WS = ctx->sws;
         WS.V.ensure(max_v);
         WS.d.ensure(max_d);
         WS.e.ensure(max_d);
@@ -1159,7 +1159,7 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         }
         // work arrays are cached in the level (grow only): cudaMalloc/cudaFree of the
         // multi-GB reflector block would otherwise dominate the stage
-        SpectralWs &WS = lev->sws;
+        SpectralWs &WS = ctx->sws;
         DevBuf<int> &d_ae = WS.ae, &d_doff = WS.doff, &d_status = WS.status;
         DevBuf<int64_t> &d_voff = WS.voff;
         DevBuf<double> &d_V = WS.V, &d_d = WS.d, &d_e = WS.e, &d_tau = WS.tau, &d_sinv = WS.sinv;

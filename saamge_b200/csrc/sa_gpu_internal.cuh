@@ -4,9 +4,11 @@
 
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -81,8 +83,14 @@ template <class T> struct DevBuf
         cap = count;
         if (g_sa_alloc_async)
         {
-            SA_CUDA(cudaMallocAsync((void **)&p, (count ? count : 1) * sizeof(T),
-                                    g_sa_alloc_stream));
+            const size_t bytes = (count ? count : 1) * sizeof(T);
+            static const bool dbg = getenv("SA_GPU_ALLOC_DEBUG") != NULL;
+            const auto t0 = std::chrono::steady_clock::now();
+            SA_CUDA(cudaMallocAsync((void **)&p, bytes, g_sa_alloc_stream));
+            if (dbg && bytes >= ((size_t)64 << 20))
+                fprintf(stderr, "[alloc] %8.1f MB in %7.2f ms\n", bytes / 1048576.,
+                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0)
+                            .count());
             async_owned = true;
         }
         else
@@ -157,8 +165,25 @@ struct HostStage
     }
 };
 
+/* Grow-only work arrays of the local spectral stage, owned by the CONTEXT and shared by all
+   its levels (calls are serial per context).  The stream-ordered pool recycles blocks of a
+   size it has seen quickly, but carving a request out of larger free blocks can take seconds:
+   one persistent set of arrays avoids both the per-level allocations and that carving. */
+struct SpectralWs
+{
+    DevBuf<int> ae, doff, status, order, nev, mtot, ev_slot, ev_idx, ws_i, gpind;
+    size_t invit_NB = 0; // eigenvectors per inverse-iteration batch the workspace holds
+    DevBuf<int64_t> voff, eval_off, evect_off;
+    DevBuf<double> V, d, e, tau, sinv, glo, ghi, tn, ws_d;
+    // large-matrix (cooperative) path
+    DevBuf<double> Twork, pbuf;
+    DevBuf<unsigned int> counters;
+    DevBuf<char> coopmats;
+};
+
 struct sa_gpu_ctx
 {
+    SpectralWs sws;
     int device = 0;
     int num_sms = 148;
     size_t smem_optin = 0;
@@ -241,18 +266,6 @@ struct LevelTables
     int with_global;
 };
 
-/* grow-only work arrays of the local spectral stage, cached per level */
-struct SpectralWs
-{
-    DevBuf<int> ae, doff, status, order, nev, mtot, ev_slot, ev_idx, ws_i, gpind;
-    size_t invit_NB = 0; // eigenvectors per inverse-iteration batch the workspace holds
-    DevBuf<int64_t> voff, eval_off, evect_off;
-    DevBuf<double> V, d, e, tau, sinv, glo, ghi, tn, ws_d;
-    // large-matrix (cooperative) path
-    DevBuf<double> Twork, pbuf;
-    DevBuf<unsigned int> counters;
-    DevBuf<char> coopmats;
-};
 
 /* pipelined upload of a level: the operator and the element blocks travel in slabs on the
    context's copy stream; slab s is complete when ev[s] has fired.  ae_need[i] is the first
@@ -319,7 +332,6 @@ struct sa_gpu_level
     DevBuf<int64_t> evect_off, eval_off;
     DevBuf<double> evals, evects, ae_D;  // ae_D offsets = AE2d_I
     double max_residual = 0.;
-    SpectralWs sws;
     // tentative P
     bool have_tent = false;
     int avoid_ess = 1;

@@ -505,8 +505,11 @@ extern "C" int sa_gpu_coarse_elmats(sa_gpu_level *finer, sa_gpu_level *coarse)
     const size_t scratch_budget = (size_t)1 << 28; // 2 GB of doubles
     int blocks = std::min(nparts, ctx->num_sms * 4);
     blocks = (int)std::max<size_t>(1, std::min<size_t>(blocks, scratch_budget / (size_t)max_scratch));
-    DevBuf<double> scratch;
-    scratch.alloc((size_t)blocks * max_scratch);
+    // scratch: the finer level's (idle) reflector block is reused when it exists -- a fresh
+    // multi-GB request can cost the stream-ordered pool over a second when it is fragmented
+    DevBuf<double> scratch_own;
+    DevBuf<double> &scratch = ctx->sws.V.p ? ctx->sws.V : scratch_own;
+    scratch.ensure((size_t)blocks * max_scratch);
     CoarseElmatArgs C;
     C.ce2d_I = coarse->e2d_I.p;
     C.ce2d_J = coarse->e2d_J.p;
