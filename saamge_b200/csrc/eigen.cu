@@ -866,7 +866,9 @@ __global__ void k_back_transform(ChunkDev C, const int *AE2d_I, const int *nev, 
     const double *sinv = C.sinv + C.doff[slot];
     double *Z = evects + evect_off_slot[slot];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int j = w; j < m; j += nw)
+    // grid.y splits the vectors of an AE over several blocks (coarse levels: dozens of
+    // vectors per AE, few AEs per chunk)
+    for (int j = blockIdx.y * nw + w; j < m; j += gridDim.y * nw)
     {
         double *z = Z + (int64_t)n * j;
         for (int k = n - 3; k >= 0; --k)
@@ -890,7 +892,7 @@ __global__ void k_back_transform(ChunkDev C, const int *AE2d_I, const int *nev, 
             z[i] *= sinv[i];
     }
     // mltest fixture: extra all-ones vector (amg/src/interp.cpp:510-524)
-    if (m_total[slot] > m)
+    if (m_total[slot] > m && blockIdx.y == 0)
         for (int i = threadIdx.x; i < n; i += blockDim.x)
             Z[i + (int64_t)n * m] = 1.0;
 }
@@ -1045,7 +1047,8 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
 
     struct PieceResult
     {
-        int a0, a1;
+        int a0, a1;            // positions in the processing order
+        std::vector<int> aes;  // AE of every slot
         std::vector<int> nev, mtot;
         DevBuf<double> evals, evects;
         std::vector<int64_t> eval_off, evect_off;
@@ -1128,19 +1131,48 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
     const bool pipe_debug = getenv("SA_GPU_PIPE_DEBUG") != NULL && lev->pending.active;
     std::vector<cudaEvent_t> dbg_ev;
     std::vector<int> dbg_need;
+    // Processing order.  Positions q in [ae_begin, ae_end) map to AEs seq[q - ae_begin]:
+    // the identity, except on levels with large AEs (cooperative path, no pipelined upload),
+    // where the AEs are taken largest first and a chunk is a few full cooperative batches.
+    // The reflector block and the inverse-iteration workspace are then those of ~100 matrices
+    // instead of the whole level (128^3 level 1: 2 GB instead of 11.4 GB; multi-GB requests
+    // cost the device memory pool 0.1-2 s each), every batch holds matrices of similar size,
+    // and since the first chunk is the largest the work arrays never grow afterwards.
+    static const int coop_gdiv = getenv("SA_GPU_COOP_DIV") ? atoi(getenv("SA_GPU_COOP_DIV")) : 300;
+    static const int coop_batches_per_chunk =
+        getenv("SA_GPU_COOP_BATCHES") ? std::max(1, atoi(getenv("SA_GPU_COOP_BATCHES"))) : 4;
+    std::vector<int> seq(ae_end - ae_begin);
+    std::iota(seq.begin(), seq.end(), ae_begin);
+    const bool sorted_seq = !lev->pending.active && !use_square && range_nmax > nmax_smem &&
+                            !getenv("SA_GPU_NO_SORTED_CHUNKS");
+    if (sorted_seq)
+        std::stable_sort(seq.begin(), seq.end(),
+                         [&](int x, int y) { return (AI[x + 1] - AI[x]) > (AI[y + 1] - AI[y]); });
+    auto nAE = [&](int q) { return AI[seq[q - ae_begin] + 1] - AI[seq[q - ae_begin]]; };
     int a0 = ae_begin;
     while (a0 < ae_end)
     {
         size_t vtot = 0;
         int a1 = a0;
         const int piece_end = *std::upper_bound(piece_ends.begin(), piece_ends.end(), a0);
+        int n_large = 0;
         while (a1 < piece_end)
         {
-            const size_t n = AI[a1 + 1] - AI[a1];
+            const size_t n = nAE(a1);
             if (a1 > a0 && vtot + vsize(n) > budget_doubles)
                 break;
+            if (sorted_seq && a1 > a0 && (int)n <= nmax_smem && nAE(a0) > nmax_smem)
+                break; // the shared-memory sized AEs start their own chunk
             vtot += vsize(n);
             ++a1;
+            if (sorted_seq && (int)n > nmax_smem)
+            {
+                const int Gq = std::max(2, std::min(ctx->num_sms, nAE(a0) / coop_gdiv));
+                // (four batches per chunk: the small per-chunk kernels -- bisection, inverse
+                // iteration, back-transformation -- are latency-bound on a single batch)
+                if (++n_large >= coop_batches_per_chunk * std::max(1, ctx->num_sms / Gq))
+                    break;
+            }
         }
         const int ns = a1 - a0;
         std::vector<int> h_ae(ns), h_doff(ns);
@@ -1149,8 +1181,8 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         int dofftot = 0, nmax = 1;
         for (int s = 0; s < ns; ++s)
         {
-            const int n = AI[a0 + s + 1] - AI[a0 + s];
-            h_ae[s] = a0 + s;
+            const int n = nAE(a0 + s);
+            h_ae[s] = seq[a0 + s - ae_begin];
             h_voff[s] = vo;
             h_doff[s] = dofftot;
             vo += (int64_t)vsize((size_t)n);
@@ -1190,7 +1222,7 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         std::vector<int> order(ns);
         std::iota(order.begin(), order.end(), 0);
         std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
-            return (AI[a0 + x + 1] - AI[a0 + x]) > (AI[a0 + y + 1] - AI[a0 + y]);
+            return nAE(a0 + x) > nAE(a0 + y);
         });
         DevBuf<int> &d_order = WS.order;
         staged_upload(ctx, ctx->stage, d_order, order.data(), ns);
@@ -1238,11 +1270,11 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         // large (global-memory tile) bucket first
         {
             int cnt = 0;
-            while (pos + cnt < ns && (AI[a0 + order[pos + cnt] + 1] - AI[a0 + order[pos + cnt]]) > nmax_smem)
+            while (pos + cnt < ns && nAE(a0 + order[pos + cnt]) > nmax_smem)
                 ++cnt;
             if (cnt && use_square)
             {
-                const int nb = AI[a0 + order[pos] + 1] - AI[a0 + order[pos]];
+                const int nb = nAE(a0 + order[pos]);
                 const size_t smem = (size_t)(3 * nb + 40) * sizeof(double);
                 SA_CUDA(cudaFuncSetAttribute(k_assemble_tridiag,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1262,12 +1294,12 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
                 int done = 0;
                 while (done < cnt)
                 {
-                    const int nb = AI[a0 + order[pos + done] + 1] - AI[a0 + order[pos + done]];
+                    const int nb = nAE(a0 + order[pos + done]);
                     const size_t smem_c = ((size_t)3 * nb + 64 + 16 * 32) * sizeof(double);
                     if (smem_c > ctx->smem_optin)
                         SA_FAIL("sa_gpu_local_spectral: AE with %d dofs exceeds the supported "
                                 "size of the large-matrix eigensolver", nb);
-                    static int gdiv = getenv("SA_GPU_COOP_DIV") ? atoi(getenv("SA_GPU_COOP_DIV")) : 300;
+                    const int gdiv = coop_gdiv;
                     // symmetric (lower-triangle) variant by default; SA_GPU_COOP_SYM=0 keeps
                     // the full-matrix kernel
                     static const int coop_sym =
@@ -1363,11 +1395,11 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         {
             const int lo_edge = (b == 0) ? 0 : std::min(bucket_edges[b - 1], nmax_smem);
             int cnt = 0;
-            while (pos + cnt < ns && (AI[a0 + order[pos + cnt] + 1] - AI[a0 + order[pos + cnt]]) > lo_edge)
+            while (pos + cnt < ns && nAE(a0 + order[pos + cnt]) > lo_edge)
                 ++cnt;
             if (!cnt)
                 continue;
-            const int nb = AI[a0 + order[pos] + 1] - AI[a0 + order[pos]];
+            const int nb = nAE(a0 + order[pos]);
             const int ai = nlaunch++ % sa_gpu_ctx::NAUX;
             cudaStream_t sb = ctx->aux[ai];
             if (!used_aux[ai])
@@ -1434,6 +1466,7 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         pieces.push_back(pr);
         pr->a0 = a0;
         pr->a1 = a1;
+        pr->aes = h_ae;
         pr->nev.resize(ns);
         pr->mtot.resize(ns);
         std::vector<int> h_status(ns);
@@ -1445,13 +1478,13 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
             if (h_status[s])
                 SA_FAIL("sa_gpu_local_spectral: AE %d has a non-positive diagonal "
                         "(SA_ASSERT(diag > 0.) in mbox_snd_D_sparse_from_sparse)",
-                        a0 + s);
+                        h_ae[s]);
         pr->eval_off.assign(ns + 1, 0);
         pr->evect_off.assign(ns + 1, 0);
         std::vector<int> ev_slot, ev_idx;
         for (int s = 0; s < ns; ++s)
         {
-            const int n = AI[a0 + s + 1] - AI[a0 + s];
+            const int n = nAE(a0 + s);
             pr->eval_off[s + 1] = pr->eval_off[s] + pr->nev[s];
             pr->evect_off[s + 1] = pr->evect_off[s] + (int64_t)n * pr->mtot[s];
             for (int j = 0; j < pr->nev[s]; ++j)
@@ -1483,6 +1516,8 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
             const size_t ws_budget = (size_t)4 << 30;
             const int64_t cap = std::max<int64_t>(32, (int64_t)(ws_budget / ((size_t)44 * nmax)) & ~(int64_t)31);
             int64_t NB = std::min<int64_t>(cap, ((int64_t)nev_total + 31) & ~(int64_t)31);
+            if (sorted_seq && a1 < ae_end) // later chunks may select a few more vectors
+                NB = (NB * 3 / 2 + 31) & ~(int64_t)31;
             NB = std::max<int64_t>(NB, (int64_t)WS.invit_NB); // grow only (see the pipelined pieces)
             NB = std::min(NB, cap);
             WS.invit_NB = (size_t)NB;
@@ -1535,8 +1570,13 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
             }
             {
                 ProfScope ps(ctx, "eig.back_transform");
-                SA_LAUNCH(ctx, k_back_transform, ns, 128, 0, C, lev->AE2d_I.p, d_nev.p, d_mtot.p,
-                          d_evect_off.p, pr->evects.p, use_square ? 0 : 0x7fffffff);
+                int max_nev = 1;
+                for (int q = 0; q < ns; ++q)
+                    max_nev = std::max(max_nev, pr->nev[q]);
+                const int gy = std::max(1, std::min(64, std::min((max_nev + 3) / 4,
+                                                                 (4 * ctx->num_sms + ns - 1) / ns)));
+                SA_LAUNCH(ctx, k_back_transform, dim3(ns, gy), 128, 0, C, lev->AE2d_I.p, d_nev.p,
+                          d_mtot.p, d_evect_off.p, pr->evects.p, use_square ? 0 : 0x7fffffff);
             }
             SA_CUDA(cudaStreamSynchronize(st)); // workspace freed at scope exit
         }
@@ -1578,8 +1618,8 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
     for (size_t p = 0; p < pieces.size(); ++p)
         for (int s = 0; s < pieces[p]->a1 - pieces[p]->a0; ++s)
         {
-            lev->h_ae_m[pieces[p]->a0 + s] = pieces[p]->mtot[s];
-            lev->h_ae_nev[pieces[p]->a0 + s] = pieces[p]->nev[s];
+            lev->h_ae_m[pieces[p]->aes[s]] = pieces[p]->mtot[s];
+            lev->h_ae_nev[pieces[p]->aes[s]] = pieces[p]->nev[s];
         }
     lev->h_eval_off.assign(nparts + 1, 0);
     lev->h_evect_off.assign(nparts + 1, 0);
@@ -1597,14 +1637,33 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
     {
         PieceResult *pr = pieces[p];
         const int ns = pr->a1 - pr->a0;
-        if (pr->eval_off[ns])
-            SA_CUDA(cudaMemcpyAsync(lev->evals.p + lev->h_eval_off[pr->a0], pr->evals.p,
-                                    pr->eval_off[ns] * sizeof(double), cudaMemcpyDeviceToDevice,
-                                    st));
-        if (pr->evect_off[ns])
-            SA_CUDA(cudaMemcpyAsync(lev->evects.p + lev->h_evect_off[pr->a0], pr->evects.p,
-                                    pr->evect_off[ns] * sizeof(double), cudaMemcpyDeviceToDevice,
-                                    st));
+        if (!sorted_seq)
+        {
+            // consecutive AEs: the chunk is one contiguous block of the flat arrays
+            if (pr->eval_off[ns])
+                SA_CUDA(cudaMemcpyAsync(lev->evals.p + lev->h_eval_off[pr->aes[0]], pr->evals.p,
+                                        pr->eval_off[ns] * sizeof(double),
+                                        cudaMemcpyDeviceToDevice, st));
+            if (pr->evect_off[ns])
+                SA_CUDA(cudaMemcpyAsync(lev->evects.p + lev->h_evect_off[pr->aes[0]],
+                                        pr->evects.p, pr->evect_off[ns] * sizeof(double),
+                                        cudaMemcpyDeviceToDevice, st));
+            continue;
+        }
+        for (int s = 0; s < ns; ++s)
+        {
+            const int ae = pr->aes[s];
+            const int64_t ne = pr->eval_off[s + 1] - pr->eval_off[s];
+            const int64_t nv = pr->evect_off[s + 1] - pr->evect_off[s];
+            if (ne)
+                SA_CUDA(cudaMemcpyAsync(lev->evals.p + lev->h_eval_off[ae],
+                                        pr->evals.p + pr->eval_off[s], ne * sizeof(double),
+                                        cudaMemcpyDeviceToDevice, st));
+            if (nv)
+                SA_CUDA(cudaMemcpyAsync(lev->evects.p + lev->h_evect_off[ae],
+                                        pr->evects.p + pr->evect_off[s], nv * sizeof(double),
+                                        cudaMemcpyDeviceToDevice, st));
+        }
     }
     lev->ae_m.upload(lev->h_ae_m.data(), nparts, st);
     lev->evect_off.upload(lev->h_evect_off.data(), nparts + 1, st);
