@@ -311,10 +311,12 @@ def main():
         fp64_peak = gl.sa_gpu_bench_fp64_peak(ctxp)
     kern_ms = prof.get("eig.assemble_tridiag", float("nan"))
     traffic = None  # DRAM bytes per step of the dominant kernel, from the committed ncu capture
+    ncu_note = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
         if tj.get("workload") == args.workload:
             traffic = tj["k_at_packed"]["dram_bytes_per_step"]
+            ncu_note = tj["k_at_packed"].get("ncu")
     except Exception:
         traffic = None
     achieved = flops / (kern_ms * 1e-3) / 1e12
@@ -328,6 +330,7 @@ def main():
         "algorithmic_flops_per_step": flops, "algorithmic_bytes_per_step": abytes,
         "kernel_ms_per_step": kern_ms, "stage_ms": prof, "traffic": traffic,
         "traffic_source": "profiles/r01_traffic.json (ncu dram bytes, per step)" if traffic else None,
+        "ncu": ncu_note,  # pipe utilisation of the committed capture (not measured in this run)
     }
 
     line = {
