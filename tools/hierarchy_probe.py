@@ -1,5 +1,6 @@
 import sys, time
-import conftest
+import os, sys
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests")); sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import saamge_b200 as sab
 n=int(sys.argv[1]); levels=int(sys.argv[2]); epa=int(sys.argv[3]); nupro=int(sys.argv[4]) if len(sys.argv)>4 else 0
 p=sab.default_params(num_levels=levels, first_elems_per_agg=52, elems_per_agg=epa, partition_kind=2, block=(32,32,32), first_nu_pro=nupro, nu_pro=nupro)

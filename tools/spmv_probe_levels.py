@@ -1,5 +1,6 @@
 import sys, ctypes
-import conftest
+import os, sys
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests")); sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import saamge_b200 as sab
 from saamge_b200 import cabi
 n=int(sys.argv[1])

@@ -1,5 +1,6 @@
 import sys, time, ctypes
-import conftest
+import os, sys
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests")); sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import saamge_b200 as sab
 n=int(sys.argv[1]); epa=int(sys.argv[2]); kind=int(sys.argv[3]) if len(sys.argv)>3 else 0
 p=sab.default_params(num_levels=2, first_elems_per_agg=epa, elems_per_agg=64, partition_kind=kind, block=((32,32,32) if kind==2 else (4,4,4)))
