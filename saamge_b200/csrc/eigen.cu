@@ -871,6 +871,52 @@ __global__ void k_back_transform(ChunkDev C, const int *AE2d_I, const int *nev, 
     for (int j = blockIdx.y * nw + w; j < m; j += gridDim.y * nw)
     {
         double *z = Z + (int64_t)n * j;
+        if (n <= 256 && n <= nmax_packed)
+        {
+            // small AEs: the vector lives in registers (8 entries per lane) for the whole walk,
+            // every reflector entry is loaded once
+            double zr[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+            {
+                const int i = lane + 32 * q;
+                zr[q] = (i < n) ? z[i] : 0.;
+            }
+            for (int k = n - 3; k >= 0; --k)
+            {
+                const double t = tau[k];
+                if (t == 0.)
+                    continue;
+                const double *vk = V + (k * n - (k * (k - 1)) / 2 - k);
+                if ((k & 3) == 3)
+                {
+                    const char *pf = (const char *)(vk + k) - 4096 + lane * 128;
+                    if (pf >= (const char *)V)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+                }
+                double vq[8];
+                double s = 0.;
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                {
+                    const int i = lane + 32 * q;
+                    vq[q] = (i > k + 1 && i < n) ? vk[i] : ((i == k + 1) ? 1. : 0.);
+                    s += vq[q] * zr[q];
+                }
+                s = warp_sum(s) * t;
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    zr[q] -= s * vq[q];
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+            {
+                const int i = lane + 32 * q;
+                if (i < n)
+                    z[i] = zr[q] * sinv[i];
+            }
+            continue;
+        }
         for (int k = n - 3; k >= 0; --k)
         {
             const double t = tau[k];
@@ -880,6 +926,14 @@ __global__ void k_back_transform(ChunkDev C, const int *AE2d_I, const int *nev, 
             const double *vk = (n <= nmax_packed)
                                    ? V + ((int64_t)k * n - ((int64_t)k * (k - 1)) / 2 - k)
                                    : V + (int64_t)n * k;
+            // the walk goes down in memory and every step depends on the previous one through
+            // z only: pull the next 4 KB of reflectors towards L2 ahead of time
+            if ((k & 3) == 3)
+            {
+                const char *pf = (const char *)(vk + k) - 4096 + lane * 128;
+                if (pf >= (const char *)V)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+            }
             double s = 0.;
             for (int i = k + 1 + lane; i < n; i += 32)
                 s += ((i == k + 1) ? 1. : vk[i]) * z[i];
@@ -1575,7 +1629,11 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
                     max_nev = std::max(max_nev, pr->nev[q]);
                 const int gy = std::max(1, std::min(64, std::min((max_nev + 3) / 4,
                                                                  (4 * ctx->num_sms + ns - 1) / ns)));
-                SA_LAUNCH(ctx, k_back_transform, dim3(ns, gy), 128, 0, C, lev->AE2d_I.p, d_nev.p,
+                // one warp per vector: blocks no wider than the vectors an AE has, so that more
+                // AEs are resident per SM (the reflector walk is a chain of dependent loads)
+                const double avg_nev = (double)nev_total / std::max(1, ns);
+                const int bt_threads = avg_nev <= 1.5 ? 32 : (avg_nev <= 3. ? 64 : 128);
+                SA_LAUNCH(ctx, k_back_transform, dim3(ns, gy), bt_threads, 0, C, lev->AE2d_I.p, d_nev.p,
                           d_mtot.p, d_evect_off.p, pr->evects.p, use_square ? 0 : 0x7fffffff);
             }
             SA_CUDA(cudaStreamSynchronize(st)); // workspace freed at scope exit
