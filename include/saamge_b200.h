@@ -91,10 +91,10 @@ typedef struct
     /* (coarse levels) finer MIS -> first coarse dof, finer num_mises+1 entries;
        needed by sa_gpu_coarse_elmats */
     const int *mis_coarsedofoffsets;
-    /* 1: pipelined upload.  sa_gpu_level_create returns while the large arrays (operator,
-          element blocks) are still being copied, in slabs, on a separate copy stream;
-          sa_gpu_local_spectral starts on the first agglomerates as soon as the slabs they
-          read have arrived.  The caller keeps every host array of this description valid
+    /* 1: pipelined upload.  sa_gpu_level_create returns after queueing the tables; the large
+          arrays (operator, element blocks) are copied on a separate copy stream in the order
+          sa_gpu_local_spectral needs them, which starts on the first agglomerates as soon as
+          the rows / blocks they read have arrived.  The caller keeps every host array of this description valid
           and unmodified until the first call that uses the level returns (or until
           sa_gpu_level_upload_wait).  Host arrays should be pinned (sa_gpu_host_register);
           pageable memory works but does not overlap.

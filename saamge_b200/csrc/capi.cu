@@ -171,13 +171,156 @@ static void upload_table(DevBuf<int> &dI, DevBuf<int> &dJ, const int *I, const i
     dJ.upload(J, (size_t)I[rows], st);
 }
 
-void sa_level_wait_slab(sa_gpu_level *lev, int slab)
+void sa_level_wait_event(sa_gpu_level *lev, int idx)
 {
     PendingUpload &P = lev->pending;
-    if (!P.active || P.ev.empty())
+    if (!P.active || idx < 0 || idx >= (int)P.ev.size())
         return;
-    slab = std::max(0, std::min(slab, (int)P.ev.size() - 1));
-    SA_CUDA(cudaStreamWaitEvent(lev->ctx->stream, P.ev[slab], 0));
+    SA_CUDA(cudaStreamWaitEvent(lev->ctx->stream, P.ev[idx], 0));
+}
+
+namespace
+{
+/* runs of entries marked 2 in [lo, hi]; unmarked gaps of at most `gap` entries are swallowed
+   (and marked) so that the number of copies stays small */
+void collect_runs(std::vector<unsigned char> &mark, int lo, int hi, int gap,
+                  std::vector<std::pair<int, int>> &runs)
+{
+    runs.clear();
+    int i = lo;
+    while (i <= hi)
+    {
+        if (mark[i] != 2)
+        {
+            ++i;
+            continue;
+        }
+        int r0 = i, r1 = i + 1; // [r0, r1)
+        int j = r1;
+        while (j <= hi)
+        {
+            if (mark[j] == 2)
+            {
+                r1 = ++j;
+                continue;
+            }
+            // look ahead: is there another entry to queue within the gap?
+            int k = j;
+            while (k <= hi && k - r1 < gap && mark[k] != 2)
+                ++k;
+            if (k <= hi && k - r1 < gap && mark[k] == 2)
+                j = k;
+            else
+                break;
+        }
+        runs.push_back(std::make_pair(r0, r1));
+        i = r1;
+    }
+}
+
+int queue_marked(sa_gpu_level *L, int elo, int ehi, int rlo, int rhi)
+{
+    PendingUpload &P = L->pending;
+    const sa_gpu_level_desc &d = P.desc;
+    cudaStream_t cs = L->ctx->copy_stream;
+    std::vector<std::pair<int, int>> runs;
+    if (d.elmat && elo <= ehi)
+    {
+        int gap = 8;
+        do
+        {
+            collect_runs(P.elem_mark, elo, ehi, gap, runs);
+            gap *= 4;
+        } while (runs.size() > 48);
+        for (size_t q = 0; q < runs.size(); ++q)
+        {
+            const int e0 = runs[q].first, e1 = runs[q].second;
+            for (int e = e0; e < e1; ++e)
+                P.elem_mark[e] = 1;
+            const size_t k0 = d.elmat_off[e0], k1 = d.elmat_off[e1];
+            if (k1 > k0)
+                SA_CUDA(cudaMemcpyAsync(L->elmat.p + k0, d.elmat + k0, (k1 - k0) * sizeof(double),
+                                        cudaMemcpyHostToDevice, cs));
+        }
+    }
+    if (d.A_I && rlo <= rhi)
+    {
+        int gap = 32;
+        do
+        {
+            collect_runs(P.row_mark, rlo, rhi, gap, runs);
+            gap *= 4;
+        } while (runs.size() > 48);
+        for (size_t q = 0; q < runs.size(); ++q)
+        {
+            const int r0 = runs[q].first, r1 = runs[q].second;
+            for (int r = r0; r < r1; ++r)
+                P.row_mark[r] = 1;
+            const size_t k0 = d.A_I[r0], k1 = d.A_I[r1];
+            if (k1 > k0)
+            {
+                SA_CUDA(cudaMemcpyAsync(L->A_own.J.p + k0, d.A_J + k0, (k1 - k0) * sizeof(int),
+                                        cudaMemcpyHostToDevice, cs));
+                SA_CUDA(cudaMemcpyAsync(L->A_own.A.p + k0, d.A_data + k0, (k1 - k0) * sizeof(double),
+                                        cudaMemcpyHostToDevice, cs));
+            }
+        }
+    }
+    cudaEvent_t ev;
+    SA_CUDA(cudaEventCreateWithFlags(&ev, P.timing ? cudaEventDefault : cudaEventDisableTiming));
+    SA_CUDA(cudaEventRecord(ev, cs));
+    P.ev.push_back(ev);
+    return (int)P.ev.size() - 1;
+}
+} // namespace
+
+int sa_level_queue_upload(sa_gpu_level *L, int a0, int a1)
+{
+    PendingUpload &P = L->pending;
+    if (!P.active)
+        return -1;
+    const sa_gpu_level_desc &d = P.desc;
+    int elo = 1 << 30, ehi = -1, rlo = 1 << 30, rhi = -1;
+    if (d.elmat)
+        for (int k = d.AE_to_elem_I[a0]; k < d.AE_to_elem_I[a1]; ++k)
+        {
+            const int e = d.AE_to_elem_J[k];
+            if (!P.elem_mark[e])
+            {
+                P.elem_mark[e] = 2;
+                elo = std::min(elo, e);
+                ehi = std::max(ehi, e);
+            }
+        }
+    if (d.A_I)
+        for (int k = d.AE_to_dof_I[a0]; k < d.AE_to_dof_I[a1]; ++k)
+        {
+            const int r = d.AE_to_dof_J[k];
+            if (!P.row_mark[r])
+            {
+                P.row_mark[r] = 2;
+                rlo = std::min(rlo, r);
+                rhi = std::max(rhi, r);
+            }
+        }
+    return queue_marked(L, elo, ehi, rlo, rhi);
+}
+
+int sa_level_queue_rest(sa_gpu_level *L)
+{
+    PendingUpload &P = L->pending;
+    if (!P.active)
+        return -1;
+    if (P.complete)
+        return (int)P.ev.size() - 1;
+    for (size_t e = 0; e < P.elem_mark.size(); ++e)
+        if (!P.elem_mark[e])
+            P.elem_mark[e] = 2;
+    for (size_t r = 0; r < P.row_mark.size(); ++r)
+        if (!P.row_mark[r])
+            P.row_mark[r] = 2;
+    P.complete = true;
+    return queue_marked(L, 0, (int)P.elem_mark.size() - 1, 0, (int)P.row_mark.size() - 1);
 }
 
 static void level_host_copies_from(sa_gpu_level *L, const sa_gpu_level_desc *d)
@@ -205,6 +348,7 @@ void sa_level_ready(sa_gpu_level *lev)
     sa_level_host_copies(lev);
     if (!P.active)
         return;
+    sa_level_queue_rest(lev);
     // the host arrays are the caller's again once this returns: block the host, not just
     // the stream
     if (!P.ev.empty())
@@ -215,6 +359,8 @@ void sa_level_ready(sa_gpu_level *lev)
     for (size_t i = 0; i < P.ev.size(); ++i)
         cudaEventDestroy(P.ev[i]);
     P.ev.clear();
+    P.elem_mark.clear();
+    P.row_mark.clear();
     P.active = false;
 }
 
@@ -359,11 +505,8 @@ extern "C" int sa_gpu_level_create(sa_gpu_ctx *ctx, const sa_gpu_level_desc *d,
     }
     else
     {
-        // Pipelined upload on the copy stream: the tables first, then the operator and the
-        // element blocks in S slabs (equal row / element ranges, interleaved), one event per
-        // slab.  The main stream only waits for the tables; the local spectral stage waits
-        // slab by slab.
-        const int S = 16;
+        // Pipelined upload: the tables go out on the copy stream now; the operator rows and
+        // the element blocks follow on demand (PendingUpload).
         cudaStream_t cs = ctx->copy_stream;
         cudaEvent_t ea; // the buffers were allocated in main-stream order
         SA_CUDA(cudaEventCreateWithFlags(&ea, cudaEventDisableTiming));
@@ -373,36 +516,13 @@ extern "C" int sa_gpu_level_create(sa_gpu_ctx *ctx, const sa_gpu_level_desc *d,
         SA_CUDA(cudaEventRecord(ea, cs));
         SA_CUDA(cudaStreamWaitEvent(st, ea, 0));
         SA_CUDA(cudaEventDestroy(ea));
-        const int rows_per = (d->ND + S - 1) / S, elems_per = (d->NE + S - 1) / S;
         PendingUpload &P = L->pending;
         P.active = true;
-        for (int sl = 0; sl < S; ++sl)
-        {
-            if (d->A_I)
-            {
-                const int r0 = std::min(d->ND, sl * rows_per), r1 = std::min(d->ND, r0 + rows_per);
-                const size_t k0 = d->A_I[r0], k1 = d->A_I[r1];
-                if (k1 > k0)
-                {
-                    SA_CUDA(cudaMemcpyAsync(L->A_own.J.p + k0, d->A_J + k0, (k1 - k0) * sizeof(int),
-                                            cudaMemcpyHostToDevice, cs));
-                    SA_CUDA(cudaMemcpyAsync(L->A_own.A.p + k0, d->A_data + k0,
-                                            (k1 - k0) * sizeof(double), cudaMemcpyHostToDevice, cs));
-                }
-            }
-            if (d->elmat)
-            {
-                const int e0 = std::min(d->NE, sl * elems_per), e1 = std::min(d->NE, e0 + elems_per);
-                const size_t k0 = d->elmat_off[e0], k1 = d->elmat_off[e1];
-                if (k1 > k0)
-                    SA_CUDA(cudaMemcpyAsync(L->elmat.p + k0, d->elmat + k0,
-                                            (k1 - k0) * sizeof(double), cudaMemcpyHostToDevice, cs));
-            }
-            cudaEvent_t ev;
-            SA_CUDA(cudaEventCreateWithFlags(&ev, dbg ? cudaEventDefault : cudaEventDisableTiming));
-            P.ev.push_back(ev);
-            SA_CUDA(cudaEventRecord(ev, cs));
-        }
+        P.complete = false;
+        P.timing = dbg;
+        P.ev.reserve(64); // (a helper thread appends while the main thread reads earlier entries)
+        P.elem_mark.assign(d->elmat ? (size_t)d->NE : 0, 0);
+        P.row_mark.assign(d->A_I ? (size_t)d->ND : 0, 0);
     }
     lap("copies issued");
     // host copies of the small index arrays
@@ -412,8 +532,6 @@ extern "C" int sa_gpu_level_create(sa_gpu_ctx *ctx, const sa_gpu_level_desc *d,
         PendingUpload &P = L->pending;
         P.desc = *d;
         P.host_copies_done = false; // deferred: sa_level_host_copies
-        P.rows_per = std::max(1, (d->ND + (int)P.ev.size() - 1) / (int)P.ev.size());
-        P.elems_per = std::max(1, (d->NE + (int)P.ev.size() - 1) / (int)P.ev.size());
     }
     else
         level_host_copies_from(L, d);

@@ -14,6 +14,9 @@
 // BuildAEStiff -> Eigensolver::SolveDirect (amg/src/spectral.cpp:124-237) ->
 // xpacks_calc_lower_eigens_dense (amg/src/xpacks.cpp:222-314).
 #include <algorithm>
+#include <atomic>
+#include <future>
+#include <thread>
 #include <cfloat>
 #include <numeric>
 
@@ -1118,24 +1121,51 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         }
     } guard{pieces};
 
-    // Pipelined upload (desc.async_upload): split the range into pieces of consecutive AEs;
-    // a piece starts as soon as the slabs its AEs read are on the device.  Worth it only
-    // when the first piece does not already need (nearly) everything.
-    // Pieces grow (1/8, 3/8, 1/2 of the range): a small first piece starts early, later
-    // ones are large enough to keep the per-piece overhead (launch tails, two host
-    // synchronisations) small while their slabs arrive behind the running piece.
+    // Pipelined upload (desc.async_upload): the range is split into pieces of consecutive AEs
+    // and the rows / element blocks each piece reads are queued on the copy stream in that
+    // order (sa_level_queue_upload), so a piece starts as soon as ITS inputs have arrived while
+    // the rest is still in flight.  Pieces grow (1/8, 3/8, 1/2 of the range): a small first
+    // piece starts early, later ones are large enough to keep the per-piece overhead (launch
+    // tails, two host synchronisations) small.
     std::vector<int> piece_ends; // ascending, last == ae_end
-    if (lev->pending.active && ae_end - ae_begin >= 64)
+    std::vector<int> piece_event;
+    if (lev->pending.active && !lev->pending.complete && ae_end - ae_begin >= 64)
     {
         const int len = ae_end - ae_begin;
-        const int e0 = ae_begin + len / 8, e1 = ae_begin + len / 2;
-        if (lev->pending.need(ae_begin, e0) + 2 < (int)lev->pending.ev.size())
-        {
-            piece_ends.push_back(e0);
-            piece_ends.push_back(e1);
-        }
+        piece_ends.push_back(ae_begin + len / 8);
+        piece_ends.push_back(ae_begin + len / 2);
     }
     piece_ends.push_back(ae_end);
+    // The first piece's request is queued here; marking and queueing the others costs the host
+    // ~15 ms at 128^3 and runs on a helper thread while this one launches the first piece.
+    std::future<void> upload_fut;
+    std::atomic<int> pieces_queued(0); // requests published by the helper (piece_event valid)
+    if (lev->pending.active)
+    {
+        piece_event.assign(piece_ends.size(), -1);
+        piece_event[0] = sa_level_queue_upload(lev, ae_begin, piece_ends[0]);
+        pieces_queued.store(1, std::memory_order_release);
+        const int dev = ctx->device;
+        upload_fut = std::async(std::launch::async,
+                                [&piece_event, &piece_ends, &pieces_queued, lev, dev] {
+            cudaSetDevice(dev);
+            try
+            {
+                for (size_t pi = 1; pi < piece_ends.size(); ++pi)
+                {
+                    piece_event[pi] =
+                        sa_level_queue_upload(lev, piece_ends[pi - 1], piece_ends[pi]);
+                    pieces_queued.store((int)pi + 1, std::memory_order_release);
+                }
+                sa_level_queue_rest(lev); // what the other stages (or other ranks' AEs) need
+            }
+            catch (...)
+            {
+                pieces_queued.store(1 << 20, std::memory_order_release); // unblock the waiter
+                throw;
+            }
+        });
+    }
 
     // Size the cached work arrays for the largest piece up front: growing them piece by
     // piece would make the stream-ordered allocator map new memory in the middle of the
@@ -1183,6 +1213,13 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
     }
 
     const bool pipe_debug = getenv("SA_GPU_PIPE_DEBUG") != NULL && lev->pending.active;
+    const auto t_host0 = std::chrono::steady_clock::now();
+    auto hlap = [&](const char *what, int a) {
+        if (pipe_debug)
+            fprintf(stderr, "[pipe-host] %-22s chunk@%d  %.2f ms\n", what, a,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0)
+                        .count());
+    };
     std::vector<cudaEvent_t> dbg_ev;
     std::vector<int> dbg_need;
     // Processing order.  Positions q in [ae_begin, ae_end) map to AEs seq[q - ae_begin]:
@@ -1282,16 +1319,22 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         staged_upload(ctx, ctx->stage, d_order, order.data(), ns);
         if (lev->pending.active)
         {
-            const int need = lev->pending.need(a0, a1);
+            const int pi = (int)(std::upper_bound(piece_ends.begin(), piece_ends.end(), a0) -
+                                 piece_ends.begin());
+            while (pieces_queued.load(std::memory_order_acquire) <= pi)
+                std::this_thread::yield(); // this piece's request has not been queued yet
+            if (pieces_queued.load(std::memory_order_acquire) >= (1 << 20))
+                upload_fut.get(); // the helper failed: rethrows
+            const int evi = piece_event[std::min(pi, (int)piece_event.size() - 1)];
             if (pipe_debug)
             {
                 cudaEvent_t e;
                 cudaEventCreate(&e);
                 cudaEventRecord(e, st);
                 dbg_ev.push_back(e);
-                dbg_need.push_back(need);
+                dbg_need.push_back(evi);
             }
-            sa_level_wait_slab(lev, need);
+            sa_level_wait_event(lev, evi);
             if (pipe_debug)
             {
                 cudaEvent_t e;
@@ -1501,6 +1544,7 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
             }
 
         delete pa;
+        hlap("assemble launched", a0);
         if (a1 == ae_end)
             sa_level_host_copies(lev); // deferred host work, hidden behind the longest queue
         // counts
@@ -1528,6 +1572,7 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         d_mtot.download(pr->mtot.data(), ns, st);
         d_status.download(h_status.data(), ns, st);
         SA_CUDA(cudaStreamSynchronize(st));
+        hlap("count synced", a0);
         for (int s = 0; s < ns; ++s)
             if (h_status[s])
                 SA_FAIL("sa_gpu_local_spectral: AE %d has a non-positive diagonal "
@@ -1636,7 +1681,9 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
                 SA_LAUNCH(ctx, k_back_transform, dim3(ns, gy), bt_threads, 0, C, lev->AE2d_I.p, d_nev.p,
                           d_mtot.p, d_evect_off.p, pr->evects.p, use_square ? 0 : 0x7fffffff);
             }
+            hlap("post kernels launched", a0);
             SA_CUDA(cudaStreamSynchronize(st)); // workspace freed at scope exit
+            hlap("chunk done", a0);
         }
         a0 = a1;
     }
@@ -1651,13 +1698,13 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         cudaEventSynchronize(e);
         cudaEventSynchronize(lev->pending.ev.back());
         float ms;
-        fprintf(stderr, "[pipe] slabs:");
+        fprintf(stderr, "[pipe] upload requests done at:");
         for (size_t i = 0; i < lev->pending.ev.size(); ++i)
         {
             cudaEventElapsedTime(&ms, dbg_ev[0], lev->pending.ev[i]);
             fprintf(stderr, " %.1f", ms);
         }
-        fprintf(stderr, "\n[pipe] pieces (need: queued released):");
+        fprintf(stderr, "\n[pipe] pieces (request: queued released):");
         for (size_t i = 0; i + 1 < dbg_ev.size(); i += 2)
         {
             float m0, m1;
@@ -1671,6 +1718,8 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
             cudaEventDestroy(dbg_ev[i]);
         cudaEventDestroy(e);
     }
+    if (upload_fut.valid())
+        upload_fut.get();
     sa_level_ready(lev); // a pipelined upload is complete from here on
     // merge the pieces into the level's flat arrays (range [ae_begin, ae_end) only)
     for (size_t p = 0; p < pieces.size(); ++p)

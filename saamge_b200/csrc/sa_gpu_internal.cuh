@@ -267,36 +267,23 @@ struct LevelTables
 };
 
 
-/* pipelined upload of a level: the operator and the element blocks travel in slabs on the
-   context's copy stream; slab s is complete when ev[s] has fired.  ae_need[i] is the first
-   slab index after which every row / element block AE i reads is on the device. */
+/* Pipelined (demand-driven) upload of a level.  sa_gpu_level_create queues the tables on the
+   context's copy stream and returns; the operator rows and the element blocks follow in the
+   order the local spectral stage asks for them: sa_level_queue_upload(a0, a1) queues exactly
+   the rows / blocks AEs [a0, a1) read and that are not queued yet (merged into at most a few
+   hundred contiguous runs) and returns the index of the event that fires when they have
+   arrived.  This works for any AE numbering; sa_level_queue_rest queues what is left. */
 struct PendingUpload
 {
     bool active = false;
+    bool complete = false; // every row / element block has been queued
     std::vector<cudaEvent_t> ev;
     // the caller keeps the host arrays valid while the upload is pending (API contract), so
     // the level's host-side copies of the index arrays are deferred until the GPU is busy
     sa_gpu_level_desc desc;
     bool host_copies_done = true;
-    int rows_per = 1, elems_per = 1;
-    /* first slab after which everything AEs [a0, a1) read is on the device */
-    int need(int a0, int a1) const
-    {
-        int me = -1, md = -1;
-        if (desc.elmat)
-            for (int k = desc.AE_to_elem_I[a0]; k < desc.AE_to_elem_I[a1]; ++k)
-                me = me > desc.AE_to_elem_J[k] ? me : desc.AE_to_elem_J[k];
-        if (desc.A_I)
-            for (int k = desc.AE_to_dof_I[a0]; k < desc.AE_to_dof_I[a1]; ++k)
-                md = md > desc.AE_to_dof_J[k] ? md : desc.AE_to_dof_J[k];
-        int s = 0;
-        if (me >= 0)
-            s = me / elems_per;
-        if (md >= 0 && md / rows_per > s)
-            s = md / rows_per;
-        const int S = (int)ev.size();
-        return s < S - 1 ? s : S - 1;
-    }
+    std::vector<unsigned char> elem_mark, row_mark; // 0 not queued, 1 queued, 2 being queued
+    bool timing = false;
 };
 
 struct sa_gpu_level
@@ -353,8 +340,10 @@ struct sa_gpu_level
 
 /* capi.cu: make the context's stream wait for a pending pipelined upload (all of it) */
 void sa_level_ready(sa_gpu_level *lev);
-/* ... or only for slabs [0, slab] (used by the local spectral stage between AE pieces) */
-void sa_level_wait_slab(sa_gpu_level *lev, int slab);
+/* demand-driven parts (see PendingUpload) */
+int sa_level_queue_upload(sa_gpu_level *lev, int a0, int a1);
+int sa_level_queue_rest(sa_gpu_level *lev);
+void sa_level_wait_event(sa_gpu_level *lev, int idx);
 /* deferred host-side copies of a pipelined level (no-op when done) */
 void sa_level_host_copies(sa_gpu_level *lev);
 
