@@ -150,9 +150,26 @@ def cpu_sample(ou, pr, p, nae, target_s, procs):
     t_start = time.time()
     os.write(go_w, b"g" * procs)
     bad = 0
-    for pid in pids:
-        _, st = os.waitpid(pid, 0)
-        bad += 1 if st != 0 else 0
+    left = set(pids)
+    deadline = t_start + max(60.0, 20.0 * target_s)
+    while left:
+        for pid in list(left):
+            done, st = os.waitpid(pid, os.WNOHANG)
+            if done:
+                left.discard(pid)
+                bad += 1 if st != 0 else 0
+        if left:
+            if time.time() > deadline:  # a worker hung (fork in a threaded process): give up
+                for pid in left:
+                    try:
+                        os.kill(pid, 9)
+                        os.waitpid(pid, 0)
+                    except OSError:
+                        pass
+                bad += len(left)
+                left = set()
+            else:
+                time.sleep(0.002)
     wall = time.time() - t_start
     for fd in (ready_r, ready_w, go_r, go_w):
         os.close(fd)
@@ -397,20 +414,24 @@ def main():
         if world == 1 and not args.no_cpu:
             import oracle_util as ou
 
-            ns, t, cores = cpu_sample(ou, pr, p, nae, args.cpu_seconds, os.cpu_count() or 1)
-            if ns == nae and t < 0.5 * args.cpu_seconds:
-                # the whole level is a short sample on this box: repeat it to ~cpu_seconds of work
-                reps = min(8, int(args.cpu_seconds / max(t, 1e-3)))
-                for _ in range(reps):
-                    ns2, t2, _c = cpu_sample(ou, pr, p, nae, args.cpu_seconds, os.cpu_count() or 1)
-                    ns += ns2
-                    t += t2
-            line["cpu_baseline"] = {"value": ns / t, "unit": "AE/s", "cores": cores, "kind": "port",
-                                    "sample": "%d AEs (passes over the first AEs of the %d of the level; assemble + D + LAPACK dsygvx), %.1f s, one single-threaded process per core on contiguous AE slices (mpirun -n P analogue)" % (ns, nae, t)}
-            # what ONE reference MPI rank does (SURVEY 8d asks for both numbers)
-            ns1, t1, c1 = cpu_sample(ou, pr, p, nae, min(5.0, args.cpu_seconds), 1)
-            line["cpu_baseline_1core"] = {"value": ns1 / t1, "unit": "AE/s", "cores": c1, "kind": "port",
-                                          "sample": "first %d AEs, %.1f s" % (ns1, t1)}
+            try:
+                ns, t, cores = cpu_sample(ou, pr, p, nae, args.cpu_seconds, os.cpu_count() or 1)
+                if ns == nae and t < 0.5 * args.cpu_seconds:
+                    # the whole level is a short sample on this box: repeat it to ~cpu_seconds of work
+                    reps = min(8, int(args.cpu_seconds / max(t, 1e-3)))
+                    for _ in range(reps):
+                        ns2, t2, _c = cpu_sample(ou, pr, p, nae, args.cpu_seconds, os.cpu_count() or 1)
+                        ns += ns2
+                        t += t2
+                line["cpu_baseline"] = {"value": ns / t, "unit": "AE/s", "cores": cores, "kind": "port",
+                                        "sample": "%d AEs (passes over the first AEs of the %d of the level; assemble + D + LAPACK dsygvx), %.1f s, one single-threaded process per core on contiguous AE slices (mpirun -n P analogue)" % (ns, nae, t)}
+                # what ONE reference MPI rank does (SURVEY 8d asks for both numbers)
+                ns1, t1, c1 = cpu_sample(ou, pr, p, nae, min(5.0, args.cpu_seconds), 1)
+                line["cpu_baseline_1core"] = {"value": ns1 / t1, "unit": "AE/s", "cores": c1, "kind": "port",
+                                              "sample": "first %d AEs, %.1f s" % (ns1, t1)}
+            except Exception as ex:  # the GPU numbers above must not be lost to a CPU-side failure
+                line["cpu_baseline"] = {"value": None, "unit": "AE/s", "cores": 0, "kind": "port",
+                                        "sample": "failed: %r (see bench.py --impl reference)" % (ex,)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
