@@ -1167,6 +1167,9 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         });
     }
 
+    // (the batch size of the inverse iteration is remembered within one call only: the
+    // workspace is NB x nmax, and nmax differs from level to level)
+    ctx->sws.invit_NB = 0;
     // Size the cached work arrays for the largest piece up front: growing them piece by
     // piece would make the stream-ordered allocator map new memory in the middle of the
     // pipeline (and leave odd-sized holes behind for the next call).

@@ -33,7 +33,11 @@ struct StageTimer
 {
     std::string name;
     double t0;
-    StageTimer(const char *n) : name(n), t0(now_s()) {}
+    StageTimer(const char *n) : name(n), t0(now_s())
+    {
+        if (getenv("SA_GPU_ALLOC_DEBUG")) // lets the allocation log be read stage by stage
+            std::fprintf(stderr, "[stage] l%d.%s begins\n", g_stage_level, n);
+    }
     ~StageTimer()
     {
         char key[96];
