@@ -1232,7 +1232,7 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
     // instead of the whole level (128^3 level 1: 2 GB instead of 11.4 GB; multi-GB requests
     // cost the device memory pool 0.1-2 s each), every batch holds matrices of similar size,
     // and since the first chunk is the largest the work arrays never grow afterwards.
-    static const int coop_gdiv = getenv("SA_GPU_COOP_DIV") ? atoi(getenv("SA_GPU_COOP_DIV")) : 300;
+    static const int coop_gdiv = getenv("SA_GPU_COOP_DIV") ? atoi(getenv("SA_GPU_COOP_DIV")) : 400;
     static const int coop_batches_per_chunk =
         getenv("SA_GPU_COOP_BATCHES") ? std::max(1, atoi(getenv("SA_GPU_COOP_BATCHES"))) : 4;
     std::vector<int> seq(ae_end - ae_begin);
