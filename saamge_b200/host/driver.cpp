@@ -7,8 +7,17 @@
 #include <limits>
 #include <type_traits>
 
+#include <cstdlib>
+
 #include "hierarchy.hpp"
 #include "part.hpp"
+
+namespace saamge
+{
+/* coarse-topology prefetch (ml.cpp) */
+void sa_topology_prefetch_start(const agg_partitioning_relations_t *rels, int nparts_target);
+void sa_topology_prefetch_drop(const agg_partitioning_relations_t *rels);
+} // namespace saamge
 
 using namespace saamge;
 
@@ -141,6 +150,7 @@ extern "C" void sa_drv_problem_destroy(void *prob_)
         return;
     if (prob->rels)
     {
+        sa_topology_prefetch_drop(prob->rels);
         // elem_to_dof / elem_to_elem were copies owned by the relations
         agg_free_partitioning(prob->rels);
     }
@@ -213,6 +223,9 @@ extern "C" int sa_drv_problem_partition(void *prob_, const sa_drv_params_t *p)
     prob->rels = agg_create_partitioning_fine(f.NE, elem_to_dof, elem_to_elem, partitioning,
                                               f.bdr_dofs.data(), &nparts, false);
     prob->times["partition"] = now_s() - t0;
+    // the METIS agglomeration of the first coarse level is a host input as well: start it now
+    if (p->num_levels > 2 && p->partition_kind != 1 && !getenv("SA_NO_TOPOLOGY_PREFETCH"))
+        sa_topology_prefetch_start(prob->rels, sa_target_nparts(f.NE, *p)[1]);
     return nparts;
 }
 

@@ -539,6 +539,8 @@ struct TopologyPrefetch
     std::future<agg_coarse_topology_t> fut;
     void start(const agg_partitioning_relations_t *rels, int nparts_target)
     {
+        if (src == rels && fut.valid())
+            return; // already under way (started when the problem was partitioned)
         drop();
         if (getenv("SA_NO_TOPOLOGY_PREFETCH"))
             return;
@@ -573,6 +575,19 @@ struct TopologyPrefetch
     }
 } g_topo_prefetch;
 } // namespace
+
+/* The coarse agglomeration of the first coarse level only needs the fine relations: drivers
+   may start it as soon as those exist (METIS agglomeration is a host-side input of the path). */
+void sa_topology_prefetch_start(const agg_partitioning_relations_t *rels, int nparts_target)
+{
+    g_topo_prefetch.start(rels, nparts_target);
+}
+
+void sa_topology_prefetch_drop(const agg_partitioning_relations_t *rels)
+{
+    if (g_topo_prefetch.src == rels)
+        g_topo_prefetch.drop();
+}
 
 static void levels_list_push_coarse_data(levels_list_t &list,
                                          agg_partitioning_relations_t *agg_part_rels,

@@ -3,6 +3,7 @@
 // (amg/src/part.cpp:56-118, 120-215).  METIS is the static library shipped with
 // the CUDA toolkit (libmetis_static.a, 64-bit idx_t, no header), so prototypes
 // and option indices (METIS 5.1 layout) are declared here by hand.
+#include <mutex>
 #include "part.hpp"
 
 #include <algorithm>
@@ -99,6 +100,10 @@ int *part_generate_partitioning(const Table &graph, const int *weights, int *par
         for (int i = 0; i < nodes_number; ++i)
             vwgt[i] = weights ? weights[i] : 1;
         std::vector<int64_t> part64((size_t)nodes_number);
+        // METIS calls are serialised: the coarse topology of the next level is prefetched on a
+        // helper thread (ml.cpp) and the thread safety of this METIS build is unknown
+        static std::mutex metis_mutex;
+        std::lock_guard<std::mutex> metis_lock(metis_mutex);
         const int stat = METIS_PartGraphKway(&nvtxs, &ncon, xadj.data(), adjncy.data(),
                                              vwgt.data(), NULL, NULL, &nparts, NULL, NULL,
                                              options, &objval, part64.data());
