@@ -404,8 +404,16 @@ def main():
                 b_spmv = 12.0 * nnz + 20.0 * nd
                 b_sm = b_spmv + 24.0 * nd
                 pk = peaks["hbm_gbs"]
+                spmv_traffic = None
+                try:
+                    tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+                    if tj.get("workload") == args.workload:
+                        spmv_traffic = tj["k_spmv"]["dram_bytes_per_launch"]
+                except Exception:
+                    spmv_traffic = None
                 line["roofline_spmv"] = {"bound": "hbm", "achieved": b_spmv / (ms * 1e-3) / 1e9, "peak": pk,
-                                         "unit": "GB/s", "frac": b_spmv / (ms * 1e-3) / 1e9 / pk, "traffic": None,
+                                         "unit": "GB/s", "frac": b_spmv / (ms * 1e-3) / 1e9 / pk,
+                                         "traffic": spmv_traffic,
                                          "ms": ms, "peak_source": peak_src, "algorithmic_bytes": b_spmv}
                 line["roofline_smoother"] = {"bound": "hbm", "achieved": b_sm / (ms2 * 1e-3) / 1e9, "peak": pk,
                                              "unit": "GB/s", "frac": b_sm / (ms2 * 1e-3) / 1e9 / pk,
