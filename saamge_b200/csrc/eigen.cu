@@ -1313,11 +1313,17 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
 
         // size buckets: slots sorted by n (largest first); shared-memory tiles for
         // n <= nmax_smem with the dynamic shared size of the bucket's largest n
+        // stable counting sort of the slots by n, largest first (the GPU waits for this)
         std::vector<int> order(ns);
-        std::iota(order.begin(), order.end(), 0);
-        std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
-            return nAE(a0 + x) > nAE(a0 + y);
-        });
+        {
+            std::vector<int> start((size_t)nmax + 2, 0);
+            for (int q = 0; q < ns; ++q)
+                start[nmax - nAE(a0 + q) + 1]++;
+            for (int v = 0; v <= nmax; ++v)
+                start[v + 1] += start[v];
+            for (int q = 0; q < ns; ++q)
+                order[start[nmax - nAE(a0 + q)]++] = q;
+        }
         DevBuf<int> &d_order = WS.order;
         staged_upload(ctx, ctx->stage, d_order, order.data(), ns);
         if (lev->pending.active)
