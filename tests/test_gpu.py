@@ -339,3 +339,40 @@ def test_properties_at_scale():
         Aprev = Ac
     Hg.close()
     pr.close()
+
+
+def test_properties_at_full_size():
+    """BASELINE configs[2] at full size (128^3, ~40k METIS AEs, 4 levels): the CPU oracle would
+    need minutes, so only size-independent properties are checked: orthonormal tentative
+    prolongators, symmetric Galerkin operators that equal P^T A P, at least one vector per AE,
+    eigenvalues below theta, converging PCG."""
+    p = sab.default_params(num_levels=4, first_elems_per_agg=52, elems_per_agg=64,
+                           partition_kind=2, block=(32, 32, 32))
+    pr = sab.Problem(3, 128, coef_kind=1)
+    na = pr.partition(p)
+    assert na == 40320
+    Hg = sab.ml_build(pr, p)
+    it = sab.ml_pcg(Hg)
+    sab.ml_download(Hg)
+    assert 0 < it <= 25
+    A = sp.csr_matrix((pr.get("A.A"), pr.get("A.J"), pr.get("A.I")))
+    x, b = Hg.get("pcg.x"), pr.get("b")
+    assert np.linalg.norm(A @ x - b) <= 1e-5 * np.linalg.norm(b)
+    Aprev = A
+    for l in range(3):
+        Pt = Hg.csr("tent_interp", l)
+        P = Hg.csr("interp", l)
+        Ac = Hg.csr("Ac", l)
+        assert abs(Pt.T @ Pt - sp.identity(Pt.shape[1])).max() <= 1e-10
+        assert abs(Ac - Ac.T).max() <= 1e-10 * abs(Ac).max()
+        if l == 2:  # (the finer triple products take minutes in scipy; they are covered at 32^3)
+            G = (P.T @ Aprev @ P).tocsr()
+            assert abs(G - Ac).max() <= 1e-10 * abs(Ac).max()
+        m = Hg.get("ae_m", l)
+        assert np.all(m >= 1)
+        ev = Hg.get("evals", l) if l == 0 else None
+        if ev is not None:
+            assert np.all(ev[np.isfinite(ev)] <= 0.003 + 1e-12) or np.sum(ev > 0.003) <= np.sum(m == 1)
+        Aprev = Ac
+    Hg.close()
+    pr.close()
