@@ -1239,6 +1239,13 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
     std::iota(seq.begin(), seq.end(), ae_begin);
     const bool sorted_seq = !lev->pending.active && !use_square && range_nmax > nmax_smem &&
                             !getenv("SA_GPU_NO_SORTED_CHUNKS");
+    // Pipelined upload with shared-memory sized AEs only: the pieces do not become chunks of
+    // their own; every occupancy class gets one launch per piece on its stream, each waiting
+    // (on the device) for that piece's upload request, and count / bisection / inverse
+    // iteration / back-transformation run once for the whole range -- no host
+    // synchronisation and no small-kernel tails between pieces.
+    const bool fused_pieces = lev->pending.active && !use_square && range_nmax <= nmax_smem &&
+                              piece_ends.size() > 1 && !getenv("SA_GPU_NO_FUSED_PIECES");
     if (sorted_seq)
         std::stable_sort(seq.begin(), seq.end(),
                          [&](int x, int y) { return (AI[x + 1] - AI[x]) > (AI[y + 1] - AI[y]); });
@@ -1248,7 +1255,8 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
     {
         size_t vtot = 0;
         int a1 = a0;
-        const int piece_end = *std::upper_bound(piece_ends.begin(), piece_ends.end(), a0);
+        const int piece_end =
+            fused_pieces ? ae_end : *std::upper_bound(piece_ends.begin(), piece_ends.end(), a0);
         int n_large = 0;
         while (a1 < piece_end)
         {
@@ -1324,9 +1332,59 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
             for (int q = 0; q < ns; ++q)
                 order[start[nmax - nAE(a0 + q)]++] = q;
         }
+        // one launch per occupancy class: the packed tile of the class's largest n decides
+        // how many blocks are resident per SM (3, 2 or 1; the launch bounds cap it at 3), so
+        // finer size classes would only add launch tails
+        std::vector<int> bucket_edges, bucket_class;
+        static const int max_class = getenv("SA_GPU_MAX_CLASS") ? atoi(getenv("SA_GPU_MAX_CLASS")) : 3;
+        for (int c = std::max(1, std::min(3, max_class)); c >= 1; --c)
+        {
+            const size_t cap = (ctx->smem_per_sm / c - 1024) / sizeof(double);
+            int n = 1;
+            while (n < nmax_smem && packed_smem_doubles((size_t)n + 1, class_threads(c)) <= cap)
+                ++n;
+            if (c == 1)
+                n = nmax_smem;
+            if (bucket_edges.empty() || n > bucket_edges.back())
+            {
+                bucket_edges.push_back(n);
+                bucket_class.push_back(c);
+            }
+        }
+        // fused pieces: regroup the slots as [class][piece][n descending]
+        const int npieces = (int)piece_ends.size();
+        std::vector<int> group_cnt; // per (bucket from the largest, piece)
+        if (fused_pieces)
+        {
+            const int nbk = (int)bucket_edges.size();
+            auto bucket_of = [&](int n) {
+                int b = 0;
+                while (b + 1 < nbk && n > bucket_edges[b])
+                    ++b;
+                return b;
+            };
+            auto piece_of = [&](int q) {
+                return (int)(std::upper_bound(piece_ends.begin(), piece_ends.end(), h_ae[q]) -
+                             piece_ends.begin());
+            };
+            group_cnt.assign((size_t)nbk * npieces, 0);
+            std::vector<int> key(ns);
+            for (int q = 0; q < ns; ++q)
+            {
+                key[q] = (nbk - 1 - bucket_of(nAE(a0 + q))) * npieces + piece_of(q);
+                group_cnt[key[q]]++;
+            }
+            std::vector<int> gstart(group_cnt.size() + 1, 0);
+            for (size_t g = 0; g < group_cnt.size(); ++g)
+                gstart[g + 1] = gstart[g] + group_cnt[g];
+            std::vector<int> regrouped(ns);
+            for (int t = 0; t < ns; ++t) // order is n-descending: stable within a group
+                regrouped[gstart[key[order[t]]]++] = order[t];
+            order.swap(regrouped);
+        }
         DevBuf<int> &d_order = WS.order;
         staged_upload(ctx, ctx->stage, d_order, order.data(), ns);
-        if (lev->pending.active)
+        if (lev->pending.active && !fused_pieces)
         {
             const int pi = (int)(std::upper_bound(piece_ends.begin(), piece_ends.end(), a0) -
                                  piece_ends.begin());
@@ -1353,25 +1411,6 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
             }
         }
         ProfScope *pa = new ProfScope(ctx, "eig.assemble_tridiag");
-        // one launch per occupancy class: the packed tile of the class's largest n decides
-        // how many blocks are resident per SM (3, 2 or 1; the launch bounds cap it at 3), so
-        // finer size classes would only add launch tails
-        std::vector<int> bucket_edges, bucket_class;
-        static const int max_class = getenv("SA_GPU_MAX_CLASS") ? atoi(getenv("SA_GPU_MAX_CLASS")) : 3;
-        for (int c = std::max(1, std::min(3, max_class)); c >= 1; --c)
-        {
-            const size_t cap = (ctx->smem_per_sm / c - 1024) / sizeof(double);
-            int n = 1;
-            while (n < nmax_smem && packed_smem_doubles((size_t)n + 1, class_threads(c)) <= cap)
-                ++n;
-            if (c == 1)
-                n = nmax_smem;
-            if (bucket_edges.empty() || n > bucket_edges.back())
-            {
-                bucket_edges.push_back(n);
-                bucket_class.push_back(c);
-            }
-        }
         int pos = 0;
         // large (global-memory tile) bucket first
         {
@@ -1497,16 +1536,9 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         SA_CUDA(cudaEventRecord(ctx->fork_ev, st));
         bool used_aux[sa_gpu_ctx::NAUX] = {false, false, false};
         int nlaunch = 0;
-        for (int b = (int)bucket_edges.size() - 1; b >= 0 && pos < ns; --b)
-        {
-            const int lo_edge = (b == 0) ? 0 : std::min(bucket_edges[b - 1], nmax_smem);
-            int cnt = 0;
-            while (pos + cnt < ns && nAE(a0 + order[pos + cnt]) > lo_edge)
-                ++cnt;
-            if (!cnt)
-                continue;
-            const int nb = nAE(a0 + order[pos]);
-            const int ai = nlaunch++ % sa_gpu_ctx::NAUX;
+        // one launch: cnt slots of d_order from gpos, tiles sized for nb dofs, occupancy class
+        // of bucket b, on side stream ai
+        auto launch_group = [&](int b, int gpos, int cnt, int nb, int ai) {
             cudaStream_t sb = ctx->aux[ai];
             if (!used_aux[ai])
             {
@@ -1523,7 +1555,7 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
                 SA_CUDA(cudaFuncSetAttribute(k_at_smem,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)ctx->smem_optin));
-                k_at_smem<<<cnt, threads, smem, sb>>>(L, C, d_order.p + pos, lev->ae_D.p);
+                k_at_smem<<<cnt, threads, smem, sb>>>(L, C, d_order.p + gpos, lev->ae_D.p);
             }
             else
             {
@@ -1532,7 +1564,7 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
                 auto launch = [&](auto kern) {
                     SA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)ctx->smem_optin - 1024));
-                    kern<<<cnt, threads, smem, sb>>>(L, C, d_order.p + pos, lev->ae_D.p);
+                    kern<<<cnt, threads, smem, sb>>>(L, C, d_order.p + gpos, lev->ae_D.p);
                 };
                 if (cls >= 3)
                     launch(k_at_packed<256, 3>);
@@ -1543,6 +1575,55 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
             }
             ctx->launches++;
             SA_CUDA(cudaGetLastError());
+        };
+        if (fused_pieces)
+        {
+            const int nbk = (int)bucket_edges.size();
+            // group (bucket from the largest, piece) starts; the tile size of a bucket is that
+            // of its largest AE over all pieces
+            std::vector<int> gpos(group_cnt.size() + 1, pos);
+            for (size_t g = 0; g < group_cnt.size(); ++g)
+                gpos[g + 1] = gpos[g] + group_cnt[g];
+            std::vector<int> bucket_nb(nbk, 1);
+            for (int bb = 0; bb < nbk; ++bb)
+                for (int pi = 0; pi < npieces; ++pi)
+                    if (group_cnt[(size_t)bb * npieces + pi])
+                        bucket_nb[bb] = std::max(bucket_nb[bb],
+                                                 nAE(a0 + order[gpos[(size_t)bb * npieces + pi]]));
+            for (int pi = 0; pi < npieces; ++pi) // piece-major: piece 0 of every class first
+            {
+                while (pieces_queued.load(std::memory_order_acquire) <= pi)
+                    std::this_thread::yield(); // this piece's request has not been queued yet
+                if (pieces_queued.load(std::memory_order_acquire) >= (1 << 20))
+                    upload_fut.get(); // the helper failed: rethrows
+                const int evi = piece_event[pi];
+                for (int bb = 0; bb < nbk; ++bb)
+                {
+                    const size_t g = (size_t)bb * npieces + pi;
+                    if (!group_cnt[g])
+                        continue;
+                    const int ai = bb % sa_gpu_ctx::NAUX;
+                    if (!used_aux[ai])
+                    {
+                        SA_CUDA(cudaStreamWaitEvent(ctx->aux[ai], ctx->fork_ev, 0));
+                        used_aux[ai] = true;
+                    }
+                    if (evi >= 0 && evi < (int)lev->pending.ev.size())
+                        SA_CUDA(cudaStreamWaitEvent(ctx->aux[ai], lev->pending.ev[evi], 0));
+                    launch_group(nbk - 1 - bb, gpos[g], group_cnt[g], bucket_nb[bb], ai);
+                }
+            }
+            pos = ns;
+        }
+        for (int b = (int)bucket_edges.size() - 1; b >= 0 && pos < ns; --b)
+        {
+            const int lo_edge = (b == 0) ? 0 : std::min(bucket_edges[b - 1], nmax_smem);
+            int cnt = 0;
+            while (pos + cnt < ns && nAE(a0 + order[pos + cnt]) > lo_edge)
+                ++cnt;
+            if (!cnt)
+                continue;
+            launch_group(b, pos, cnt, nAE(a0 + order[pos]), nlaunch++ % sa_gpu_ctx::NAUX);
             pos += cnt;
         }
         for (int i = 0; i < sa_gpu_ctx::NAUX; ++i)
