@@ -1129,10 +1129,23 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
     // tails, two host synchronisations) small.
     std::vector<int> piece_ends; // ascending, last == ae_end
     std::vector<int> piece_event;
+    int range_nmax = 1;
+    for (int i = ae_begin; i < ae_end; ++i)
+        range_nmax = std::max(range_nmax, AI[i + 1] - AI[i]);
+    // (when the pieces can be fused into one chunk -- see fused_pieces below -- a piece costs
+    // only launch tails, so the first one is smaller and starts earlier)
+    const bool can_fuse = lev->pending.active && !use_square && range_nmax <= nmax_smem &&
+                          !getenv("SA_GPU_NO_FUSED_PIECES");
     if (lev->pending.active && !lev->pending.complete && ae_end - ae_begin >= 64)
     {
         const int len = ae_end - ae_begin;
-        piece_ends.push_back(ae_begin + len / 8);
+        if (can_fuse && len >= 1024)
+        {
+            piece_ends.push_back(ae_begin + len / 16);
+            piece_ends.push_back(ae_begin + 3 * len / 16);
+        }
+        else
+            piece_ends.push_back(ae_begin + len / 8);
         piece_ends.push_back(ae_begin + len / 2);
     }
     piece_ends.push_back(ae_end);
@@ -1173,9 +1186,6 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
     // Size the cached work arrays for the largest piece up front: growing them piece by
     // piece would make the stream-ordered allocator map new memory in the middle of the
     // pipeline (and leave odd-sized holes behind for the next call).
-    int range_nmax = 1;
-    for (int i = ae_begin; i < ae_end; ++i)
-        range_nmax = std::max(range_nmax, AI[i + 1] - AI[i]);
     if (piece_ends.size() > 1)
     {
         size_t max_v = 0, max_d = 0, max_ns = 0;
@@ -1244,8 +1254,7 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
     // (on the device) for that piece's upload request, and count / bisection / inverse
     // iteration / back-transformation run once for the whole range -- no host
     // synchronisation and no small-kernel tails between pieces.
-    const bool fused_pieces = lev->pending.active && !use_square && range_nmax <= nmax_smem &&
-                              piece_ends.size() > 1 && !getenv("SA_GPU_NO_FUSED_PIECES");
+    const bool fused_pieces = can_fuse && piece_ends.size() > 1;
     if (sorted_seq)
         std::stable_sort(seq.begin(), seq.end(),
                          [&](int x, int y) { return (AI[x + 1] - AI[x]) > (AI[y + 1] - AI[y]); });
