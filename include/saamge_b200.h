@@ -222,6 +222,15 @@ int sa_gpu_host_unregister(const void *p);
    thread blocks since the last call (diagnostics) */
 int sa_gpu_debug_phase_clocks(double *out8);
 
+/* Diagnostics of the large-AE eigensolver (two-stage tridiagonalisation, twostage.cu): reduces
+   the dense symmetric n x n matrix A (host, column-major) to tridiagonal form (d_out, e_out;
+   T_out: band + reflectors, tau1_out) and keeps the reflectors on the device;
+   sa_gpu_debug_twostage_back then maps nvec eigenvectors of that tridiagonal matrix (Y, n x nvec,
+   in/out) back to eigenvectors of A.  Any output pointer may be NULL. */
+int sa_gpu_debug_twostage(sa_gpu_ctx *ctx, int n, const double *A, double *T_out, double *tau1_out,
+                          double *d_out, double *e_out);
+int sa_gpu_debug_twostage_back(sa_gpu_ctx *ctx, int n, int nvec, double *Y);
+
 /* ---- device-pointer entry points (row-partitioned multi-GPU solve: the caller owns the
  *      vectors on the device, e.g. torch tensors, and drives the halo exchange) ----
  * Device addresses of a level's CSR matrix (valid while the level lives). */

@@ -432,10 +432,10 @@ static __device__ bool sa_dev_assemble_AE_staged(const LevelTables &L, int part,
 ///     the reference's order); the element block column is read contiguously;
 ///   - the finished column is written out coalesced.
 /// Shared memory: 2 * H ints (H = power of two >= 2 n) + warps * n doubles.
-/// parts[m]: AE of matrix m; matrix m at Tbase + m * tstride.
+/// parts[m]: AE of matrix m; matrix m at Tbase + m * tstride (or Tbase + toffs[m]).
 static __global__ void k_assemble_large(LevelTables L, const int *parts, const int *slot_list,
                                         const int *ae_of_slot, double *Tbase, int64_t tstride,
-                                        int Hlog)
+                                        const int64_t *toffs, int Hlog)
 {
     extern __shared__ double smem_al[];
     const int m = blockIdx.y;
@@ -448,7 +448,7 @@ static __global__ void k_assemble_large(LevelTables L, const int *parts, const i
     int *hkey = (int *)smem_al;
     int *hval = hkey + H;
     double *buf = (double *)(hval + H) + (size_t)wid * n;
-    double *T = Tbase + (int64_t)m * tstride;
+    double *T = Tbase + (toffs ? toffs[m] : (int64_t)m * tstride);
     for (int q = tid; q < H; q += NT)
         hkey[q] = -1;
     __syncthreads();
@@ -518,7 +518,7 @@ static __global__ void k_assemble_large(LevelTables L, const int *parts, const i
 static inline bool sa_launch_assemble_large(sa_gpu_ctx *ctx, const LevelTables &L, const int *d_parts,
                                             const int *d_slot_list, const int *d_ae_of_slot,
                                             int nmat, int nmax, double *Tbase, int64_t tstride,
-                                            cudaStream_t stream)
+                                            const int64_t *d_toffs, cudaStream_t stream)
 {
     if (L.with_global || nmat <= 0)
         return false;
@@ -538,7 +538,7 @@ static inline bool sa_launch_assemble_large(sa_gpu_ctx *ctx, const LevelTables &
     SA_CUDA(cudaFuncSetAttribute(k_assemble_large, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
     k_assemble_large<<<dim3(nsplit, nmat), NW * 32, smem, stream>>>(L, d_parts, d_slot_list,
-                                                                     d_ae_of_slot, Tbase, tstride, Hlog);
+                                                                     d_ae_of_slot, Tbase, tstride, d_toffs, Hlog);
     ctx->launches++;
     SA_CUDA(cudaGetLastError());
     return true;

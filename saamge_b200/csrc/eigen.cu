@@ -73,7 +73,8 @@ __device__ unsigned long long g_phase_clk[8];
 // memory (n <= nmax_smem), otherwise directly in the V block of the AE.
 __global__ void k_assemble_tridiag(LevelTables L, ChunkDev C, const int *slot_list, int nslots,
                                    int tile_in_smem, double *ae_D, double *tile_base,
-                                   int64_t tile_stride, int stop_after_scale, int preassembled)
+                                   int64_t tile_stride, int stop_after_scale, int preassembled,
+                                   const int64_t *tile_offs)
 {
     extern __shared__ double sm[];
     const int slot = slot_list[blockIdx.x];
@@ -87,7 +88,9 @@ __global__ void k_assemble_tridiag(LevelTables L, ChunkDev C, const int *slot_li
     double *w = v + n;
     double *dg = w + n;
     double *T = tile_in_smem ? (dg + n)
-                             : (tile_base ? tile_base + (int64_t)blockIdx.x * tile_stride : Vout);
+                             : (tile_base ? tile_base + (tile_offs ? tile_offs[blockIdx.x]
+                                                                   : (int64_t)blockIdx.x * tile_stride)
+                                          : Vout);
     const int ld = n;
     double *dd = C.d + C.doff[slot], *ee = C.e + C.doff[slot], *tt = C.tau + C.doff[slot],
            *sinv = C.sinv + C.doff[slot];
@@ -1100,7 +1103,15 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
     }
     // reflector block of an AE: packed triangle when it goes through the shared-memory
     // kernel, full square otherwise
-    auto vsize = [&](size_t n) -> size_t { return !use_square ? n * (n + 1) / 2 : n * n; };
+    // Large AEs (n > nmax_smem) go through the two-stage path (twostage.cu) unless
+    // SA_GPU_LARGE_PATH=coop selects the one-stage cooperative kernels: their reflectors live in
+    // the matrix itself (n^2 doubles of Twork per AE, kept until the back-transformation).
+    static const bool use_ts = !(getenv("SA_GPU_LARGE_PATH") && 0 == strcmp(getenv("SA_GPU_LARGE_PATH"), "coop"));
+    auto is_ts = [&](size_t n) { return use_ts && !use_square && (int)n > nmax_smem; };
+    auto vsize = [&](size_t n) -> size_t {
+        return is_ts(n) ? 0 : (!use_square ? n * (n + 1) / 2 : n * n);
+    };
+    auto footprint = [&](size_t n) -> size_t { return is_ts(n) ? n * n + 64 * n : vsize(n); };
 
     struct PieceResult
     {
@@ -1262,7 +1273,7 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
     int a0 = ae_begin;
     while (a0 < ae_end)
     {
-        size_t vtot = 0;
+        size_t vtot = 0, ftot = 0;
         int a1 = a0;
         const int piece_end =
             fused_pieces ? ae_end : *std::upper_bound(piece_ends.begin(), piece_ends.end(), a0);
@@ -1270,13 +1281,14 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         while (a1 < piece_end)
         {
             const size_t n = nAE(a1);
-            if (a1 > a0 && vtot + vsize(n) > budget_doubles)
+            if (a1 > a0 && ftot + footprint(n) > budget_doubles)
                 break;
             if (sorted_seq && a1 > a0 && (int)n <= nmax_smem && nAE(a0) > nmax_smem)
                 break; // the shared-memory sized AEs start their own chunk
             vtot += vsize(n);
+            ftot += footprint(n);
             ++a1;
-            if (sorted_seq && (int)n > nmax_smem)
+            if (sorted_seq && (int)n > nmax_smem && !is_ts(n))
             {
                 const int Gq = std::max(2, std::min(ctx->num_sms, nAE(a0) / coop_gdiv));
                 // (four batches per chunk: the small per-chunk kernels -- bisection, inverse
@@ -1421,6 +1433,7 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         }
         ProfScope *pa = new ProfScope(ctx, "eig.assemble_tridiag");
         int pos = 0;
+        int ts_cnt = 0, ts_nmax = 0; // large AEs of this chunk on the two-stage path
         // large (global-memory tile) bucket first
         {
             int cnt = 0;
@@ -1434,7 +1447,66 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)ctx->smem_optin));
                 SA_LAUNCH(ctx, k_assemble_tridiag, cnt, 512, smem, L, C, d_order.p + pos, cnt, 0,
-                          lev->ae_D.p, (double *)nullptr, (int64_t)0, 0, 0);
+                          lev->ae_D.p, (double *)nullptr, (int64_t)0, 0, 0, (const int64_t *)nullptr);
+            }
+            else if (cnt && use_ts)
+            {
+                // two-stage path: assemble + scale every large matrix of the chunk into Twork
+                // (exact offsets), dense -> band -> tridiagonal (twostage.cu)
+                const int nb0 = nAE(a0 + order[pos]);
+                std::vector<int64_t> h_toff(cnt);
+                std::vector<int64_t> h_mats((size_t)cnt * (sizeof(sa_ts_mat) / sizeof(int64_t)));
+                static_assert(sizeof(sa_ts_mat) % sizeof(int64_t) == 0, "descriptor upload");
+                sa_ts_mat *hm = (sa_ts_mat *)h_mats.data();
+                std::vector<int> h_ts_of_slot(ns, -1);
+                int64_t tt = 0, dd = 0;
+                for (int b = 0; b < cnt; ++b)
+                {
+                    const int n = nAE(a0 + order[pos + b]);
+                    h_toff[b] = tt;
+                    tt += (int64_t)n * n;
+                    dd += n;
+                }
+                WS.Twork.ensure((size_t)tt);
+                WS.ts_band.ensure((size_t)dd * 64);
+                WS.ts_tau1.ensure((size_t)dd);
+                dd = 0;
+                for (int b = 0; b < cnt; ++b)
+                {
+                    const int slot = order[pos + b];
+                    const int n = nAE(a0 + slot);
+                    hm[b].n = n;
+                    hm[b].T = WS.Twork.p + h_toff[b];
+                    hm[b].band = WS.ts_band.p + dd * 64;
+                    hm[b].d = C.d + h_doff[slot];
+                    hm[b].e = C.e + h_doff[slot];
+                    hm[b].tau1 = WS.ts_tau1.p + dd;
+                    hm[b].tauz = C.tau + h_doff[slot];
+                    h_ts_of_slot[slot] = b;
+                    dd += n;
+                }
+                staged_upload(ctx, ctx->stage, WS.ts_toff, h_toff.data(), cnt);
+                staged_upload(ctx, ctx->stage, WS.ts_mats, h_mats.data(), h_mats.size());
+                staged_upload(ctx, ctx->stage, WS.ts_of_slot, h_ts_of_slot.data(), ns);
+                SA_CUDA(cudaFuncSetAttribute(k_assemble_tridiag,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)ctx->smem_optin));
+                const size_t smem_a = (size_t)(3 * nb0 + 40) * sizeof(double);
+                if (smem_a > ctx->smem_optin)
+                    SA_FAIL("sa_gpu_local_spectral: AE with %d dofs exceeds the supported size of "
+                            "the large-matrix eigensolver", nb0);
+                {
+                    ProfScope ps(ctx, "eig.large_assemble");
+                    const bool pre = sa_launch_assemble_large(ctx, L, nullptr, d_order.p + pos,
+                                                              C.ae_of_slot, cnt, nb0, WS.Twork.p, 0,
+                                                              WS.ts_toff.p, st);
+                    SA_LAUNCH(ctx, k_assemble_tridiag, cnt, 512, smem_a, L, C, d_order.p + pos, cnt, 0,
+                              lev->ae_D.p, WS.Twork.p, (int64_t)0, 1, pre ? 1 : 0,
+                              (const int64_t *)WS.ts_toff.p);
+                }
+                sa_ts_reduce(ctx, (const sa_ts_mat *)WS.ts_mats.p, cnt, nb0, st);
+                ts_cnt = cnt;
+                ts_nmax = nb0;
             }
             else if (cnt)
             {
@@ -1495,10 +1567,10 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
                         // assembly by columns with all SMs, then D + scaling per matrix
                         const bool pre = sa_launch_assemble_large(
                             ctx, L, nullptr, d_order.p + pos + done, C.ae_of_slot, B, nb, WS.Twork.p,
-                            tstride, st);
+                            tstride, nullptr, st);
                         SA_LAUNCH(ctx, k_assemble_tridiag, B, 512, smem_a, L, C,
                                   d_order.p + pos + done, B, 0, lev->ae_D.p, WS.Twork.p, tstride, 1,
-                                  pre ? 1 : 0);
+                                  pre ? 1 : 0, (const int64_t *)nullptr);
                     }
                     std::vector<CoopMatrix> hm(B);
                     for (int b = 0; b < B; ++b)
@@ -1765,6 +1837,12 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
                     }
                     s0 = s1;
                 }
+            }
+            if (ts_cnt)
+            {
+                ProfScope ps(ctx, "eig.ts_back");
+                sa_ts_back(ctx, (const sa_ts_mat *)WS.ts_mats.p, WS.ts_of_slot.p, d_ev_slot.p, d_ev_idx.p,
+                           nev_total, d_evect_off.p, pr->evects.p, ts_nmax, st);
             }
             {
                 ProfScope ps(ctx, "eig.back_transform");

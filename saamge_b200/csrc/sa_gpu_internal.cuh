@@ -179,6 +179,21 @@ struct SpectralWs
     DevBuf<double> Twork, pbuf;
     DevBuf<unsigned int> counters;
     DevBuf<char> coopmats;
+    // large-matrix two-stage path (twostage.cu)
+    DevBuf<double> ts_band, ts_tau1, ts_wsV, ts_wsW;
+    DevBuf<int> ts_of_slot;
+    DevBuf<int64_t> ts_toff, ts_mats;
+};
+
+/* one matrix of the two-stage tridiagonalisation (twostage.cu) */
+struct sa_ts_mat
+{
+    int n;
+    double *T;    // n x n column-major, lower triangle valid on entry; reflectors on exit
+    double *band; // 64 x n band + bulge storage of stage 2
+    double *d, *e; // tridiagonal matrix (out)
+    double *tau1; // n: tau of the stage-1 reflectors, by column (out)
+    double *tauz; // n or NULL: zeroed (the one-stage reflector array of the slot)
 };
 
 struct sa_gpu_ctx
@@ -363,5 +378,14 @@ void dev_spmv_rows(sa_gpu_ctx *ctx, int mode, int nrows, double avg, const int *
                    const double *b, const double *dinv, double mult, double *y);
 void dev_exclusive_scan_i32(sa_gpu_ctx *ctx, const int *in, int *out, int n); // out has n+1
 void dev_exclusive_scan_i64(sa_gpu_ctx *ctx, const int64_t *in, int64_t *out, int n);
+
+/* ---- twostage.cu ---- */
+/* dense -> band -> tridiagonal for nmats matrices (sorted largest first; nmax = largest n) */
+void sa_ts_reduce(sa_gpu_ctx *ctx, const sa_ts_mat *d_mats, int nmats, int nmax, cudaStream_t st);
+/* z <- Q1 Q2 z for every eigenvector of the chunk whose slot went through sa_ts_reduce */
+void sa_ts_back(sa_gpu_ctx *ctx, const sa_ts_mat *d_mats, const int *d_ts_of_slot, const int *d_ev_slot,
+                const int *d_ev_idx, int nev_total, const int64_t *d_evect_off_slot, double *d_evects,
+                int nmax, cudaStream_t st);
+size_t sa_ts_s1_smem_bytes(int nmax, int *w_in_out);
 
 #endif

@@ -546,7 +546,7 @@ extern "C" int sa_gpu_coarse_elmats(sa_gpu_level *finer, sa_gpu_level *coarse)
         {
             const int cnt = std::min(blocks, nparts - e0);
             if (!sa_launch_assemble_large(ctx, L, d_parts.p + e0, nullptr, nullptr, cnt, nmax,
-                                          scratch.p, max_scratch, st))
+                                          scratch.p, max_scratch, nullptr, st))
             {
                 if (e0 != 0)
                     SA_FAIL("sa_gpu_coarse_elmats: large assembly became unavailable");
