@@ -178,6 +178,121 @@ def cpu_sample(ou, pr, p, nae, target_s, procs):
     return ns, wall, procs
 
 
+def _fork_map(fn, nworkers):
+    """Runs fn(i) for i < nworkers in forked single-threaded processes that start together;
+    returns the list of float results (the children only run CPU code)."""
+    import multiprocessing as mp
+
+    res = mp.RawArray(ctypes.c_double, nworkers)
+    ready_r, ready_w = os.pipe()
+    go_r, go_w = os.pipe()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    pids = []
+    for i in range(nworkers):
+        pid = os.fork()
+        if pid == 0:
+            rc = 0
+            try:
+                os.write(ready_w, b"r")
+                os.read(go_r, 1)
+                res[i] = float(fn(i))
+            except BaseException:
+                rc = 1
+            os._exit(rc)
+        pids.append(pid)
+    got = 0
+    while got < nworkers:
+        got += len(os.read(ready_r, nworkers - got))
+    os.write(go_w, b"g" * nworkers)
+    bad = 0
+    for pid in pids:
+        _, st = os.waitpid(pid, 0)
+        bad += 1 if st != 0 else 0
+    for fd in (ready_r, ready_w, go_r, go_w):
+        os.close(fd)
+    if bad:
+        raise RuntimeError("%d CPU worker processes failed" % bad)
+    return list(res)
+
+
+def cpu_hierarchy_baseline(ou, sab, H, pr, p, nae, level0_rate, procs, its_gpu):
+    """CPU (oracle port) time of what the north star targets -- setup local spectral stage of
+    EVERY level + PCG solve -- on the box's host cores, from bounded samples:
+      level 0   : nae / (AE/s of the level-0 sample already measured: assemble + D + dsygvx)
+      level l>0 : `procs` AE matrices of the level, downloaded from the GPU hierarchy
+                  (sa_gpu_build_AE_stiff), D + dsygvx on one single-threaded process each, all
+                  at once; core-seconds scaled by sum(n^3) of the level / sum(n^3) of the sample
+                  and divided by the cores.  Levels whose AEs are too large to sample in seconds
+                  are extrapolated with the previous level's measured seconds per n^3.
+      PCG       : the oracle's kalchev_pcg + V-cycle (OpenMP over rows) on the DOWNLOADED
+                  operators of the same hierarchy for 2 iterations, scaled to the GPU's count.
+    The setup figure omits tentative P / RAP / topology on the CPU: it is a lower bound."""
+    import numpy as np
+
+    o = ou.oracle(1)  # the per-AE workers are single-threaded processes
+    g = sab.gpu_lib()
+    h = sab.host_lib()
+    h.sa_drv_ml_gpu_level.restype = ctypes.c_void_p
+    h.sa_drv_ml_gpu_level.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    o.sa_orc_time_dense_AE.restype = ctypes.c_double
+    o.sa_orc_time_dense_AE.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.c_double,
+                                       ctypes.POINTER(ctypes.c_int)]
+    o.sa_orc_time_pcg_on_hierarchy.restype = ctypes.c_double
+    o.sa_orc_time_pcg_on_hierarchy.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                               ctypes.POINTER(ctypes.c_int)]
+    ncoarsen = int(H.scalar("num_coarsenings", 0))
+    detail = [{"level": 0, "cpu_s": nae / level0_rate, "how": "level-0 sample rate x %d AEs" % nae}]
+    sec_per_n3 = None
+    for l in range(1, ncoarsen):
+        sizes = np.diff(H.get("AE_to_dof.I", l)).astype(np.int64)
+        n3 = float((sizes.astype(float) ** 3).sum())
+        nparts = len(sizes)
+        if np.median(sizes) <= 2600:
+            order = np.argsort(sizes)
+            k = min(procs, nparts)
+            pick = order[np.linspace(0, nparts - 1, k).astype(int)]
+            lev = ctypes.c_void_p(h.sa_drv_ml_gpu_level(H.handle, l))
+            mats = []
+            for part in pick:
+                n = int(sizes[part])
+                A = np.zeros(n * n)
+                rc = g.sa_gpu_build_AE_stiff(lev, int(part), A.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+                if rc != 0:
+                    raise RuntimeError(g.sa_gpu_last_error().decode())
+                mats.append((n, A))
+
+            def work(i):
+                n, A = mats[i]
+                return o.sa_orc_time_dense_AE(n, A.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), p.theta, None)
+
+            ts = _fork_map(work, k)
+            n3s = float(sum(float(n) ** 3 for n, _ in mats))
+            sec_per_n3 = sum(ts) / n3s
+            cpu_s = sec_per_n3 * n3 / min(procs, nparts)
+            detail.append({"level": l, "cpu_s": cpu_s, "how": "%d of %d AEs (n = %d..%d) on %d cores at once, "
+                           "%.1f core-seconds, scaled by sum n^3" % (k, nparts, min(n for n, _ in mats),
+                                                                    max(n for n, _ in mats), k, sum(ts))})
+        elif sec_per_n3 is not None:
+            cpu_s = sec_per_n3 * n3 / min(procs, nparts)
+            detail.append({"level": l, "cpu_s": cpu_s, "how": "%d AEs (median n = %d): extrapolated with level %d's "
+                           "measured seconds per n^3, %d cores busy" % (nparts, int(np.median(sizes)), l - 1,
+                                                                        min(procs, nparts))})
+    cpu_setup = sum(d["cpu_s"] for d in detail)
+    sab.ml_download(H)
+    o = ou.oracle(0)  # the solve uses every core (OpenMP over rows)
+    run_iters = 2
+    it = ctypes.c_int()
+    t = o.sa_orc_time_pcg_on_hierarchy(H.handle, run_iters, 1e-12, 0.0, ctypes.byref(it))
+    cpu_pcg = t * (its_gpu + 1) / (run_iters + 1)
+    return {"cpu_setup_s": cpu_setup, "cpu_setup_covers": "local spectral stage (assemble + D + dsygvx) of every "
+            "level; tentative P / RAP / topology not included (lower bound)", "cpu_setup_detail": detail,
+            "cpu_pcg_s": cpu_pcg, "cpu_pcg_how": "oracle kalchev_pcg + V-cycle on the downloaded operators, %d "
+            "V-cycles in %.2f s on %d OpenMP threads, scaled to %d iterations" % (run_iters + 1, t,
+                                                                                 o.sa_orc_num_threads(), its_gpu),
+            "cores": procs}
+
+
 def run_reference(args, rank, world):
     """CPU arm: the oracle port on all host cores; rank 0 only."""
     if rank != 0:

@@ -98,6 +98,9 @@ typedef struct
           and unmodified until the first call that uses the level returns (or until
           sa_gpu_level_upload_wait).  Host arrays should be pinned (sa_gpu_host_register);
           pageable memory works but does not overlap.
+       2: as 1, and the operator rows / element blocks that sa_gpu_local_spectral(level, theta,
+          ae_begin, ae_end) does not read stay on the host until another entry point needs them
+          (a rank of a sharded stage uploads the inputs of its own AEs only).
        0: all copies are complete when sa_gpu_level_create returns. */
     int async_upload;
 } sa_gpu_level_desc;
@@ -115,6 +118,8 @@ void sa_gpu_level_destroy(sa_gpu_level *level);
    levels) to the device memory pool.  Results are kept; a later sa_gpu_local_spectral
    simply allocates them again. */
 int sa_gpu_level_trim(sa_gpu_level *level);
+/* operator + element-block bytes a pipelined upload has queued so far */
+double sa_gpu_level_uploaded_bytes(sa_gpu_level *level);
 /* Blocks until a pipelined upload (desc.async_upload) has finished; no-op otherwise. */
 int sa_gpu_level_upload_wait(sa_gpu_level *level);
 
@@ -142,6 +147,17 @@ int sa_gpu_get_spectral(sa_gpu_level *level, double *evals, double *evects, doub
  * caller).  Layout as returned by sa_gpu_get_spectral. */
 int sa_gpu_set_spectral(sa_gpu_level *level, int ae_begin, int ae_end, const int *ae_m,
                         const double *evals, const double *evects, const double *D);
+/* Device-side exchange for a local spectral stage sharded over several GPUs (the reference
+ * distributes the AEs over MPI ranks, amg/src/interp.cpp:387): after
+ * sa_gpu_local_spectral(level, theta, ae_begin, ae_end) the caller announces the counts of ALL
+ * AEs (ae_m_full, nparts ints, gathered from the ranks); the level's result arrays are laid out
+ * for the full set with this rank's slice already in place, and their device addresses are
+ * returned so that the caller's collective (NCCL broadcast / all-gather over NVLink) can write
+ * the other ranks' slices straight into them -- no host bounce.  Layout as sa_gpu_get_spectral:
+ * evals offsets = prefix sums of ae_m, evects offsets = prefix sums of n_i * m_i, D offsets =
+ * AE_to_dof.I.  The arrays are complete once every slice has arrived (caller synchronises). */
+int sa_gpu_spectral_gather_begin(sa_gpu_level *level, int ae_begin, int ae_end, const int *ae_m_full,
+                                 double **d_evals, double **d_evects, double **d_D);
 /* assembled dense AE matrix (n x n column-major) of one AE -- the value of
  * ElementMatrixProvider::BuildAEStiff(part) (amg/inc/elmat.hpp:71) */
 int sa_gpu_build_AE_stiff(sa_gpu_level *level, int part, double *dense_out);
@@ -230,6 +246,8 @@ int sa_gpu_debug_phase_clocks(double *out8);
 int sa_gpu_debug_twostage(sa_gpu_ctx *ctx, int n, const double *A, double *T_out, double *tau1_out,
                           double *d_out, double *e_out);
 int sa_gpu_debug_twostage_back(sa_gpu_ctx *ctx, int n, int nvec, double *Y);
+/* cycle counters of the phases of the two-stage kernels since the last call (diagnostics) */
+int sa_gpu_debug_ts_clocks(double *out16);
 
 /* ---- device-pointer entry points (row-partitioned multi-GPU solve: the caller owns the
  *      vectors on the device, e.g. torch tensors, and drives the halo exchange) ----

@@ -85,8 +85,11 @@ double sa_drv_get_scalar(void *obj, const char *name, int level);
 void *sa_drv_bench_create(void *prob, const sa_drv_params_t *p, int device);
 void sa_drv_bench_destroy(void *bench);
 /* mode 0: inputs resident on the device, returns device milliseconds (CUDA events);
-   mode 1: end to end from host buffers (H2D of all inputs + compute + D2H of results) */
+   mode 1: end to end from host buffers (H2D of all inputs + compute + D2H of results)
+   mode 2: as 1 for one rank of a sharded stage (only the inputs / results of its AE range move) */
 double sa_drv_bench_step(void *bench, int mode, int ae_begin, int ae_end);
+/* the resident sa_gpu_level of the bench (for the sharded stage + device-side exchange) */
+void *sa_drv_bench_level(void *bench);
 /* "h2d_bytes", "d2h_bytes", "launches", "flops", "bytes", "sum_m", "pinned", "phase.N" */
 double sa_drv_bench_scalar(void *bench, const char *name);
 /* device stage profile of the process-wide context (see sa_gpu_ctx_profile) */

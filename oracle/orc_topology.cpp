@@ -5,6 +5,7 @@
 // instead of one function with itself.  Nothing here calls the product's table routines:
 // mfem::Table's Mult / Transpose are restated below from MFEM's documented behaviour
 // (Transpose: counting sort, rows ascending; Mult: marker array, first-encounter order).
+#include <cmath>
 #include <cstring>
 #include <map>
 
@@ -239,12 +240,41 @@ orc_create_partitioning_coarse(const agg_partitioning_relations_t &fine, const S
     rels->nparts = *nparts;
 
     // finedof_to_dof: the diag block of Dof_TrueDof * interp * TrueDof_Dof^T is interp's own
-    // pattern on one process (:1445-1479)
+    // pattern on one process (:1445-1479).
+    // DEVIATION (documented in DESIGN.md): upstream takes the raw pattern, whose exact zeros are
+    // an accident of LAPACK round-off: rows of essential boundary dofs are zeroed BEFORE the SVD
+    // (contrib_filter_boundary, amg/src/contrib.cpp:102-163) and dgesvd returns either exact zeros
+    // or dust (~1e-16) there; symmetric agglomerates give singular vectors with entries that are
+    // zero up to round-off; contrib_tent_insert_simple keeps every entry with abs(v) > 0 (:188).
+    // Whether such an entry exists decides the first-encounter ORDER of the coarse dofs inside
+    // coarse elements / AEs, so upstream's local numbering is not reproducible across LAPACK
+    // builds.  The rule used on both sides here: a fine dof whose prolongator row has at least one
+    // entry above 1e-10 of the largest entry connects to ALL coarse dofs of its MIS (in order);
+    // a row without such an entry (essential boundary) connects to none.
+    double pmax = 0.;
+    for (size_t q = 0; q < tent_interp.A.size(); ++q)
+        pmax = std::max(pmax, fabs(tent_interp.A[q]));
     Table finedof_to_dof;
     finedof_to_dof.nrows = tent_interp.h;
     finedof_to_dof.ncols = tent_interp.w;
-    finedof_to_dof.I = tent_interp.I;
-    finedof_to_dof.J = tent_interp.J;
+    finedof_to_dof.I.assign((size_t)tent_interp.h + 1, 0);
+    for (int d = 0; d < tent_interp.h; ++d)
+    {
+        bool live = false;
+        for (int q = tent_interp.I[d]; q < tent_interp.I[d + 1]; ++q)
+            if (fabs(tent_interp.A[q]) > 1e-10 * pmax)
+            {
+                live = true;
+                // every entry of the row lies in the block of the dof's own MIS
+                SA_ASSERT(tent_interp.J[q] >= rels->mis_coarsedofoffsets[fine.mises[d]] &&
+                          tent_interp.J[q] < rels->mis_coarsedofoffsets[fine.mises[d] + 1]);
+            }
+        if (live)
+            for (int c = rels->mis_coarsedofoffsets[fine.mises[d]];
+                 c < rels->mis_coarsedofoffsets[fine.mises[d] + 1]; ++c)
+                finedof_to_dof.J.push_back(c);
+        finedof_to_dof.I[d + 1] = (int)finedof_to_dof.J.size();
+    }
     Table *elem_to_dof = new Table;
     orc_table_mult(*fine.AE_to_dof, finedof_to_dof, *elem_to_dof);
     elem_to_dof->ncols = off;

@@ -1240,8 +1240,9 @@ extern "C" void *sa_orc_ml_build(void *prob_, const sa_drv_params_t *p)
             int nparts = nparts_arr[i];
             int *partitioning = sa_prescribed_coarse_partitioning(
                 *prob, *p, i, F->agg_part_rels->nparts, &nparts);
-            agg_partitioning_relations_t *rels = agg_create_partitioning_coarse(
-                *F->agg_part_rels, F->mis_numcoarsedof.data(), &nparts, avoid, partitioning);
+            // the oracle's own restatement (orc_topology.cpp), not the product's construction
+            agg_partitioning_relations_t *rels = orc_create_partitioning_coarse(
+                *F->agg_part_rels, *F->ltent_interp, F->mis_numcoarsedof.data(), &nparts, partitioning);
             H->rels.push_back(rels);
             char key[64];
             std::snprintf(key, sizeof key, "l%d.topology", i);
@@ -1310,6 +1311,39 @@ extern "C" double sa_orc_time_local_spectral(void *prob_, const sa_drv_params_t 
     return now_s() - t0;
 }
 
+/* Local spectral stage (a2-a7) of the finest level for AEs [ae_begin, ae_end), results returned:
+   m_out[i - ae_begin] accepted vectors, evals_out[(i - ae_begin) * eval_cap + j] (first
+   min(m, eval_cap) eigenvalues), D_out at the AE's offset in AE_to_dof (caller passes the full
+   array).  Single threaded: callers that want all cores fork processes over AE ranges (the
+   LAPACK in this image serialises concurrent calls from one process). */
+extern "C" int sa_orc_local_spectral(void *prob_, const sa_drv_params_t *p, int ae_begin, int ae_end,
+                                     int *m_out, double *evals_out, int eval_cap, double *D_out)
+{
+    sa_problem_t *prob = (sa_problem_t *)prob_;
+    const agg_partitioning_relations_t &rels = *prob->rels;
+    ElementMatrixStandardGeometric emp(rels, prob->fem->A, prob->fem->elmat.data(), prob->fem->ne);
+    ae_end = std::min(ae_end, rels.nparts);
+    for (int i = ae_begin; i < ae_end; ++i)
+    {
+        SparseMatrix *AE = emp.BuildAEStiff(i);
+        SparseMatrix *B = mbox_snd_D_sparse_from_sparse(*AE);
+        DenseMatrix cut, deA, deB;
+        Vector evals;
+        mbox_convert_sparse_to_dense(*AE, deA);
+        mbox_convert_sparse_to_dense(*B, deB);
+        xpacks_calc_lower_eigens_dense(deA, evals, cut, deB, p->first_theta, true);
+        m_out[i - ae_begin] = cut.Width();
+        for (int j = 0; j < eval_cap; ++j)
+            evals_out[(size_t)(i - ae_begin) * eval_cap + j] = j < (int)evals.size() ? evals[j] : 0.;
+        const int off = rels.AE_to_dof->GetI()[i];
+        for (int k = 0; k < AE->h; ++k)
+            D_out[off + k] = B->A[k];
+        delete AE;
+        delete B;
+    }
+    return 0;
+}
+
 extern "C" int sa_orc_check_mises(void *prob_)
 {
     sa_problem_t *prob = (sa_problem_t *)prob_;
@@ -1325,4 +1359,133 @@ extern "C" int sa_orc_check_mises(void *prob_)
     if (mis_to_dof.I != rels.mis_to_dof->I || mis_to_dof.J != rels.mis_to_dof->J)
         return 3;
     return 0;
+}
+
+extern "C" int sa_orc_check_relations(void *prob_)
+{
+    sa_problem_t *prob = (sa_problem_t *)prob_;
+    return orc_check_fine_relations(*prob->rels, prob->fem->bdr_dofs.data(), prob->fem->NE);
+}
+
+/* Builds the relations of coarse level `level` (>= 1) of an ORACLE hierarchy a second time with
+   the PRODUCT's construction (saamge_b200/host/aggregates.cpp) from the same inputs and compares
+   every table: 0 = identical, else the index of the first differing table (1 elem_to_dof,
+   2 dof_to_elem, 3 AE_to_elem, 4 AE_to_dof, 5 dof_to_AE, 6 dof_id_inAE, 7 sizes, 8 mises,
+   9 mis_to_dof, 10 mis_to_AE, 11 AE_to_mis, 12 agg_flags). */
+extern "C" int sa_orc_check_coarse_relations(void *hier, int level)
+{
+    sa_hierarchy_t *H = (sa_hierarchy_t *)hier;
+    oracle_ml_t *ml = (oracle_ml_t *)H->impl;
+    if (level < 1 || level >= (int)H->rels.size())
+        return -1;
+    const agg_partitioning_relations_t &fine = *H->rels[level - 1];
+    const agg_partitioning_relations_t &o = *H->rels[level];
+    int nparts = o.nparts;
+    int *part = new int[fine.nparts];
+    std::memcpy(part, o.partitioning, sizeof(int) * fine.nparts);
+    agg_partitioning_relations_t *p = agg_create_partitioning_coarse(
+        fine, ml->levels[level - 1]->mis_numcoarsedof.data(), &nparts,
+        H->params.avoid_ess_bdr_dofs != 0, part);
+    int bad = 0, idx = 0;
+    auto cmp_t = [&](const Table *a, const Table *b) {
+        ++idx;
+        if (!bad && (a->nrows != b->nrows || a->I != b->I || a->J != b->J))
+            bad = idx;
+    };
+    cmp_t(p->elem_to_dof, o.elem_to_dof);
+    cmp_t(p->dof_to_elem, o.dof_to_elem);
+    cmp_t(p->AE_to_elem, o.AE_to_elem);
+    cmp_t(p->AE_to_dof, o.AE_to_dof);
+    cmp_t(p->dof_to_AE, o.dof_to_AE);
+    ++idx;
+    if (!bad && std::memcmp(p->dof_id_inAE, o.dof_id_inAE, sizeof(int) * o.dof_to_AE->Size_of_connections()))
+        bad = idx;
+    ++idx;
+    if (!bad && (p->ND != o.ND || p->num_mises != o.num_mises))
+        bad = idx;
+    ++idx;
+    if (!bad && std::memcmp(p->mises, o.mises, sizeof(int) * o.ND))
+        bad = idx;
+    if (!bad)
+    {
+        cmp_t(p->mis_to_dof, o.mis_to_dof);
+        cmp_t(p->mis_to_AE, o.mis_to_AE);
+        cmp_t(p->AE_to_mis, o.AE_to_mis);
+        ++idx;
+        if (!bad && std::memcmp(p->agg_flags, o.agg_flags, (size_t)o.ND))
+            bad = idx;
+    }
+    agg_free_partitioning(p);
+    return bad;
+}
+
+/* ---- CPU baselines on inputs taken from a hierarchy the GPU built (bench.py) ---- */
+
+/* Eigen stage of one AE given its assembled dense matrix (n x n column-major): weighted-l1 D
+   (mbox_snd_D_sparse_from_sparse), densification of A and B, dsygvx
+   (xpacks_calc_lower_eigens_dense) -- what Eigensolver::SolveDirect does after BuildAEStiff
+   (amg/src/spectral.cpp:124-237).  Returns seconds; *m_out = accepted vectors. */
+extern "C" double sa_orc_time_dense_AE(int n, const double *A, double theta, int *m_out)
+{
+    SparseMatrix Asp;
+    Asp.h = Asp.w = n;
+    Asp.I.assign((size_t)n + 1, 0);
+    for (int i = 0; i < n; ++i)
+    {
+        for (int j = 0; j < n; ++j)
+            if (A[(size_t)j * n + i] != 0. || i == j)
+            {
+                Asp.J.push_back(j);
+                Asp.A.push_back(A[(size_t)j * n + i]);
+            }
+        Asp.I[i + 1] = (int)Asp.J.size();
+    }
+    const double t0 = now_s();
+    SparseMatrix *B = mbox_snd_D_sparse_from_sparse(Asp);
+    DenseMatrix deA, deB, cut;
+    Vector evals;
+    mbox_convert_sparse_to_dense(Asp, deA);
+    mbox_convert_sparse_to_dense(*B, deB);
+    xpacks_calc_lower_eigens_dense(deA, evals, cut, deB, theta, true);
+    const double t = now_s() - t0;
+    if (m_out)
+        *m_out = cut.Width();
+    delete B;
+    return t;
+}
+
+/* The reference's CPU solve (kalchev_pcg + V-cycle with the SAS polynomial smoother, OpenMP over
+   rows) on the operators of a DOWNLOADED hierarchy (sa_drv_ml_download): same P, Ac, Dinv_neg as
+   the GPU solve uses.  Runs at most run_iters iterations (a bounded sample of a long solve);
+   returns seconds, *iters_out = iterations done (negative = not converged within run_iters). */
+extern "C" double sa_orc_time_pcg_on_hierarchy(void *hier, int run_iters, double rtol, double atol,
+                                               int *iters_out)
+{
+    sa_hierarchy_t *H = (sa_hierarchy_t *)hier;
+    const int nl = (int)H->levels.size();
+    oracle_ml_t ml;
+    for (int i = 0; i < nl; ++i)
+    {
+        oracle_level_t *L = new oracle_level_t;
+        ml.levels.push_back(L);
+        const sa_level_results_t &R = H->levels[i];
+        L->A = (i == 0) ? &H->prob->fem->A : ml.levels[i - 1]->Ac;
+        L->interp = new SparseMatrix(R.interp);
+        L->restr = new SparseMatrix;
+        SpTranspose(*L->interp, *L->restr);
+        L->Ac = new SparseMatrix(R.Ac);
+        L->Dinv_neg = new Vector(R.Dinv_neg);
+        L->nu = H->params.nu_relax;
+        L->roots = smpr_sas_poly_roots(L->nu, &L->degree);
+    }
+    factor_coarsest(*ml.levels.back());
+    const SparseMatrix &A = H->prob->fem->A;
+    const Vector &b = H->prob->fem->b;
+    Vector x(b.size(), 0.);
+    const double t0 = now_s();
+    const int it = kalchev_pcg(A, ml, b, x, run_iters, rtol, atol, NULL);
+    const double t = now_s() - t0;
+    if (iters_out)
+        *iters_out = it;
+    return t;
 }

@@ -140,6 +140,15 @@ int kalchev_pcg(const SparseMatrix &A, const oracle_ml_t &ml, const Vector &b, V
 void agg_construct_mises_local_scan(const Table &dof_to_AE, std::vector<int> &mises,
                                     Table &mis_to_dof);
 
+/* ---- independent restatement of the topology construction (orc_topology.cpp;
+        amg/src/aggregates.cpp:198-236, 501-653, 712-853, 1202-1244, 1357-1832) ---- */
+void orc_table_transpose(const Table &A, Table &At, int ncols);
+void orc_table_mult(const Table &A, const Table &B, Table &C);
+agg_partitioning_relations_t *
+orc_create_partitioning_coarse(const agg_partitioning_relations_t &fine, const SparseMatrix &tent_interp,
+                               const int *mis_numcoarsedof, int *nparts, int *partitioning);
+int orc_check_fine_relations(const agg_partitioning_relations_t &p, const agg_dof_status_t *bdr_dofs, int NE);
+
 } // namespace saamge_oracle
 
 extern "C" {
@@ -154,6 +163,13 @@ double sa_orc_time_local_spectral(void *prob, const sa_drv_params_t *p, int ae_b
                                   int ae_end);
 /* checks the hashed MIS construction of the host library against the scan */
 int sa_orc_check_mises(void *prob);
+int sa_orc_check_coarse_relations(void *hier, int level);
+/* CPU baselines on inputs taken from a GPU-built hierarchy (bench.py) */
+double sa_orc_time_dense_AE(int n, const double *A, double theta, int *m_out);
+double sa_orc_time_pcg_on_hierarchy(void *hier, int run_iters, double rtol, double atol, int *iters_out);
+/* rebuilds every fine-level table of the problem with the oracle's own restatement and compares
+   (0 = all equal, else the index of the first differing table, see orc_check_fine_relations) */
+int sa_orc_check_relations(void *prob);
 int sa_orc_num_threads(void);
 }
 

@@ -197,19 +197,26 @@ class Hierarchy:
 _exchange_keepalive = []
 
 
-def enable_sharding(dist, group=None):
-    """Shard the AE loop of every level over the ranks of `dist` (torch.distributed, NCCL on
-    GPUs): each rank computes its AE range, the per-AE results are all-gathered."""
+class _DevArray:
+    """Zero-copy view of device memory owned by the CUDA library for torch
+    (torch.as_tensor understands __cuda_array_interface__)."""
+
+    def __init__(self, ptr, count, typestr="<f8"):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def make_exchange(dist, group=None):
+    """exchange(gpu_level_pointer, a, b, nparts): combines the per-AE results of a local spectral
+    stage every rank ran on its own AE range [a, b) so that all ranks hold the full set."""
     from . import sharding
 
-    h = host_lib()
     g = gpu_lib()
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
-    CB = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int)
+    world = dist.get_world_size(group)
     ip = ctypes.POINTER(ctypes.c_int)
     dp = ctypes.POINTER(ctypes.c_double)
 
-    def exchange(level, a, b, nparts):
+    def exchange_host(level, a, b, nparts):
+        # any backend (gloo in the CPU tests): device -> host -> collective -> host -> device
         lev = ctypes.c_void_p(level)
         n = np.zeros(nparts, dtype=np.int32)
         m = np.zeros(nparts, dtype=np.int32)
@@ -229,7 +236,58 @@ def enable_sharding(dist, group=None):
                                    fZ.ctypes.data_as(dp), fD.ctypes.data_as(dp))
         assert rc == 0, g.sa_gpu_last_error()
 
-    cb = CB(exchange)
+    def exchange_device(level, a, b, nparts):
+        # NCCL on the level's own device arrays (sa_gpu_spectral_gather_begin): the counts are
+        # combined with one all-reduce, then every rank broadcasts its slice of the eigenvalues,
+        # eigenvectors and D straight into the other ranks' arrays over NVLink
+        import torch
+
+        lev = ctypes.c_void_p(level)
+        n = np.zeros(nparts, dtype=np.int32)
+        m = np.zeros(nparts, dtype=np.int32)
+        g.sa_gpu_get_AE_sizes(lev, n.ctypes.data_as(ip))
+        g.sa_gpu_get_spectral_counts(lev, m.ctypes.data_as(ip))
+        m[:a] = 0
+        m[b:] = 0
+        tm = torch.from_numpy(m).cuda()
+        dist.all_reduce(tm, group=group)
+        rng = torch.tensor([a, b], dtype=torch.int64, device="cuda")
+        rngs = [torch.zeros_like(rng) for _ in range(world)]
+        dist.all_gather(rngs, rng, group=group)
+        mfull = np.ascontiguousarray(tm.cpu().numpy(), dtype=np.int32)
+        ranges = [(int(r[0]), int(r[1])) for r in torch.stack(rngs).cpu().numpy()]
+        pe, pz, pd = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        rc = g.sa_gpu_spectral_gather_begin(lev, a, b, mfull.ctypes.data_as(ip), ctypes.byref(pe), ctypes.byref(pz),
+                                            ctypes.byref(pd))
+        assert rc == 0, g.sa_gpu_last_error()
+        n64, m64 = n.astype(np.int64), mfull.astype(np.int64)
+        offs = (np.concatenate([[0], np.cumsum(m64)]), np.concatenate([[0], np.cumsum(m64 * n64)]),
+                np.concatenate([[0], np.cumsum(n64)]))
+        for ptr, off in zip((pe, pz, pd), offs):
+            if not ptr.value or off[-1] == 0:
+                continue
+            T = torch.as_tensor(_DevArray(ptr.value, int(off[-1])), device="cuda")
+            for r, (ar, br) in enumerate(ranges):
+                if off[br] > off[ar]:
+                    dist.broadcast(T[int(off[ar]):int(off[br])], src=r, group=group)
+        torch.cuda.synchronize()
+
+    def exchange(level, a, b, nparts):
+        if dist.get_backend(group) == "nccl" and not os.environ.get("SA_SHARD_HOST_EXCHANGE"):
+            exchange_device(level, a, b, nparts)
+        else:
+            exchange_host(level, a, b, nparts)
+
+    return exchange
+
+
+def enable_sharding(dist, group=None):
+    """Shard the AE loop of every level over the ranks of `dist` (torch.distributed, NCCL on
+    GPUs): each rank computes its AE range, the per-AE results are exchanged (make_exchange)."""
+    h = host_lib()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    CB = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int)
+    cb = CB(make_exchange(dist, group))
     _exchange_keepalive.append(cb)
     h.sa_drv_set_sharding.argtypes = [ctypes.c_int, ctypes.c_int, CB]
     h.sa_drv_set_sharding(rank, world, cb)

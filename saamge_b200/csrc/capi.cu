@@ -239,8 +239,11 @@ int queue_marked(sa_gpu_level *L, int elo, int ehi, int rlo, int rhi)
                 P.elem_mark[e] = 1;
             const size_t k0 = d.elmat_off[e0], k1 = d.elmat_off[e1];
             if (k1 > k0)
+            {
                 SA_CUDA(cudaMemcpyAsync(L->elmat.p + k0, d.elmat + k0, (k1 - k0) * sizeof(double),
                                         cudaMemcpyHostToDevice, cs));
+                P.bytes_queued += (double)(k1 - k0) * sizeof(double);
+            }
         }
     }
     if (d.A_I && rlo <= rhi)
@@ -263,6 +266,7 @@ int queue_marked(sa_gpu_level *L, int elo, int ehi, int rlo, int rhi)
                                         cudaMemcpyHostToDevice, cs));
                 SA_CUDA(cudaMemcpyAsync(L->A_own.A.p + k0, d.A_data + k0, (k1 - k0) * sizeof(double),
                                         cudaMemcpyHostToDevice, cs));
+                P.bytes_queued += (double)(k1 - k0) * (sizeof(double) + sizeof(int));
             }
         }
     }
@@ -362,6 +366,11 @@ void sa_level_ready(sa_gpu_level *lev)
     P.elem_mark.clear();
     P.row_mark.clear();
     P.active = false;
+}
+
+extern "C" double sa_gpu_level_uploaded_bytes(sa_gpu_level *lev)
+{
+    return lev->pending.bytes_queued;
 }
 
 extern "C" int sa_gpu_level_trim(sa_gpu_level *lev)
@@ -520,6 +529,8 @@ extern "C" int sa_gpu_level_create(sa_gpu_ctx *ctx, const sa_gpu_level_desc *d,
         P.active = true;
         P.complete = false;
         P.timing = dbg;
+        P.lazy_rest = d->async_upload == 2;
+        P.bytes_queued = 0.;
         P.ev.reserve(64); // (a helper thread appends while the main thread reads earlier entries)
         P.elem_mark.assign(d->elmat ? (size_t)d->NE : 0, 0);
         P.row_mark.assign(d->A_I ? (size_t)d->ND : 0, 0);
@@ -552,7 +563,18 @@ extern "C" void sa_gpu_level_destroy(sa_gpu_level *level)
     if (!level)
         return;
     cudaSetDevice(level->ctx->device);
-    sa_level_ready(level);
+    PendingUpload &P = level->pending;
+    if (P.active && P.lazy_rest && !P.complete)
+    {
+        // a lazily uploaded level that never needed the rest: wait for what is in flight only
+        cudaStreamSynchronize(level->ctx->copy_stream);
+        for (size_t i = 0; i < P.ev.size(); ++i)
+            cudaEventDestroy(P.ev[i]);
+        P.ev.clear();
+        P.active = false;
+    }
+    else
+        sa_level_ready(level);
     delete level;
 }
 

@@ -1181,7 +1181,8 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
                         sa_level_queue_upload(lev, piece_ends[pi - 1], piece_ends[pi]);
                     pieces_queued.store((int)pi + 1, std::memory_order_release);
                 }
-                sa_level_queue_rest(lev); // what the other stages (or other ranks' AEs) need
+                if (!lev->pending.lazy_rest)
+                    sa_level_queue_rest(lev); // what the other stages (or other ranks' AEs) need
             }
             catch (...)
             {
@@ -1897,7 +1898,14 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
     }
     if (upload_fut.valid())
         upload_fut.get();
-    sa_level_ready(lev); // a pipelined upload is complete from here on
+    if (lev->pending.active && lev->pending.lazy_rest && !lev->pending.complete)
+    {
+        // lazy mode: only this range's inputs were queued; they have arrived (every piece waited
+        // for its request).  The rest follows when another entry point calls sa_level_ready.
+        sa_level_host_copies(lev);
+    }
+    else
+        sa_level_ready(lev); // a pipelined upload is complete from here on
     // merge the pieces into the level's flat arrays (range [ae_begin, ae_end) only)
     for (size_t p = 0; p < pieces.size(); ++p)
         for (int s = 0; s < pieces[p]->a1 - pieces[p]->a0; ++s)
@@ -2048,6 +2056,61 @@ extern "C" int sa_gpu_set_spectral(sa_gpu_level *lev, int ae_begin, int ae_end, 
     }
     else
         SA_FAIL("sa_gpu_set_spectral: only the full range is supported");
+    SA_API_END
+}
+
+extern "C" int sa_gpu_spectral_gather_begin(sa_gpu_level *lev, int ae_begin, int ae_end,
+                                            const int *ae_m_full, double **d_evals, double **d_evects,
+                                            double **d_D)
+{
+    SA_API_BEGIN
+    if (!lev->have_spectral)
+        SA_FAIL("sa_gpu_spectral_gather_begin: no spectral data");
+    sa_gpu_ctx *ctx = lev->ctx;
+    cudaStream_t st = ctx->stream;
+    const int nparts = lev->nparts;
+    const std::vector<int> &AI = lev->h_AE2d_I;
+    ae_begin = std::max(0, ae_begin);
+    ae_end = std::min(nparts, ae_end);
+    for (int i = ae_begin; i < ae_end; ++i)
+        if (lev->h_ae_m[i] != ae_m_full[i] || lev->h_ae_nev[i] != ae_m_full[i])
+            SA_FAIL("sa_gpu_spectral_gather_begin: counts of the local range do not match (AE %d: "
+                    "%d vectors here, %d announced; injected vectors cannot be sharded)",
+                    i, lev->h_ae_m[i], ae_m_full[i]);
+    std::vector<int64_t> eo(nparts + 1, 0), zo(nparts + 1, 0);
+    for (int i = 0; i < nparts; ++i)
+    {
+        eo[i + 1] = eo[i] + ae_m_full[i];
+        zo[i + 1] = zo[i] + (int64_t)(AI[i + 1] - AI[i]) * ae_m_full[i];
+    }
+    // full-size arrays with the local slice moved to its final place
+    DevBuf<double> evals2, evects2;
+    evals2.alloc((size_t)eo[nparts]);
+    evects2.alloc((size_t)zo[nparts]);
+    const int64_t ne = lev->h_eval_off[ae_end] - lev->h_eval_off[ae_begin];
+    const int64_t nz = lev->h_evect_off[ae_end] - lev->h_evect_off[ae_begin];
+    if (ne)
+        SA_CUDA(cudaMemcpyAsync(evals2.p + eo[ae_begin], lev->evals.p + lev->h_eval_off[ae_begin],
+                                ne * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (nz)
+        SA_CUDA(cudaMemcpyAsync(evects2.p + zo[ae_begin], lev->evects.p + lev->h_evect_off[ae_begin],
+                                nz * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    lev->evals.swap(evals2);
+    lev->evects.swap(evects2);
+    lev->h_ae_m.assign(ae_m_full, ae_m_full + nparts);
+    lev->h_ae_nev = lev->h_ae_m;
+    lev->h_eval_off = eo;
+    lev->h_evect_off = zo;
+    lev->ae_m.upload(lev->h_ae_m.data(), nparts, st);
+    lev->evect_off.upload(lev->h_evect_off.data(), nparts + 1, st);
+    lev->eval_off.upload(lev->h_eval_off.data(), nparts + 1, st);
+    SA_CUDA(cudaStreamSynchronize(st)); // the caller's collectives run on its own stream
+    if (d_evals)
+        *d_evals = lev->evals.p;
+    if (d_evects)
+        *d_evects = lev->evects.p;
+    if (d_D)
+        *d_D = lev->ae_D.p;
     SA_API_END
 }
 

@@ -183,6 +183,7 @@ struct SpectralWs
     DevBuf<double> ts_band, ts_tau1, ts_wsV, ts_wsW;
     DevBuf<int> ts_of_slot;
     DevBuf<int64_t> ts_toff, ts_mats;
+    DevBuf<unsigned long long> ts_slots;
 };
 
 /* one matrix of the two-stage tridiagonalisation (twostage.cu) */
@@ -299,6 +300,10 @@ struct PendingUpload
     bool host_copies_done = true;
     std::vector<unsigned char> elem_mark, row_mark; // 0 not queued, 1 queued, 2 being queued
     bool timing = false;
+    // desc.async_upload == 2: what the local spectral stage does not read stays on the host until
+    // another entry point needs it (sharded stage: a rank uploads its own AEs' inputs only)
+    bool lazy_rest = false;
+    double bytes_queued = 0.; // operator + element block bytes queued so far
 };
 
 struct sa_gpu_level

@@ -26,7 +26,11 @@
 // tau).  tests/twostage_ref.py is the numpy statement of exactly this algorithm and layout.
 #include <algorithm>
 
+#include <cooperative_groups.h>
+
 #include "sa_gpu_internal.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace
 {
@@ -37,7 +41,21 @@ constexpr int TS_NW = 16;   // warps of the stage-1 block
 constexpr int TS_LD = 36;   // leading dimension of the 32-wide shared operand tiles (== 4 mod 16)
 constexpr int TS_LDB = 64;  // rows of the band storage (band + bulge)
 constexpr int TS_S2_NW = 8; // warps (concurrent sweeps) of the stage-2 block
-constexpr int TS_S2_PER_WARP = 32 * 33 + 96; // doubles of shared memory per stage-2 warp
+constexpr int TS_S2_PER_WARP = 32 * 33 + 32 * 17 + 96; // doubles of shared memory per stage-2 warp
+
+// cycle counters of the phases of the two kernels summed over blocks (diagnostics):
+// 0 panel QR, 1 Gram + Tf, 2 symm, 3 X = W Tf, 4 S + M, 5 Z, 6 syr2k, 7 band copy,
+// 8 stage-2 ticks, 9 stage-2 cycles, 10 stage-2 steps
+__device__ unsigned long long g_ts_clk[16];
+#define TS_CLK(idx)                                                            \
+    do {                                                                       \
+        if (threadIdx.x == 0)                                                  \
+        {                                                                      \
+            const long long now__ = clock64();                                 \
+            atomicAdd(&g_ts_clk[idx], (unsigned long long)(now__ - tclk));     \
+            tclk = now__;                                                      \
+        }                                                                      \
+    } while (0)
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
 {
@@ -97,6 +115,26 @@ __device__ __forceinline__ double warp_transpose_reduce32(double (&v)[32])
         v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
     }
     return v[0];
+}
+
+/* Loads of data another thread block of the cluster may have written (cluster mode: a matrix is
+   shared by the blocks of a thread-block cluster): L2 only, never a stale L1 line. */
+template <bool CL> __device__ __forceinline__ double ldx(const double *p)
+{
+    if (CL)
+        return __ldcg(p);
+    return *p;
+}
+
+/* which block of the cluster owns pass q (256 rows) of the row-distributed phases */
+__device__ __forceinline__ bool s1_owns(int q, int rank, int CS) { return CS == 1 || (q % CS) == rank; }
+/* ... and of the triangular update (cost grows with q): dealt in snake order */
+__device__ __forceinline__ bool s1_owns_tri(int q, int rank, int CS)
+{
+    if (CS == 1)
+        return true;
+    const int round = q / CS, pos = q % CS;
+    return ((round & 1) ? CS - 1 - pos : pos) == rank;
 }
 
 /* dlarfg on (alpha, |x|^2): beta, tau and the scale 1 / (alpha - beta) of the tail */
@@ -174,8 +212,9 @@ __device__ __forceinline__ void s1_block_reduce(const S1Smem S, double (&v)[W])
 /* out (32 x 33 in shared memory) = A^T B over r rows; A, B: r x 32 column-major with leading
    dimension ld in global memory.  DMMA, rows dealt to the warps in slabs of 32, partial
    products reduced through S.U in two rounds of 8 warps (fixed order). */
+template <bool CL>
 __device__ __noinline__ void s1_gram(const S1Smem S, const double *__restrict__ A, const double *__restrict__ B,
-                        int ld, int r, double *out)
+                                     int ld, int r, double *out)
 {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -196,8 +235,8 @@ __device__ __noinline__ void s1_gram(const S1Smem S, const double *__restrict__ 
 #pragma unroll
             for (int q = 0; q < 4; ++q)
             {
-                a[q] = ok ? A[row + (size_t)ld * (q * 8 + g)] : 0.;
-                b[q] = ok ? B[row + (size_t)ld * (q * 8 + g)] : 0.;
+                a[q] = ok ? ldx<CL>(A + row + (size_t)ld * (q * 8 + g)) : 0.;
+                b[q] = ok ? ldx<CL>(B + row + (size_t)ld * (q * 8 + g)) : 0.;
             }
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi)
@@ -237,8 +276,9 @@ __device__ __noinline__ void s1_gram(const S1Smem S, const double *__restrict__ 
    On exit: P holds R on / above its diagonal and the reflector tails below; Vc (r x 32, leading
    dimension ldv) holds the reflectors with explicit unit diagonal and zeros above (columns
    >= nr are zero); S.taus / tau_out hold tau. */
+template <bool CL>
 __device__ __noinline__ void s1_panel_qr(const S1Smem S, double *__restrict__ P, int ld, int r, int nr, int w_in,
-                            double *__restrict__ Vc, int ldv, double *__restrict__ tau_out)
+                                         double *__restrict__ Vc, int ldv, double *__restrict__ tau_out)
 {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     double *Ps = S.U;
@@ -262,7 +302,7 @@ __device__ __noinline__ void s1_panel_qr(const S1Smem S, double *__restrict__ P,
         for (int idx = tid; idx < rows * w; idx += TS_NT)
         {
             const int cc = idx / rows, i = idx - cc * rows;
-            Ps[cc * ldp + i] = P[(c0 + i) + (size_t)ld * (c0 + cc)];
+            Ps[cc * ldp + i] = ldx<CL>(P + (c0 + i) + (size_t)ld * (c0 + cc));
         }
         if (tid < 72)
         {
@@ -371,7 +411,7 @@ __device__ __noinline__ void s1_panel_qr(const S1Smem S, double *__restrict__ P,
                 double p[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    p[j] = P[(c0 + i) + (size_t)ld * (q0 + j)];
+                    p[j] = ldx<CL>(P + (c0 + i) + (size_t)ld * (q0 + j));
 #pragma unroll
                 for (int cc = 0; cc < 8; ++cc)
                     if (cc < w)
@@ -417,7 +457,7 @@ __device__ __noinline__ void s1_panel_qr(const S1Smem S, double *__restrict__ P,
                     }
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    P[(c0 + i) + (size_t)ld * (q0 + j)] -= d[j];
+                    P[(c0 + i) + (size_t)ld * (q0 + j)] = ldx<CL>(P + (c0 + i) + (size_t)ld * (q0 + j)) - d[j];
             }
             __syncthreads();
         }
@@ -428,16 +468,23 @@ __device__ __noinline__ void s1_panel_qr(const S1Smem S, double *__restrict__ P,
 
 /* W = A22 V.  A22: r x r symmetric, LOWER triangle valid, leading dimension ld; V, W: r x 32,
    leading dimension ldv.  Every warp owns a strip of 16 rows per pass (256 rows per pass);
-   A fragments come straight from global memory (element (i, k) lives at max(i,k) + ld min(i,k)),
-   prefetched one 32-column chunk ahead; the V chunk is shared through S.U (double buffered). */
+   A fragments come straight from global memory (element (i, k) lives at max(i,k) + ld min(i,k);
+   L2 only, they are used once), prefetched one 32-column chunk ahead; the V chunk is shared
+   through S.U: fetched into registers before the MMAs of the current chunk, parked in shared
+   memory after them (double buffered, one barrier per chunk).
+   (Measured alternative, slower by 25 %: no barriers, V fragments re-read through L1.) */
+template <bool CL>
 __device__ __noinline__ void s1_symm(const S1Smem S, const double *__restrict__ A2, int ld, int r,
-                        const double *__restrict__ V, double *__restrict__ W, int ldv)
+                                     const double *__restrict__ V, double *__restrict__ W, int ldv, int rank,
+                                     int CS)
 {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     double *Vs = S.U; // 2 x [32 columns][TS_LD]
     for (int pass0 = 0; pass0 < r; pass0 += TS_NW * 16)
     {
+        if (!s1_owns(pass0 / (TS_NW * 16), rank, CS))
+            continue;
         const int i0 = pass0 + wid * 16;
         const bool active = i0 < r;
         const int ra = i0 + g, rb = i0 + 8 + g;
@@ -456,20 +503,24 @@ __device__ __noinline__ void s1_symm(const S1Smem S, const double *__restrict__ 
                 const bool kok = active && k < r;
                 const int lo_a = min(ra, k), hi_a = max(ra, k);
                 const int lo_b = min(rb, k), hi_b = max(rb, k);
-                an[0][kk] = (kok && ra < r) ? A2[hi_a + (size_t)ld * lo_a] : 0.;
-                an[1][kk] = (kok && rb < r) ? A2[hi_b + (size_t)ld * lo_b] : 0.;
+                an[0][kk] = (kok && ra < r) ? __ldcg(A2 + hi_a + (size_t)ld * lo_a) : 0.;
+                an[1][kk] = (kok && rb < r) ? __ldcg(A2 + hi_b + (size_t)ld * lo_b) : 0.;
             }
         };
-        auto load_v = [&](int k0, int buf) {
-            // 32 rows x 32 columns -> Vs[buf][c][k]
-            for (int idx = tid; idx < 1024; idx += TS_NT)
-            {
-                const int c = idx >> 5, k = idx & 31;
-                Vs[buf * 32 * TS_LD + c * TS_LD + k] = (k0 + k < r) ? V[(k0 + k) + (size_t)ldv * c] : 0.;
-            }
+        const int vc0 = tid >> 5, vk = tid & 31; // entries (vc0, vk) and (vc0 + 16, vk) of a chunk
+        double vreg[2];
+        auto fetch_v = [&](int k0) {
+            const bool ok = k0 + vk < r;
+            vreg[0] = ok ? ldx<CL>(V + (k0 + vk) + (size_t)ldv * vc0) : 0.;
+            vreg[1] = ok ? ldx<CL>(V + (k0 + vk) + (size_t)ldv * (vc0 + 16)) : 0.;
+        };
+        auto park_v = [&](int buf) {
+            Vs[buf * 32 * TS_LD + vc0 * TS_LD + vk] = vreg[0];
+            Vs[buf * 32 * TS_LD + (vc0 + 16) * TS_LD + vk] = vreg[1];
         };
         load_a(0);
-        load_v(0, 0);
+        fetch_v(0);
+        park_v(0);
         int buf = 0;
         for (int k0 = 0; k0 < r; k0 += 32, buf ^= 1)
         {
@@ -481,10 +532,11 @@ __device__ __noinline__ void s1_symm(const S1Smem S, const double *__restrict__ 
                 a[1][kk] = an[1][kk];
             }
             __syncthreads(); // Vs[buf] is complete; everyone is done with Vs[buf ^ 1]
-            if (k0 + 32 < r)
+            const bool more = k0 + 32 < r;
+            if (more)
             {
                 load_a(k0 + 32);
-                load_v(k0 + 32, buf ^ 1);
+                fetch_v(k0 + 32);
             }
             if (active)
             {
@@ -504,6 +556,8 @@ __device__ __noinline__ void s1_symm(const S1Smem S, const double *__restrict__ 
                     }
                 }
             }
+            if (more)
+                park_v(buf ^ 1);
         }
         if (active)
         {
@@ -529,16 +583,20 @@ __device__ __noinline__ void s1_symm(const S1Smem S, const double *__restrict__ 
 
 /* A22 -= Z V^T + V Z^T on the lower triangle (rank-64 update), DMMA.  A warp owns a strip of 16
    rows per pass and keeps its [-Z | -V] fragments in registers; the [V | Z]^T operand of a block
-   of 32 columns is shared through S.U (double buffered); C fragments are read, updated in the
-   accumulator and written back. */
+   of 32 columns is shared through S.U (registers -> shared memory, double buffered); C fragments
+   are read (L2 only), updated in the accumulator and written back. */
+template <bool CL>
 __device__ __noinline__ void s1_syr2k(const S1Smem S, double *__restrict__ A2, int ld, int r,
-                         const double *__restrict__ V, const double *__restrict__ Z, int ldv)
+                                      const double *__restrict__ V, const double *__restrict__ Z, int ldv,
+                                      int rank, int CS)
 {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     double *Bs = S.U; // 2 x [64 k][TS_LD]
     for (int pass0 = 0; pass0 < r; pass0 += TS_NW * 16)
     {
+        if (!s1_owns_tri(pass0 / (TS_NW * 16), rank, CS))
+            continue;
         const int i0 = pass0 + wid * 16;
         const bool active = i0 < r;
         const int ra = i0 + g, rb = i0 + 8 + g;
@@ -548,121 +606,167 @@ __device__ __noinline__ void s1_syr2k(const S1Smem S, double *__restrict__ A2, i
         {
             const int k = kk * 4 + t;
             const double *src = (k < 32) ? Z + (size_t)ldv * k : V + (size_t)ldv * (k - 32);
-            a[0][kk] = (active && ra < r) ? -src[ra] : 0.;
-            a[1][kk] = (active && rb < r) ? -src[rb] : 0.;
+            a[0][kk] = (active && ra < r) ? -ldx<CL>(src + ra) : 0.;
+            a[1][kk] = (active && rb < r) ? -ldx<CL>(src + rb) : 0.;
         }
         const int jend = min(r, pass0 + TS_NW * 16); // columns needed by this pass
-        auto load_b = [&](int j0, int buf) {
-            // Bs[k][j] = (k < 32) ? V[j0 + j][k] : Z[j0 + j][k - 32]
-            for (int idx = tid; idx < 2048; idx += TS_NT)
+        // Bs[k][j] = (k < 32) ? V[j0 + j][k] : Z[j0 + j][k - 32]; four entries per thread
+        const int bj = tid & 31, bk0 = tid >> 5; // entries k = bk0 + 16 q
+        double breg[4];
+        auto fetch_b = [&](int j0) {
+            const bool ok = j0 + bj < r;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
             {
-                const int k = idx >> 5, j = idx & 31;
+                const int k = bk0 + 16 * q;
                 const double *src = (k < 32) ? V + (size_t)ldv * k : Z + (size_t)ldv * (k - 32);
-                Bs[buf * 64 * TS_LD + k * TS_LD + j] = (j0 + j < r) ? src[j0 + j] : 0.;
+                breg[q] = ok ? ldx<CL>(src + j0 + bj) : 0.;
             }
         };
-        load_b(0, 0);
+        auto park_b = [&](int buf) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                Bs[buf * 64 * TS_LD + (bk0 + 16 * q) * TS_LD + bj] = breg[q];
+        };
+        fetch_b(0);
+        park_b(0);
         int buf = 0;
         for (int j0 = 0; j0 < jend; j0 += 32, buf ^= 1)
         {
             __syncthreads();
-            if (j0 + 32 < jend)
-                load_b(j0 + 32, buf ^ 1);
-            if (!active || j0 > i0 + 15)
-                continue; // block entirely above the strip
-            double c[2][4][2];
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni)
+            const bool more = j0 + 32 < jend;
+            if (more)
+                fetch_b(j0 + 32);
+            if (active && j0 <= i0 + 15)
             {
-                const int j = j0 + ni * 8 + 2 * t;
-                c[0][ni][0] = (ra < r && j <= ra) ? A2[ra + (size_t)ld * j] : 0.;
-                c[0][ni][1] = (ra < r && j + 1 <= ra) ? A2[ra + (size_t)ld * (j + 1)] : 0.;
-                c[1][ni][0] = (rb < r && j <= rb) ? A2[rb + (size_t)ld * j] : 0.;
-                c[1][ni][1] = (rb < r && j + 1 <= rb) ? A2[rb + (size_t)ld * (j + 1)] : 0.;
-            }
-            const double *bb = Bs + buf * 64 * TS_LD;
-#pragma unroll
-            for (int kk = 0; kk < 16; ++kk)
-            {
-                double b[4];
-#pragma unroll
-                for (int ni = 0; ni < 4; ++ni)
-                    b[ni] = bb[(kk * 4 + t) * TS_LD + ni * 8 + g];
+                double c[2][4][2];
 #pragma unroll
                 for (int ni = 0; ni < 4; ++ni)
                 {
-                    dmma884(c[0][ni][0], c[0][ni][1], a[0][kk], b[ni]);
-                    dmma884(c[1][ni][0], c[1][ni][1], a[1][kk], b[ni]);
+                    const int j = j0 + ni * 8 + 2 * t;
+                    c[0][ni][0] = (ra < r && j <= ra) ? __ldcg(A2 + ra + (size_t)ld * j) : 0.;
+                    c[0][ni][1] = (ra < r && j + 1 <= ra) ? __ldcg(A2 + ra + (size_t)ld * (j + 1)) : 0.;
+                    c[1][ni][0] = (rb < r && j <= rb) ? __ldcg(A2 + rb + (size_t)ld * j) : 0.;
+                    c[1][ni][1] = (rb < r && j + 1 <= rb) ? __ldcg(A2 + rb + (size_t)ld * (j + 1)) : 0.;
+                }
+                const double *bb = Bs + buf * 64 * TS_LD;
+#pragma unroll
+                for (int kk = 0; kk < 16; ++kk)
+                {
+                    double b[4];
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni)
+                        b[ni] = bb[(kk * 4 + t) * TS_LD + ni * 8 + g];
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni)
+                    {
+                        dmma884(c[0][ni][0], c[0][ni][1], a[0][kk], b[ni]);
+                        dmma884(c[1][ni][0], c[1][ni][1], a[1][kk], b[ni]);
+                    }
+                }
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
+                {
+                    const int j = j0 + ni * 8 + 2 * t;
+                    if (ra < r && j <= ra)
+                        A2[ra + (size_t)ld * j] = c[0][ni][0];
+                    if (ra < r && j + 1 <= ra)
+                        A2[ra + (size_t)ld * (j + 1)] = c[0][ni][1];
+                    if (rb < r && j <= rb)
+                        A2[rb + (size_t)ld * j] = c[1][ni][0];
+                    if (rb < r && j + 1 <= rb)
+                        A2[rb + (size_t)ld * (j + 1)] = c[1][ni][1];
                 }
             }
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni)
-            {
-                const int j = j0 + ni * 8 + 2 * t;
-                if (ra < r && j <= ra)
-                    A2[ra + (size_t)ld * j] = c[0][ni][0];
-                if (ra < r && j + 1 <= ra)
-                    A2[ra + (size_t)ld * (j + 1)] = c[0][ni][1];
-                if (rb < r && j <= rb)
-                    A2[rb + (size_t)ld * j] = c[1][ni][0];
-                if (rb < r && j + 1 <= rb)
-                    A2[rb + (size_t)ld * (j + 1)] = c[1][ni][1];
-            }
+            if (more)
+                park_b(buf ^ 1);
         }
         __syncthreads();
     }
 }
 
-/* X = W Tf in place: x[c] = sum_{c2 <= c} w[c2] Tf[c2][c], accumulated row of Tf by row of Tf
-   (volatile: the compiler must not hoist the 528 factor entries out of the row loop) */
-__device__ __noinline__ void s1_apply_tf(const S1Smem S, double *__restrict__ Wb, int ldws, int r)
+/* rows a block owns in the row-distributed phases: all of them (CS == 1), else the passes of
+   256 rows dealt by s1_owns; calls f(i) for every owned row i < r */
+template <class F> __device__ __forceinline__ void s1_for_rows(int r, int rank, int CS, F f)
+{
+    if (CS == 1)
+    {
+        for (int i = threadIdx.x; i < r; i += TS_NT)
+            f(i);
+        return;
+    }
+    for (int q = rank; q * (TS_NW * 16) < r; q += CS)
+    {
+        const int i = q * (TS_NW * 16) + threadIdx.x;
+        if (threadIdx.x < TS_NW * 16 && i < r)
+            f(i);
+    }
+}
+
+/* X = W Tf in place, row by row: x[c] = sum_{c2 <= c} w[c2] Tf[c2][c], computed from the last
+   column down so that it can overwrite w (volatile: the compiler must not hoist the 528 factor
+   entries out of the row loop) */
+__device__ __noinline__ void s1_apply_tf(const S1Smem S, double *__restrict__ Wb, int ldws, int r, int rank,
+                                         int CS)
 {
     const volatile double *Tf = S.Tf;
-    for (int i = threadIdx.x; i < r; i += TS_NT)
-    {
+    s1_for_rows(r, rank, CS, [&](int i) {
         double x[32];
 #pragma unroll
         for (int c = 0; c < 32; ++c)
-            x[c] = 0.;
-#pragma unroll 1
-        for (int c2 = 0; c2 < 32; ++c2)
-        {
-            const double w = Wb[i + (size_t)ldws * c2];
+            x[c] = Wb[i + (size_t)ldws * c]; // (written by this block's own symm pass)
 #pragma unroll
-            for (int c = 0; c < 32; ++c)
-                x[c] += w * Tf[c2 * 33 + c]; // (zero below the diagonal)
+        for (int c = 31; c >= 0; --c)
+        {
+            double s = 0.;
+#pragma unroll
+            for (int c2 = 0; c2 <= c; ++c2)
+                s += x[c2] * Tf[c2 * 33 + c];
+            x[c] = s;
         }
 #pragma unroll
         for (int c = 0; c < 32; ++c)
             Wb[i + (size_t)ldws * c] = x[c];
-    }
+    });
 }
 
 /* Z = X - V M in place in Wb (M = S.G) */
+template <bool CL>
 __device__ __noinline__ void s1_form_z(const S1Smem S, const double *__restrict__ Vc, double *__restrict__ Wb,
-                                       int ldws, int r)
+                                       int ldws, int r, int rank, int CS)
 {
     const volatile double *Mm = S.G;
-    for (int i = threadIdx.x; i < r; i += TS_NT)
-    {
-        double z[32];
+    s1_for_rows(r, rank, CS, [&](int i) {
+        double v[32];
 #pragma unroll
         for (int c = 0; c < 32; ++c)
-            z[c] = Wb[i + (size_t)ldws * c];
+            v[c] = ldx<CL>(Vc + i + (size_t)ldws * c);
 #pragma unroll 1
-        for (int c2 = 0; c2 < 32; ++c2)
+        for (int c0 = 0; c0 < 32; c0 += 8)
         {
-            const double v = Vc[i + (size_t)ldws * c2];
+            double z[8];
 #pragma unroll
-            for (int c = 0; c < 32; ++c)
-                z[c] -= v * Mm[c2 * 33 + c];
+            for (int j = 0; j < 8; ++j)
+                z[j] = Wb[i + (size_t)ldws * (c0 + j)];
+#pragma unroll
+            for (int c2 = 0; c2 < 32; ++c2)
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    z[j] -= v[c2] * Mm[c2 * 33 + c0 + j];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                Wb[i + (size_t)ldws * (c0 + j)] = z[j];
         }
-#pragma unroll
-        for (int c = 0; c < 32; ++c)
-            Wb[i + (size_t)ldws * c] = z[c];
-    }
+    });
 }
 
+/* CL = false: one block per matrix, matrices from a work queue (largest first).
+   CL = true:  launched with thread-block clusters; the CS blocks of a cluster share one matrix
+   (a handful of very large matrices would otherwise occupy a handful of SMs): the panel
+   factorisation runs on block 0, the small replicated pieces (Gram matrices, Tf, M) on every
+   block, the row / tile passes of W = A22 V, X, Z and the rank-64 update are dealt to the
+   blocks; four cluster barriers per panel. */
+template <bool CL>
 __global__ void __launch_bounds__(TS_NT, 1)
 k_sy2sb(const sa_ts_mat *__restrict__ mats, int nmats, unsigned int *queue, double *wsV, double *wsW,
         int ldws, int w_in)
@@ -671,40 +775,65 @@ k_sy2sb(const sa_ts_mat *__restrict__ mats, int nmats, unsigned int *queue, doub
     const S1Smem S = s1_carve(sm_s1);
     __shared__ int s_next;
     const int tid = threadIdx.x;
-    double *Vc = wsV + (size_t)blockIdx.x * ldws * TS_B;
-    double *Wb = wsW + (size_t)blockIdx.x * ldws * TS_B;
+    int rank = 0, CS = 1;
+    if (CL)
+    {
+        cg::cluster_group cl = cg::this_cluster();
+        rank = (int)cl.block_rank();
+        CS = (int)cl.num_blocks();
+    }
+    const int unit = blockIdx.x / CS, nunits = gridDim.x / CS; // cluster (or block) index
+    auto group_sync = [&]() {
+        if (CL)
+            cg::this_cluster().sync();
+        else
+            __syncthreads();
+    };
+    double *Vc = wsV + (size_t)unit * ldws * TS_B;
+    double *Wb = wsW + (size_t)unit * ldws * TS_B;
+    int mi = CL ? unit - nunits : 0;
     while (true)
     {
-        __syncthreads();
-        if (tid == 0)
-            s_next = (int)atomicAdd(queue, 1u);
-        __syncthreads();
-        const int mi = s_next;
+        if (CL)
+            mi += nunits; // static deal: every block of the cluster sees the same sequence
+        else
+        {
+            __syncthreads();
+            if (tid == 0)
+                s_next = (int)atomicAdd(queue, 1u);
+            __syncthreads();
+            mi = s_next;
+        }
         if (mi >= nmats)
             break;
         const sa_ts_mat M = mats[mi];
         const int n = M.n;
         double *T = M.T;
-        for (int i = tid; i < n; i += TS_NT)
-        {
-            M.tau1[i] = 0.;
-            if (M.tauz)
-                M.tauz[i] = 0.; // the one-stage back-transformation sees no reflectors
-        }
+        if (rank == 0)
+            for (int i = tid; i < n; i += TS_NT)
+            {
+                M.tau1[i] = 0.;
+                if (M.tauz)
+                    M.tauz[i] = 0.; // the one-stage back-transformation sees no reflectors
+            }
+        long long tclk = clock64();
         for (int j0 = 0; n - j0 - TS_B >= 2; j0 += TS_B)
         {
             const int r = n - j0 - TS_B;
             const int nr = min(TS_B, r - 1);
             double *P = T + (j0 + TS_B) + (size_t)n * j0;
             double *A2 = T + (j0 + TS_B) + (size_t)n * (j0 + TS_B);
-            s1_panel_qr(S, P, n, r, nr, w_in, Vc, ldws, M.tau1 + j0);
+            if (rank == 0)
+                s1_panel_qr<CL>(S, P, n, r, nr, w_in, Vc, ldws, M.tau1 + j0);
+            group_sync();
+            TS_CLK(0);
             // compact WY factor: G = V^T V, Tf[:c, c] = -tau_c Tf[:c, :c] G[:c, c]
-            s1_gram(S, Vc, Vc, ldws, r, S.G);
+            s1_gram<CL>(S, Vc, Vc, ldws, r, S.G);
             if (tid < 32)
             {
                 for (int c = 0; c < TS_B; ++c)
                 {
-                    const double tau = S.taus[c];
+                    const double tau = ldx<CL>(M.tau1 + j0 + c);
                     double s = 0.;
                     if (tid < c)
                         for (int q = tid; q < c; ++q)
@@ -715,11 +844,14 @@ k_sy2sb(const sa_ts_mat *__restrict__ mats, int nmats, unsigned int *queue, doub
                 }
             }
             __syncthreads();
-            s1_symm(S, A2, n, r, Vc, Wb, ldws);
-            s1_apply_tf(S, Wb, ldws, r);
-            __syncthreads();
+            TS_CLK(1);
+            s1_symm<CL>(S, A2, n, r, Vc, Wb, ldws, rank, CS);
+            TS_CLK(2);
+            s1_apply_tf(S, Wb, ldws, r, rank, CS);
+            group_sync();
+            TS_CLK(3);
             // S = V^T X, M = 1/2 Tf^T S
-            s1_gram(S, Vc, Wb, ldws, r, S.G);
+            s1_gram<CL>(S, Vc, Wb, ldws, r, S.G);
             double mreg[2];
 #pragma unroll
             for (int q = 0; q < 2; ++q)
@@ -737,115 +869,138 @@ k_sy2sb(const sa_ts_mat *__restrict__ mats, int nmats, unsigned int *queue, doub
                 const int e = tid + q * TS_NT;
                 S.G[(e >> 5) * 33 + (e & 31)] = mreg[q];
             }
-            __syncthreads();
-            s1_form_z(S, Vc, Wb, ldws, r);
-            __syncthreads();
-            s1_syr2k(S, A2, n, r, Vc, Wb, ldws);
+            // (cluster mode: every block must have read X for its Gram matrix before any block
+            // overwrites rows with Z)
+            group_sync();
+            TS_CLK(4);
+            s1_form_z<CL>(S, Vc, Wb, ldws, r, rank, CS);
+            group_sync();
+            TS_CLK(5);
+            s1_syr2k<CL>(S, A2, n, r, Vc, Wb, ldws, rank, CS);
+            group_sync();
+            TS_CLK(6);
         }
-        __syncthreads();
+        group_sync();
         // band (+ zeroed bulge rows) for stage 2: band[k + 64 j] = A[j + k][j]
-        for (size_t idx = tid; idx < (size_t)n * TS_LDB; idx += TS_NT)
+        for (size_t idx = (size_t)rank * TS_NT + tid; idx < (size_t)n * TS_LDB; idx += (size_t)CS * TS_NT)
         {
             const int j = (int)(idx / TS_LDB), k = (int)(idx % TS_LDB);
-            M.band[idx] = (k <= TS_B && j + k < n) ? T[(j + k) + (size_t)n * j] : 0.;
+            M.band[idx] = (k <= TS_B && j + k < n) ? ldx<CL>(T + (j + k) + (size_t)n * j) : 0.;
         }
+        TS_CLK(7);
     }
 }
 
 // ------------------------------------------------------------------------------- stage 2
 
-/* D <- H D H for the symmetric L x L diagonal block at i0 of the band (H = I - tau v v^T,
-   lane a holds v_a; lanes >= L hold 0).  Ds: 32 x 33 per-warp tile, vs / qs: 32 doubles. */
+/* Stage 2: band -> tridiagonal by bulge chasing.
+   A TEAM of G thread blocks (8 warps each) works on one matrix; teams take the matrices
+   team, team + nteams, ... of the list.  Warp gw of the team runs the sweeps gw, gw + NWT, ...
+   (NWT = 8 G).  Sweep s may run its step t once sweep s-1 has completed step t+1 (the blocks the
+   two touch overlap up to there), so consecutive sweeps follow each other two steps apart -- a
+   dataflow pipeline without block-wide barriers: every warp publishes (matrix, sweep, completed
+   steps) in a global slot after a step (behind a __threadfence) and polls the slot of the warp
+   that owns the previous sweep before the next one.  Band data is read with ld.global.cg (the
+   other warps of the team may sit on other SMs).
+   Lane a of a warp owns row a of the 32 x 32 blocks:
+     O (off-diagonal block, rows i0.., columns st..): right application of the previous
+       reflector, new reflector from its first column, left application to the other columns
+       (column sums through a 32 x 17 shared half tile);
+     D (diagonal block at i0): H D H with the symmetric rank-2 formula; the lower triangle lives
+       in registers, the transposed part is read from a 32 x 33 shared tile. */
+__device__ __forceinline__ unsigned long long s2_enc(int mi, int sweep, int steps)
+{
+    return ((unsigned long long)(mi + 1) << 40) | ((unsigned long long)sweep << 16) |
+           (unsigned long long)steps;
+}
+
 __device__ __forceinline__ void s2_two_sided(double *__restrict__ Bd, int i0, int L, double v, double tau,
                                              double *Ds, double *vs, double *qs)
 {
     const int a = threadIdx.x & 31;
-    // lower triangle, column by column (coalesced)
-    for (int c = 0; c < L; ++c)
-        if (a >= c && a < L)
-            Ds[a * 33 + c] = Bd[(a - c) + (size_t)TS_LDB * (i0 + c)];
+    double Dl[32]; // row a of the lower triangle
+#pragma unroll
+    for (int c = 0; c < 32; ++c)
+        Dl[c] = (a >= c && a < L) ? __ldcg(Bd + (a - c) + (size_t)TS_LDB * (i0 + c)) : 0.;
+#pragma unroll
+    for (int c = 0; c < 32; ++c)
+        Ds[a * 33 + c] = Dl[c];
     vs[a] = v;
     __syncwarp();
     double p = 0.;
-    if (a < L)
+#pragma unroll
+    for (int c = 0; c < 32; ++c)
     {
-        for (int c = 0; c < L; ++c)
-        {
-            const double dac = (c <= a) ? Ds[a * 33 + c] : Ds[c * 33 + a];
-            p += dac * vs[c];
-        }
-        p *= tau;
+        // D(a, c): own row for c <= a, column a of row c otherwise (zero outside the block)
+        const double dac = (c <= a) ? Dl[c] : Ds[c * 33 + a];
+        p += dac * vs[c];
     }
+    p *= tau;
     const double pv = warp_sum(p * v);
     const double q = p - 0.5 * tau * pv * v;
     qs[a] = q;
     __syncwarp();
-    for (int c = 0; c < L; ++c)
+#pragma unroll
+    for (int c = 0; c < 32; ++c)
         if (a >= c && a < L)
-            Bd[(a - c) + (size_t)TS_LDB * (i0 + c)] = Ds[a * 33 + c] - v * qs[c] - q * vs[c];
+            Bd[(a - c) + (size_t)TS_LDB * (i0 + c)] = Dl[c] - v * qs[c] - q * vs[c];
     __syncwarp();
 }
 
 __global__ void __launch_bounds__(TS_S2_NW * 32, 2)
-k_sb2st(const sa_ts_mat *__restrict__ mats, int nmats, unsigned int *queue)
+k_sb2st(const sa_ts_mat *__restrict__ mats, int nmats, int G, unsigned long long *slots)
 {
-    extern __shared__ double sm_s2[]; // per warp: tile 32 x 33, v, q, w
-    __shared__ int s_sweep[TS_S2_NW], s_steps[TS_S2_NW];
-    __shared__ int s_next;
+    extern __shared__ double sm_s2[]; // per warp: tile 32 x 33, half tile 32 x 17, v, q, w
     const int tid = threadIdx.x, a = tid & 31, wid = tid >> 5;
-    double *Ds = sm_s2 + (size_t)wid * TS_S2_PER_WARP, *vs = Ds + 32 * 33, *qs = vs + 32, *ws = qs + 32;
-    while (true)
+    double *Ds = sm_s2 + (size_t)wid * TS_S2_PER_WARP, *Os = Ds + 32 * 33, *vs = Os + 32 * 17,
+           *qs = vs + 32, *ws = qs + 32;
+    const int team = blockIdx.x / G, nteams = gridDim.x / G;
+    const int NWT = G * TS_S2_NW;
+    const int gw = (blockIdx.x % G) * TS_S2_NW + wid;
+    volatile unsigned long long *tslots = slots + (size_t)team * NWT;
+    volatile unsigned long long *myslot = tslots + gw;
+    volatile unsigned long long *prevslot = tslots + (gw + NWT - 1) % NWT;
+    long long tclk = clock64();
+    unsigned int mysteps = 0;
+    for (int mi = team; mi < nmats; mi += nteams)
     {
-        __syncthreads();
-        if (tid == 0)
-            s_next = (int)atomicAdd(queue, 1u);
-        __syncthreads();
-        const int mi = s_next;
-        if (mi >= nmats)
-            break;
         const sa_ts_mat M = mats[mi];
         const int n = M.n;
         double *Bd = M.band;
         double *T = M.T;
         const int nsweeps = n - 2; // sweeps 0 .. n-3
-        // warp state
-        int s = wid;         // current sweep
-        int t = 0;           // next step of the sweep
-        double vp = 0.;      // lane c: previous reflector entry
-        double taup = 0.;
-        int st = 0, Lp = 0;
-        if (a == 0)
+        for (int s = gw; s < nsweeps; s += NWT)
         {
-            s_sweep[wid] = s;
-            s_steps[wid] = 0;
-        }
-        __syncthreads();
-        while (true)
-        {
-            // ---- may this warp run step t of sweep s now?
-            bool go = false;
-            const bool alive = s < nsweeps;
-            if (alive)
+            const int nsteps = 1 + (n - 2 - s) / TS_B;
+            double vp = 0., taup = 0.;
+            int st = 0, Lp = 0;
+            if (a == 0)
+                *myslot = s2_enc(mi, s, 0);
+            for (int t = 0; t < nsteps; ++t)
             {
-                if (s == 0)
-                    go = true;
-                else
+                // ---- wait until sweep s-1 is two steps ahead (or done)
+                if (s > 0)
                 {
-                    const int pw = (wid + TS_S2_NW - 1) % TS_S2_NW;
-                    const int ps = s_sweep[pw], pt = s_steps[pw];
-                    go = (ps > s - 1) || (ps == s - 1 && pt >= t + 2);
+                    if (a == 0)
+                    {
+                        while (true)
+                        {
+                            const unsigned long long pv = *prevslot;
+                            const int pm = (int)(pv >> 40), ps = (int)((pv >> 16) & 0xffffffull),
+                                      pt = (int)(pv & 0xffffull);
+                            if (pm > mi + 1 || (pm == mi + 1 && (ps > s - 1 || (ps == s - 1 && pt >= t + 2))))
+                                break;
+                            __nanosleep(100);
+                        }
+                    }
+                    __syncwarp();
+                    __threadfence();
                 }
-            }
-            if (__syncthreads_and(!alive))
-                break;
-            if (go)
-            {
-                const int nsteps = 1 + (n - 2 - s) / TS_B;
                 if (t == 0)
                 {
                     const int i0 = s + 1;
                     const int L = min(TS_B, n - i0);
-                    const double x = (a < L) ? Bd[(1 + a) + (size_t)TS_LDB * s] : 0.;
+                    const double x = (a < L) ? __ldcg(Bd + (1 + a) + (size_t)TS_LDB * s) : 0.;
                     const double xn2 = warp_sum(a >= 1 ? x * x : 0.);
                     const double alpha = __shfl_sync(0xffffffffu, x, 0);
                     double beta, tau, scal;
@@ -870,7 +1025,7 @@ k_sb2st(const sa_ts_mat *__restrict__ mats, int nmats, unsigned int *queue)
                     double O[32];
 #pragma unroll
                     for (int c = 0; c < 32; ++c)
-                        O[c] = (a < L && c < Lp) ? Bd[(TS_B + a - c) + (size_t)TS_LDB * (st + c)] : 0.;
+                        O[c] = (a < L && c < Lp) ? __ldcg(Bd + (TS_B + a - c) + (size_t)TS_LDB * (st + c)) : 0.;
                     vs[a] = vp;
                     __syncwarp();
                     double u = 0.;
@@ -890,18 +1045,26 @@ k_sb2st(const sa_ts_mat *__restrict__ mats, int nmats, unsigned int *queue)
                     ts_larfg(alpha, xn2, beta, tau, scal);
                     const double v = (a == 0) ? 1. : (a < L ? x * scal : 0.);
                     O[0] = (a == 0) ? beta : 0.;
-                    // left application to columns 1..: w_c = sum_a v_a O[a][c] (transposed
-                    // through the per-warp tile: lane c sums down column c)
-#pragma unroll
-                    for (int c = 0; c < 32; ++c)
-                        Ds[a * 33 + c] = O[c];
+                    // left application to columns 1..: w_c = tau sum_a v_a O[a][c], transposed
+                    // through a half tile (16 columns at a time; lane l sums 16 rows of column l & 15)
                     vs[a] = v;
-                    __syncwarp();
-                    double wc = 0.;
-#pragma unroll 8
-                    for (int r2 = 0; r2 < 32; ++r2)
-                        wc += vs[r2] * Ds[r2 * 33 + a];
-                    ws[a] = (a == 0) ? 0. : tau * wc;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                    {
+                        __syncwarp();
+#pragma unroll
+                        for (int c = 0; c < 16; ++c)
+                            Os[a * 17 + c] = O[16 * h + c];
+                        __syncwarp();
+                        const int cc = a & 15, r0 = (a >> 4) * 16;
+                        double wc = 0.;
+#pragma unroll
+                        for (int r2 = 0; r2 < 16; ++r2)
+                            wc += vs[r0 + r2] * Os[(r0 + r2) * 17 + cc];
+                        wc += __shfl_xor_sync(0xffffffffu, wc, 16);
+                        if (a < 16)
+                            ws[16 * h + a] = (h == 0 && a == 0) ? 0. : tau * wc;
+                    }
                     __syncwarp();
 #pragma unroll
                     for (int c = 1; c < 32; ++c)
@@ -919,27 +1082,36 @@ k_sb2st(const sa_ts_mat *__restrict__ mats, int nmats, unsigned int *queue)
                     st = i0;
                     Lp = L;
                 }
-                ++t;
-                if (t >= nsteps)
-                {
-                    s += TS_S2_NW;
-                    t = 0;
-                }
+                ++mysteps;
+                // ---- publish: the step's stores are visible before the slot changes
+                __threadfence();
+                __syncwarp();
+                if (a == 0)
+                    *myslot = s2_enc(mi, s, t + 1);
             }
-            __syncthreads(); // everyone has read the progress slots and finished its step
-            if (go && a == 0)
-            {
-                s_sweep[wid] = s;
-                s_steps[wid] = t;
-            }
-            __syncthreads();
         }
-        __syncthreads();
-        for (int j = tid; j < n; j += blockDim.x)
-        {
-            M.d[j] = Bd[(size_t)TS_LDB * j];
-            M.e[j] = (j + 1 < n) ? Bd[1 + (size_t)TS_LDB * j] : 0.;
-        }
+        // no sweeps left for this warp on this matrix: successors must not wait for it
+        if (a == 0)
+            *myslot = s2_enc(mi, 0xffffff, 0);
+    }
+    if (a == 0)
+    {
+        atomicAdd(&g_ts_clk[10], (unsigned long long)mysteps);
+        atomicAdd(&g_ts_clk[9], (unsigned long long)(clock64() - tclk));
+    }
+}
+
+/* d, e of the tridiagonal matrices (after every team is done) */
+__global__ void k_sb2st_extract(const sa_ts_mat *__restrict__ mats, int nmats)
+{
+    const int mi = blockIdx.x;
+    if (mi >= nmats)
+        return;
+    const sa_ts_mat M = mats[mi];
+    for (int j = threadIdx.x; j < M.n; j += blockDim.x)
+    {
+        M.d[j] = M.band[(size_t)TS_LDB * j];
+        M.e[j] = (j + 1 < M.n) ? M.band[1 + (size_t)TS_LDB * j] : 0.;
     }
 }
 
@@ -1043,26 +1215,73 @@ void sa_ts_reduce(sa_gpu_ctx *ctx, const sa_ts_mat *d_mats, int nmats, int nmax,
     if (smem > ctx->smem_optin)
         SA_FAIL("two-stage eigensolver: AE with %d dofs exceeds the supported size", nmax);
     SpectralWs &WS = ctx->sws;
-    const int grid1 = std::min(nmats, ctx->num_sms);
+    // clusters of CS blocks per matrix when there are far fewer matrices than SMs
+    const int cs_env = getenv("SA_GPU_TS_CLUSTER") ? atoi(getenv("SA_GPU_TS_CLUSTER")) : -1; // (tests)
+    int CS = 1;
+    if (cs_env >= 1)
+        CS = cs_env;
+    else if (nmats * 2 <= ctx->num_sms && nmax >= 1024)
+        CS = (nmats * 8 <= ctx->num_sms) ? 8 : (nmats * 4 <= ctx->num_sms ? 4 : 2);
+    const int nunits = (CS > 1) ? nmats : std::min(nmats, ctx->num_sms);
     const int ldws = (nmax + 3) & ~3;
-    WS.ts_wsV.ensure((size_t)grid1 * ldws * TS_B);
-    WS.ts_wsW.ensure((size_t)grid1 * ldws * TS_B);
+    WS.ts_wsV.ensure((size_t)nunits * ldws * TS_B);
+    WS.ts_wsW.ensure((size_t)nunits * ldws * TS_B);
     WS.counters.ensure(4);
     SA_CUDA(cudaMemsetAsync(WS.counters.p, 0, 4 * sizeof(unsigned int), st));
-    SA_CUDA(cudaFuncSetAttribute(k_sy2sb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         ProfScope ps(ctx, "eig.ts_stage1");
-        k_sy2sb<<<grid1, TS_NT, smem, st>>>(d_mats, nmats, WS.counters.p, WS.ts_wsV.p, WS.ts_wsW.p, ldws,
-                                           w_in);
+        if (CS == 1)
+        {
+            SA_CUDA(cudaFuncSetAttribute(k_sy2sb<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_sy2sb<false><<<nunits, TS_NT, smem, st>>>(d_mats, nmats, WS.counters.p, WS.ts_wsV.p, WS.ts_wsW.p,
+                                                        ldws, w_in);
+        }
+        else
+        {
+            SA_CUDA(cudaFuncSetAttribute(k_sy2sb<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cudaLaunchConfig_t cfg;
+            std::memset(&cfg, 0, sizeof cfg);
+            cfg.gridDim = dim3(nunits * CS);
+            cfg.blockDim = dim3(TS_NT);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = CS;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            unsigned int *queue = WS.counters.p;
+            double *wv = WS.ts_wsV.p, *ww = WS.ts_wsW.p;
+            int ldws_ = ldws, w_in_ = w_in, nm = nmats;
+            SA_CUDA(cudaLaunchKernelEx(&cfg, k_sy2sb<true>, d_mats, nm, queue, wv, ww, ldws_, w_in_));
+        }
         ctx->launches++;
         SA_CUDA(cudaGetLastError());
     }
     {
         ProfScope ps(ctx, "eig.ts_stage2");
-        const int grid2 = std::min(nmats, 2 * ctx->num_sms);
+        // teams of G blocks per matrix: one block when there are many matrices, up to 8 when a
+        // handful of large ones would otherwise leave most SMs idle
+        // (measured at 630 matrices of n ~ 2000: teams of 5 blocks, which would keep the bands
+        // of the matrices in flight in L2, are 40 % slower than one block per matrix -- passing
+        // the band between SMs costs more than streaming it from HBM)
+        const int cap = 2 * ctx->num_sms;
+        int G = std::max(1, std::min(8, cap / nmats));
+        G = std::min(G, std::max(1, (nmax / (2 * TS_B) + TS_S2_NW - 1) / TS_S2_NW)); // useful concurrency
+        const int nteams = std::min(nmats, cap / G);
+        const size_t nslots = (size_t)nteams * G * TS_S2_NW;
+        WS.ts_slots.ensure(nslots);
+        SA_CUDA(cudaMemsetAsync(WS.ts_slots.p, 0, nslots * sizeof(unsigned long long), st));
         const size_t smem2 = (size_t)TS_S2_NW * TS_S2_PER_WARP * sizeof(double);
         SA_CUDA(cudaFuncSetAttribute(k_sb2st, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-        k_sb2st<<<grid2, TS_S2_NW * 32, smem2, st>>>(d_mats, nmats, WS.counters.p + 1);
+        // (all blocks are co-resident: grid <= 2 blocks per SM)
+        k_sb2st<<<nteams * G, TS_S2_NW * 32, smem2, st>>>(d_mats, nmats, G,
+                                                         (unsigned long long *)WS.ts_slots.p);
+        ctx->launches++;
+        SA_CUDA(cudaGetLastError());
+        k_sb2st_extract<<<nmats, 256, 0, st>>>(d_mats, nmats);
         ctx->launches++;
         SA_CUDA(cudaGetLastError());
     }
@@ -1147,4 +1366,16 @@ extern "C" int sa_gpu_debug_twostage_back(sa_gpu_ctx *ctx, int n, int nvec, doub
     dY.download(Y, (size_t)n * nvec, st);
     SA_CUDA(cudaStreamSynchronize(st));
     SA_API_END
+}
+
+extern "C" int sa_gpu_debug_ts_clocks(double *out16)
+{
+    unsigned long long h[16], z[16];
+    std::memset(z, 0, sizeof z);
+    if (cudaMemcpyFromSymbol(h, g_ts_clk, sizeof h) != cudaSuccess)
+        return 1;
+    cudaMemcpyToSymbol(g_ts_clk, z, sizeof z);
+    for (int i = 0; i < 16; ++i)
+        out16[i] = (double)h[i];
+    return 0;
 }

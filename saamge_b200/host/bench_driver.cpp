@@ -12,6 +12,7 @@
 #include "saamge.hpp"
 
 extern "C" {
+double sa_gpu_level_uploaded_bytes(sa_gpu_level *level);
 int sa_gpu_host_register(const void *p, size_t bytes);
 int sa_gpu_host_unregister(const void *p);
 int sa_gpu_debug_phase_clocks(double *out8);
@@ -29,7 +30,7 @@ struct sa_bench_t
     std::vector<int64_t> offsets;
     std::vector<int> ae_m;
     std::vector<double> evals, evects;
-    double h2d_bytes = 0., d2h_bytes = 0.;
+    double h2d_bytes = 0., d2h_bytes = 0., h2d_bytes_last = 0., table_bytes = 0.;
     bool pinned = false;
     std::vector<const void *> registered;
     double e2e_phase_ms[3] = {0., 0., 0.}; // upload, compute, read back (last mode-1 step)
@@ -111,6 +112,7 @@ extern "C" void *sa_drv_bench_create(void *prob_, const sa_drv_params_t *p, int 
     d.elmat_off = B->offsets.data();
     d.assemble_with_global = 1;
     B->h2d_bytes = desc_bytes(d);
+    B->table_bytes = B->h2d_bytes - (d.A_I ? 12. * d.A_I[d.ND] : 0.) - (d.elmat ? 8. * d.elmat_off[d.NE] : 0.);
     // pin the large host arrays so the e2e copies run at full PCIe speed
     // (every array the level upload reads: element blocks, operator, relation tables)
     bool ok = pin(B, f.elmat.data(), f.elmat.size() * sizeof(double));
@@ -138,6 +140,8 @@ extern "C" void *sa_drv_bench_create(void *prob_, const sa_drv_params_t *p, int 
     return B;
 }
 
+extern "C" void *sa_drv_bench_level(void *b_) { return ((sa_bench_t *)b_)->lev; }
+
 extern "C" void sa_drv_bench_destroy(void *b_)
 {
     sa_bench_t *B = (sa_bench_t *)b_;
@@ -150,7 +154,9 @@ extern "C" void sa_drv_bench_destroy(void *b_)
 }
 
 /* mode 0: device-resident inputs, AEs [ae_begin, ae_end); returns device ms
-   mode 1: end to end from host buffers: upload, compute, read back m / lambda / vectors */
+   mode 1: end to end from host buffers: upload, compute, read back m / lambda / vectors
+   mode 2: as 1 for one rank of a sharded stage: only the inputs AEs [ae_begin, ae_end) read are
+           uploaded (desc.async_upload = 2) and only their results are read back */
 extern "C" double sa_drv_bench_step(void *b_, int mode, int ae_begin, int ae_end)
 {
     sa_bench_t *B = (sa_bench_t *)b_;
@@ -176,7 +182,7 @@ extern "C" double sa_drv_bench_step(void *b_, int mode, int ae_begin, int ae_end
     // operator / element blocks is still in flight (SA_BENCH_SYNC_UPLOAD=1 turns it off)
     static const bool sync_upload = getenv("SA_BENCH_SYNC_UPLOAD") != NULL;
     sa_gpu_level_desc desc = B->desc;
-    desc.async_upload = (breakdown || sync_upload) ? 0 : 1;
+    desc.async_upload = (breakdown || sync_upload) ? 0 : (mode == 2 ? 2 : 1);
     sa_gpu_check(sa_gpu_level_create(B->ctx, &desc, NULL, &lev), "sa_gpu_level_create");
     if (breakdown)
     {
@@ -196,6 +202,8 @@ extern "C" double sa_drv_bench_step(void *b_, int mode, int ae_begin, int ae_end
     size_t ne = 0, nv = 0;
     for (int i = 0; i < r.nparts; ++i)
     {
+        if (mode == 2 && (i < ae_begin || i >= ae_end))
+            B->ae_m[i] = 0; // (counts outside the range are not this rank's)
         ne += B->ae_m[i];
         nv += (size_t)B->ae_m[i] * r.AE_to_dof->RowSize(i);
     }
@@ -207,6 +215,8 @@ extern "C" double sa_drv_bench_step(void *b_, int mode, int ae_begin, int ae_end
         B->e2e_phase_ms[2] = ms_since(t0);
     const double ms = sa_gpu_ctx_timer(B->ctx, 0);
     B->d2h_bytes = 8. * (ne + nv) + 4. * r.nparts;
+    if (mode == 2)
+        B->h2d_bytes_last = sa_gpu_level_uploaded_bytes(lev) + B->table_bytes;
     sa_gpu_level_destroy(lev);
     return ms;
 }
@@ -217,6 +227,7 @@ extern "C" double sa_drv_bench_scalar(void *b_, const char *name_)
     const std::string name(name_);
     const agg_partitioning_relations_t &r = *B->prob->rels;
     if (name == "h2d_bytes") return B->h2d_bytes;
+    if (name == "h2d_bytes_last") return B->h2d_bytes_last;
     if (name == "d2h_bytes") return B->d2h_bytes;
     if (name == "pinned") return B->pinned ? 1. : 0.;
     if (name == "e2e.upload_ms") return B->e2e_phase_ms[0];

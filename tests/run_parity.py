@@ -42,7 +42,7 @@ def main():
     print("pcg iters gpu", itg, "oracle", ito)
     print("brr gpu", Hg.get("pcg.brr")[:8], "\nbrr orc", Ho.get("pcg.brr")[:8])
     print("final res gpu", Hg.scalar("pcg.final_res_norm"), "orc", Ho.scalar("pcg.final_res_norm"))
-    res = parity.compare_hierarchies(Hg, Ho)
+    res = parity.compare_hierarchies(Hg, Ho, expect_levels=levels - 1)
     for l, m in enumerate(res):
         print("level", l, json.dumps(m, indent=1))
     ok = True

@@ -1,0 +1,130 @@
+"""Parity of the CUDA path against the CPU oracle ON the BASELINE.json configurations:
+  C1  2D Poisson 256^2 quads, 2-level, METIS, theta = 0.003              (full hierarchy)
+  C2  3D diffusion 64^3 hex, lognormal 1e6 contrast, 3-level              (full hierarchy)
+  C3  3D diffusion 128^3 hex, ~40k METIS AEs: every level-0 AE            (m, lambda, D)
+  C4-like  order-2 hex, 64-element AEs of n = 729 (large-matrix eigensolver on the finest level)
+Tolerances are the north star's (parity.assert_level_ok).  The oracle side of C3 runs one
+single-threaded process per host core (the mpirun -n P analogue bench.py uses)."""
+import ctypes
+import multiprocessing as mp
+import os
+
+import numpy as np
+import pytest
+
+import oracle_util as ou
+import parity
+import saamge_b200 as sab
+from saamge_b200 import cabi
+
+pytestmark = pytest.mark.gpu
+THETA = 0.003
+
+
+def _full(dim, n, order, coef, levels, fepa, epa, kind, blk, expect_levels=None, **kw):
+    p = sab.default_params(num_levels=levels, first_elems_per_agg=fepa, elems_per_agg=epa, partition_kind=kind,
+                           block=(blk, blk, blk), **kw)
+    pr = sab.Problem(dim, n, order=order, coef_kind=coef)
+    pr.partition(p)
+    Ho = ou.orc_build(pr, p)
+    ito = ou.orc_pcg(Ho)
+    Hg = sab.ml_build(pr, p)
+    itg = sab.ml_pcg(Hg)
+    sab.ml_download(Hg)
+    res = parity.compare_hierarchies(Hg, Ho, expect_levels=levels - 1 if expect_levels is None else expect_levels)
+    for l, m in enumerate(res):
+        parity.assert_level_ok(m, l)
+    assert itg > 0 and abs(itg - ito) <= 1, (itg, ito)
+    rg, ro = Hg.scalar("pcg.final_res_norm"), Ho.scalar("pcg.final_res_norm")
+    assert abs(rg - ro) <= 1e-6 * max(ro, 1e-300) + 1e-12
+    counts = parity.pattern_counts(res)
+    for h in (Hg, Ho):
+        h.close()
+    pr.close()
+    return res, counts, itg
+
+
+def test_c1_poisson_256sq_two_level():
+    res, counts, it = _full(2, 256, 1, 0, 2, 256, 256, 0, 16)
+    print("C1: iterations", it, "pattern-only entries", counts)
+
+
+def test_c2_diffusion_64cubed_three_level():
+    res, counts, it = _full(3, 64, 1, 1, 3, 52, 64, 2, 32)
+    print("C2: iterations", it, "pattern-only entries", counts)
+
+
+def test_q2_large_fine_level_agglomerates():
+    """order 2, 4 x 4 x 4 element blocks: n = 9^3 = 729 dofs per AE -> two-stage eigensolver on
+    the finest level (BASELINE configs[3] at a size the oracle finishes in a minute)."""
+    res, counts, it = _full(3, 16, 2, 1, 2, 64, 8, 1, 4)
+    print("Q2: iterations", it, "pattern-only entries", counts)
+
+
+def _oracle_worker(args):
+    handle, pbytes, a0, a1, cap, m_sh, ev_sh, D_sh = args
+    o = ou.oracle(1)
+    p = sab.Params.from_buffer_copy(pbytes)
+    ip, dp = ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)
+    o.sa_orc_local_spectral.argtypes = [ctypes.c_void_p, ctypes.POINTER(sab.Params), ctypes.c_int, ctypes.c_int,
+                                        ip, dp, ctypes.c_int, dp]
+    m = np.frombuffer(m_sh, dtype=np.int32)
+    ev = np.frombuffer(ev_sh, dtype=np.float64)
+    D = np.frombuffer(D_sh, dtype=np.float64)
+    rc = o.sa_orc_local_spectral(handle, ctypes.byref(p), a0, a1, m[a0:].ctypes.data_as(ip),
+                                 ev[a0 * cap:].ctypes.data_as(dp), cap, D.ctypes.data_as(dp))
+    return rc
+
+
+def test_c3_level0_every_agglomerate_against_the_oracle():
+    p = sab.default_params(num_levels=4, first_elems_per_agg=52, elems_per_agg=64, partition_kind=2, block=(32, 32, 32))
+    pr = sab.Problem(3, 128, coef_kind=1, contrast=1e6, seed=12345)
+    nae = pr.partition(p)
+    assert nae == 40320
+    ou.oracle(1)  # load before forking
+    AI = pr.get("AE_to_dof.I")
+    cap = 8
+    m_sh = mp.RawArray(ctypes.c_int32, nae)
+    ev_sh = mp.RawArray(ctypes.c_double, nae * cap)
+    D_sh = mp.RawArray(ctypes.c_double, int(AI[-1]))
+    procs = os.cpu_count() or 1
+    bounds = [nae * i // procs for i in range(procs + 1)]
+    pbytes = bytes(p)
+    # workers first (fork before this process touches CUDA)
+    ctxmp = mp.get_context("fork")
+    workers = []
+    for i in range(procs):
+        w = ctxmp.Process(target=_oracle_worker,
+                          args=((pr.handle, pbytes, bounds[i], bounds[i + 1], cap, m_sh, ev_sh, D_sh),))
+        w.start()
+        workers.append(w)
+    for w in workers:
+        w.join()
+        assert w.exitcode == 0
+    mo = np.frombuffer(m_sh, dtype=np.int32)
+    evo = np.frombuffer(ev_sh, dtype=np.float64).reshape(nae, cap)
+    Do = np.frombuffer(D_sh, dtype=np.float64)
+
+    ctx = cabi.Context(0)
+    lev = cabi.Level(ctx, pr)
+    lev.local_spectral(THETA)
+    mg, evg, Zg, Dg = lev.spectral()
+    lev.close()
+    ctx.close()
+    assert np.array_equal(mg, mo), ("ae_m differs on %d AEs" % int(np.sum(mg != mo)))
+    assert mo.max() <= cap
+    eo = np.concatenate([[0], np.cumsum(mg)])
+    worst = 0.0
+    near_theta = 0
+    for i in range(nae):
+        lg = evg[eo[i]:eo[i + 1]]
+        lo = evo[i, :mg[i]]
+        worst = max(worst, float(np.max(np.abs(lg - lo) / np.maximum(np.abs(lo), 1.0))))
+        if np.any(np.abs(lo - THETA) <= 1e-12):
+            near_theta += 1
+    assert worst <= 1e-10, worst
+    drel = float(np.max(np.abs(Dg - Do) / np.abs(Do)))
+    assert drel <= 1e-11, drel
+    print("C3 level 0: 40320 AEs, ae_m identical, max eigenvalue error %.2e, D relerr %.2e, "
+          "AEs with an eigenvalue within 1e-12 of theta: %d" % (worst, drel, near_theta))
+    pr.close()

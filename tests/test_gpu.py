@@ -43,6 +43,11 @@ CONFIGS = [
 ]
 
 
+# configurations whose MIS bases differ from LAPACK's by a rotation on some level (degenerate
+# singular values): number of levels that can be compared entry by entry
+ROTATION_GAUGE_LEVELS = {}
+
+
 @pytest.mark.parametrize("cfg", CONFIGS)
 def test_parity_vs_oracle(cfg):
     dim, n, order, coef, levels, fepa, epa, nupro, kind, blk, cblk = cfg
@@ -52,9 +57,15 @@ def test_parity_vs_oracle(cfg):
     pr = sab.Problem(dim, n, order=order, coef_kind=coef)
     pr.partition(p)
     Hg, Ho, itg, ito = _run(pr, p)
-    res = parity.compare_hierarchies(Hg, Ho)
+    # every coarsening is compared entry by entry -- no silently skipped levels -- except where the
+    # configuration is known to produce a rotation gauge (see parity.compare_hierarchies)
+    expect = ROTATION_GAUGE_LEVELS.get(cfg, levels - 1)
+    res = parity.compare_hierarchies(Hg, Ho, expect_levels=expect)
     for l, m in enumerate(res):
         parity.assert_level_ok(m, l)
+    for m in res[-1].get("coarser_invariants", []):
+        assert m["maps_mismatch"] == [] and m["ND"][0] == m["ND"][1], m
+        assert m.get("operator_spectrum_err", 0.0) <= 1e-9, m
     assert abs(itg - ito) <= 1
     assert itg > 0
     rg, ro = Hg.scalar("pcg.final_res_norm"), Ho.scalar("pcg.final_res_norm")
@@ -83,7 +94,7 @@ def test_reference_ctest_pins_on_gpu(order, levels, pinned):
     pr, p = fixtures.mltest_problem(order, levels)
     Hg, Ho, itg, ito = _run(pr, p)
     assert abs(itg - pinned) <= 1 and abs(itg - ito) <= 1
-    res = parity.compare_hierarchies(Hg, Ho)
+    res = parity.compare_hierarchies(Hg, Ho, expect_levels=levels - 1)
     # The fixture injects an all-ones vector that is not an eigenvector; with the 1e6
     # checkerboard its MIS restrictions have singular values down to ~1e-8 sigma_0, so
     # the kept singular vectors are only determined to eps / 1e-8 (in LAPACK as well).

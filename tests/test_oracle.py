@@ -101,3 +101,34 @@ def test_pcg_converges_and_residual():
     assert brr[-1] < 1e-12 * brr[0]
     H.close()
     pr.close()
+
+
+@pytest.mark.parametrize("cfg", [
+    # dim, n, order, levels, first_epa, epa, kind, block
+    (3, 16, 1, 3, 64, 8, 0, 4),
+    (2, 64, 1, 3, 64, 16, 0, 4),
+    (3, 12, 2, 3, 27, 8, 1, 3),
+    (3, 20, 1, 3, 52, 24, 0, 4),
+])
+def test_topology_two_independent_constructions(cfg):
+    """The product's hash / sort construction of agg_partitioning_relations_t
+    (saamge_b200/host/aggregates.cpp) against the oracle's own line-faithful restatement of
+    amg/src/aggregates.cpp (oracle/orc_topology.cpp): every table of the fine level and of every
+    coarse level must be identical -- the 'bit-exact maps' check is not one function against
+    itself."""
+    import ctypes
+
+    dim, n, order, levels, fepa, epa, kind, blk = cfg
+    o = ou.oracle()
+    o.sa_orc_check_relations.argtypes = [ctypes.c_void_p]
+    o.sa_orc_check_coarse_relations.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    p = sab.default_params(num_levels=levels, first_elems_per_agg=fepa, elems_per_agg=epa, partition_kind=kind,
+                           block=(blk, blk, blk), coarse_block=2)
+    pr = sab.Problem(dim, n, order=order, coef_kind=1)
+    pr.partition(p)
+    assert o.sa_orc_check_relations(pr.handle) == 0
+    H = ou.orc_build(pr, p)
+    for l in range(1, levels - 1):
+        assert o.sa_orc_check_coarse_relations(H.handle, l) == 0, l
+    H.close()
+    pr.close()

@@ -51,6 +51,14 @@ def _gpu_reduce(ctx, A):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("n,cluster", [(130, 2), (300, 4), (700, 8)])
+def test_cuda_two_stage_cluster_mode(n, cluster, monkeypatch):
+    """Thread-block clusters sharing one matrix (what a handful of very large AEs get)."""
+    monkeypatch.setenv("SA_GPU_TS_CLUSTER", str(cluster))
+    test_cuda_two_stage_matches_the_statement(n, False)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("n,graded", [(3, False), (20, False), (33, False), (34, False), (35, False), (64, False),
                                       (65, False), (66, False), (97, True), (130, False), (257, True),
                                       (300, False), (700, True), (1203, False)])

@@ -10,6 +10,7 @@ h=sab.host_lib(); h.sa_drv_gpu_profile.argtypes=[ctypes.c_int,ctypes.c_char_p,ct
 t=time.time(); H=sab.ml_build(pr,p); print("ml_build %.2fs"%(time.time()-t), flush=True)
 buf=ctypes.create_string_buffer(8192); h.sa_drv_gpu_profile(-1,buf,8192); print("PROF", buf.value.decode().replace("\n","; "))
 g=sab.gpu_lib(); clk=(ctypes.c_double*8)(); g.sa_gpu_debug_phase_clocks(clk); print("PHASE Mcycles", [round(x/1e6,1) for x in clk])
+ts=(ctypes.c_double*16)(); g.sa_gpu_debug_ts_clocks(ts); print("TS Mcycles qr,gram,symm,Xtf,S,Z,syr2k,band | s2 ticks, s2 Mcyc, s2 steps:", [round(x/1e6,1) for x in ts[:8]], ts[8], round(ts[9]/1e6,1), ts[10])
 tm=H.times(); print({k:round(v,3) for k,v in tm.items()})
 for l in range(levels-1):
     print("level",l,"ND",H.scalar("ND",l),"nparts",H.scalar("nparts",l),"mises",H.scalar("num_mises",l))
