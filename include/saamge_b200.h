@@ -147,6 +147,13 @@ int sa_gpu_get_spectral(sa_gpu_level *level, double *evals, double *evects, doub
  * caller).  Layout as returned by sa_gpu_get_spectral. */
 int sa_gpu_set_spectral(sa_gpu_level *level, int ae_begin, int ae_end, const int *ae_m,
                         const double *evals, const double *evects, const double *D);
+/* Guard-band report of the two threshold decisions of the setup (SURVEY hard part 2): number of
+ * AEs (of the last sa_gpu_local_spectral range) with an eigenvalue within 1e-12 of theta, i.e.
+ * whose m = #{lambda <= theta} (amg/src/xpacks.cpp:233-234) another equally accurate eigensolver
+ * could count differently, and number of MISes (last sa_gpu_tentative_P) with a singular value
+ * within a factor 10 of the rank cut 1e-10 sigma_0 (amg/src/xpacks.cpp:609-610).  The decisions
+ * themselves are taken exactly as the reference takes them; this only counts the fragile ones. */
+int sa_gpu_get_borderline(sa_gpu_level *level, int *theta_borderline, int *rank_borderline);
 /* Device-side exchange for a local spectral stage sharded over several GPUs (the reference
  * distributes the AEs over MPI ranks, amg/src/interp.cpp:387): after
  * sa_gpu_local_spectral(level, theta, ae_begin, ae_end) the caller announces the counts of ALL
@@ -188,6 +195,10 @@ int sa_gpu_rap(sa_gpu_level *level);
 /* ElementMatrixParallelCoarse::GetMatrix for every finer AE (amg/src/elmat.cpp:105-195):
  * coarse element matrices P_e^T A_AE(e) P_e, kept on the device of \a coarse. */
 int sa_gpu_coarse_elmats(sa_gpu_level *finer, sa_gpu_level *coarse);
+/* ElementMatrixProvider::GetMatrix(elno) of the level's provider (amg/inc/elmat.hpp:62): the
+ * dense block of one element (ne x ne column-major; on coarse levels the block
+ * sa_gpu_coarse_elmats produced).  out may be NULL to query *ne_out only. */
+int sa_gpu_get_element_matrix(sa_gpu_level *level, int elno, double *out, int *ne_out);
 /* read back: nc_e^2 doubles per finer AE, column-major, concatenated */
 int sa_gpu_get_coarse_elmats(sa_gpu_level *coarse, double *celmat);
 
@@ -214,6 +225,14 @@ int sa_gpu_poly_smooth(sa_gpu_level *level, const double *b, double *x, int degr
 int sa_gpu_solver_create(sa_gpu_ctx *ctx, sa_gpu_level **levels, int nlevels, int nu_relax,
                          sa_gpu_solver **solver);
 void sa_gpu_solver_destroy(sa_gpu_solver *solver);
+/* The smoother plug smpr_ft (amg/inc/smpr.hpp:59-60; tg_data_t::pre_smoother / post_smoother,
+ * amg/inc/tg_data.hpp:68-69, amg/src/tg.cpp:48-57, 411-414): user relaxation of level `level`
+ * of the V-cycle, x <- relax(A_level, b, x), called with HOST vectors (n = dofs of the level).
+ * NULL keeps the device SAS polynomial smoother.  A user smoother makes the cycle leave the
+ * device twice per level and cycle; it exists for interface completeness. */
+typedef void (*sa_gpu_smoother_ft)(int level, int n, const double *b, double *x, void *data);
+int sa_gpu_solver_set_smoothers(sa_gpu_solver *solver, int level, sa_gpu_smoother_ft pre,
+                                sa_gpu_smoother_ft post, void *data);
 /* VCycleSolver::Mult (amg/src/solve.cpp:309-323) = tg_cycle_atb from x = 0
  * (amg/src/tg.cpp:91-132); host buffers */
 int sa_gpu_vcycle(sa_gpu_solver *solver, const double *b, double *x);

@@ -9,6 +9,121 @@
 static thread_local char g_err[1024] = "";
 cudaStream_t g_sa_alloc_stream = nullptr;
 bool g_sa_alloc_async = false;
+int g_sa_alloc_device = -1, g_sa_alloc_refs = 0;
+
+// ---- device arena (see sa_gpu_internal.cuh)
+#include <map>
+namespace
+{
+struct Arena
+{
+    char *base = nullptr;
+    size_t size = 0;
+    std::map<size_t, size_t> free_blocks; // offset -> size
+    std::map<size_t, size_t> used;        // offset -> size
+} g_arena;
+const size_t ARENA_ALIGN = 512;
+} // namespace
+
+void *sa_arena_alloc(size_t bytes)
+{
+    if (!g_arena.base)
+        return nullptr;
+    bytes = (bytes + ARENA_ALIGN - 1) & ~(ARENA_ALIGN - 1);
+    for (std::map<size_t, size_t>::iterator it = g_arena.free_blocks.begin(); it != g_arena.free_blocks.end(); ++it)
+        if (it->second >= bytes)
+        {
+            const size_t off = it->first, sz = it->second;
+            g_arena.free_blocks.erase(it);
+            if (sz > bytes)
+                g_arena.free_blocks[off + bytes] = sz - bytes;
+            g_arena.used[off] = bytes;
+            return g_arena.base + off;
+        }
+    return nullptr;
+}
+
+bool sa_arena_free(void *p)
+{
+    if (!g_arena.base || (char *)p < g_arena.base || (char *)p >= g_arena.base + g_arena.size)
+        return false;
+    size_t off = (size_t)((char *)p - g_arena.base);
+    std::map<size_t, size_t>::iterator u = g_arena.used.find(off);
+    if (u == g_arena.used.end())
+        return false;
+    size_t sz = u->second;
+    g_arena.used.erase(u);
+    // coalesce with the neighbours
+    std::map<size_t, size_t>::iterator nx = g_arena.free_blocks.lower_bound(off);
+    if (nx != g_arena.free_blocks.end() && off + sz == nx->first)
+    {
+        sz += nx->second;
+        g_arena.free_blocks.erase(nx);
+    }
+    nx = g_arena.free_blocks.lower_bound(off);
+    if (nx != g_arena.free_blocks.begin())
+    {
+        std::map<size_t, size_t>::iterator pv = nx;
+        --pv;
+        if (pv->first + pv->second == off)
+        {
+            off = pv->first;
+            sz += pv->second;
+            g_arena.free_blocks.erase(pv);
+        }
+    }
+    g_arena.free_blocks[off] = sz;
+    return true;
+}
+
+static void arena_create(int device)
+{
+    if (g_arena.base)
+        return;
+    const char *e = getenv("SA_GPU_ARENA_GB");
+    const char *na = getenv("SA_GPU_NO_ASYNC_ALLOC");
+    if (na && na[0] == '1')
+        return; // (the plain cudaMalloc test path)
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess)
+        return;
+    double gb = e ? atof(e) : std::min(96., 0.6 * (double)free_b / 1073741824.);
+    if (gb <= 0.)
+        return;
+    size_t bytes = (size_t)(gb * 1073741824.) & ~(size_t)0xfffff;
+    static const bool dbg = getenv("SA_GPU_ALLOC_DEBUG") != NULL;
+    const auto t0 = std::chrono::steady_clock::now();
+    void *p = nullptr;
+    while (bytes >= ((size_t)1 << 30) && cudaMalloc(&p, bytes) != cudaSuccess)
+    {
+        cudaGetLastError();
+        p = nullptr;
+        bytes /= 2;
+    }
+    if (!p)
+        return;
+    if (dbg)
+        fprintf(stderr, "[arena] %.1f GB reserved in %.1f ms\n", bytes / 1073741824.,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    g_arena.base = (char *)p;
+    g_arena.size = bytes;
+    g_arena.free_blocks.clear();
+    g_arena.used.clear();
+    g_arena.free_blocks[0] = bytes;
+    (void)device;
+}
+
+static void arena_destroy()
+{
+    // only when nothing lives in it any more (buffers may outlive the last context)
+    if (g_arena.base && g_arena.used.empty())
+    {
+        cudaFree(g_arena.base);
+        g_arena.base = nullptr;
+        g_arena.size = 0;
+        g_arena.free_blocks.clear();
+    }
+}
 
 void sa_gpu_set_error(const char *fmt, ...)
 {
@@ -40,7 +155,28 @@ extern "C" int sa_gpu_ctx_create(int device, sa_gpu_ctx **out)
     ctx->num_sms = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
     ctx->smem_per_sm = prop.sharedMemPerMultiprocessor;
-    SA_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    // Device memory is allocated and freed in stream order on the context's main stream, so a
+    // buffer is never recycled while a kernel still uses it.  The allocation stream is a process
+    // global (DevBuf has no context pointer): contexts created while another one is alive share
+    // its main stream (same device only), and the stream goes away with the last of them.
+    if (g_sa_alloc_refs > 0)
+    {
+        if (g_sa_alloc_device != device)
+        {
+            delete ctx;
+            SA_FAIL("sa_gpu_ctx_create: a context on device %d is alive; this process cannot open "
+                    "another one on device %d (one device per process)", g_sa_alloc_device, device);
+        }
+        ctx->stream = g_sa_alloc_stream;
+    }
+    else
+    {
+        SA_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        g_sa_alloc_stream = ctx->stream;
+        g_sa_alloc_device = device;
+        arena_create(device);
+    }
+    ++g_sa_alloc_refs;
     SA_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     SA_CUDA(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
     for (int i = 0; i < sa_gpu_ctx::NAUX; ++i)
@@ -57,14 +193,14 @@ extern "C" int sa_gpu_ctx_create(int device, sa_gpu_ctx **out)
         int supported = 0;
         cudaDeviceGetAttribute(&supported, cudaDevAttrMemoryPoolsSupported, device);
         const char *na = getenv("SA_GPU_NO_ASYNC_ALLOC");
-        if (supported && !(na && na[0] == '1') && !g_sa_alloc_async)
+        g_sa_alloc_async = false;
+        if (supported && !(na && na[0] == '1'))
         {
             cudaMemPool_t pool;
             if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
             {
                 unsigned long long thr = ~0ull;
                 cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-                g_sa_alloc_stream = ctx->stream;
                 g_sa_alloc_async = true;
             }
         }
@@ -84,11 +220,26 @@ extern "C" void sa_gpu_ctx_destroy(sa_gpu_ctx *ctx)
         cudaEventDestroy(ctx->ev0);
     if (ctx->ev1)
         cudaEventDestroy(ctx->ev1);
-    if (ctx->stream == g_sa_alloc_stream)
+    if (ctx->pev0)
+        cudaEventDestroy(ctx->pev0);
+    if (ctx->pev1)
+        cudaEventDestroy(ctx->pev1);
+    // work arrays first (stream-ordered frees need the stream)
+    ctx->sws.~SpectralWs();
+    new (&ctx->sws) SpectralWs();
+    bool last = false;
+    if (ctx->stream)
     {
-        // buffers that outlive the context fall back to synchronous frees on the null stream
         cudaStreamSynchronize(ctx->stream);
-        g_sa_alloc_stream = nullptr;
+        if (--g_sa_alloc_refs <= 0)
+        {
+            // buffers that outlive the last context are freed with cudaFree (DevBuf::release)
+            g_sa_alloc_refs = 0;
+            g_sa_alloc_stream = nullptr;
+            g_sa_alloc_async = false;
+            last = true;
+            arena_destroy();
+        }
     }
     if (ctx->copy_stream)
         cudaStreamDestroy(ctx->copy_stream);
@@ -101,7 +252,7 @@ extern "C" void sa_gpu_ctx_destroy(sa_gpu_ctx *ctx)
     }
     if (ctx->fork_ev)
         cudaEventDestroy(ctx->fork_ev);
-    if (ctx->stream)
+    if (ctx->stream && last)
         cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

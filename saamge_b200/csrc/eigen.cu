@@ -583,7 +583,8 @@ k_at_smem(LevelTables L, ChunkDev C, const int *slot_list, double *ae_D)
 
 // one thread per slot: number of eigenvalues in (-1, theta] and search bounds
 __global__ void k_count(ChunkDev C, const int *AE2d_I, int nslots, double theta, int inject_ae0,
-                        int *nev, int *m_total, double *glo, double *ghi, double *tnorm_out)
+                        int *nev, int *m_total, double *glo, double *ghi, double *tnorm_out,
+                        int *borderline)
 {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= nslots)
@@ -607,6 +608,30 @@ __global__ void k_count(ChunkDev C, const int *AE2d_I, int nslots, double theta,
     gu = gu + 2.1 * tn * DBL_EPSILON * n + 2.1 * pivmin;
     // e2 is kept in tau's place?  no: squared on the fly in the bisection kernel
     int cnt_hi = 0, cnt_lo = 0;
+    {
+        // guard band of the decision m = #{lambda <= theta} (amg/src/xpacks.cpp:233-234): Sturm
+        // counts at theta -+ 1e-12 differ iff an eigenvalue lies within 1e-12 of theta, where a
+        // different (equally accurate) eigensolver may count differently.  Reported only.
+        const double tb = 1e-12 * fmax(1., fabs(theta));
+        double qa = d[0] - (theta - tb), qb = d[0] - (theta + tb);
+        int ca = 0, cb = 0;
+        if (fabs(qa) < pivmin) qa = -pivmin;
+        if (fabs(qb) < pivmin) qb = -pivmin;
+        ca += (qa <= 0.);
+        cb += (qb <= 0.);
+        for (int i = 1; i < n; ++i)
+        {
+            const double e2 = e[i - 1] * e[i - 1];
+            qa = d[i] - e2 / qa - (theta - tb);
+            qb = d[i] - e2 / qb - (theta + tb);
+            if (fabs(qa) < pivmin) qa = -pivmin;
+            if (fabs(qb) < pivmin) qb = -pivmin;
+            ca += (qa <= 0.);
+            cb += (qb <= 0.);
+        }
+        if (ca != cb)
+            atomicAdd(borderline, 1);
+    }
     {
         // counts with e^2 formed on the fly
         double q = d[0] - theta, ql = d[0] - (-1.);
@@ -1071,6 +1096,8 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         lev->h_ae_nev.assign(nparts, 0);
     }
     lev->ae_D.ensure(AI[nparts]);
+    lev->borderline.ensure(2);
+    SA_CUDA(cudaMemsetAsync(lev->borderline.p, 0, sizeof(int), st));
 
     // chunks of consecutive AEs bounded by the reflector storage budget
     // (measured: smaller chunks do not pay -- 128^3 level 1 takes 5.6 s in one 9 GB chunk, 6.0 s in
@@ -1730,7 +1757,7 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         {
             ProfScope ps(ctx, "eig.count");
             SA_LAUNCH(ctx, k_count, (ns + 127) / 128, 128, 0, C, lev->AE2d_I.p, ns, theta,
-                      inject_ones_ae0, d_nev.p, d_mtot.p, d_glo.p, d_ghi.p, d_tn.p);
+                      inject_ones_ae0, d_nev.p, d_mtot.p, d_glo.p, d_ghi.p, d_tn.p, lev->borderline.p);
         }
         PieceResult *pr = new PieceResult;
         pieces.push_back(pr);
@@ -2056,6 +2083,22 @@ extern "C" int sa_gpu_set_spectral(sa_gpu_level *lev, int ae_begin, int ae_end, 
     }
     else
         SA_FAIL("sa_gpu_set_spectral: only the full range is supported");
+    SA_API_END
+}
+
+extern "C" int sa_gpu_get_borderline(sa_gpu_level *lev, int *theta_borderline, int *rank_borderline)
+{
+    SA_API_BEGIN
+    int h[2] = {0, 0};
+    if (lev->borderline.p)
+    {
+        lev->borderline.download(h, 2, lev->ctx->stream);
+        SA_CUDA(cudaStreamSynchronize(lev->ctx->stream));
+    }
+    if (theta_borderline)
+        *theta_borderline = h[0];
+    if (rank_borderline)
+        *rank_borderline = lev->have_tent ? h[1] : 0;
     SA_API_END
 }
 

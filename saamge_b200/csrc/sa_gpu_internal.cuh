@@ -50,8 +50,19 @@ void sa_gpu_set_error(const char *fmt, ...);
 /* stream used for stream-ordered allocation (set by sa_gpu_ctx_create; one context per
    process is the expected use).  With a pool release threshold of "never", cudaMallocAsync /
    cudaFreeAsync recycle device memory without the cost of cudaMalloc / cudaFree. */
-extern cudaStream_t g_sa_alloc_stream;
-extern bool g_sa_alloc_async;
+extern cudaStream_t g_sa_alloc_stream; // main stream of the live context(s); nullptr when none
+extern bool g_sa_alloc_async;          // stream-ordered pool in use
+extern int g_sa_alloc_device, g_sa_alloc_refs;
+
+/* Device arena (capi.cu): one slab reserved when the first context is created; DevBuf takes its
+   memory from it with a first-fit free list.  The stream-ordered pool of the driver was measured
+   to take 0.1 - 1 s for single multi-GB requests at unpredictable points of a hierarchy build
+   (growing / re-mapping the pool); sub-allocating a slab costs microseconds.  Safe for the same
+   reason the pool was: every kernel that touches a DevBuf is ordered on the one main stream, so a
+   block handed out again is only written by work queued after the work that used it before.
+   Requests the arena cannot serve fall back to the pool.  SA_GPU_ARENA_GB=0 disables it. */
+void *sa_arena_alloc(size_t bytes);       // nullptr: not served
+bool sa_arena_free(void *p);              // false: not an arena pointer
 
 template <class T> struct DevBuf
 {
@@ -67,7 +78,10 @@ template <class T> struct DevBuf
     {
         if (p)
         {
-            if (async_owned)
+            if (arena_owned)
+                sa_arena_free(p);
+            // (no live context: plain cudaFree, which is valid for pool memory and synchronises)
+            else if (async_owned && g_sa_alloc_stream)
                 cudaFreeAsync(p, g_sa_alloc_stream);
             else
                 cudaFree(p);
@@ -75,13 +89,21 @@ template <class T> struct DevBuf
         p = nullptr;
         n = 0;
         cap = 0;
+        arena_owned = false;
     }
+    bool arena_owned = false;
     void alloc(size_t count)
     {
         release();
         n = count;
         cap = count;
-        if (g_sa_alloc_async)
+        if ((p = (T *)sa_arena_alloc((count ? count : 1) * sizeof(T))) != nullptr)
+        {
+            arena_owned = true;
+            async_owned = false;
+            return;
+        }
+        if (g_sa_alloc_async && g_sa_alloc_stream)
         {
             const size_t bytes = (count ? count : 1) * sizeof(T);
             static const bool dbg = getenv("SA_GPU_ALLOC_DEBUG") != NULL;
@@ -129,6 +151,7 @@ template <class T> struct DevBuf
         std::swap(n, o.n);
         std::swap(cap, o.cap);
         std::swap(async_owned, o.async_owned);
+        std::swap(arena_owned, o.arena_owned);
     }
 };
 
@@ -339,6 +362,10 @@ struct sa_gpu_level
     DevBuf<int64_t> evect_off, eval_off;
     DevBuf<double> evals, evects, ae_D;  // ae_D offsets = AE2d_I
     double max_residual = 0.;
+    // [0]: AEs with an eigenvalue within 1e-12 of theta, [1]: MISes with a singular value within
+    // 10x of the rank cut (decisions made on round-off; reported, not altered)
+    DevBuf<int> borderline;
+    int h_theta_borderline = 0;
     // tentative P
     bool have_tent = false;
     int avoid_ess = 1;

@@ -13,6 +13,11 @@ struct SolverLevel
 {
     sa_gpu_level *lev = nullptr;
     DevBuf<double> b, xa, xb, r; // rhs, ping/pong iterate, residual (size ND of the level)
+    // user smoothers (smpr_ft plug, amg/inc/smpr.hpp:59-60): host callbacks; NULL = the fused
+    // device SAS polynomial smoother
+    sa_gpu_smoother_ft pre = nullptr, post = nullptr;
+    void *smoother_data = nullptr;
+    std::vector<double> hb, hx;
 };
 
 struct sa_gpu_solver
@@ -306,9 +311,26 @@ double *dev_vcycle(sa_gpu_solver *S, int l)
     sa_gpu_level *lev = SL.lev;
     const DevCsr &A = *lev->A;
     double *xcur = SL.xa.p, *xalt = SL.xb.p;
+    const int nl = lev->ND;
+    // a user smoother runs on the host: vectors go down and the iterate comes back (slow path,
+    // there for API completeness; the default never leaves the device)
+    auto host_smooth = [&](sa_gpu_smoother_ft f, bool x_is_zero) {
+        cudaStream_t st = ctx->stream;
+        SL.hb.resize(nl);
+        SL.hx.assign(nl, 0.);
+        SL.b.download(SL.hb.data(), nl, st);
+        if (!x_is_zero)
+            SA_CUDA(cudaMemcpyAsync(SL.hx.data(), xcur, (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, st));
+        SA_CUDA(cudaStreamSynchronize(st));
+        f(l, nl, SL.hb.data(), SL.hx.data(), SL.smoother_data);
+        SA_CUDA(cudaMemcpyAsync(xcur, SL.hx.data(), (size_t)nl * sizeof(double), cudaMemcpyHostToDevice, st));
+    };
     // x = 0 (iterative_mode == false); pre-smoother
-    dev_poly_smooth(ctx, A, lev->Dinv_neg.p, SL.b.p, &xcur, &xalt, S->degree, S->roots.data(),
-                    true);
+    if (SL.pre)
+        host_smooth(SL.pre, true);
+    else
+        dev_poly_smooth(ctx, A, lev->Dinv_neg.p, SL.b.p, &xcur, &xalt, S->degree, S->roots.data(),
+                        true);
     // res = b - A x ; resc = restr * res
     dev_residual(ctx, A, xcur, SL.b.p, SL.r.p);
     double *xc = nullptr;
@@ -327,8 +349,11 @@ double *dev_vcycle(sa_gpu_solver *S, int l)
     // x += interp * xc
     dev_spmv_add(ctx, lev->P, xc, xcur);
     // post-smoother
-    dev_poly_smooth(ctx, A, lev->Dinv_neg.p, SL.b.p, &xcur, &xalt, S->degree, S->roots.data(),
-                    false);
+    if (SL.post)
+        host_smooth(SL.post, false);
+    else
+        dev_poly_smooth(ctx, A, lev->Dinv_neg.p, SL.b.p, &xcur, &xalt, S->degree, S->roots.data(),
+                        false);
     return xcur;
 }
 
@@ -463,6 +488,18 @@ extern "C" int sa_gpu_solver_create(sa_gpu_ctx *ctx, sa_gpu_level **levels, int 
 }
 
 extern "C" void sa_gpu_solver_destroy(sa_gpu_solver *S) { delete S; }
+
+extern "C" int sa_gpu_solver_set_smoothers(sa_gpu_solver *S, int level, sa_gpu_smoother_ft pre,
+                                           sa_gpu_smoother_ft post, void *data)
+{
+    SA_API_BEGIN
+    if (level < 0 || level >= (int)S->L.size())
+        SA_FAIL("sa_gpu_solver_set_smoothers: bad level %d", level);
+    S->L[level]->pre = pre;
+    S->L[level]->post = post;
+    S->L[level]->smoother_data = data;
+    SA_API_END
+}
 
 extern "C" int sa_gpu_vcycle(sa_gpu_solver *S, const double *b, double *x)
 {

@@ -39,7 +39,7 @@ struct MisWork
 };
 
 __global__ void k_mis_svd(LevelTables L, MisWork W, const int *ae_m, const int64_t *evect_off,
-                          const double *evects, int avoid_ess, int nmis)
+                          const double *evects, int avoid_ess, int nmis, int *borderline)
 {
     const int lane = threadIdx.x & 31;
     const int mis = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -180,7 +180,7 @@ __global__ void k_mis_svd(LevelTables L, MisWork W, const int *ae_m, const int64
     }
     // xpack_orth_set: keep sigma_i > eps * sigma_0; at most min(s, c) singular values exist
     const double cut = 1.e-10 * smax;
-    int k = 0;
+    int k = 0, near = 0;
     for (int q = 0; q < c; ++q)
     {
         const double *xq = X + (int64_t)s * q;
@@ -190,7 +190,13 @@ __global__ void k_mis_svd(LevelTables L, MisWork W, const int *ae_m, const int64
         a = sqrt(wsum(a));
         if (a > cut)
             ++k;
+        // guard band: a singular value within a factor 10 of the rank cut decides the number of
+        // coarse dofs on round-off (reported through sa_gpu_get_borderline, not altered)
+        if (a > 0.1 * cut && a <= 10. * cut)
+            near = 1;
     }
+    if (near && lane == 0)
+        atomicAdd(borderline, 1);
     k = min(k, min(s, c));
     if (lane == 0)
     {
@@ -405,8 +411,10 @@ extern "C" int sa_gpu_tentative_P(sa_gpu_level *lev, int avoid_ess_bdr_dofs,
     W.ncols = d_ncols.p;
     W.ncd = lev->mis_ncd.p;
     const int wpb = 4;
+    lev->borderline.ensure(2);
+    SA_CUDA(cudaMemsetAsync(lev->borderline.p + 1, 0, sizeof(int), st));
     SA_LAUNCH(ctx, k_mis_svd, (nmis + wpb - 1) / wpb, wpb * 32, 0, L, W, lev->ae_m.p,
-              lev->evect_off.p, lev->evects.p, avoid_ess_bdr_dofs, nmis);
+              lev->evect_off.p, lev->evects.p, avoid_ess_bdr_dofs, nmis, lev->borderline.p + 1);
     lev->h_mis_ncd.resize(nmis);
     lev->mis_ncd.download(lev->h_mis_ncd.data(), nmis, st);
     SA_CUDA(cudaStreamSynchronize(st));
@@ -561,6 +569,26 @@ extern "C" int sa_gpu_coarse_elmats(sa_gpu_level *finer, sa_gpu_level *coarse)
         SA_LAUNCH(ctx, k_coarse_elmat, blocks, 256, smem, L, C, 0, nparts, 0);
     SA_CUDA(cudaStreamSynchronize(st));
     coarse->have_elmat = true;
+    SA_API_END
+}
+
+extern "C" int sa_gpu_get_element_matrix(sa_gpu_level *lev, int elno, double *out, int *ne_out)
+{
+    SA_API_BEGIN
+    sa_level_ready(lev);
+    if (!lev->have_elmat)
+        SA_FAIL("sa_gpu_get_element_matrix: the level has no element matrices");
+    if (elno < 0 || elno >= lev->NE)
+        SA_FAIL("sa_gpu_get_element_matrix: bad element index %d", elno);
+    const int ne = lev->h_e2d_I[elno + 1] - lev->h_e2d_I[elno];
+    if (ne_out)
+        *ne_out = ne;
+    if (out)
+    {
+        SA_CUDA(cudaMemcpyAsync(out, lev->elmat.p + lev->h_elmat_off[elno], (size_t)ne * ne * sizeof(double),
+                                cudaMemcpyDeviceToHost, lev->ctx->stream));
+        SA_CUDA(cudaStreamSynchronize(lev->ctx->stream));
+    }
     SA_API_END
 }
 

@@ -135,25 +135,50 @@ ElementMatrixParallelCoarse::ElementMatrixParallelCoarse(
     is_geometric = false;
 }
 
-Matrix *ElementMatrixParallelCoarse::GetMatrix(int elno, bool &free_matr) const
+/* The level whose ELEMENTS these matrices are is the coarser neighbour of `level` (the finer
+   level the provider was built from, amg/src/elmat.cpp:105-130); its device handle holds the
+   blocks sa_gpu_coarse_elmats produced. */
+static sa_gpu_level *coarse_gpu_level(const levels_level_t *finer_level)
 {
-    (void)elno;
-    (void)free_matr;
-    // the blocks exist only on the device of the coarse level; read them back with
-    // sa_gpu_get_coarse_elmats (tg_download_results does).
-    std::fprintf(stderr, "ASSERT: ElementMatrixParallelCoarse::GetMatrix: element matrices are "
-                         "device resident; use tg_download_results\n");
-    std::abort();
-    return NULL;
+    SA_ASSERT(finer_level && finer_level->coarser && finer_level->coarser->tg_data &&
+              finer_level->coarser->tg_data->gpu);
+    return finer_level->coarser->tg_data->gpu;
 }
 
+// amg/src/elmat.cpp:105-195: the coarse element matrix P_e^T A_AE(e) P_e of finer AE elno, read
+// back from the device (caller frees: free_matr = true, amg/src/elmat.cpp:177)
+Matrix *ElementMatrixParallelCoarse::GetMatrix(int elno, bool &free_matr) const
+{
+    sa_gpu_level *g = coarse_gpu_level(level);
+    int ne = 0;
+    sa_gpu_check(sa_gpu_get_element_matrix(g, elno, NULL, &ne), "sa_gpu_get_element_matrix");
+    DenseMatrix *M = new DenseMatrix(ne, ne);
+    sa_gpu_check(sa_gpu_get_element_matrix(g, elno, M->Data(), &ne), "sa_gpu_get_element_matrix");
+    free_matr = true;
+    return M;
+}
+
+// agg_build_AE_stiffm of coarse AE elno (amg/src/aggregates.cpp:959-1086), assembled on the device
 SparseMatrix *ElementMatrixParallelCoarse::BuildAEStiff(int elno) const
 {
-    (void)elno;
-    std::fprintf(stderr, "ASSERT: ElementMatrixParallelCoarse::BuildAEStiff: use the level's "
-                         "sa_gpu_build_AE_stiff\n");
-    std::abort();
-    return NULL;
+    sa_gpu_level *g = coarse_gpu_level(level);
+    const int n = agg_part_rels.AE_to_dof->RowSize(elno);
+    std::vector<double> dense((size_t)n * n);
+    sa_gpu_check(sa_gpu_build_AE_stiff(g, elno, dense.data()), "sa_gpu_build_AE_stiff");
+    SparseMatrix *S = new SparseMatrix;
+    S->h = S->w = n;
+    S->I.assign((size_t)n + 1, 0);
+    for (int i = 0; i < n; ++i)
+    {
+        for (int j = 0; j < n; ++j)
+            if (dense[(size_t)j * n + i] != 0.)
+            {
+                S->J.push_back(j);
+                S->A.push_back(dense[(size_t)j * n + i]);
+            }
+        S->I[i + 1] = (int)S->J.size();
+    }
+    return S;
 }
 
 static void fill_desc(sa_gpu_level_desc &d, const agg_partitioning_relations_t &r)
@@ -323,9 +348,9 @@ tg_data_t *tg_init_data(const SparseMatrix *A, const agg_partitioning_relations_
                         int nu_pro, int nu_relax, double theta, bool smooth_interp,
                         double smooth_drop_tol, bool use_arpack)
 {
-    (void)A;
     tg_data_t *tg_data = new tg_data_t;
     std::memset(tg_data, 0, sizeof(*tg_data));
+    tg_data->A_host = A; // (NULL on coarse levels: read back on demand)
     tg_data->theta = theta;
     interp_data_t *id = new interp_data_t;
     std::memset(id, 0, sizeof(*id));
@@ -447,6 +472,49 @@ void tg_build_hierarchy(const SparseMatrix *Ag, tg_data_t &tg_data,
     d.elmat = elem_data->DenseBlocks();
     d.elmat_off = elem_data->DenseBlockOffsets();
     d.assemble_with_global = elem_data->AssembledMatrix() ? 1 : 0;
+    // A provider that only implements the reference contract (GetMatrix / BuildAEStiff,
+    // amg/inc/elmat.hpp:53-77) has no batched view: pack its element matrices into one
+    // contiguous array by calling GetMatrix(e, free_matr) for every element -- the only place
+    // the callback runs, on the host, before any kernel launch (amg/inc/elmat.hpp:32-35).
+    std::vector<double> packed;
+    std::vector<int64_t> packed_off;
+    if (!d.elmat && !finer)
+    {
+        const int NE = d.NE;
+        packed_off.assign((size_t)NE + 1, 0);
+        for (int e = 0; e < NE; ++e)
+        {
+            const int ne = agg_part_rels.elem_to_dof->RowSize(e);
+            packed_off[e + 1] = packed_off[e] + (int64_t)ne * ne;
+        }
+        packed.assign((size_t)packed_off[NE], 0.);
+        for (int e = 0; e < NE; ++e)
+        {
+            bool free_matr = false;
+            Matrix *M = elem_data->GetMatrix(e, free_matr);
+            SA_ASSERT(M);
+            const int ne = agg_part_rels.elem_to_dof->RowSize(e);
+            double *dst = packed.data() + packed_off[e];
+            if (const DenseMatrix *D = dynamic_cast<const DenseMatrix *>(M))
+            {
+                SA_ASSERT(D->Height() == ne && D->Width() == ne);
+                std::memcpy(dst, D->Data(), sizeof(double) * ne * ne);
+            }
+            else if (const SparseMatrix *S = dynamic_cast<const SparseMatrix *>(M))
+            {
+                SA_ASSERT(S->Height() == ne && S->Width() == ne);
+                for (int i = 0; i < ne; ++i)
+                    for (int q = S->I[i]; q < S->I[i + 1]; ++q)
+                        dst[(size_t)S->J[q] * ne + i] += S->A[q];
+            }
+            else
+                SA_ASSERT(!"ElementMatrixProvider::GetMatrix returned an unknown matrix type");
+            if (free_matr)
+                delete M;
+        }
+        d.elmat = packed.data();
+        d.elmat_off = packed_off.data();
+    }
     if (tg_data.gpu)
         sa_gpu_level_destroy(tg_data.gpu);
     tg_data.gpu = NULL;
@@ -522,6 +590,7 @@ void tg_free_data(tg_data_t *tg_data)
         delete tg_data->interp_data;
     }
     sa_gpu_level_destroy(tg_data->gpu);
+    delete tg_data->A_host_owned;
     delete tg_data->elem_data; // tg_data takes ownership (amg/src/tg.cpp:518,946)
     delete tg_data;
 }
@@ -685,6 +754,51 @@ void ml_impose_cycle(ml_data_t &ml_data, bool Wcycle)
     sa_gpu_check(sa_gpu_solver_create(proc_gpu_ctx(), levels.data(), (int)levels.size(),
                                       ml_data.nu_relax, &ml_data.gpu_solver),
                  "sa_gpu_solver_create");
+    // user smoothers (tg_data_t::pre_smoother / post_smoother): host callbacks through a trampoline
+    i = 0;
+    for (levels_level_t *level = ml_data.levels_list.finest; level; level = level->coarser, ++i)
+    {
+        tg_data_t *tg = level->tg_data;
+        if (!tg->pre_smoother && !tg->post_smoother)
+            continue;
+        if (!tg->A_host)
+        {
+            // the operator of a coarse level lives on the device: read it back once
+            int rows = 0, cols = 0, nnz = 0;
+            sa_gpu_check(sa_gpu_get_csr_sizes(tg->gpu, SA_GPU_MAT_A, &rows, &cols, &nnz), "sa_gpu_get_csr_sizes");
+            SparseMatrix *A = new SparseMatrix;
+            A->h = rows;
+            A->w = cols;
+            A->I.resize((size_t)rows + 1);
+            A->J.resize(std::max(1, nnz));
+            A->A.resize(std::max(1, nnz));
+            sa_gpu_check(sa_gpu_get_csr(tg->gpu, SA_GPU_MAT_A, A->I.data(), A->J.data(), A->A.data()), "sa_gpu_get_csr");
+            A->J.resize(nnz);
+            A->A.resize(nnz);
+            tg->A_host_owned = A;
+            tg->A_host = A;
+        }
+        struct tramp
+        {
+            static void pre(int, int n, const double *b, double *x, void *data)
+            {
+                tg_data_t *t = (tg_data_t *)data;
+                Vector vb(b, b + n), vx(x, x + n);
+                t->pre_smoother(*t->A_host, vb, vx, t->smoother_data);
+                std::copy(vx.begin(), vx.end(), x);
+            }
+            static void post(int, int n, const double *b, double *x, void *data)
+            {
+                tg_data_t *t = (tg_data_t *)data;
+                Vector vb(b, b + n), vx(x, x + n);
+                t->post_smoother(*t->A_host, vb, vx, t->smoother_data);
+                std::copy(vx.begin(), vx.end(), x);
+            }
+        };
+        sa_gpu_check(sa_gpu_solver_set_smoothers(ml_data.gpu_solver, i, tg->pre_smoother ? tramp::pre : NULL,
+                                                 tg->post_smoother ? tramp::post : NULL, tg),
+                     "sa_gpu_solver_set_smoothers");
+    }
 }
 
 // amg/src/ml.cpp:379-472

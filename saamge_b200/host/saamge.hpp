@@ -131,6 +131,11 @@ double *smpr_sas_poly_roots(int &nu, int *degree);
 
 class VCycleSolver;
 
+/*! Smoother plug (amg/inc/smpr.hpp:59-60): x <- relax(A, b, x); \a data is whatever the caller
+    stored in tg_data_t::smoother_data (the reference passes tg_data->poly_data).  \a A is the
+    operator of the level (read back from the device on coarse levels, cached). */
+typedef void (*smpr_ft)(const SparseMatrix &A, const Vector &b, Vector &x, void *data);
+
 typedef struct
 {
     interp_data_t *interp_data;
@@ -145,6 +150,13 @@ typedef struct
     int tag;
     ElementMatrixProvider *elem_data;
     bool have_Ac;
+    /*! tg_data_t::pre_smoother / post_smoother (amg/inc/tg_data.hpp:68-69).  NULL (default) =
+        smpr_sym_poly, the SAS polynomial smoother, fused on the device; anything else is called
+        on the host by the V-cycle (ml_impose_cycle installs it). */
+    smpr_ft pre_smoother, post_smoother;
+    void *smoother_data;
+    const SparseMatrix *A_host; /*!< operator of the level for user smoothers (finest: the caller's) */
+    SparseMatrix *A_host_owned;
 } tg_data_t;
 
 typedef struct levels_level_struct

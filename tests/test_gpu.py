@@ -387,3 +387,24 @@ def test_properties_at_full_size():
         Aprev = Ac
     Hg.close()
     pr.close()
+
+
+def test_contexts_can_be_reopened_and_share_the_allocation_stream():
+    """the stream-ordered allocator must survive a context being destroyed and
+    another one created (test fixtures do exactly that), and a second live context must not
+    allocate on a stream its kernels do not run on."""
+    pr, p = _problem()
+    for _ in range(3):
+        c1 = cabi.Context(0)
+        c2 = cabi.Context(0)  # alive at the same time: shares c1's main stream
+        l1, l2 = cabi.Level(c1, pr), cabi.Level(c2, pr)
+        l1.local_spectral(0.003)
+        l2.local_spectral(0.003)
+        a, b = l1.spectral(), l2.spectral()
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+        l1.close()
+        c1.close()  # the survivor keeps working
+        l2.local_spectral(0.003)
+        l2.close()
+        c2.close()
+    pr.close()
