@@ -2002,6 +2002,15 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
             SA_FAIL("sa_gpu_local_spectral: non-finite eigenvector entries");
     }
     lev->have_spectral = true;
+    if (ctx->profile && getenv("SA_GPU_SPECTRAL_DEBUG"))
+    {
+        // per-call stage profile (diagnostics): printed and cleared
+        fprintf(stderr, "[spectral] nparts %d range %d..%d nmax %d:", nparts, ae_begin, ae_end, range_nmax);
+        for (size_t i = 0; i < ctx->prof.size(); ++i)
+            fprintf(stderr, " %s %.1f", ctx->prof[i].first.c_str(), ctx->prof[i].second);
+        fprintf(stderr, "\n");
+        ctx->prof.clear();
+    }
     SA_API_END
 }
 

@@ -33,6 +33,7 @@ struct sa_gpu_solver
     // PCG work vectors on level 0
     DevBuf<double> pb, px, pr, pd, pz;
     DevBuf<double> dots; // device scalars
+    DevBuf<double> dot_partials; // per-block partial sums of k_dot (fixed summation order)
     ~sa_gpu_solver()
     {
         for (size_t i = 0; i < L.size(); ++i)
@@ -254,8 +255,20 @@ __global__ void k_dot(int n, const double *a, const double *b, double *out)
         for (int o = 16; o > 0; o >>= 1)
             t += __shfl_xor_sync(0xffffffffu, t, o);
         if (threadIdx.x == 0)
-            atomicAdd(out, t);
+            out[blockIdx.x] = t; // per-block partial; summed in block order by k_dot_final
     }
+}
+
+// deterministic second pass: one warp adds the block partials in a fixed order
+__global__ void k_dot_final(int nblocks, const double *partials, double *out)
+{
+    double s = 0.;
+    for (int i = threadIdx.x; i < nblocks; i += 32)
+        s += partials[i];
+    for (int o = 16; o > 0; o >>= 1)
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0)
+        *out = s;
 }
 
 // x += alpha d ; r -= alpha z
@@ -281,9 +294,10 @@ __global__ void k_pcg_dir(int n, double beta, const double *z, double *d)
 double dev_dot(sa_gpu_solver *S, int n, const double *a, const double *b)
 {
     sa_gpu_ctx *ctx = S->ctx;
-    SA_CUDA(cudaMemsetAsync(S->dots.p, 0, sizeof(double), ctx->stream));
     const int blocks = std::max(1, std::min(ctx->num_sms * 4, (n + 255) / 256));
-    SA_LAUNCH(ctx, k_dot, blocks, 256, 0, n, a, b, S->dots.p);
+    S->dot_partials.ensure(blocks);
+    SA_LAUNCH(ctx, k_dot, blocks, 256, 0, n, a, b, S->dot_partials.p);
+    SA_LAUNCH(ctx, k_dot_final, 1, 32, 0, blocks, S->dot_partials.p, S->dots.p);
     double h = 0.;
     SA_CUDA(cudaMemcpyAsync(&h, S->dots.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     SA_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -1267,7 +1267,10 @@ void sa_ts_reduce(sa_gpu_ctx *ctx, const sa_ts_mat *d_mats, int nmats, int nmax,
         // (measured at 630 matrices of n ~ 2000: teams of 5 blocks, which would keep the bands
         // of the matrices in flight in L2, are 40 % slower than one block per matrix -- passing
         // the band between SMs costs more than streaming it from HBM)
-        const int cap = 2 * ctx->num_sms;
+        // blocks in flight: every chase step re-reads what the previous sweep wrote two steps earlier,
+        // so the reuse distance is (warps in flight) x 24 KB x 2 -- SA_GPU_TS_S2_BPS (blocks per SM)
+        const int bps = getenv("SA_GPU_TS_S2_BPS") ? std::max(1, std::min(2, atoi(getenv("SA_GPU_TS_S2_BPS")))) : 2;
+        const int cap = bps * ctx->num_sms;
         int G = std::max(1, std::min(8, cap / nmats));
         G = std::min(G, std::max(1, (nmax / (2 * TS_B) + TS_S2_NW - 1) / TS_S2_NW)); // useful concurrency
         const int nteams = std::min(nmats, cap / G);

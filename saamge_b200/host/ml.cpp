@@ -263,6 +263,125 @@ static SparseMatrix *build_AE_stiff_on_device(const agg_partitioning_relations_t
     return S;
 }
 
+/* ------------------------------------------------------------------ Eigensolver */
+
+Eigensolver::Eigensolver(const int *aggregates, const agg_partitioning_relations_t &agg_part_rels,
+                         int threshold)
+    : agg_part_rels(agg_part_rels), threshold(threshold), count_solves(0), count_direct_solves(0),
+      count_max_used(0), smallest_eigenvalue_skipped(1.)
+{
+    (void)aggregates;
+}
+
+void Eigensolver::GetStatistics(int &o_count_solves, int &o_count_direct_solves, int &o_count_max_used,
+                                double &o_smallest_eigenvalue_skipped)
+{
+    o_count_solves = count_solves;
+    o_count_direct_solves = count_direct_solves;
+    o_count_max_used = count_max_used;
+    o_smallest_eigenvalue_skipped = smallest_eigenvalue_skipped;
+}
+
+bool Eigensolver::Solve(const SparseMatrix &A, SparseMatrix *&B, int part, int agg_id, int aggregate_size,
+                        double &theta, DenseMatrix &cut_evects)
+{
+    (void)part;
+    (void)agg_id;
+    (void)aggregate_size;
+    const int n = A.Width();
+    SA_ASSERT(A.Width() == A.Size());
+    SA_ASSERT(theta >= 0. && theta <= 1. + 1e-12);
+    count_solves++;
+    count_direct_solves++; // the device path is always direct (no ARPACK)
+    // a level of one AE whose single element is the whole matrix
+    std::vector<int> I01(2), iota(n), zerosI((size_t)n + 1), zeros(std::max(1, n), 0), onesI((size_t)n + 1);
+    I01[0] = 0;
+    I01[1] = n;
+    for (int i = 0; i < n; ++i)
+        iota[i] = i;
+    for (int i = 0; i <= n; ++i)
+        onesI[i] = i;
+    std::vector<char> flags(std::max(1, n), 0);
+    std::vector<double> dense((size_t)n * n, 0.);
+    for (int i = 0; i < n; ++i)
+        for (int q = A.I[i]; q < A.I[i + 1]; ++q)
+            dense[(size_t)A.J[q] * n + i] = A.A[q];
+    const int64_t eoff[2] = {0, (int64_t)n * n};
+    const int one01[2] = {0, 1};
+    const int zero1[1] = {0};
+    sa_gpu_level_desc d;
+    std::memset(&d, 0, sizeof d);
+    d.ND = n;
+    d.NE = 1;
+    d.nparts = 1;
+    d.num_mises = 1;
+    d.elem_to_dof_I = I01.data();
+    d.elem_to_dof_J = iota.data();
+    d.dof_to_elem_I = onesI.data();
+    d.dof_to_elem_J = zeros.data();
+    d.AE_to_elem_I = one01;
+    d.AE_to_elem_J = zero1;
+    d.AE_to_dof_I = I01.data();
+    d.AE_to_dof_J = iota.data();
+    d.dof_to_AE_I = onesI.data();
+    d.dof_to_AE_J = zeros.data();
+    d.dof_id_inAE = iota.data();
+    d.partitioning = zero1;
+    d.agg_flags = flags.data();
+    d.mis_to_dof_I = I01.data();
+    d.mis_to_dof_J = iota.data();
+    d.mis_to_AE_I = one01;
+    d.mis_to_AE_J = zero1;
+    d.AE_to_mis_I = one01;
+    d.AE_to_mis_J = zero1;
+    d.mises = zeros.data();
+    // (an operator is only read in with_global mode; give the level an empty one)
+    d.A_I = zerosI.data();
+    d.A_J = zeros.data();
+    static const double zero = 0.;
+    d.A_data = &zero;
+    d.elmat = dense.data();
+    d.elmat_off = eoff;
+    d.assemble_with_global = 0;
+    sa_gpu_level *lev = NULL;
+    sa_gpu_check(sa_gpu_level_create(proc_gpu_ctx(), &d, NULL, &lev), "sa_gpu_level_create");
+    sa_gpu_check(sa_gpu_local_spectral(lev, theta, 0, 1, 0), "sa_gpu_local_spectral");
+    int m = 0;
+    sa_gpu_check(sa_gpu_get_spectral_counts(lev, &m), "sa_gpu_get_spectral_counts");
+    last_evals.assign(m, 0.);
+    std::vector<double> Z((size_t)n * m), D(n);
+    sa_gpu_check(sa_gpu_get_spectral(lev, last_evals.data(), Z.data(), D.data()), "sa_gpu_get_spectral");
+    sa_gpu_level_destroy(lev);
+    if (!B)
+    {
+        B = new SparseMatrix;
+        B->h = B->w = n;
+        B->I.resize((size_t)n + 1);
+        B->J.resize(n);
+        B->A.resize(n);
+        for (int i = 0; i < n; ++i)
+        {
+            B->I[i] = B->J[i] = i;
+            B->A[i] = D[i];
+        }
+        B->I[n] = n;
+    }
+    // append to cut_evects (amg/src/spectral.cpp:199-222)
+    const int beg = cut_evects.Width();
+    DenseMatrix out(n, beg + m);
+    if (beg)
+    {
+        SA_ASSERT(cut_evects.Height() == n);
+        std::memcpy(out.Data(), cut_evects.Data(), sizeof(double) * (size_t)n * beg);
+    }
+    std::memcpy(out.Data() + (size_t)n * beg, Z.data(), sizeof(double) * (size_t)n * m);
+    cut_evects = out;
+    count_max_used = std::max(count_max_used, m);
+    if (theta < 0.)
+        theta = 0.;
+    return m > 0;
+}
+
 /* ---------------------------------------------------------------- parameters */
 
 MultilevelParameters::MultilevelParameters(int coarsenings, int *nparts_arr_arg,
@@ -974,6 +1093,185 @@ static int *block_coarse_partitioner(int level, int num_elem, int *nparts, void 
 {
     block_partitioner_data_t *d = (block_partitioner_data_t *)data;
     return sa_prescribed_coarse_partitioning(*d->prob, *d->p, level, num_elem, nparts);
+}
+
+/* ---- user-style plug-ins for the boundary test (what a reference user would write) ---- */
+namespace
+{
+// implements ONLY the reference contract (amg/inc/elmat.hpp:53-77): no batched view
+class UserGetMatrixProvider : public ElementMatrixProvider
+{
+public:
+    UserGetMatrixProvider(const agg_partitioning_relations_t &rels, const fem_problem_t &f)
+        : ElementMatrixProvider(rels), f_(f)
+    {
+    }
+    virtual Matrix *GetMatrix(int elno, bool &free_matr) const
+    {
+        DenseMatrix *M = new DenseMatrix(f_.ne, f_.ne);
+        std::memcpy(M->Data(), f_.elmat.data() + (size_t)elno * f_.ne * f_.ne, sizeof(double) * f_.ne * f_.ne);
+        free_matr = true;
+        return M;
+    }
+    virtual SparseMatrix *BuildAEStiff(int) const
+    {
+        SA_ASSERT(!"not used: the hierarchy builder batches the AEs");
+        return NULL;
+    }
+
+private:
+    const fem_problem_t &f_;
+};
+
+// a user smoother with the smpr_ft signature: the SAS polynomial smoother written out on the host
+// (amg/inc/smpr.hpp:319-339), so the V-cycle must give the same iteration count as the device one
+struct user_smoother_data_t
+{
+    int degree;
+    const double *roots;
+    Vector dinv_neg;
+    int calls;
+};
+void user_host_smoother(const SparseMatrix &A, const Vector &b, Vector &x, void *data)
+{
+    user_smoother_data_t *d = (user_smoother_data_t *)data;
+    d->calls++;
+    const int n = (int)b.size();
+    Vector t(n);
+    for (int k = 0; k < d->degree; ++k)
+    {
+        SpMult(A, x.data(), t.data());
+        for (int i = 0; i < n; ++i)
+            x[i] += (1. / d->roots[k]) * d->dinv_neg[i] * (t[i] - b[i]);
+    }
+}
+user_smoother_data_t g_user_smoother;
+} // namespace
+
+/* flags bit 0: element matrices through a GetMatrix-only provider; bit 1: user smoother
+   (host callback) on the finest level.  Returns a hierarchy handle like sa_drv_ml_build. */
+extern "C" void *sa_drv_ml_build_user(void *prob_, const sa_drv_params_t *p, int device, int flags)
+{
+    sa_problem_t *prob = (sa_problem_t *)prob_;
+    SA_ASSERT(prob && prob->rels);
+    proc_gpu_init(device);
+    sa_hierarchy_t *H = new sa_hierarchy_t;
+    H->prob = prob;
+    H->params = *p;
+    product_impl_t *pi = new product_impl_t;
+    H->impl = pi;
+    H->impl_free = product_impl_free;
+    H->owns_rels = false;
+    const fem_problem_t &f = *prob->fem;
+    std::vector<int> nparts_arr = sa_target_nparts(f.NE, *p);
+    std::vector<int64_t> offsets((size_t)f.NE + 1);
+    for (int e = 0; e <= f.NE; ++e)
+        offsets[e] = (int64_t)e * f.ne * f.ne;
+    ElementMatrixProvider *emp;
+    if (flags & 1)
+        emp = new UserGetMatrixProvider(*prob->rels, f);
+    else
+        emp = new ElementMatrixDenseArray(*prob->rels, f.elmat.data(), offsets.data());
+    MultilevelParameters mlp(p->num_levels - 1, nparts_arr.data(), p->first_nu_pro, p->nu_pro,
+                             p->nu_relax, p->first_theta, p->theta, -1, false, false, false);
+    mlp.set_coarse_direct(true);
+    block_partitioner_data_t bpd = {prob, p};
+    if (p->partition_kind == 1 || !prob->coarse_partitions.empty())
+        mlp.set_coarse_partitioner(block_coarse_partitioner, &bpd);
+    const double t0 = now_s();
+    pi->ml = ml_produce_data(f.A, prob->rels, emp, mlp);
+    if (flags & 2)
+    {
+        tg_data_t *tg = pi->ml->levels_list.finest->tg_data;
+        g_user_smoother.degree = tg->poly_data->degree;
+        g_user_smoother.roots = tg->poly_data->roots;
+        g_user_smoother.dinv_neg.resize(f.A.Height());
+        g_user_smoother.calls = 0;
+        sa_gpu_check(sa_gpu_get_Dinv_neg(tg->gpu, g_user_smoother.dinv_neg.data()), "sa_gpu_get_Dinv_neg");
+        tg->pre_smoother = user_host_smoother;
+        tg->post_smoother = user_host_smoother;
+        tg->smoother_data = &g_user_smoother;
+        ml_impose_cycle(*pi->ml, false);
+    }
+    sa_gpu_ctx_sync(proc_gpu_ctx());
+    H->times["setup"] = now_s() - t0;
+    for (levels_level_t *l = pi->ml->levels_list.finest; l; l = l->coarser)
+        H->rels.push_back(l->agg_part_rels);
+    return H;
+}
+
+extern "C" int sa_drv_user_smoother_calls(void) { return g_user_smoother.calls; }
+
+/* Eigensolver::Solve through the C++ mirror on a dense symmetric matrix (n x n column-major):
+   returns m, evals (cap entries), vectors (n x m) and the diagonal B. */
+extern "C" int sa_drv_eigensolver_solve(int device, int n, const double *A, double theta, int cap,
+                                        double *evals, double *evects, double *Bdiag)
+{
+    proc_gpu_init(device);
+    SparseMatrix S;
+    S.h = S.w = n;
+    S.I.assign((size_t)n + 1, 0);
+    for (int i = 0; i < n; ++i)
+    {
+        for (int j = 0; j < n; ++j)
+            if (A[(size_t)j * n + i] != 0. || i == j)
+            {
+                S.J.push_back(j);
+                S.A.push_back(A[(size_t)j * n + i]);
+            }
+        S.I[i + 1] = (int)S.J.size();
+    }
+    agg_partitioning_relations_t dummy;
+    std::memset(&dummy, 0, sizeof dummy);
+    Eigensolver es(NULL, dummy);
+    SparseMatrix *B = NULL;
+    DenseMatrix cut;
+    double th = theta;
+    es.Solve(S, B, 0, 0, n, th, cut);
+    const int m = cut.Width();
+    for (int j = 0; j < std::min(m, cap); ++j)
+    {
+        evals[j] = es.LastEigenvalues()[j];
+        std::memcpy(evects + (size_t)j * n, cut.Data() + (size_t)j * n, sizeof(double) * n);
+    }
+    for (int i = 0; i < n; ++i)
+        Bdiag[i] = B->A[i];
+    delete B;
+    return m;
+}
+
+/* ElementMatrixParallelCoarse::GetMatrix / BuildAEStiff of the provider of coarse level `level`
+   (>= 1): reads element elno / assembles AE ae through the C++ mirror; dense column-major out. */
+extern "C" int sa_drv_coarse_provider_probe(void *hier, int level, int elno, double *elmat_out, int *ne_out,
+                                            int ae, double *AE_out, int *n_out)
+{
+    sa_hierarchy_t *H = (sa_hierarchy_t *)hier;
+    product_impl_t *pi = (product_impl_t *)H->impl;
+    levels_level_t *l = levels_list_get_level(pi->ml->levels_list, level);
+    if (!l || !l->tg_data || !l->tg_data->elem_data)
+        return 1;
+    const ElementMatrixProvider *emp = l->tg_data->elem_data;
+    bool fr = false;
+    Matrix *M = emp->GetMatrix(elno, fr);
+    const DenseMatrix *D = dynamic_cast<const DenseMatrix *>(M);
+    if (!D)
+        return 2;
+    *ne_out = D->Height();
+    if (elmat_out)
+        std::memcpy(elmat_out, D->Data(), sizeof(double) * D->Height() * D->Width());
+    if (fr)
+        delete M;
+    SparseMatrix *S = emp->BuildAEStiff(ae);
+    *n_out = S->Height();
+    if (AE_out)
+    {
+        std::fill(AE_out, AE_out + (size_t)S->h * S->h, 0.);
+        for (int i = 0; i < S->h; ++i)
+            for (int q = S->I[i]; q < S->I[i + 1]; ++q)
+                AE_out[(size_t)S->J[q] * S->h + i] = S->A[q];
+    }
+    delete S;
+    return 0;
 }
 
 extern "C" void *sa_drv_ml_build(void *prob_, const sa_drv_params_t *p, int device)

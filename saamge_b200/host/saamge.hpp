@@ -230,6 +230,35 @@ typedef struct
     int nu_relax;
 } ml_data_t;
 
+/* ---- the local eigensolver as a class (amg/inc/spectral.hpp:91-224) ---- */
+/*! Same shape as the reference's Eigensolver: Solve() computes, for the given AE matrix \a A, the
+    weighted-l1 diagonal \a B (allocated when NULL; the caller frees, amg/inc/spectral.hpp:147-150)
+    and the eigenvectors of A z = lambda B z with lambda <= theta (at least one), appended as the
+    columns of \a cut_evects, normalised z^T B z = 1.  The hierarchy builder does not call it AE by
+    AE (it batches all AEs of a level in sa_gpu_local_spectral); Solve() runs that same device
+    path on a level of one AE whose single element matrix is \a A.  Returns true when a vector
+    was added. */
+class Eigensolver
+{
+public:
+    Eigensolver(const int *aggregates, const agg_partitioning_relations_t &agg_part_rels,
+                int threshold = 0x7fffffff);
+    virtual ~Eigensolver() {}
+    virtual bool Solve(const SparseMatrix &A, SparseMatrix *&B, int part, int agg_id,
+                       int aggregate_size, double &theta, DenseMatrix &cut_evects);
+    void GetStatistics(int &o_count_solves, int &o_count_direct_solves, int &o_count_max_used,
+                       double &o_smallest_eigenvalue_skipped);
+    /// eigenvalues of the last Solve (ascending)
+    const Vector &LastEigenvalues() const { return last_evals; }
+
+private:
+    const agg_partitioning_relations_t &agg_part_rels;
+    int threshold;
+    int count_solves, count_direct_solves, count_max_used;
+    double smallest_eigenvalue_skipped;
+    Vector last_evals;
+};
+
 /* ---- two-grid entry points ---- */
 tg_data_t *tg_init_data(const SparseMatrix *A, const agg_partitioning_relations_t &agg_part_rels,
                         int nu_pro, int nu_relax, double theta, bool smooth_interp,
