@@ -546,11 +546,18 @@ def main():
         if world > 1:
             sab.enable_sharding(dist)
             barrier()
+        # host input side: page-lock the problem's arrays so the finest level goes up through the
+        # pipelined path (the eigen stage starts while the operator / element blocks are in flight)
+        h.sa_drv_problem_pin.restype = ctypes.c_double
+        h.sa_drv_problem_pin.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        pin_s = h.sa_drv_problem_pin(pr.handle, local_rank)
+        barrier()
         t0 = time.time()
         H = sab.ml_build(pr, p, local_rank)
         barrier()
         setup_s = max_over_ranks(time.time() - t0)
-        hier = {"levels": w["levels"], "setup_s": setup_s, "setup_sharded_over_gpus": world}
+        hier = {"levels": w["levels"], "setup_s": setup_s, "setup_sharded_over_gpus": world,
+                "host_pin_s": pin_s}
         if world > 1:
             from saamge_b200.dist_solve import DistSolver
 

@@ -303,6 +303,9 @@ __global__ void k_coarse_elmat(LevelTables L, CoarseElmatArgs C, int e_begin, in
     extern __shared__ double sm[];
     double *ubuf = sm;                              // max_mis
     int *lidbuf = (int *)(sm + C.max_mis);          // max_mis
+    // gridDim.y blocks share one AE: block (x, y) owns the coarse columns lc == y (mod gridDim.y)
+    // in both products (W = A P_e and out = P_e^T W are independent column by column)
+    const int split = blockIdx.y, nsplit = gridDim.y;
     for (int e = e_begin + blockIdx.x; e < e_end; e += gridDim.x)
     {
         const int n = L.AE2d_I[e + 1] - L.AE2d_I[e];
@@ -315,7 +318,7 @@ __global__ void k_coarse_elmat(LevelTables L, CoarseElmatArgs C, int e_begin, in
         if (!preassembled) // (large AEs: k_assemble_large has filled the tile of this block)
             sa_dev_assemble_AE(L, e, T, n);
         // W = A_AE * P_e, column by column
-        for (int lc = 0; lc < nc; ++lc)
+        for (int lc = split; lc < nc; lc += nsplit)
         {
             const int cd = C.ce2d_J[cb + lc];
             const int mis = C.cdof_mis[cd];
@@ -354,7 +357,7 @@ __global__ void k_coarse_elmat(LevelTables L, CoarseElmatArgs C, int e_begin, in
                 ubuf[r] = U[r];
             }
             __syncthreads();
-            for (int lc2 = threadIdx.x; lc2 < nc; lc2 += blockDim.x)
+            for (int lc2 = split + nsplit * (int)threadIdx.x; lc2 < nc; lc2 += nsplit * (int)blockDim.x)
             {
                 double acc = 0.;
                 for (int r = 0; r < s; ++r)
@@ -510,7 +513,7 @@ extern "C" int sa_gpu_coarse_elmats(sa_gpu_level *finer, sa_gpu_level *coarse)
     coarse->elmat_off.upload(coarse->h_elmat_off.data(), (size_t)nparts + 1, st);
     coarse->elmat.alloc(coarse->h_elmat_off[nparts]);
     // bounded scratch: persistent blocks
-    const size_t scratch_budget = (size_t)1 << 28; // 2 GB of doubles
+    const size_t scratch_budget = (size_t)1 << 29; // 4 GB of doubles
     int blocks = std::min(nparts, ctx->num_sms * 4);
     blocks = (int)std::max<size_t>(1, std::min<size_t>(blocks, scratch_budget / (size_t)max_scratch));
     // scratch: the finer level's (idle) reflector block is reused when it exists -- a fresh
@@ -561,7 +564,9 @@ extern "C" int sa_gpu_coarse_elmats(sa_gpu_level *finer, sa_gpu_level *coarse)
                 rounds = false;
                 break;
             }
-            SA_LAUNCH(ctx, k_coarse_elmat, cnt, 256, smem, L, C, e0, e0 + cnt, 1);
+            // few AEs per round: several blocks per AE (columns dealt to them)
+            const int nsplit = std::max(1, std::min(8, (3 * ctx->num_sms) / std::max(1, cnt)));
+            SA_LAUNCH(ctx, k_coarse_elmat, dim3(cnt, nsplit), 256, smem, L, C, e0, e0 + cnt, 1);
         }
         SA_CUDA(cudaStreamSynchronize(st)); // iota / d_parts go out of scope
     }

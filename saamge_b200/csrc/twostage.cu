@@ -183,7 +183,7 @@ __device__ __forceinline__ S1Smem s1_carve(double *sm)
     return S;
 }
 constexpr int TS_S1_FIXED = TS_NW * 32 + 64 + 2 * 32 * 33 + 72 + 72 + 32 + 64; // doubles before U
-constexpr int TS_S1_UMIN = 8 * 1024;                                           // Gram partials
+constexpr int TS_S1_UMIN = 2 * 64 * 36 + 16 * 64 * 16;                         // syr2k operand tiles (>= Gram partials)
 
 /* Sums W (<= 8) values per thread over the block; totals land in S.sval[0..W-1] (visible to all
    threads on return).  Deterministic: warp shuffles, then warps in order. */
@@ -469,10 +469,11 @@ __device__ __noinline__ void s1_panel_qr(const S1Smem S, double *__restrict__ P,
 /* W = A22 V.  A22: r x r symmetric, LOWER triangle valid, leading dimension ld; V, W: r x 32,
    leading dimension ldv.  Every warp owns a strip of 16 rows per pass (256 rows per pass);
    A fragments come straight from global memory (element (i, k) lives at max(i,k) + ld min(i,k);
-   L2 only, they are used once), prefetched one 32-column chunk ahead; the V chunk is shared
-   through S.U: fetched into registers before the MMAs of the current chunk, parked in shared
-   memory after them (double buffered, one barrier per chunk).
-   (Measured alternative, slower by 25 %: no barriers, V fragments re-read through L1.) */
+   L2 only, they are used once), prefetched one 32-column chunk ahead into a SECOND register set
+   (the chunk loop is unrolled by two: ncu showed the loads of a single set waiting for the DMMAs
+   that still read it); the V chunk is shared through S.U: fetched into registers before the MMAs
+   of the current chunk, parked in shared memory after them (double buffered, one barrier per
+   chunk).  (Measured alternative, slower by 25 %: no barriers, V fragments re-read through L1.) */
 template <bool CL>
 __device__ __noinline__ void s1_symm(const S1Smem S, const double *__restrict__ A2, int ld, int r,
                                      const double *__restrict__ V, double *__restrict__ W, int ldv, int rank,
@@ -494,8 +495,8 @@ __device__ __noinline__ void s1_symm(const S1Smem S, const double *__restrict__ 
 #pragma unroll
             for (int ni = 0; ni < 4; ++ni)
                 acc[mi][ni][0] = acc[mi][ni][1] = 0.;
-        double an[2][8]; // next chunk's A fragments
-        auto load_a = [&](int k0) {
+        double A0[2][8], A1[2][8];
+        auto load_a = [&](double (&A)[2][8], int k0) {
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk)
             {
@@ -503,8 +504,8 @@ __device__ __noinline__ void s1_symm(const S1Smem S, const double *__restrict__ 
                 const bool kok = active && k < r;
                 const int lo_a = min(ra, k), hi_a = max(ra, k);
                 const int lo_b = min(rb, k), hi_b = max(rb, k);
-                an[0][kk] = (kok && ra < r) ? __ldcg(A2 + hi_a + (size_t)ld * lo_a) : 0.;
-                an[1][kk] = (kok && rb < r) ? __ldcg(A2 + hi_b + (size_t)ld * lo_b) : 0.;
+                A[0][kk] = (kok && ra < r) ? __ldcg(A2 + hi_a + (size_t)ld * lo_a) : 0.;
+                A[1][kk] = (kok && rb < r) ? __ldcg(A2 + hi_b + (size_t)ld * lo_b) : 0.;
             }
         };
         const int vc0 = tid >> 5, vk = tid & 31; // entries (vc0, vk) and (vc0 + 16, vk) of a chunk
@@ -518,46 +519,51 @@ __device__ __noinline__ void s1_symm(const S1Smem S, const double *__restrict__ 
             Vs[buf * 32 * TS_LD + vc0 * TS_LD + vk] = vreg[0];
             Vs[buf * 32 * TS_LD + (vc0 + 16) * TS_LD + vk] = vreg[1];
         };
-        load_a(0);
-        fetch_v(0);
-        park_v(0);
-        int buf = 0;
-        for (int k0 = 0; k0 < r; k0 += 32, buf ^= 1)
-        {
-            double a[2][8];
+        auto compute = [&](const double (&A)[2][8], int buf) {
+            if (!active)
+                return;
+            const double *vb = Vs + buf * 32 * TS_LD;
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk)
             {
-                a[0][kk] = an[0][kk];
-                a[1][kk] = an[1][kk];
-            }
-            __syncthreads(); // Vs[buf] is complete; everyone is done with Vs[buf ^ 1]
-            const bool more = k0 + 32 < r;
-            if (more)
-            {
-                load_a(k0 + 32);
-                fetch_v(k0 + 32);
-            }
-            if (active)
-            {
-                const double *vb = Vs + buf * 32 * TS_LD;
+                double b[4];
 #pragma unroll
-                for (int kk = 0; kk < 8; ++kk)
+                for (int ni = 0; ni < 4; ++ni)
+                    b[ni] = vb[(ni * 8 + g) * TS_LD + kk * 4 + t];
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
                 {
-                    double b[4];
-#pragma unroll
-                    for (int ni = 0; ni < 4; ++ni)
-                        b[ni] = vb[(ni * 8 + g) * TS_LD + kk * 4 + t];
-#pragma unroll
-                    for (int ni = 0; ni < 4; ++ni)
-                    {
-                        dmma884(acc[0][ni][0], acc[0][ni][1], a[0][kk], b[ni]);
-                        dmma884(acc[1][ni][0], acc[1][ni][1], a[1][kk], b[ni]);
-                    }
+                    dmma884(acc[0][ni][0], acc[0][ni][1], A[0][kk], b[ni]);
+                    dmma884(acc[1][ni][0], acc[1][ni][1], A[1][kk], b[ni]);
                 }
             }
-            if (more)
-                park_v(buf ^ 1);
+        };
+        load_a(A0, 0);
+        fetch_v(0);
+        park_v(0);
+        for (int k0 = 0; k0 < r; k0 += 64)
+        {
+            __syncthreads(); // Vs[0] is complete; everyone is done with Vs[1]
+            const bool more1 = k0 + 32 < r;
+            if (more1)
+            {
+                load_a(A1, k0 + 32);
+                fetch_v(k0 + 32);
+            }
+            compute(A0, 0);
+            if (!more1)
+                break;
+            park_v(1);
+            __syncthreads(); // Vs[1] is complete; everyone is done with Vs[0]
+            const bool more2 = k0 + 64 < r;
+            if (more2)
+            {
+                load_a(A0, k0 + 64);
+                fetch_v(k0 + 64);
+            }
+            compute(A1, 1);
+            if (more2)
+                park_v(0);
         }
         if (active)
         {
@@ -582,9 +588,10 @@ __device__ __noinline__ void s1_symm(const S1Smem S, const double *__restrict__ 
 }
 
 /* A22 -= Z V^T + V Z^T on the lower triangle (rank-64 update), DMMA.  A warp owns a strip of 16
-   rows per pass and keeps its [-Z | -V] fragments in registers; the [V | Z]^T operand of a block
-   of 32 columns is shared through S.U (registers -> shared memory, double buffered); C fragments
-   are read (L2 only), updated in the accumulator and written back. */
+   rows per pass; its [-Z | -V] operand (16 x 64) sits in a per-warp, XOR-swizzled shared tile
+   (registers spilled when it lived there: ncu), the [V | Z]^T operand of a block of 32 columns is
+   shared by all warps through S.U (registers -> shared memory, double buffered); the C fragments
+   of the NEXT column block are prefetched (L2 only) while the current one is updated. */
 template <bool CL>
 __device__ __noinline__ void s1_syr2k(const S1Smem S, double *__restrict__ A2, int ld, int r,
                                       const double *__restrict__ V, const double *__restrict__ Z, int ldv,
@@ -592,7 +599,8 @@ __device__ __noinline__ void s1_syr2k(const S1Smem S, double *__restrict__ A2, i
 {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    double *Bs = S.U; // 2 x [64 k][TS_LD]
+    double *Bs = S.U;                                         // 2 x [64 k][TS_LD]
+    double *As = S.U + 2 * 64 * TS_LD + (size_t)wid * 64 * 16; // per warp: [64 k][16 rows], swizzled
     for (int pass0 = 0; pass0 < r; pass0 += TS_NW * 16)
     {
         if (!s1_owns_tri(pass0 / (TS_NW * 16), rank, CS))
@@ -600,15 +608,15 @@ __device__ __noinline__ void s1_syr2k(const S1Smem S, double *__restrict__ A2, i
         const int i0 = pass0 + wid * 16;
         const bool active = i0 < r;
         const int ra = i0 + g, rb = i0 + 8 + g;
-        double a[2][16];
-#pragma unroll
-        for (int kk = 0; kk < 16; ++kk)
+        // strip operand: element (k, row) at k * 16 + (row ^ ((k & 3) << 2)); k < 32: -Z, else -V
+        __syncwarp();
+        for (int idx = lane; idx < 64 * 16; idx += 32)
         {
-            const int k = kk * 4 + t;
+            const int k = idx >> 4, row = idx & 15;
             const double *src = (k < 32) ? Z + (size_t)ldv * k : V + (size_t)ldv * (k - 32);
-            a[0][kk] = (active && ra < r) ? -ldx<CL>(src + ra) : 0.;
-            a[1][kk] = (active && rb < r) ? -ldx<CL>(src + rb) : 0.;
+            As[k * 16 + (row ^ ((k & 3) << 2))] = (active && i0 + row < r) ? -ldx<CL>(src + i0 + row) : 0.;
         }
+        __syncwarp();
         const int jend = min(r, pass0 + TS_NW * 16); // columns needed by this pass
         // Bs[k][j] = (k < 32) ? V[j0 + j][k] : Z[j0 + j][k - 32]; four entries per thread
         const int bj = tid & 31, bk0 = tid >> 5; // entries k = bk0 + 16 q
@@ -628,40 +636,59 @@ __device__ __noinline__ void s1_syr2k(const S1Smem S, double *__restrict__ A2, i
             for (int q = 0; q < 4; ++q)
                 Bs[buf * 64 * TS_LD + (bk0 + 16 * q) * TS_LD + bj] = breg[q];
         };
+        double cn[2][4][2]; // C fragments of the next column block
+        auto load_c = [&](int j0) {
+            const bool in = active && j0 < jend && j0 <= i0 + 15;
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+            {
+                const int j = j0 + ni * 8 + 2 * t;
+                cn[0][ni][0] = (in && ra < r && j <= ra) ? __ldcg(A2 + ra + (size_t)ld * j) : 0.;
+                cn[0][ni][1] = (in && ra < r && j + 1 <= ra) ? __ldcg(A2 + ra + (size_t)ld * (j + 1)) : 0.;
+                cn[1][ni][0] = (in && rb < r && j <= rb) ? __ldcg(A2 + rb + (size_t)ld * j) : 0.;
+                cn[1][ni][1] = (in && rb < r && j + 1 <= rb) ? __ldcg(A2 + rb + (size_t)ld * (j + 1)) : 0.;
+            }
+        };
         fetch_b(0);
         park_b(0);
+        load_c(0);
         int buf = 0;
         for (int j0 = 0; j0 < jend; j0 += 32, buf ^= 1)
         {
+            double c[2][4][2];
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+            {
+                c[0][ni][0] = cn[0][ni][0];
+                c[0][ni][1] = cn[0][ni][1];
+                c[1][ni][0] = cn[1][ni][0];
+                c[1][ni][1] = cn[1][ni][1];
+            }
             __syncthreads();
             const bool more = j0 + 32 < jend;
             if (more)
+            {
                 fetch_b(j0 + 32);
+                load_c(j0 + 32);
+            }
             if (active && j0 <= i0 + 15)
             {
-                double c[2][4][2];
-#pragma unroll
-                for (int ni = 0; ni < 4; ++ni)
-                {
-                    const int j = j0 + ni * 8 + 2 * t;
-                    c[0][ni][0] = (ra < r && j <= ra) ? __ldcg(A2 + ra + (size_t)ld * j) : 0.;
-                    c[0][ni][1] = (ra < r && j + 1 <= ra) ? __ldcg(A2 + ra + (size_t)ld * (j + 1)) : 0.;
-                    c[1][ni][0] = (rb < r && j <= rb) ? __ldcg(A2 + rb + (size_t)ld * j) : 0.;
-                    c[1][ni][1] = (rb < r && j + 1 <= rb) ? __ldcg(A2 + rb + (size_t)ld * (j + 1)) : 0.;
-                }
                 const double *bb = Bs + buf * 64 * TS_LD;
 #pragma unroll
                 for (int kk = 0; kk < 16; ++kk)
                 {
+                    const int k = kk * 4 + t;
+                    const double a0 = As[k * 16 + (g ^ (t << 2))];
+                    const double a1 = As[k * 16 + ((8 + g) ^ (t << 2))];
                     double b[4];
 #pragma unroll
                     for (int ni = 0; ni < 4; ++ni)
-                        b[ni] = bb[(kk * 4 + t) * TS_LD + ni * 8 + g];
+                        b[ni] = bb[k * TS_LD + ni * 8 + g];
 #pragma unroll
                     for (int ni = 0; ni < 4; ++ni)
                     {
-                        dmma884(c[0][ni][0], c[0][ni][1], a[0][kk], b[ni]);
-                        dmma884(c[1][ni][0], c[1][ni][1], a[1][kk], b[ni]);
+                        dmma884(c[0][ni][0], c[0][ni][1], a0, b[ni]);
+                        dmma884(c[1][ni][0], c[1][ni][1], a1, b[ni]);
                     }
                 }
 #pragma unroll

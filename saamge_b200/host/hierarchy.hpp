@@ -23,6 +23,7 @@ struct sa_problem_t
     // explicit coarse partitions (fixtures): coarsening index -> element -> AE
     std::map<int, std::vector<int>> coarse_partitions;
     std::map<std::string, double> times;
+    std::vector<const void *> pinned; // host arrays registered by sa_drv_problem_pin
 };
 
 struct sa_hierarchy_t

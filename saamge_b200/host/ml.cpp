@@ -571,6 +571,12 @@ void interp_sparse_tent_assemble(const agg_partitioning_relations_t &agg_part_re
 }
 
 // amg/src/tg.cpp:502-540 (spectral branch) + tg_assemble_and_smooth (:432-473)
+/* Pipelined upload of the finest level (desc.async_upload = 1): allowed when the caller has
+   promised that the host arrays of the level stay valid and are page-locked (sa_drv_problem_pin);
+   the eigen stage then starts while the operator / element blocks are still in flight. */
+static bool g_async_finest_upload = false;
+void sa_set_async_finest_upload(bool on) { g_async_finest_upload = on; }
+
 void tg_build_hierarchy(const SparseMatrix *Ag, tg_data_t &tg_data,
                         const agg_partitioning_relations_t &agg_part_rels,
                         ElementMatrixProvider *elem_data, bool avoid_ess_bdr_dofs,
@@ -634,6 +640,8 @@ void tg_build_hierarchy(const SparseMatrix *Ag, tg_data_t &tg_data,
         d.elmat = packed.data();
         d.elmat_off = packed_off.data();
     }
+    if (!finer && g_async_finest_upload && packed.empty() && d.elmat)
+        d.async_upload = 1;
     if (tg_data.gpu)
         sa_gpu_level_destroy(tg_data.gpu);
     tg_data.gpu = NULL;
@@ -1198,6 +1206,51 @@ extern "C" void *sa_drv_ml_build_user(void *prob_, const sa_drv_params_t *p, int
     for (levels_level_t *l = pi->ml->levels_list.finest; l; l = l->coarser)
         H->rels.push_back(l->agg_part_rels);
     return H;
+}
+
+/* Page-locks the large host arrays of the problem (element blocks, operator, relation tables)
+   and lets sa_drv_ml_build upload the finest level through the pipelined path.  Part of the host
+   input producer (like the pinning of sa_drv_bench_create); returns seconds spent. */
+extern "C" double sa_drv_problem_pin(void *prob_, int device)
+{
+    sa_problem_t *prob = (sa_problem_t *)prob_;
+    proc_gpu_init(device);
+    const double t0 = now_s();
+    if (prob->pinned.empty())
+    {
+        const fem_problem_t &f = *prob->fem;
+        const agg_partitioning_relations_t &r = *prob->rels;
+        auto pin = [&](const void *p, size_t bytes) {
+            if (p && bytes && sa_gpu_host_register(p, bytes) == 0)
+                prob->pinned.push_back(p);
+        };
+        pin(f.elmat.data(), f.elmat.size() * sizeof(double));
+        pin(f.A.GetData(), f.A.A.size() * sizeof(double));
+        pin(f.A.GetJ(), f.A.J.size() * sizeof(int));
+        pin(f.A.GetI(), f.A.I.size() * sizeof(int));
+        const Table *tabs[] = {r.elem_to_dof, r.dof_to_elem, r.AE_to_elem, r.AE_to_dof,
+                               r.dof_to_AE,   r.mis_to_dof,  r.mis_to_AE,  r.AE_to_mis};
+        for (const Table *t : tabs)
+        {
+            pin(t->GetI(), t->I.size() * sizeof(int));
+            pin(t->GetJ(), t->J.size() * sizeof(int));
+        }
+        pin(r.dof_id_inAE, (size_t)r.dof_to_AE->Size_of_connections() * sizeof(int));
+        pin(r.partitioning, (size_t)f.NE * sizeof(int));
+        pin(r.agg_flags, (size_t)r.ND);
+        pin(r.mises, (size_t)r.ND * sizeof(int));
+    }
+    sa_set_async_finest_upload(true);
+    return now_s() - t0;
+}
+
+extern "C" void sa_drv_problem_unpin(void *prob_)
+{
+    sa_problem_t *prob = (sa_problem_t *)prob_;
+    for (size_t i = 0; i < prob->pinned.size(); ++i)
+        sa_gpu_host_unregister(prob->pinned[i]);
+    prob->pinned.clear();
+    sa_set_async_finest_upload(false);
 }
 
 extern "C" int sa_drv_user_smoother_calls(void) { return g_user_smoother.calls; }

@@ -316,6 +316,9 @@ int kalchev_pcg(ml_data_t &ml_data, const Vector &b, Vector &x, int print_iter,
 void tg_download_results(const tg_data_t &tg_data, const agg_partitioning_relations_t &rels,
                          tg_data_t *coarser, sa_level_results_t &R);
 
+/* pipelined upload of the finest level (see ml.cpp) */
+void sa_set_async_finest_upload(bool on);
+
 /* coarse-topology prefetch (ml.cpp) */
 void sa_topology_prefetch_start(const agg_partitioning_relations_t *rels, int nparts_target);
 void sa_topology_prefetch_drop(const agg_partitioning_relations_t *rels);

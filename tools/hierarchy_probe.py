@@ -7,6 +7,8 @@ p=sab.default_params(num_levels=levels, first_elems_per_agg=52, elems_per_agg=ep
 t=time.time(); pr=sab.Problem(3,n,coef_kind=1); na=pr.partition(p); print("host inputs %.1fs AEs %d"%(time.time()-t,na), flush=True)
 import ctypes
 h=sab.host_lib(); h.sa_drv_gpu_profile.argtypes=[ctypes.c_int,ctypes.c_char_p,ctypes.c_int]
+h.sa_drv_problem_pin.restype=ctypes.c_double; h.sa_drv_problem_pin.argtypes=[ctypes.c_void_p,ctypes.c_int]
+if not os.environ.get('SA_NO_PIN'): print('pin %.3fs'%h.sa_drv_problem_pin(pr.handle,0))
 t=time.time(); H=sab.ml_build(pr,p); print("ml_build %.2fs"%(time.time()-t), flush=True)
 buf=ctypes.create_string_buffer(8192); h.sa_drv_gpu_profile(-1,buf,8192); print("PROF", buf.value.decode().replace("\n","; "))
 g=sab.gpu_lib(); clk=(ctypes.c_double*8)(); g.sa_gpu_debug_phase_clocks(clk); print("PHASE Mcycles", [round(x/1e6,1) for x in clk])
