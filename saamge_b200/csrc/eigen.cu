@@ -579,6 +579,7 @@ k_at_smem(LevelTables L, ChunkDev C, const int *slot_list, double *ae_D)
 }
 
 #include "eigen_packed.cuh"
+#include "eigen_reg.cuh"
 #include "eigen_large.cuh"
 
 // one thread per slot: number of eigenvalues in (-1, theta] and search bounds
@@ -1386,6 +1387,23 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         // finer size classes would only add launch tails
         std::vector<int> bucket_edges, bucket_class;
         static const int max_class = getenv("SA_GPU_MAX_CLASS") ? atoi(getenv("SA_GPU_MAX_CLASS")) : 3;
+        // register-resident kernel (k_at_reg<S>, class 100 + S) for n <= 160 unless
+        // SA_GPU_SMALL_PATH=packed keeps round 1's shared-memory kernel for every size
+        static const bool use_reg =
+            !(getenv("SA_GPU_SMALL_PATH") && 0 == strcmp(getenv("SA_GPU_SMALL_PATH"), "packed"));
+        if (use_reg && !use_square)
+        {
+            static const int reg_S[] = {2, 4, 6, 7, 8, 9, 10, 11};
+            for (int S : reg_S)
+            {
+                const int edge = std::min(16 * S, nmax_smem);
+                if (bucket_edges.empty() || edge > bucket_edges.back())
+                {
+                    bucket_edges.push_back(edge);
+                    bucket_class.push_back(100 + S);
+                }
+            }
+        }
         for (int c = std::max(1, std::min(3, max_class)); c >= 1; --c)
         {
             const size_t cap = (ctx->smem_per_sm / c - 1024) / sizeof(double);
@@ -1433,6 +1451,20 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         }
         DevBuf<int> &d_order = WS.order;
         staged_upload(ctx, ctx->stage, d_order, order.data(), ns);
+        // distributed copies of the matrices that go through k_tridiag_reg
+        size_t g_total = 0, g_used = 0;
+        for (int q = 0; q < ns; ++q)
+        {
+            const int n = nAE(a0 + q);
+            if (n > nmax_smem)
+                continue;
+            size_t b = 0;
+            while (b + 1 < bucket_edges.size() && n > bucket_edges[b])
+                ++b;
+            if (bucket_class[b] >= 100)
+                g_total += reg_tile_doubles(bucket_class[b] - 100);
+        }
+        WS.G.ensure(g_total);
         if (lev->pending.active && !fused_pieces)
         {
             const int pi = (int)(std::upper_bound(piece_ends.begin(), piece_ends.end(), a0) -
@@ -1669,11 +1701,80 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
             else
             {
                 const int cls = bucket_class[b], threads = class_threads(cls);
+                if (cls >= 100)
+                {
+                    // k_at_packed (assembly + scaling, occupancy class by tile size) writes the
+                    // matrices of this launch to G, k_tridiag_reg<S> reduces them
+                    const int S = cls - 100;
+                    double *Gl = WS.G.p + g_used;
+                    g_used += (size_t)cnt * reg_tile_doubles(S);
+                    int pc = 1;
+                    for (int c3 = 3; c3 >= 2; --c3)
+                        if (packed_smem_doubles((size_t)nb, class_threads(c3)) <=
+                            (ctx->smem_per_sm / c3 - 1024) / sizeof(double))
+                        {
+                            pc = c3;
+                            break;
+                        }
+                    const int pthreads = class_threads(pc);
+                    const size_t psmem = packed_smem_doubles((size_t)nb, pthreads) * sizeof(double);
+                    auto launch_asm = [&](auto kern) {
+                        SA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int)ctx->smem_optin - 1024));
+                        kern<<<cnt, pthreads, psmem, sb>>>(L, C, d_order.p + gpos, lev->ae_D.p, Gl, S);
+                    };
+                    if (pc >= 3)
+                        launch_asm(k_at_packed<256, 3>);
+                    else if (pc == 2)
+                        launch_asm(k_at_packed<384, 2>);
+                    else
+                        launch_asm(k_at_packed<512, 1>);
+                    SA_CUDA(cudaGetLastError());
+                    auto launch_reg = [&](auto kern, int SB) {
+                        const size_t smem = reg_smem_doubles(S, SB) * sizeof(double);
+                        SA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int)ctx->smem_optin - 1024));
+                        kern<<<cnt, 256, smem, sb>>>(C, lev->AE2d_I.p, d_order.p + gpos, Gl);
+                    };
+                    // two resident blocks per SM (128 registers per thread: 4 x 4 local blocks in
+                    // registers, the rest in shared memory) where two tiles fit the shared memory
+                    // of an SM: the steps are latency bound, a second matrix in flight hides it
+                    static const int occ2 = getenv("SA_GPU_REG_OCC2") ? atoi(getenv("SA_GPU_REG_OCC2")) : 1;
+                    switch (S)
+                    {
+                    case 2: launch_reg(k_tridiag_reg<2, 0, 2>, 0); break;
+                    case 4: launch_reg(k_tridiag_reg<4, 0, 2>, 0); break;
+                    case 6:
+                        if (occ2)
+                            launch_reg(k_tridiag_reg<6, 2, 2>, 2);
+                        else
+                            launch_reg(k_tridiag_reg<6, 0, 1>, 0);
+                        break;
+                    case 7:
+                        if (occ2)
+                            launch_reg(k_tridiag_reg<7, 3, 2>, 3);
+                        else
+                            launch_reg(k_tridiag_reg<7, 0, 1>, 0);
+                        break;
+                    case 8:
+                        if (occ2)
+                            launch_reg(k_tridiag_reg<8, 4, 2>, 4);
+                        else
+                            launch_reg(k_tridiag_reg<8, 0, 1>, 0);
+                        break;
+                    case 9: launch_reg(k_tridiag_reg<9, 1, 1>, 1); break;
+                    case 10: launch_reg(k_tridiag_reg<10, 2, 1>, 2); break;
+                    default: launch_reg(k_tridiag_reg<11, 3, 1>, 3); break;
+                    }
+                    ctx->launches += 2;
+                    SA_CUDA(cudaGetLastError());
+                    return;
+                }
                 const size_t smem = packed_smem_doubles((size_t)nb, threads) * sizeof(double);
                 auto launch = [&](auto kern) {
                     SA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)ctx->smem_optin - 1024));
-                    kern<<<cnt, threads, smem, sb>>>(L, C, d_order.p + gpos, lev->ae_D.p);
+                    kern<<<cnt, threads, smem, sb>>>(L, C, d_order.p + gpos, lev->ae_D.p, (double *)nullptr, 0);
                 };
                 if (cls >= 3)
                     launch(k_at_packed<256, 3>);

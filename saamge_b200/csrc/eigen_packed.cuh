@@ -53,7 +53,7 @@ __device__ __forceinline__ double packed_row_dot(const double *T, const int *cjm
 
 template <int NTMAX, int MINB>
 __global__ void __launch_bounds__(NTMAX, MINB)
-k_at_packed(LevelTables L, ChunkDev C, const int *slot_list, double *ae_D)
+k_at_packed(LevelTables L, ChunkDev C, const int *slot_list, double *ae_D, double *G, int GS)
 {
     extern __shared__ double sm[];
     const int slot = slot_list[blockIdx.x];
@@ -150,6 +150,23 @@ k_at_packed(LevelTables L, ChunkDev C, const int *slot_list, double *ae_D)
     if (tid == 0)
         atomicAdd(&g_phase_clk[1], (unsigned long long)(tc2 - tc1));
 
+    if (G)
+    {
+        // The reduction runs in k_tridiag_reg (eigen_reg.cuh): write the scaled matrix in its
+        // layout -- full square, entry (16 a + r, 16 b + c) at (a GS + b) 256 + 16 r + c.
+        double *Gt = G + (size_t)blockIdx.x * GS * GS * 256;
+        const int tot = GS * GS * 256;
+        for (int q = tid; q < tot; q += NT)
+        {
+            const int e = q >> 8, t = q & 255;
+            const int i = 16 * (e / GS) + (t >> 4), j = 16 * (e % GS) + (t & 15);
+            double x = 0.;
+            if (i < n && j < n)
+                x = i >= j ? T[cjm[j] + i] : T[cjm[i] + j];
+            __stcs(Gt + q, x);
+        }
+        return;
+    }
     // ---- Householder tridiagonalisation (dsytd2 recurrences, lower)
     {
         double part2 = 0.;

@@ -198,6 +198,7 @@ struct SpectralWs
     size_t invit_NB = 0; // eigenvectors per inverse-iteration batch the workspace holds
     DevBuf<int64_t> voff, eval_off, evect_off;
     DevBuf<double> V, d, e, tau, sinv, glo, ghi, tn, ws_d;
+    DevBuf<double> G; // distributed copies of the matrices reduced by k_tridiag_reg
     // large-matrix (cooperative) path
     DevBuf<double> Twork, pbuf;
     DevBuf<unsigned int> counters;

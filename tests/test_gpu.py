@@ -123,6 +123,7 @@ def test_atleast_one_fallback_and_tiny_theta():
 @pytest.mark.parametrize("env", [
     {"SA_GPU_COOP_SYM": "0"},        # full-matrix cooperative kernel (k_tridiag_coop)
     {"SA_GPU_SQUARE_TILE": "1"},     # square shared-memory tile kernel (k_at_smem)
+    {"SA_GPU_SMALL_PATH": "packed"}, # round 1's packed shared-memory kernel instead of k_tridiag_reg
     {"SA_GPU_NO_ASYNC_ALLOC": "1"},  # plain cudaMalloc instead of the stream-ordered pool
     {"SA_GPU_COARSE_BLOCKED_MIN": "1"},  # blocked coarsest factorisation even for tiny n
 ])
