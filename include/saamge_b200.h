@@ -288,6 +288,38 @@ int sa_gpu_solver_dev_coarse(sa_gpu_solver *solver, const double *b, double *x);
 /* polynomial degree, roots (at most cap entries) and coarsest size of a solver */
 int sa_gpu_solver_info(sa_gpu_solver *solver, int *degree, double *roots, int cap, int *nc);
 
+/* ---- row-partitioned multi-GPU solve (dist.cu): one process per GPU, NCCL over NVLink ----
+ * Replaces the reference's hypre ParCSR matvecs with their MPI halo exchange inside
+ * tg_cycle_atb (amg/src/tg.cpp:91-132), smpr_compute_poly (amg/inc/smpr.hpp:319-339) and
+ * kalchev_pcg (amg/src/mfem_addons.cpp:106-248).  Every rank holds the hierarchy and owns the
+ * rows [n q / N, n (q + 1) / N) of every level. */
+typedef struct sa_gpu_comm sa_gpu_comm;
+typedef struct sa_gpu_dist_solver sa_gpu_dist_solver;
+/* rank 0: 128-byte NCCL unique id, to be handed to every rank by the caller's launcher */
+int sa_gpu_nccl_unique_id(void *id128);
+/* collective over the nranks processes (nranks == 1: no NCCL communicator is created) */
+int sa_gpu_comm_create(sa_gpu_ctx *ctx, const void *id128, int nranks, int rank, sa_gpu_comm **out);
+void sa_gpu_comm_destroy(sa_gpu_comm *comm);
+/* halo plans (packed boundary lists per matrix and peer), vectors; the solver must outlive it */
+int sa_gpu_dist_solver_create(sa_gpu_solver *solver, sa_gpu_comm *comm, sa_gpu_dist_solver **out);
+void sa_gpu_dist_solver_destroy(sa_gpu_dist_solver *d);
+/* PCG from x0 = 0 with the V-cycle preconditioner; b, x: full-length host vectors (x: the rank's
+ * rows, or the whole solution on every rank when gather != 0); iters as kalchev_pcg returns it
+ * (negative: not converged / SPD breakdown); brr_hist: (Br, r) per iteration; solve_seconds:
+ * device time of the iteration (CUDA events on the library's stream) */
+int sa_gpu_dist_pcg(sa_gpu_dist_solver *d, const double *b, double *x, int maxiter, double rtol,
+                    double atol, int gather, int *iters, double *brr_hist, int hist_cap,
+                    int *hist_len, double *solve_seconds);
+int sa_gpu_dist_solver_stats(sa_gpu_dist_solver *d, int *row_begin, int *row_end, long *halo_calls,
+                             long *halo_doubles);
+/* host only (no GPU needed): the exchange lists of `rank` for one CSR pattern partitioned by
+ * rows (row_part) and columns (col_part), nranks + 1 entries each.  send_cnt / recv_cnt: per
+ * peer; send_idx / recv_idx: concatenated, peer-major, ascending.  Returns 2 (and the needed
+ * sizes in n_send / n_recv) when a capacity is too small. */
+int sa_gpu_halo_plan(int rows, const int *I, const int *J, int nranks, int rank, const int *row_part,
+                     const int *col_part, int *send_cnt, int *recv_cnt, int *send_idx, int send_cap,
+                     int *recv_idx, int recv_cap, int *n_send, int *n_recv);
+
 /* ---- micro-benchmarks used by bench.py for the roofline denominators ---- */
 /* runs `reps` SpMVs y = A x on device-resident vectors; returns ms per SpMV */
 double sa_gpu_bench_spmv(sa_gpu_level *level, int which, int reps);

@@ -61,28 +61,29 @@ def test_allgather_spectral_world2():
 
 
 def test_halo_plan_is_consistent():
-    """Every piece a rank plans to receive is planned as a send by its owner and lies in the
-    owner's range; together the pieces cover the needed range outside the own rows."""
-    from saamge_b200.dist_solve import _ranges, halo_plan
+    """sa_gpu_halo_plan (host side of the row-partitioned solve, saamge_b200/csrc/dist.cu): what a
+    rank plans to receive from q is exactly what q plans to send to it, lies in q's column range,
+    and together with the own range covers every column the rank's rows reference."""
+    import scipy.sparse as sp
+
+    from saamge_b200.dist_solve import _ranges, halo_plan_lists
 
     rng = np.random.default_rng(1)
     for world in (2, 3, 8):
-        n = 1000
-        part = _ranges(n, world)
-        need = []
-        for q in range(world):
-            lo = max(0, part[q] - int(rng.integers(0, 300)))
-            hi = min(n, part[q + 1] + int(rng.integers(0, 300)))
-            need.append((lo, hi))
-        plans = [halo_plan(need, part, q) for q in range(world)]
-        for me in range(world):
-            sends, recvs = plans[me]
-            covered = np.zeros(n, dtype=bool)
-            covered[part[me]:part[me + 1]] = True
-            for q, lo, hi in recvs:
-                assert part[q] <= lo < hi <= part[q + 1]
-                assert (me, lo, hi) in plans[q][0]
-                covered[lo:hi] = True
-            assert covered[need[me][0]:need[me][1]].all()
-            for q, lo, hi in sends:
-                assert (me, lo, hi) in plans[q][1]
+        for rows, cols in ((1000, 1000), (1000, 317), (40, 1000)):
+            M = sp.random(rows, cols, density=0.01, random_state=int(rng.integers(1 << 30)), format="csr")
+            M = (M + sp.eye(rows, cols, k=0) + sp.eye(rows, cols, k=1)).tocsr()
+            M.sort_indices()
+            rp, cp = _ranges(rows, world), _ranges(cols, world)
+            plans = [halo_plan_lists(M.indptr, M.indices, world, q, rp, cp) for q in range(world)]
+            for me in range(world):
+                send, recv = plans[me]
+                ref = np.unique(M.indices[M.indptr[rp[me]]:M.indptr[rp[me + 1]]])
+                outside = ref[(ref < cp[me]) | (ref >= cp[me + 1])]
+                got = np.concatenate(recv) if world else np.zeros(0, dtype=np.int32)
+                assert np.array_equal(np.sort(got), outside)
+                assert len(recv[me]) == 0 and len(send[me]) == 0
+                for q in range(world):
+                    assert np.all((recv[q] >= cp[q]) & (recv[q] < cp[q + 1]))
+                    assert np.array_equal(recv[q], plans[q][0][me])  # q sends what I expect
+                    assert np.all(np.diff(recv[q]) > 0)
