@@ -493,24 +493,25 @@ def main():
     traffic = None  # DRAM bytes per step of the dominant kernel, from the committed ncu capture
     ncu_note = None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         if tj.get("workload") == args.workload and world == 1:
-            traffic = tj["k_at_packed"]["dram_bytes_per_step"]
-            ncu_note = tj["k_at_packed"].get("ncu")
+            traffic = tj["eigen_stage"]["dram_bytes_per_step"]
+            ncu_note = tj["eigen_stage"].get("ncu")
     except Exception:
         traffic = None
     achieved = flops / (kern_ms * 1e-3) / 1e12
     roofline = {
-        "kernel": "k_at_packed (assemble + weighted-l1 scaling + Householder tridiagonalisation; "
-                  "one launch per occupancy class, side by side on three streams, timed together)",
-        "bound": "fp64", "bound_detail": "FP64 FMA pipe; the kernel is shared-memory / latency bound at n ~ 125 "
-                                         "(no tensor instruction: BLAS-2 shaped work)",
+        "kernel": "k_tridiag_reg<S> (register-resident Householder tridiagonalisation, one launch per size "
+                  "class and upload piece) fed by k_at_packed (assembly + weighted-l1 scaling); classes side by "
+                  "side on three streams, timed together",
+        "bound": "fp64", "bound_detail": "FP64 FMA pipe; at n ~ 125 the ~n dependent Householder steps are latency / "
+                                         "issue bound (no tensor instruction: BLAS-2 shaped work)",
         "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
         "frac": (achieved / fp64_peak) if fp64_peak else None,
         "peak_source": "measured in this run: dependent-free DFMA loop (sa_gpu_bench_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
         "algorithmic_flops_per_step": flops, "algorithmic_bytes_per_step": abytes,
         "kernel_ms_per_step": kern_ms, "stage_ms": prof, "traffic": traffic,
-        "traffic_source": "profiles/r01_traffic.json (ncu dram bytes, per step)" if traffic else None,
+        "traffic_source": "profiles/r02_traffic.json (ncu dram bytes of the k_at_packed + k_tridiag_reg launches of one step)" if traffic else None,
         "ncu": ncu_note,  # pipe utilisation of the committed capture (not measured in this run)
     }
 
@@ -558,29 +559,40 @@ def main():
         setup_s = max_over_ranks(time.time() - t0)
         hier = {"levels": w["levels"], "setup_s": setup_s, "setup_sharded_over_gpus": world,
                 "host_pin_s": pin_s}
-        if world > 1:
-            from saamge_b200.dist_solve import DistSolver
+        from saamge_b200.dist_solve import DistSolver
 
-            S = DistSolver(H, dist)
-            bvec = pr.get("b")
-            S.pcg(bvec, maxiter=2)  # warm-up (NCCL channels)
-            barrier()
-            t0 = time.time()
-            _x, its_d, _brr = S.pcg(bvec)
-            barrier()
-            hier["pcg_s"] = max_over_ranks(time.time() - t0)
-            hier["pcg_gpus"] = world
-            hier["pcg_iterations"] = int(its_d)
-            its = int(its_d)
+        # PCG of the library's row-partitioned solver (saamge_b200/csrc/dist.cu) on all N ranks;
+        # N = 1: the same loop without any exchange
+        S = DistSolver(H, dist if world > 1 else None)
+        bvec = pr.get("b")
+        S.pcg(bvec, maxiter=2)  # warm-up (NCCL channels)
+        barrier()
+        t0 = time.time()
+        _x, its_d, _brr = S.pcg(bvec)
+        barrier()
+        hier["pcg_s"] = max_over_ranks(time.time() - t0)
+        hier["pcg_device_s"] = max_over_ranks(S.solve_seconds)
+        hier["pcg_gpus"] = world
+        hier["pcg_iterations"] = int(its_d)
+        its = int(its_d)
+        bpi = S.bytes_per_iteration()
+        hbm = peaks.get("hbm_gbs") if peaks else None
+        ach = bpi * abs(its) / hier["pcg_device_s"] / 1e9 if its else None
+        hier["roofline_pcg"] = {
+            "bound": "hbm", "achieved": ach, "peak": (hbm * world) if hbm else None, "unit": "GB/s",
+            "frac": (ach / (hbm * world)) if (ach and hbm) else None, "traffic": None,
+            "ms_per_iteration": 1e3 * hier["pcg_device_s"] / max(1, abs(its)),
+            "algorithmic_bytes_per_iteration": bpi,
+            "what": "per level (2 deg + 1) A-SpMVs + fused smoother vectors + 2 P-SpMVs, one A-SpMV and 56 B/row "
+                    "of vector traffic on the finest level (SURVEY section 8d); peak = N x measured copy bandwidth",
+            "levels_rows_nnzA_nnzP": S.level_info()}
+        halo = S.stats()
+        hier["halo"] = {"exchanges": int(halo[2]), "doubles_sent_by_rank0": int(halo[3])} if world > 1 else None
         if rank == 0:
             t0 = time.time()
             its1 = sab.ml_pcg(H, 1000, 1e-12, 0.0)
             t1 = time.time() - t0
-            if world == 1:
-                hier.update({"pcg_s": t1, "pcg_gpus": 1, "pcg_iterations": its1})
-                its = its1
-            else:
-                hier.update({"pcg_s_one_gpu": t1, "pcg_iterations_one_gpu": its1})
+            hier.update({"pcg_s_host_api_one_gpu": t1, "pcg_iterations_one_gpu": its1})
             hier.update({"final_residual": H.scalar("pcg.final_res_norm"),
                          "stage_s": {k: round(v, 4) for k, v in H.times().items()},
                          "dofs": [int(H.scalar("ND", l)) for l in range(w["levels"] - 1)]})

@@ -312,6 +312,8 @@ int sa_gpu_dist_pcg(sa_gpu_dist_solver *d, const double *b, double *x, int maxit
                     int *hist_len, double *solve_seconds);
 int sa_gpu_dist_solver_stats(sa_gpu_dist_solver *d, int *row_begin, int *row_end, long *halo_calls,
                              long *halo_doubles);
+/* rows, nnz(A), nnz(P) of one level (for the bytes-per-iteration roofline of the solve) */
+int sa_gpu_dist_solver_level_info(sa_gpu_dist_solver *d, int level, int *rows, long *nnz_A, long *nnz_P);
 /* host only (no GPU needed): the exchange lists of `rank` for one CSR pattern partitioned by
  * rows (row_part) and columns (col_part), nranks + 1 entries each.  send_cnt / recv_cnt: per
  * peer; send_idx / recv_idx: concatenated, peer-major, ascending.  Returns 2 (and the needed

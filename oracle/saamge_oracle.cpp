@@ -1264,6 +1264,141 @@ extern "C" void *sa_orc_ml_build(void *prob_, const sa_drv_params_t *p)
     return H;
 }
 
+/* ---- algebraic entry: the oracle's own restatement of ExtractSubMatrices and of the
+   ElementMatrixArray provider (amg/src/tg.cpp:580-668, amg/src/elmat.cpp:197-225); the relations
+   are the caller's (cells = dofs), as in tg_produce_data_algebraic (amg/src/tg.cpp:862-886) ---- */
+namespace saamge_oracle
+{
+static void orc_extract_submatrices(const SparseMatrix &A, const agg_partitioning_relations_t &rels,
+                                    std::vector<SparseMatrix *> &out)
+{
+    const int nparts = rels.nparts;
+    out.assign(nparts, (SparseMatrix *)NULL);
+    for (int part = 0; part < nparts; ++part)
+    {
+        const int localsize = rels.AE_to_dof->RowSize(part);
+        const int *row = rels.AE_to_dof->GetRow(part);
+        // LIL build with Set(), rows finalised with ascending columns
+        std::vector<std::map<int, double>> lil(localsize);
+        for (int i = 0; i < localsize; ++i)
+        {
+            const int glob_dof = row[i];
+            for (int j = A.I[glob_dof]; j < A.I[glob_dof + 1]; ++j)
+            {
+                const int glob_neigh = A.J[j];
+                if (agg_elem_in_col(glob_neigh, part, *rels.dof_to_AE) < 0)
+                    continue;
+                const int local_neigh = agg_map_id_glob_to_AE(glob_neigh, part, rels);
+                if (0. != A.A[j])
+                    lil[i][local_neigh] = A.A[j];
+            }
+        }
+        if (localsize > 1)
+        {
+            for (int i = 0; i < localsize; ++i)
+            {
+                double rowsum = 0.;
+                for (std::map<int, double>::const_iterator it = lil[i].begin(); it != lil[i].end(); ++it)
+                    rowsum += it->second;
+                if (lil[i].size() > 1)
+                    lil[i][i] += -rowsum;
+                if (lil[i][i] <= 0.0)
+                    lil[i][i] = 1.0;
+            }
+        }
+        else
+            lil[0][0] = 1.0;
+        SparseMatrix *S = new SparseMatrix;
+        S->h = S->w = localsize;
+        S->I.assign((size_t)localsize + 1, 0);
+        for (int i = 0; i < localsize; ++i)
+        {
+            for (std::map<int, double>::const_iterator it = lil[i].begin(); it != lil[i].end(); ++it)
+            {
+                S->J.push_back(it->first);
+                S->A.push_back(it->second);
+            }
+            S->I[i + 1] = (int)S->J.size();
+        }
+        out[part] = S;
+    }
+}
+
+class OrcElementMatrixArray : public ElementMatrixProvider
+{
+public:
+    OrcElementMatrixArray(const agg_partitioning_relations_t &rels, const std::vector<SparseMatrix *> &m)
+        : ElementMatrixProvider(rels), m_(m)
+    {
+    }
+    virtual ~OrcElementMatrixArray()
+    {
+        for (size_t i = 0; i < m_.size(); ++i)
+            delete m_[i];
+    }
+    virtual Matrix *GetMatrix(int elno, bool &free_matr) const
+    {
+        free_matr = true;
+        return BuildAEStiff(elno);
+    }
+    // (a copy: the oracle's level owns and frees what BuildAEStiff returns)
+    virtual SparseMatrix *BuildAEStiff(int elno) const { return new SparseMatrix(*m_[elno]); }
+
+private:
+    std::vector<SparseMatrix *> m_;
+};
+} // namespace saamge_oracle
+
+extern "C" void *sa_orc_ml_build_algebraic(void *prob_, const sa_drv_params_t *p)
+{
+    sa_problem_t *prob = (sa_problem_t *)prob_;
+    SA_ASSERT(prob && prob->rels);
+    sa_hierarchy_t *H = new sa_hierarchy_t;
+    H->prob = prob;
+    H->params = *p;
+    oracle_ml_t *ml = new oracle_ml_t;
+    H->impl = ml;
+    H->impl_free = oracle_impl_free;
+    const int coarsenings = p->num_levels - 1;
+    std::vector<int> nparts_arr = sa_target_nparts(prob->fem->NE, *p);
+    const bool avoid = p->avoid_ess_bdr_dofs != 0;
+    const double tstart = now_s();
+    H->rels.push_back(prob->rels);
+    for (int i = 0; i < coarsenings; ++i)
+    {
+        oracle_level_t *L = new oracle_level_t;
+        ml->levels.push_back(L);
+        if (i == 0)
+        {
+            L->agg_part_rels = prob->rels;
+            L->A = &prob->fem->A;
+            std::vector<SparseMatrix *> mats;
+            orc_extract_submatrices(prob->fem->A, *prob->rels, mats);
+            L->elem_data = new OrcElementMatrixArray(*prob->rels, mats);
+        }
+        else
+        {
+            oracle_level_t *F = ml->levels[i - 1];
+            int nparts = nparts_arr[i];
+            int *partitioning = sa_prescribed_coarse_partitioning(*prob, *p, i, F->agg_part_rels->nparts, &nparts);
+            agg_partitioning_relations_t *rels = orc_create_partitioning_coarse(
+                *F->agg_part_rels, *F->ltent_interp, F->mis_numcoarsedof.data(), &nparts, partitioning);
+            H->rels.push_back(rels);
+            L->agg_part_rels = rels;
+            L->A = F->Ac;
+            L->elem_data = new ElementMatrixParallelCoarse(*rels, F);
+        }
+        tg_build_level(*L, i == 0 ? p->first_nu_pro : p->nu_pro, p->nu_relax,
+                       i == 0 ? p->first_theta : p->theta, avoid, H->times, i);
+    }
+    factor_coarsest(*ml->levels.back());
+    H->times["setup"] = now_s() - tstart;
+    H->levels.resize(coarsenings);
+    for (int i = 0; i < coarsenings; ++i)
+        export_level(*ml->levels[i], H->levels[i], i + 1 < coarsenings ? ml->levels[i + 1]->elem_data : NULL);
+    return H;
+}
+
 extern "C" int sa_orc_ml_pcg(void *hier, int maxiter, double rtol, double atol)
 {
     sa_hierarchy_t *H = (sa_hierarchy_t *)hier;

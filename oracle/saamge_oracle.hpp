@@ -156,6 +156,8 @@ extern "C" {
    read with sa_drv_get / freed with sa_drv_hier_destroy from the host library. */
 void sa_orc_init(const char *lapack_path, int num_threads);
 void *sa_orc_ml_build(void *prob, const sa_drv_params_t *p);
+/* algebraic entry (problem from sa_drv_problem_from_matrix): ExtractSubMatrices + ElementMatrixArray */
+void *sa_orc_ml_build_algebraic(void *prob, const sa_drv_params_t *p);
 int sa_orc_ml_pcg(void *hier, int maxiter, double rtol, double atol);
 /* times only the local spectral stage (a2-a7) on AEs [ae_begin, ae_end) of the
    finest level; returns seconds */

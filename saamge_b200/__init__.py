@@ -144,6 +144,31 @@ class Problem:
         self.handle = host_lib().sa_drv_problem_create(dim, n, ny, nz, order, coef_kind, contrast, seed)
         self.dim, self.n, self.order = dim, n, order
 
+    @classmethod
+    def from_matrix(cls, A, elems_per_agg, b=None, isolated=()):
+        """Algebraic entry (amg/test/algebraic/algebraic.cpp:219-262): cells = dofs, agglomerates
+        = METIS parts of the matrix graph, `isolated` dofs become agglomerates of their own.
+        A: scipy CSR.  The problem comes back already partitioned."""
+        import scipy.sparse as sp
+
+        A = sp.csr_matrix(A)
+        A.sort_indices()
+        h = host_lib()
+        h.sa_drv_problem_from_matrix.restype = ctypes.c_void_p
+        h.sa_drv_problem_from_matrix.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                 ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+        I = np.ascontiguousarray(A.indptr, dtype=np.int32)
+        J = np.ascontiguousarray(A.indices, dtype=np.int32)
+        V = np.ascontiguousarray(A.data, dtype=np.float64)
+        iso = np.ascontiguousarray(list(isolated), dtype=np.int32)
+        bb = None if b is None else np.ascontiguousarray(b, dtype=np.float64)
+        self = cls.__new__(cls)
+        self.handle = h.sa_drv_problem_from_matrix(A.shape[0], I.ctypes.data, J.ctypes.data, V.ctypes.data,
+                                                   None if bb is None else bb.ctypes.data, elems_per_agg,
+                                                   iso.ctypes.data if len(iso) else None, len(iso))
+        self.dim, self.n, self.order = 0, A.shape[0], 1
+        return self
+
     def partition(self, params):
         return host_lib().sa_drv_problem_partition(self.handle, ctypes.byref(params))
 
@@ -304,6 +329,14 @@ def ml_build(problem, params, device=0):
     """ml_produce_data through the B200 path; returns a Hierarchy."""
     h = host_lib().sa_drv_ml_build(problem.handle, ctypes.byref(params), device)
     return Hierarchy(h)
+
+
+def ml_build_algebraic(problem, params, device=0):
+    """tg_produce_data_algebraic / ml form (amg/src/tg.cpp:862-886) for a Problem.from_matrix."""
+    h = host_lib()
+    h.sa_drv_ml_build_algebraic.restype = ctypes.c_void_p
+    h.sa_drv_ml_build_algebraic.argtypes = [ctypes.c_void_p, ctypes.POINTER(Params), ctypes.c_int]
+    return Hierarchy(h.sa_drv_ml_build_algebraic(problem.handle, ctypes.byref(params), device))
 
 
 def ml_pcg(hier, maxiter=1000, rtol=1e-12, atol=0.0):

@@ -693,3 +693,16 @@ extern "C" int sa_gpu_dist_solver_stats(sa_gpu_dist_solver *D, int *row_begin, i
     *halo_doubles = D->halo_doubles;
     SA_API_END
 }
+
+/* sizes of one level of the distributed solver: rows, nnz(A), nnz(P); returns 1 past the last */
+extern "C" int sa_gpu_dist_solver_level_info(sa_gpu_dist_solver *D, int level, int *rows, long *nnz_A,
+                                             long *nnz_P)
+{
+    SA_API_BEGIN
+    if (level < 0 || level >= (int)D->L.size())
+        SA_FAIL("sa_gpu_dist_solver_level_info: no level %d", level);
+    *rows = D->L[level]->n;
+    *nnz_A = D->L[level]->A.M->nnz;
+    *nnz_P = D->L[level]->P.M->nnz;
+    SA_API_END
+}

@@ -261,6 +261,46 @@ __global__ void k_pcg_dir(int n, double beta, const double *z, double *d)
     d[i] = z[i] + beta * d[i];
 }
 
+// the same updates with alpha = *nom / *den and beta = *betanom / *nom read from device scalars
+// (the host reads one scalar per iteration, for the convergence test)
+__global__ void k_pcg_update_dev(int n, const double *nom, const double *den, const double *d,
+                                 const double *z, double *x, double *r)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const double alpha = *nom / *den;
+    x[i] = x[i] + alpha * d[i];
+    r[i] = r[i] - alpha * z[i];
+}
+__global__ void k_pcg_dir_dev(int n, const double *betanom, const double *nom, const double *z,
+                              double *d)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const double beta = *betanom / *nom;
+    d[i] = z[i] + beta * d[i];
+}
+
+// (a, b) into the device scalar S->dots[slot]; no host synchronisation
+void dev_dot_async(sa_gpu_solver *S, int n, const double *a, const double *b, int slot)
+{
+    sa_gpu_ctx *ctx = S->ctx;
+    const int blocks = std::max(1, std::min(ctx->num_sms * 4, (n + 255) / 256));
+    S->dot_partials.ensure(blocks);
+    SA_LAUNCH(ctx, k_dot, blocks, 256, 0, n, a, b, S->dot_partials.p);
+    SA_LAUNCH(ctx, k_dot_final, 1, 32, 0, blocks, S->dot_partials.p, S->dots.p + slot);
+}
+double dev_read_scalar(sa_gpu_solver *S, int slot)
+{
+    double h = 0.;
+    SA_CUDA(cudaMemcpyAsync(&h, S->dots.p + slot, sizeof(double), cudaMemcpyDeviceToHost,
+                            S->ctx->stream));
+    SA_CUDA(cudaStreamSynchronize(S->ctx->stream));
+    return h;
+}
+
 double dev_dot(sa_gpu_solver *S, int n, const double *a, const double *b)
 {
     sa_gpu_ctx *ctx = S->ctx;
@@ -518,13 +558,16 @@ static int pcg_resident(sa_gpu_solver *S, int max_num_iter, double RTOLERANCE, d
     const int tb = 256, gb = (dim + tb - 1) / tb;
     double *x = S->px.p, *b = S->pb.p, *r = S->pr.p, *d = S->pd.p, *z = S->pz.p;
     int i, iters = 0, hl = 0;
-    double r0, den, nom, betanom = 0., alpha, beta;
+    double r0, den, nom, betanom = 0.;
 
     dev_residual(ctx, A, x, b, r); // r = b - A x
     precond(S, r, z);
     SA_CUDA(cudaMemcpyAsync(d, z, (size_t)dim * sizeof(double), cudaMemcpyDeviceToDevice,
                             ctx->stream));
-    nom = dev_dot(S, dim, z, r);
+    // device scalars: dots[1 + s_nom] = nom, dots[3] = den, dots[1 + s_beta] = betanom
+    int s_nom = 0, s_beta = 1;
+    dev_dot_async(S, dim, z, r, 1 + s_nom);
+    nom = dev_read_scalar(S, 1 + s_nom);
     if (brr_hist && hl < hist_cap)
         brr_hist[hl++] = nom;
     if (hist_len)
@@ -534,15 +577,16 @@ static int pcg_resident(sa_gpu_solver *S, int max_num_iter, double RTOLERANCE, d
     if (nom < r0)
         return -1;
     dev_spmv(ctx, A, d, z);
-    den = dev_dot(S, dim, z, d);
+    dev_dot_async(S, dim, z, d, 3);
+    den = dev_read_scalar(S, 3);
     if (0. == den)
         return -1;
     for (i = 1; i <= max_num_iter; i++)
     {
-        alpha = nom / den;
-        SA_LAUNCH(ctx, k_pcg_update, gb, tb, 0, dim, alpha, d, z, x, r);
+        SA_LAUNCH(ctx, k_pcg_update_dev, gb, tb, 0, dim, S->dots.p + 1 + s_nom, S->dots.p + 3, d, z, x, r);
         precond(S, r, z);
-        betanom = dev_dot(S, dim, r, z);
+        dev_dot_async(S, dim, r, z, 1 + s_beta);
+        betanom = dev_read_scalar(S, 1 + s_beta); // the one host read per iteration
         if (brr_hist && hl < hist_cap)
             brr_hist[hl++] = betanom;
         if (betanom < 0.0)
@@ -555,11 +599,10 @@ static int pcg_resident(sa_gpu_solver *S, int max_num_iter, double RTOLERANCE, d
             iters = i;
             break;
         }
-        beta = betanom / nom;
-        SA_LAUNCH(ctx, k_pcg_dir, gb, tb, 0, dim, beta, z, d);
+        SA_LAUNCH(ctx, k_pcg_dir_dev, gb, tb, 0, dim, S->dots.p + 1 + s_beta, S->dots.p + 1 + s_nom, z, d);
         dev_spmv(ctx, A, d, z);
-        den = dev_dot(S, dim, d, z);
-        nom = betanom;
+        dev_dot_async(S, dim, d, z, 3);
+        std::swap(s_nom, s_beta);
     }
     if (i > max_num_iter)
         iters = -(i - 1);

@@ -115,6 +115,33 @@ class DistSolver:
         assert rc == 0, self.g.sa_gpu_last_error()
         return r0.value, r1.value, hc.value, hd.value
 
+    def level_info(self):
+        """[(rows, nnz(A), nnz(P))] per level."""
+        out = []
+        self.g.sa_gpu_dist_solver_level_info.argtypes = [ctypes.c_void_p, ctypes.c_int, _ip,
+                                                         ctypes.POINTER(ctypes.c_long),
+                                                         ctypes.POINTER(ctypes.c_long)]
+        l = 0
+        while True:
+            n, a, p = ctypes.c_int(), ctypes.c_long(), ctypes.c_long()
+            if self.g.sa_gpu_dist_solver_level_info(self.d, l, ctypes.byref(n), ctypes.byref(a), ctypes.byref(p)):
+                break
+            out.append((n.value, a.value, p.value))
+            l += 1
+        return out
+
+    def bytes_per_iteration(self, degree=10):
+        """Algorithmic HBM bytes of one PCG iteration: per level
+        (2 deg + 1) A-SpMV equivalents (12 nnz + 20 rows, + 24 rows per fused smoother step) and
+        two P-SpMVs; plus one A-SpMV and ~56 rows of vector traffic on the finest level."""
+        tot = 0.0
+        info = self.level_info()
+        for (n, a, p) in info:
+            spmv = 12.0 * a + 20.0 * n
+            tot += (2 * degree + 1) * spmv + 2 * degree * 24.0 * n + 2 * (12.0 * p + 20.0 * n)
+        n0, a0, _ = info[0]
+        return tot + 12.0 * a0 + 20.0 * n0 + 56.0 * n0
+
     def pcg(self, b_host, maxiter=1000, rtol=1e-12, atol=0.0, gather=False):
         """kalchev_pcg, x0 = 0.  Returns (x, iters, brr); x: full-length host vector holding the
         rank's rows (the whole solution with gather=True)."""

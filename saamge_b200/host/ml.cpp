@@ -1370,6 +1370,38 @@ extern "C" void *sa_drv_ml_build(void *prob_, const sa_drv_params_t *p, int devi
     return H;
 }
 
+/* Algebraic entry (algebraic.cpp): the problem comes from sa_drv_problem_from_matrix; local
+   matrices by ExtractSubMatrices, then the ordinary multilevel build.  Level 0 of the handle
+   reports the caller's relations (cells = dofs). */
+extern "C" void *sa_drv_ml_build_algebraic(void *prob_, const sa_drv_params_t *p, int device)
+{
+    sa_problem_t *prob = (sa_problem_t *)prob_;
+    SA_ASSERT(prob && prob->rels);
+    proc_gpu_init(device);
+    sa_hierarchy_t *H = new sa_hierarchy_t;
+    H->prob = prob;
+    H->params = *p;
+    product_impl_t *pi = new product_impl_t;
+    H->impl = pi;
+    H->impl_free = product_impl_free;
+    H->owns_rels = false;
+    const fem_problem_t &f = *prob->fem;
+    std::vector<int> nparts_arr = sa_target_nparts(f.NE, *p);
+    nparts_arr[0] = prob->rels->nparts;
+    const double t0 = now_s();
+    MultilevelParameters mlp(p->num_levels - 1, nparts_arr.data(), p->first_nu_pro, p->nu_pro,
+                             p->nu_relax, p->first_theta, p->theta, -1, false, false, false);
+    mlp.set_coarse_direct(true);
+    pi->ml = ml_produce_data_algebraic(f.A, *prob->rels, mlp);
+    sa_gpu_ctx_sync(proc_gpu_ctx());
+    H->times["setup"] = now_s() - t0;
+    for (size_t i = 0; i < g_stage_log.size(); ++i)
+        H->times[g_stage_log[i].first] += g_stage_log[i].second;
+    for (levels_level_t *l = pi->ml->levels_list.finest; l; l = l->coarser)
+        H->rels.push_back(l == pi->ml->levels_list.finest ? prob->rels : l->agg_part_rels);
+    return H;
+}
+
 extern "C" int sa_drv_ml_download(void *hier)
 {
     sa_hierarchy_t *H = (sa_hierarchy_t *)hier;

@@ -78,6 +78,29 @@ private:
     const int64_t *offsets_;
 };
 
+/// Agglomerate matrices given directly (amg/inc/elmat.hpp:142-151): GetMatrix and BuildAEStiff
+/// both return the matrix of agglomerate \a elno (not a copy; the provider owns the matrices).
+/// BatchedRelations(): relations whose elements are the agglomerates -- the form in which the
+/// device path takes them (one dense element block per agglomerate).
+class ElementMatrixArray : public ElementMatrixProvider
+{
+public:
+    ElementMatrixArray(const agg_partitioning_relations_t &agg_part_rels,
+                       const std::vector<SparseMatrix *> &elem_matrs);
+    virtual ~ElementMatrixArray();
+    virtual Matrix *GetMatrix(int elno, bool &free_matr) const;
+    virtual SparseMatrix *BuildAEStiff(int elno) const;
+    virtual const double *DenseBlocks() const { return blocks_.data(); }
+    virtual const int64_t *DenseBlockOffsets() const { return offsets_.data(); }
+    const agg_partitioning_relations_t &BatchedRelations() const { return *brels_; }
+
+private:
+    std::vector<SparseMatrix *> elem_matrs_;
+    std::vector<double> blocks_;
+    std::vector<int64_t> offsets_;
+    agg_partitioning_relations_t *brels_;
+};
+
 struct levels_level_struct;
 
 /// Coarse "element" matrices P_e^T A_AE(e) P_e of the finer level's AEs; they are
@@ -284,10 +307,25 @@ void interp_sparse_tent_assemble(const agg_partitioning_relations_t &agg_part_re
                                  interp_data_t &interp_data, tg_data_t &tg_data,
                                  bool avoid_ess_bdr_dofs);
 
+/* ---- algebraic (matrix-only) entry: algebraic.cpp; amg/src/tg.cpp:580-668, 862-886,
+        amg/src/fem.cpp:720-762 ---- */
+void ExtractSubMatrices(const SparseMatrix &A, const agg_partitioning_relations_t &agg_part_rels,
+                        std::vector<SparseMatrix *> &agglomerate_element_matrices);
+agg_partitioning_relations_t *fem_create_partitioning_from_matrix(const SparseMatrix &A, int *nparts,
+                                                                   const std::vector<int> &isolated_cells);
+tg_data_t *tg_produce_data_algebraic(const SparseMatrix &Alocal, const SparseMatrix &Ag,
+                                     const agg_partitioning_relations_t &agg_part_rels, int nu_pro,
+                                     int nu_relax, double spectral_tol, bool smooth_interp,
+                                     int polynomial_coarse_arg, bool use_window, bool use_arpack,
+                                     bool avoid_ess_bdr_dofs);
+SparseMatrix *ReadHypreMat(const char *filename);
+
 /* ---- multilevel entry points ---- */
 ml_data_t *ml_produce_data(const SparseMatrix &Ag, agg_partitioning_relations_t *agg_part_rels,
                            ElementMatrixProvider *elem_data_finest,
                            const MultilevelParameters &mlp);
+ml_data_t *ml_produce_data_algebraic(const SparseMatrix &Ag, const agg_partitioning_relations_t &agg_part_rels,
+                                     const MultilevelParameters &mlp);
 void ml_produce_hierarchy_from_level(int coarsenings, int starting_level, ml_data_t &ml_data,
                                      const MultilevelParameters &mlp);
 void ml_impose_cycle(ml_data_t &ml_data, bool Wcycle);

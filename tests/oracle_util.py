@@ -45,3 +45,10 @@ def orc_build(problem, params):
 
 def orc_pcg(hier, maxiter=1000, rtol=1e-12, atol=0.0):
     return oracle().sa_orc_ml_pcg(hier.handle, maxiter, rtol, atol)
+
+
+def orc_build_algebraic(problem, params):
+    o = oracle()
+    o.sa_orc_ml_build_algebraic.restype = ctypes.c_void_p
+    o.sa_orc_ml_build_algebraic.argtypes = [ctypes.c_void_p, ctypes.POINTER(sab.Params)]
+    return sab.Hierarchy(o.sa_orc_ml_build_algebraic(problem.handle, ctypes.byref(params)))

@@ -128,3 +128,31 @@ def test_c3_level0_every_agglomerate_against_the_oracle():
     print("C3 level 0: 40320 AEs, ae_m identical, max eigenvalue error %.2e, D relerr %.2e, "
           "AEs with an eigenvalue within 1e-12 of theta: %d" % (worst, drel, near_theta))
     pr.close()
+
+
+def test_algebraic_entry_anisotropic_matrix():
+    """tg_produce_data_algebraic / ExtractSubMatrices on the reference's
+    own input (amg/data/anisotropic.mat.00000 -> tests/golden/anisotropic_mat.npz): CUDA path vs the
+    oracle's separate restatement, stage by stage, and the PCG iteration count (upstream pin: 12,
+    soft -- see tests/test_oracle.py::test_algebraic_ctest_pin)."""
+    import scipy.sparse as sp
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "anisotropic_mat.npz"))
+    A = sp.csr_matrix((z["data"], z["indices"], z["indptr"]), shape=tuple(z["shape"]))
+    pr = sab.Problem.from_matrix(A, 128, isolated=[0])
+    p = sab.default_params(num_levels=2, first_elems_per_agg=128, elems_per_agg=128, first_nu_pro=0, nu_pro=0)
+    p.first_theta = p.theta = 0.01
+    Ho = ou.orc_build_algebraic(pr, p)
+    ito = ou.orc_pcg(Ho)
+    Hg = sab.ml_build_algebraic(pr, p)
+    itg = sab.ml_pcg(Hg)
+    sab.ml_download(Hg)
+    res = parity.compare_hierarchies(Hg, Ho, expect_levels=1)
+    for l, m in enumerate(res):
+        parity.assert_level_ok(m, l)
+    assert itg > 0 and abs(itg - ito) <= 1 and 9 <= itg <= 15, (itg, ito)
+    x = Hg.get("pcg.x")
+    assert np.linalg.norm(A @ x - 1.0) <= 1e-4 * np.sqrt(A.shape[0])  # (stopping test is on (Br, r))
+    for h in (Hg, Ho):
+        h.close()
+    pr.close()

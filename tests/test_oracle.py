@@ -1,5 +1,7 @@
 """CPU tests of the oracle: the reference's own pins, the golden fixtures, and
 self-consistency of every stage (the oracle is what the CUDA path is judged against)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -131,4 +133,41 @@ def test_topology_two_independent_constructions(cfg):
     for l in range(1, levels - 1):
         assert o.sa_orc_check_coarse_relations(H.handle, l) == 0, l
     H.close()
+    pr.close()
+
+
+def _anisotropic_problem():
+    import scipy.sparse as sp
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "anisotropic_mat.npz"))
+    A = sp.csr_matrix((z["data"], z["indices"], z["indptr"]), shape=tuple(z["shape"]))
+    # algebraic driver: dof 0 (a decoupled identity row) is eliminated before partitioning and
+    # put back as a coarse dof of its own (amg/test/algebraic/algebraic.cpp:219-262, 279-282)
+    pr = sab.Problem.from_matrix(A, 128, isolated=[0])
+    p = sab.default_params(num_levels=2, first_elems_per_agg=128, elems_per_agg=128, first_nu_pro=0, nu_pro=0)
+    p.first_theta = p.theta = 0.01
+    return A, pr, p
+
+
+def test_algebraic_ctest_pin():
+    """The `algebraic` CTest (amg/test/CMakeLists.txt:72-78): anisotropic.mat.00000, 128 cells per
+    agglomerate, theta = 0.01, nu_pro = 0 -> "Outer PCG converged in 12 iterations".  A SOFT pin
+    (SURVEY section 8c): upstream's run depends on METIS 5.0.2's partition (here: the toolkit's
+    METIS 5.1), ARPACK for the local problems and a BoomerAMG coarse solve.  The oracle gives 15."""
+    A, pr, p = _anisotropic_problem()
+    assert pr.scalar("nparts") == 32 and pr.scalar("ND") == 4096
+    Ho = ou.orc_build_algebraic(pr, p)
+    it = ou.orc_pcg(Ho)
+    assert 12 - 3 <= it <= 12 + 3, it
+    sz = np.diff(Ho.get("AE_to_dof.I", 0))
+    assert sz.sum() == 4096 and sz[-1] == 1  # non-overlapping agglomerates, dof 0 alone
+    # local matrices of ExtractSubMatrices: zero row sums => the constant is in every local
+    # near-null space => at least one vector per agglomerate and P reproduces constants
+    m = Ho.get("ae_m", 0)
+    assert np.all(m >= 1)
+    P = Ho.csr("interp", 0)
+    ones = np.ones(4096)
+    coef = np.linalg.lstsq(P.toarray(), ones, rcond=None)[0]
+    assert np.linalg.norm(P @ coef - ones) <= 1e-8 * np.linalg.norm(ones)
+    Ho.close()
     pr.close()

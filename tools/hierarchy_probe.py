@@ -17,3 +17,8 @@ tm=H.times(); print({k:round(v,3) for k,v in tm.items()})
 for l in range(levels-1):
     print("level",l,"ND",H.scalar("ND",l),"nparts",H.scalar("nparts",l),"mises",H.scalar("num_mises",l))
 t=time.time(); it=sab.ml_pcg(H); print("pcg iters",it,"%.3fs"%(time.time()-t),"res",H.scalar("pcg.final_res_norm"))
+# device-scalar PCG of dist.cu on one rank (no exchange) + operator sizes per level
+from saamge_b200.dist_solve import DistSolver
+S=DistSolver(H,None); b=pr.get("b"); S.pcg(b,maxiter=2)
+t=time.time(); x,it2,brr=S.pcg(b); print("dist-path pcg (1 rank) iters",it2,"wall %.3fs device %.4fs -> %.2f ms/iteration"%(time.time()-t,S.solve_seconds,1e3*S.solve_seconds/max(1,abs(it2))))
+print("levels (rows, nnzA, nnzP)", S.level_info(), "bytes/iteration %.3e -> %.0f GB/s"%(S.bytes_per_iteration(), S.bytes_per_iteration()*abs(it2)/S.solve_seconds/1e9))
