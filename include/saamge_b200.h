@@ -300,6 +300,31 @@ int sa_gpu_nccl_unique_id(void *id128);
 /* collective over the nranks processes (nranks == 1: no NCCL communicator is created) */
 int sa_gpu_comm_create(sa_gpu_ctx *ctx, const void *id128, int nranks, int rank, sa_gpu_comm **out);
 void sa_gpu_comm_destroy(sa_gpu_comm *comm);
+/* ---- sharded setup (SURVEY.md section 8e rows "Tentative P a8-a9" and "Smoothed P / RAP
+   a13-a14"): one process per GPU, every rank holds the level's tables and ran
+   sa_gpu_local_spectral on its own AE range ae_part[rank] .. ae_part[rank + 1].
+
+   sa_gpu_dist_tentative_P: mirror of the reduce-to-owner exchange of
+   ContribTent::CommunicateEigenvectors (amg/src/contrib.cpp:492-549) -- the MIS owner is the rank
+   of the lowest-numbered AE containing it (amg/src/aggregates.cpp:583-593); ONE grouped
+   ncclSend / ncclRecv all-to-all-v moves the MIS-restricted eigenvector blocks to the owners, the
+   owners run the batched SVD (SVDInsert, amg/src/contrib.cpp:551-687), mis_numcoarsedof is
+   all-reduced (the MPI_Scan of :684) and the bases go back to every rank (sec.Broadcast,
+   amg/src/aggregates.cpp:1618).  stats4 (optional): owned MISes, bytes sent, bytes received,
+   bytes of the gathered bases.
+   sa_gpu_dist_coarse_elmats: ElementMatrixParallelCoarse::GetMatrix (amg/src/elmat.cpp:105-195)
+   for the rank's own finer AEs + all-gather-v (ae_part NULL: the ranges of the tentative stage).
+   sa_gpu_dist_smooth_P / sa_gpu_dist_rap: interp_smooth (amg/src/interp.cpp:172-229) and
+   tg_coarse_matr (amg/inc/tg.hpp:695-709) as row-partitioned SpGEMM (hypre ParMult / RAP own a
+   row block per rank); every rank ends with the complete P, R, Ac. */
+int sa_gpu_dist_tentative_P(sa_gpu_level *level, sa_gpu_comm *comm, const int *ae_part,
+                            int avoid_ess_bdr_dofs, int *mis_numcoarsedof, int *NDc_out,
+                            double *stats4);
+int sa_gpu_dist_coarse_elmats(sa_gpu_level *finer, sa_gpu_level *coarse, sa_gpu_comm *comm,
+                              const int *ae_part);
+int sa_gpu_dist_smooth_P(sa_gpu_level *level, sa_gpu_comm *comm, int degree, const double *roots);
+int sa_gpu_dist_rap(sa_gpu_level *level, sa_gpu_comm *comm, double *bytes_moved);
+
 /* halo plans (packed boundary lists per matrix and peer), vectors; the solver must outlive it */
 int sa_gpu_dist_solver_create(sa_gpu_solver *solver, sa_gpu_comm *comm, sa_gpu_dist_solver **out);
 void sa_gpu_dist_solver_destroy(sa_gpu_dist_solver *d);

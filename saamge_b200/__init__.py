@@ -306,11 +306,52 @@ def make_exchange(dist, group=None):
     return exchange
 
 
-def enable_sharding(dist, group=None):
-    """Shard the AE loop of every level over the ranks of `dist` (torch.distributed, NCCL on
-    GPUs): each rank computes its AE range, the per-AE results are exchanged (make_exchange)."""
+def library_comm(dist, group=None):
+    """sa_gpu_comm (NCCL communicator owned by the CUDA library) over the ranks of `dist`:
+    rank 0 makes the 128-byte unique id, the launcher's process group hands it to everyone.
+    Collective.  Returns a ctypes.c_void_p; free with gpu_lib().sa_gpu_comm_destroy."""
+    g, h = gpu_lib(), host_lib()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    h.sa_drv_ctx.restype = ctypes.c_void_p
+    g.sa_gpu_nccl_unique_id.argtypes = [ctypes.c_void_p]
+    g.sa_gpu_comm_create.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                     ctypes.POINTER(ctypes.c_void_p)]
+    g.sa_gpu_comm_destroy.argtypes = [ctypes.c_void_p]
+    g.sa_gpu_comm_destroy.restype = None
+    ident = ctypes.create_string_buffer(128)
+    box = [None]
+    if rank == 0:
+        assert g.sa_gpu_nccl_unique_id(ident) == 0, g.sa_gpu_last_error()
+        box = [ident.raw]
+    dist.broadcast_object_list(box, src=0, group=group)
+    ident = ctypes.create_string_buffer(box[0], 128)
+    comm = ctypes.c_void_p()
+    rc = g.sa_gpu_comm_create(ctypes.c_void_p(h.sa_drv_ctx()), ident, world, rank, ctypes.byref(comm))
+    assert rc == 0, g.sa_gpu_last_error()
+    return comm
+
+
+_owner_comm = []
+
+
+def enable_sharding(dist, group=None, mode="owner"):
+    """Shard the setup over the ranks of `dist` (torch.distributed; NCCL on GPUs).
+    mode "owner" (default with NCCL): every rank computes its AE range and keeps its
+    eigenvectors; the tentative prolongator is built by the MIS owners after one all-to-all-v of
+    MIS-restricted blocks, coarse element matrices by AE range, P smoothing / RAP by row blocks --
+    all inside the CUDA library over its own NCCL communicator (sa_gpu_dist_*).
+    mode "replicate": only the AE loop is sharded; the per-AE results are all-gathered
+    (make_exchange) and every later stage runs replicated on every rank (round 1's scheme; the
+    only one available with the gloo backend)."""
     h = host_lib()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if mode == "owner" and dist.get_backend(group) == "nccl" and world > 1 \
+            and not os.environ.get("SA_SHARD_REPLICATE"):
+        comm = library_comm(dist, group)
+        _owner_comm.append(comm)
+        h.sa_drv_set_sharding_comm.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        h.sa_drv_set_sharding_comm(comm, rank, world)
+        return
     CB = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int)
     cb = CB(make_exchange(dist, group))
     _exchange_keepalive.append(cb)
@@ -318,8 +359,22 @@ def enable_sharding(dist, group=None):
     h.sa_drv_set_sharding(rank, world, cb)
 
 
+def sharding_stats():
+    """Bytes moved by the owner-sharded setup stages of this rank since enable_sharding:
+    MIS blocks sent / received, gathered MIS bases, product rows received."""
+    h = host_lib()
+    out = (ctypes.c_double * 8)()
+    h.sa_drv_sharding_stats(out)
+    return {"mis_blocks_sent": out[0], "mis_blocks_received": out[1], "mis_bases_allreduced": out[2],
+            "spgemm_rows_received": out[3]}
+
+
 def disable_sharding():
     h = host_lib()
+    h.sa_drv_set_sharding_comm.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    h.sa_drv_set_sharding_comm(None, 0, 1)
+    while _owner_comm:
+        gpu_lib().sa_gpu_comm_destroy(_owner_comm.pop())
     CB = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int)
     h.sa_drv_set_sharding.argtypes = [ctypes.c_int, ctypes.c_int, CB]
     h.sa_drv_set_sharding(0, 1, CB())

@@ -13,32 +13,16 @@
 // NCCL is resolved at run time (the copy already loaded by the process -- torch's -- else
 // SA_NCCL_LIB, else libnccl.so.2): the library has no link-time dependency on it.
 #include <dlfcn.h>
-#include <nccl.h>
 
 #include <algorithm>
 #include <cmath>
 
+#include "nccl_dl.cuh"
 #include "solve_internal.cuh"
 
-namespace
-{
-struct NcclApi
-{
-    void *lib = nullptr;
-    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
-    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
-    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*GroupStart)() = nullptr;
-    ncclResult_t (*GroupEnd)() = nullptr;
-    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
-                              cudaStream_t) = nullptr;
-    const char *(*GetErrorString)(ncclResult_t) = nullptr;
-};
-NcclApi g_nccl;
+static NcclApi g_nccl;
 
-const NcclApi &nccl()
+const NcclApi &sa_nccl()
 {
     if (g_nccl.lib)
         return g_nccl;
@@ -67,20 +51,7 @@ const NcclApi &nccl()
     return g_nccl;
 }
 
-#define SA_NCCL(call)                                                              \
-    do {                                                                           \
-        ncclResult_t r__ = (call);                                                 \
-        if (r__ != ncclSuccess)                                                    \
-            SA_FAIL("%s:%d: %s -> %s", __FILE__, __LINE__, #call, nccl().GetErrorString(r__)); \
-    } while (0)
-} // namespace
-
-struct sa_gpu_comm
-{
-    sa_gpu_ctx *ctx = nullptr;
-    ncclComm_t comm = nullptr;
-    int rank = 0, nranks = 1;
-};
+static inline const NcclApi &nccl() { return sa_nccl(); }
 
 /* ---- halo plan (host; no GPU needed: tests/test_dist_plan.py) ---------------------------- */
 
@@ -483,6 +454,21 @@ extern "C" int sa_gpu_comm_create(sa_gpu_ctx *ctx, const void *id128, int nranks
             delete C;
             SA_FAIL("ncclCommInitRank: %s", nccl().GetErrorString(r));
         }
+        // NCCL connects channels lazily (first collective / first send-recv per peer: 0.5 - 2 s
+        // measured): do it here, not inside the first timed stage
+        DevBuf<int> w;
+        w.alloc((size_t)2 * nranks + 2);
+        w.zero(ctx->stream);
+        SA_NCCL(nccl().AllReduce(w.p, w.p, 1, ncclInt32, ncclSum, C->comm, ctx->stream));
+        SA_NCCL(nccl().GroupStart());
+        for (int q = 0; q < nranks; ++q)
+            if (q != rank)
+            {
+                SA_NCCL(nccl().Send(w.p + 1, 1, ncclInt32, q, C->comm, ctx->stream));
+                SA_NCCL(nccl().Recv(w.p + 2 + q, 1, ncclInt32, q, C->comm, ctx->stream));
+            }
+        SA_NCCL(nccl().GroupEnd());
+        SA_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     *out = C;
     SA_API_END

@@ -1,0 +1,177 @@
+// Sharded setup stages over the ranks of a communicator, next to the
+// sharded tentative prolongator / coarse element matrices of tentative.cu:
+//   sa_dev_allgatherv      in-place all-gather-v on device arrays (grouped ncclSend / ncclRecv)
+//   sa_gpu_dist_smooth_P   interp_smooth (amg/src/interp.cpp:172-229) and
+//   sa_gpu_dist_rap        tg_coarse_matr (amg/inc/tg.hpp:695-709) as ROW-PARTITIONED SpGEMM: the
+//                          reference's hypre ParMult / RAP own a row block per MPI rank; here every
+//                          rank forms its row block of each product with the single-GPU SpGEMM
+//                          kernels and the blocks are all-gathered (row counts, then column indices
+//                          and values straight into the full CSR arrays), because the next stage of
+//                          the replicated hierarchy reads all rows.
+#include <algorithm>
+
+#include "nccl_dl.cuh"
+
+void sa_dev_allgatherv(sa_gpu_comm *C, void *buf, const int64_t *offs, size_t elem_bytes)
+{
+    const NcclApi &N = sa_nccl();
+    cudaStream_t st = C->ctx->stream;
+    const int nr = C->nranks, me = C->rank;
+    char *b = (char *)buf;
+    const size_t mine = (size_t)(offs[me + 1] - offs[me]) * elem_bytes;
+    SA_NCCL(N.GroupStart());
+    for (int q = 0; q < nr; ++q)
+    {
+        if (q == me)
+            continue;
+        if (mine)
+            SA_NCCL(N.Send(b + (size_t)offs[me] * elem_bytes, mine, ncclChar, q, C->comm, st));
+        const size_t theirs = (size_t)(offs[q + 1] - offs[q]) * elem_bytes;
+        if (theirs)
+            SA_NCCL(N.Recv(b + (size_t)offs[q] * elem_bytes, theirs, ncclChar, q, C->comm, st));
+    }
+    SA_NCCL(N.GroupEnd());
+}
+
+namespace
+{
+__global__ void k_row_counts(int r0, int r1, const int *I_local, int *cnt_full)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < r1 - r0)
+        cnt_full[r0 + i] = I_local[i + 1] - I_local[i];
+}
+
+/* out = A * B with the rows of A dealt to the ranks in equal contiguous blocks; every rank ends
+   with the complete product.  bytes_moved (optional) += what this rank received. */
+void dist_spgemm(sa_gpu_comm *C, const DevCsr &A, const DevCsr &B, DevCsr &out, double *bytes_moved)
+{
+    sa_gpu_ctx *ctx = C->ctx;
+    cudaStream_t st = ctx->stream;
+    const int nr = C->nranks, me = C->rank;
+    const int rows = A.rows;
+    std::vector<int64_t> rp((size_t)nr + 1);
+    for (int q = 0; q <= nr; ++q)
+        rp[q] = ((int64_t)rows * q) / nr;
+    const int r0 = (int)rp[me], r1 = (int)rp[me + 1];
+    // my row block (a view of A's rows: the row pointers keep their absolute offsets)
+    DevCsr Av, loc;
+    Av.rows = r1 - r0;
+    Av.cols = A.cols;
+    Av.nnz = A.nnz;
+    Av.I.view(A.I.p + r0, (size_t)(r1 - r0) + 1);
+    Av.J.view(A.J.p, (size_t)A.nnz);
+    Av.A.view(A.A.p, (size_t)A.nnz);
+    dev_spgemm(ctx, Av, B, loc);
+    // row counts of everyone -> row pointers of the full product
+    DevBuf<int> cnt;
+    cnt.alloc((size_t)rows);
+    if (r1 > r0)
+        SA_LAUNCH(ctx, k_row_counts, (r1 - r0 + 255) / 256, 256, 0, r0, r1, loc.I.p, cnt.p);
+    sa_dev_allgatherv(C, cnt.p, rp.data(), sizeof(int));
+    out.rows = rows;
+    out.cols = B.cols;
+    out.I.alloc((size_t)rows + 1);
+    dev_exclusive_scan_i32(ctx, cnt.p, out.I.p, rows);
+    std::vector<int> hI((size_t)rows + 1);
+    out.I.download(hI.data(), (size_t)rows + 1, st);
+    SA_CUDA(cudaStreamSynchronize(st));
+    out.nnz = hI[rows];
+    out.J.alloc((size_t)out.nnz);
+    out.A.alloc((size_t)out.nnz);
+    std::vector<int64_t> np((size_t)nr + 1);
+    for (int q = 0; q <= nr; ++q)
+        np[q] = hI[rp[q]];
+    if (np[me + 1] - np[me] != loc.nnz)
+        SA_FAIL("dist_spgemm: row block has %d entries, the gathered row pointers say %lld", loc.nnz,
+                (long long)(np[me + 1] - np[me]));
+    if (loc.nnz)
+    {
+        SA_CUDA(cudaMemcpyAsync(out.J.p + np[me], loc.J.p, (size_t)loc.nnz * sizeof(int),
+                                cudaMemcpyDeviceToDevice, st));
+        SA_CUDA(cudaMemcpyAsync(out.A.p + np[me], loc.A.p, (size_t)loc.nnz * sizeof(double),
+                                cudaMemcpyDeviceToDevice, st));
+    }
+    sa_dev_allgatherv(C, out.J.p, np.data(), sizeof(int));
+    sa_dev_allgatherv(C, out.A.p, np.data(), sizeof(double));
+    SA_CUDA(cudaStreamSynchronize(st));
+    if (bytes_moved)
+        *bytes_moved += (double)(out.nnz - loc.nnz) * 12. + (double)(rows - (r1 - r0)) * 4.;
+}
+
+__global__ void k_scale_rows_add_identity_d(int rows, const int *I, const int *J, double *A,
+                                            const double *dinv_neg, double mult)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows)
+        return;
+    const double s = dinv_neg[r] * mult;
+    for (int p = I[r]; p < I[r + 1]; ++p)
+    {
+        double v = A[p] * s;
+        if (J[p] == r)
+            v += 1.;
+        A[p] = v;
+    }
+}
+} // namespace
+
+extern "C" int sa_gpu_dist_rap(sa_gpu_level *lev, sa_gpu_comm *C, double *bytes_moved)
+{
+    SA_API_BEGIN
+    sa_level_ready(lev);
+    if (!C || C->nranks < 2 || !C->comm)
+        SA_FAIL("sa_gpu_dist_rap: needs a communicator of at least two ranks");
+    if (!lev->have_P)
+        SA_FAIL("sa_gpu_dist_rap: no prolongator (call sa_gpu_smooth_P)");
+    if (bytes_moved)
+        *bytes_moved = 0.;
+    DevCsr AP;
+    dist_spgemm(C, *lev->A, lev->P, AP, bytes_moved);
+    dist_spgemm(C, lev->R, AP, lev->Ac, bytes_moved);
+    lev->have_Ac = true;
+    SA_API_END
+}
+
+extern "C" int sa_gpu_dist_smooth_P(sa_gpu_level *lev, sa_gpu_comm *C, int degree, const double *roots)
+{
+    SA_API_BEGIN
+    if (!C || C->nranks < 2 || !C->comm)
+        SA_FAIL("sa_gpu_dist_smooth_P: needs a communicator of at least two ranks");
+    if (degree <= 0) // P = clone(tent), R = P^T: nothing to partition
+        return sa_gpu_smooth_P(lev, degree, roots);
+    sa_level_ready(lev);
+    sa_gpu_ctx *ctx = lev->ctx;
+    cudaStream_t st = ctx->stream;
+    if (!lev->have_tent)
+        SA_FAIL("sa_gpu_dist_smooth_P: no tentative prolongator");
+    if (!lev->have_Dinv)
+        SA_FAIL("sa_gpu_dist_smooth_P: sa_gpu_build_Dinv_neg has not been called");
+    // the factors I - tau_k^-1 D^-1 A share A's pattern; P_(k+1) = factor * P_k by row blocks
+    const DevCsr &A = *lev->A;
+    DevCsr cur;
+    const DevCsr *src = &lev->Ptent;
+    for (int k = 0; k < degree; ++k)
+    {
+        DevCsr iter;
+        iter.rows = A.rows;
+        iter.cols = A.cols;
+        iter.nnz = A.nnz;
+        iter.I.view(A.I.p, (size_t)A.rows + 1);
+        iter.J.view(A.J.p, (size_t)A.nnz);
+        iter.A.alloc((size_t)A.nnz);
+        SA_CUDA(cudaMemcpyAsync(iter.A.p, A.A.p, (size_t)A.nnz * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        SA_LAUNCH(ctx, k_scale_rows_add_identity_d, (A.rows + 255) / 256, 256, 0, A.rows, iter.I.p,
+                  iter.J.p, iter.A.p, lev->Dinv_neg.p, 1. / roots[k]);
+        DevCsr next;
+        dist_spgemm(C, iter, *src, next, nullptr);
+        cur.swap(next);
+        src = &cur;
+    }
+    lev->P.swap(cur);
+    dev_csr_transpose(ctx, lev->P, lev->R);
+    SA_CUDA(cudaStreamSynchronize(st));
+    lev->have_P = true;
+    lev->have_Ac = false;
+    SA_API_END
+}

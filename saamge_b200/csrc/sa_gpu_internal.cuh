@@ -74,8 +74,23 @@ template <class T> struct DevBuf
     DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { release(); }
     bool async_owned = false;
+    bool is_view = false; // points into memory owned by someone else (never freed here)
+    void view(T *ptr, size_t count)
+    {
+        release();
+        p = ptr;
+        n = cap = count;
+        is_view = true;
+    }
     void release()
     {
+        if (p && is_view)
+        {
+            p = nullptr;
+            n = cap = 0;
+            is_view = false;
+            return;
+        }
         if (p)
         {
             if (arena_owned)
@@ -147,6 +162,7 @@ template <class T> struct DevBuf
     }
     void swap(DevBuf &o)
     {
+        std::swap(is_view, o.is_view);
         std::swap(p, o.p);
         std::swap(n, o.n);
         std::swap(cap, o.cap);
@@ -375,6 +391,7 @@ struct sa_gpu_level
     DevBuf<int> mis_ncd, mis_cd_off;     // coarse dof offsets per MIS (num_mises+1)
     DevBuf<int64_t> mis_off;
     DevBuf<double> mis_tent;
+    std::vector<int> h_ae_part;          // AE ranges of the ranks of a sharded setup (nranks + 1)
     int NDc = 0;
     DevCsr Ptent, P, R, Ac;
     bool have_P = false, have_Ac = false;

@@ -511,6 +511,43 @@ void sa_set_sharding(int rank, int world, sa_spectral_exchange_ft exchange)
     g_shard_exchange = exchange;
 }
 
+/* Owner-sharded setup (SURVEY section 8e rows "Tentative P" and "Smoothed P / RAP"): with a
+   library communicator installed the eigenvectors stay on the rank that computed them; the
+   tentative prolongator is built by the MIS owners after one all-to-all-v of MIS-restricted
+   blocks (sa_gpu_dist_tentative_P), the coarse element matrices by the AE owners, and the
+   smoothing / RAP products by row blocks (sa_gpu_dist_smooth_P, sa_gpu_dist_rap). */
+static sa_gpu_comm *g_shard_comm = NULL;
+static double g_shard_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+void sa_set_sharding_comm(sa_gpu_comm *comm, int rank, int world)
+{
+    g_shard_comm = comm;
+    if (comm)
+    {
+        g_shard_rank = rank;
+        g_shard_world = world;
+    }
+    for (int i = 0; i < 8; ++i)
+        g_shard_stats[i] = 0.;
+}
+
+const double *sa_sharding_stats() { return g_shard_stats; }
+
+static bool owner_sharded() { return g_shard_comm != NULL && g_shard_world > 1; }
+
+static std::vector<int> shard_part(const agg_partitioning_relations_t &rels)
+{
+    std::vector<int> part((size_t)g_shard_world + 1, 0);
+    for (int q = 0; q < g_shard_world; ++q)
+    {
+        int a = 0, b = 0;
+        sa_shard_range(rels, q, g_shard_world, &a, &b);
+        part[q] = a;
+        part[q + 1] = b;
+    }
+    return part;
+}
+
 void sa_shard_range(const agg_partitioning_relations_t &rels, int rank, int world, int *begin,
                     int *end)
 {
@@ -538,6 +575,14 @@ void interp_compute_vectors(const agg_partitioning_relations_t &agg_part_rels,
                             const interp_data_t &interp_data, tg_data_t &tg_data, double &theta)
 {
     StageTimer tm("local_spectral");
+    if (owner_sharded() && !interp_data.testmesh_inject)
+    {
+        // this rank's AEs only; nothing is exchanged here (see interp_sparse_tent_assemble)
+        int a = 0, b = 0;
+        sa_shard_range(agg_part_rels, g_shard_rank, g_shard_world, &a, &b);
+        sa_gpu_check(sa_gpu_local_spectral(tg_data.gpu, theta, a, b, 0), "sa_gpu_local_spectral");
+        return;
+    }
     if (g_shard_world > 1 && g_shard_exchange)
     {
         int a = 0, b = 0;
@@ -563,9 +608,22 @@ void interp_sparse_tent_assemble(const agg_partitioning_relations_t &agg_part_re
     interp_data.mis_numcoarsedof = new int[agg_part_rels.num_mises > 0 ? agg_part_rels.num_mises : 1];
     int NDc = 0;
     StageTimer tm("tentative");
-    sa_gpu_check(sa_gpu_tentative_P(tg_data.gpu, avoid_ess_bdr_dofs ? 1 : 0,
-                                    interp_data.mis_numcoarsedof, &NDc),
-                 "sa_gpu_tentative_P");
+    if (owner_sharded() && !interp_data.testmesh_inject)
+    {
+        const std::vector<int> part = shard_part(agg_part_rels);
+        double st4[4] = {0, 0, 0, 0};
+        sa_gpu_check(sa_gpu_dist_tentative_P(tg_data.gpu, g_shard_comm, part.data(),
+                                             avoid_ess_bdr_dofs ? 1 : 0,
+                                             interp_data.mis_numcoarsedof, &NDc, st4),
+                     "sa_gpu_dist_tentative_P");
+        g_shard_stats[0] += st4[1]; // bytes of MIS blocks sent to their owners
+        g_shard_stats[1] += st4[2]; // ... received as owner
+        g_shard_stats[2] += st4[3]; // bytes of the all-reduced MIS bases
+    }
+    else
+        sa_gpu_check(sa_gpu_tentative_P(tg_data.gpu, avoid_ess_bdr_dofs ? 1 : 0,
+                                        interp_data.mis_numcoarsedof, &NDc),
+                     "sa_gpu_tentative_P");
     interp_data.num_mises = agg_part_rels.num_mises;
     interp_data.coarse_truedof_offset = 0;
 }
@@ -656,7 +714,12 @@ void tg_build_hierarchy(const SparseMatrix *Ag, tg_data_t &tg_data,
         // ElementMatrixParallelCoarse: P_e^T A_AE P_e of every finer AE, on the device
         SA_ASSERT(finer && finer->gpu);
         StageTimer tm("coarse_elmats");
-        sa_gpu_check(sa_gpu_coarse_elmats(finer->gpu, tg_data.gpu), "sa_gpu_coarse_elmats");
+        if (owner_sharded() && finer->interp_data && !finer->interp_data->testmesh_inject)
+            // (NULL: the AE ranges sa_gpu_dist_tentative_P used on the finer level)
+            sa_gpu_check(sa_gpu_dist_coarse_elmats(finer->gpu, tg_data.gpu, g_shard_comm, NULL),
+                         "sa_gpu_dist_coarse_elmats");
+        else
+            sa_gpu_check(sa_gpu_coarse_elmats(finer->gpu, tg_data.gpu), "sa_gpu_coarse_elmats");
     }
     {
         // smpr_update_Dinv_neg (tg_init_data -> smpr_init_poly_data in the reference)
@@ -670,9 +733,15 @@ void tg_build_hierarchy(const SparseMatrix *Ag, tg_data_t &tg_data,
     // tg_smooth_interp (amg/inc/tg.hpp:678-693)
     interp_data_t &id = *tg_data.interp_data;
     StageTimer tm("smooth_P");
-    sa_gpu_check(sa_gpu_smooth_P(tg_data.gpu, tg_data.smooth_interp ? id.interp_smoother_degree : 0,
-                                 id.interp_smoother_roots),
-                 "sa_gpu_smooth_P");
+    if (owner_sharded())
+        sa_gpu_check(sa_gpu_dist_smooth_P(tg_data.gpu, g_shard_comm,
+                                          tg_data.smooth_interp ? id.interp_smoother_degree : 0,
+                                          id.interp_smoother_roots),
+                     "sa_gpu_dist_smooth_P");
+    else
+        sa_gpu_check(sa_gpu_smooth_P(tg_data.gpu, tg_data.smooth_interp ? id.interp_smoother_degree : 0,
+                                     id.interp_smoother_roots),
+                     "sa_gpu_smooth_P");
     tg_data.have_Ac = false;
 }
 
@@ -697,7 +766,14 @@ void tg_update_coarse_operator(tg_data_t *tg_data, bool perform_solve_init, bool
     (void)coarse_direct;
     SA_ASSERT(tg_data && tg_data->gpu);
     StageTimer tm("rap");
-    sa_gpu_check(sa_gpu_rap(tg_data->gpu), "sa_gpu_rap");
+    if (owner_sharded())
+    {
+        double moved = 0.;
+        sa_gpu_check(sa_gpu_dist_rap(tg_data->gpu, g_shard_comm, &moved), "sa_gpu_dist_rap");
+        g_shard_stats[3] += moved; // bytes of product rows received from the other ranks
+    }
+    else
+        sa_gpu_check(sa_gpu_rap(tg_data->gpu), "sa_gpu_rap");
     tg_data->have_Ac = true;
 }
 
@@ -1072,6 +1148,17 @@ void tg_download_results(const tg_data_t &tg_data, const agg_partitioning_relati
 extern "C" void sa_drv_set_sharding(int rank, int world, sa_drv_exchange_ft cb)
 {
     saamge::sa_set_sharding(rank, world, (saamge::sa_spectral_exchange_ft)cb);
+}
+
+extern "C" void sa_drv_set_sharding_comm(void *comm, int rank, int world)
+{
+    saamge::sa_set_sharding_comm((sa_gpu_comm *)comm, rank, world);
+}
+
+extern "C" void sa_drv_sharding_stats(double *out8)
+{
+    for (int i = 0; i < 8; ++i)
+        out8[i] = saamge::sa_sharding_stats()[i];
 }
 
 /* ------------------------------------------------------ driver entry points */

@@ -41,6 +41,11 @@ typedef void (*sa_spectral_exchange_ft)(sa_gpu_level *level, int begin, int end,
 void sa_set_sharding(int rank, int world, sa_spectral_exchange_ft exchange);
 void sa_shard_range(const agg_partitioning_relations_t &rels, int rank, int world, int *begin,
                     int *end);
+/// Owner-sharded setup: with a library communicator (sa_gpu_comm_create) installed, the tentative
+/// prolongator is built by the MIS owners (sa_gpu_dist_tentative_P), coarse element matrices by
+/// the AE owners, smoothing / RAP by row blocks; NULL restores the replicated stages.
+void sa_set_sharding_comm(sa_gpu_comm *comm, int rank, int world);
+const double *sa_sharding_stats();
 
 /* ---- element-matrix providers ---- */
 class ElementMatrixStandardGeometric : public ElementMatrixProvider

@@ -1,6 +1,8 @@
-"""Run under torchrun on N GPUs: full hierarchy build with the AE loop of every level
-sharded over the ranks gives the same PCG iteration count / residual history as the
-unsharded build (rank 0 prints PASS/FAIL and timings)."""
+"""Run under torchrun on N GPUs: full hierarchy build sharded over the ranks -- mode "replicate"
+(AE loop sharded, results all-gathered) and mode "owner" (MIS-owner tentative P after one
+all-to-all-v, coarse element matrices by AE range, row-partitioned smoothing / RAP: the
+sa_gpu_dist_* stages) -- gives the same prolongators, coarse operators, PCG iteration count and
+residual history as the unsharded build (rank 0 prints PASS/FAIL and timings)."""
 import os
 import sys
 import time
@@ -31,23 +33,44 @@ def main():
     t_single = time.time() - t0
     it0 = sab.ml_pcg(H0)
     brr0 = H0.get("pcg.brr")
+    sab.ml_download(H0)
+    ref = [(H0.csr("interp", l), H0.csr("Ac", l)) for l in range(levels - 1)]
     H0.close()
-    sab.enable_sharding(dist)
-    dist.barrier()
-    t0 = time.time()
-    H1 = sab.ml_build(pr, p, lrank)
-    torch.cuda.synchronize()
-    dist.barrier()
-    t_shard = time.time() - t0
-    it1 = sab.ml_pcg(H1)
-    brr1 = H1.get("pcg.brr")
-    k = min(len(brr0), len(brr1), 4)
-    ok = (it0 == it1) and np.allclose(brr0[:k], brr1[:k], rtol=1e-6)
+    ok = True
+    for mode in ("replicate", "owner"):
+        sab.enable_sharding(dist, mode=mode)
+        dist.barrier()
+        t0 = time.time()
+        H1 = sab.ml_build(pr, p, lrank)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t_shard = time.time() - t0
+        it1 = sab.ml_pcg(H1)
+        brr1 = H1.get("pcg.brr")
+        k = min(len(brr0), len(brr1), 4)
+        good = (it0 == it1) and np.allclose(brr0[:k], brr1[:k], rtol=1e-6)
+        sab.ml_download(H1)
+        worst = 0.0
+        for l in range(levels - 1):
+            P1, A1 = H1.csr("interp", l), H1.csr("Ac", l)
+            P0, A0 = ref[l]
+            if P1.shape != P0.shape or A1.shape != A0.shape:
+                good = False
+                continue
+            eP = abs(P1 - P0).max() / max(abs(P0).max(), 1e-300)
+            eA = abs(A1 - A0).max() / max(abs(A0).max(), 1e-300)
+            worst = max(worst, eP, eA)
+        good = good and worst <= 1e-10
+        ok = ok and good
+        print("rank %d mode %s iters %d/%d max rel. difference of P / Ac %.1e setup single %.2fs sharded %.2fs "
+              "stages %s moved %s" % (rank, mode, it0, it1, worst, t_single, t_shard,
+                                    {k: round(v, 3) for k, v in H1.times().items()
+                                     if k.split(".")[-1] in ("local_spectral", "tentative", "rap", "coarse_elmats")},
+                                    sab.sharding_stats() if mode == "owner" else None), flush=True)
+        H1.close()
+        sab.disable_sharding()
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
-    print("rank %d iters %d/%d setup single %.2fs sharded %.2fs stages %s" % (
-        rank, it0, it1, t_single, t_shard,
-        {k: round(v, 2) for k, v in H1.times().items() if "local_spectral" in k}), flush=True)
     if rank == 0:
         print("MGPU_HIERARCHY", "PASS" if int(t.item()) == 1 else "FAIL", flush=True)
     dist.destroy_process_group()
