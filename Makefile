@@ -23,9 +23,19 @@ gpu: $(LIBDIR)/libsaamge_b200.so
 host: $(LIBDIR)/libsaamge_host.so
 oracle: oracle/liboracle.so
 
-$(LIBDIR)/libsaamge_b200.so: $(CU_SRC) $(CU_HDR)
+OBJDIR = build/obj
+CU_OBJ = $(patsubst saamge_b200/csrc/%.cu,$(OBJDIR)/%.o,$(CU_SRC))
+
+# one object per translation unit (kernels are file-local: no relocatable device code), so a
+# change to one .cu recompiles that file only; `make -j` builds them side by side
+$(OBJDIR)/%.o: saamge_b200/csrc/%.cu $(CU_HDR)
+	@mkdir -p $(OBJDIR) $(LIBDIR)
+	$(NVCC) $(NVFLAGS) -c -o $@ $< -Iinclude 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; false)
+
+$(LIBDIR)/libsaamge_b200.so: $(CU_OBJ)
 	@mkdir -p $(LIBDIR)
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(CU_SRC) -Iinclude -lcudart 2> $(LIBDIR)/ptxas.log || (cat $(LIBDIR)/ptxas.log; false)
+	$(NVCC) -shared -o $@ $(CU_OBJ) -lcudart
+	@cat $(OBJDIR)/*.ptxas.log > $(LIBDIR)/ptxas.log
 
 $(LIBDIR)/libsaamge_host.so: $(HOST_SRC) $(HOST_HDR) $(LIBDIR)/libsaamge_b200.so
 	@mkdir -p $(LIBDIR)
@@ -37,6 +47,6 @@ oracle/liboracle.so: $(ORC_SRC) $(ORC_HDR) $(HOST_HDR) $(LIBDIR)/libsaamge_host.
 	    -L$(LIBDIR) -lsaamge_host -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)' -ldl -lm
 
 clean:
-	rm -f $(LIBDIR)/*.so $(LIBDIR)/ptxas.log oracle/liboracle.so
+	rm -rf $(LIBDIR)/*.so $(LIBDIR)/ptxas.log oracle/liboracle.so $(OBJDIR)
 
 .PHONY: all gpu host oracle clean
