@@ -22,6 +22,7 @@
 
 #include "assemble.cuh"
 #include "sa_gpu_internal.cuh"
+#include "cholsi.cuh"
 #include "tridiag_math.cuh"
 
 namespace
@@ -1369,6 +1370,116 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         C.sinv = d_sinv.p;
         C.status = d_status.p;
 
+        // Chunks of large AEs only (sorted_seq: the large AEs of a level come first, largest
+        // first): Cholesky + shift-invert subspace iteration (cholsi.cu) delivers the pairs with
+        // lambda <= theta directly -- no tridiagonalisation, Sturm counts, inverse iteration or
+        // back-transformation.  Any matrix it cannot do (all SA_CS_K Ritz values <= theta, a
+        // non-positive pivot, no convergence) sends the whole chunk through the two-stage path
+        // below instead.  SA_GPU_LARGE_PATH=twostage / coop keep the tridiagonalisations.
+        static const bool use_chol =
+            use_ts && !(getenv("SA_GPU_LARGE_PATH") && 0 == strcmp(getenv("SA_GPU_LARGE_PATH"), "twostage"));
+        if (use_chol && sorted_seq && nAE(a0) > nmax_smem && nAE(a1 - 1) > nmax_smem && !inject_ones_ae0)
+        {
+            const int cnt = ns, nb0 = nAE(a0);
+            std::vector<int64_t> h_toff(cnt);
+            int64_t tt = 0;
+            for (int b = 0; b < cnt; ++b)
+            {
+                h_toff[b] = tt;
+                tt += (int64_t)nAE(a0 + b) * nAE(a0 + b);
+            }
+            WS.Twork.ensure((size_t)tt);
+            WS.cs_X.ensure((size_t)dofftot * SA_CS_K);
+            WS.cs_Z.ensure((size_t)dofftot * SA_CS_K);
+            WS.cs_lam.ensure((size_t)cnt * SA_CS_K);
+            WS.cs_info.ensure((size_t)cnt * 2);
+            SA_CUDA(cudaMemsetAsync(WS.cs_info.p, 0, (size_t)cnt * 2 * sizeof(int), st));
+            static_assert(sizeof(sa_cs_mat) % sizeof(int64_t) == 0, "descriptor upload");
+            std::vector<int64_t> h_mats((size_t)cnt * (sizeof(sa_cs_mat) / sizeof(int64_t)));
+            sa_cs_mat *hm = (sa_cs_mat *)h_mats.data();
+            std::vector<int> ident(cnt);
+            for (int b = 0; b < cnt; ++b)
+            {
+                ident[b] = b;
+                hm[b].n = nAE(a0 + b);
+                hm[b].slot = b;
+                hm[b].T = WS.Twork.p + h_toff[b];
+                hm[b].X = WS.cs_X.p + (size_t)h_doff[b] * SA_CS_K;
+                hm[b].Z = WS.cs_Z.p + (size_t)h_doff[b] * SA_CS_K;
+                hm[b].lam = WS.cs_lam.p + (size_t)b * SA_CS_K;
+                hm[b].info = WS.cs_info.p + 2 * b;
+            }
+            staged_upload(ctx, ctx->stage, WS.order, ident.data(), cnt);
+            staged_upload(ctx, ctx->stage, WS.ts_toff, h_toff.data(), cnt);
+            staged_upload(ctx, ctx->stage, WS.cs_mats, h_mats.data(), h_mats.size());
+            SA_CUDA(cudaFuncSetAttribute(k_assemble_tridiag, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)ctx->smem_optin));
+            const size_t smem_a = (size_t)(3 * nb0 + 40) * sizeof(double);
+            if (smem_a > ctx->smem_optin)
+                SA_FAIL("sa_gpu_local_spectral: AE with %d dofs exceeds the supported size of "
+                        "the large-matrix eigensolver", nb0);
+            {
+                ProfScope ps(ctx, "eig.large_assemble");
+                const bool pre = sa_launch_assemble_large(ctx, L, nullptr, WS.order.p, C.ae_of_slot, cnt,
+                                                          nb0, WS.Twork.p, 0, WS.ts_toff.p, st);
+                SA_LAUNCH(ctx, k_assemble_tridiag, cnt, 512, smem_a, L, C, WS.order.p, cnt, 0,
+                          lev->ae_D.p, WS.Twork.p, (int64_t)0, 1, pre ? 1 : 0,
+                          (const int64_t *)WS.ts_toff.p);
+            }
+            sa_cs_factor_iterate(ctx, (const sa_cs_mat *)WS.cs_mats.p, cnt, nb0, theta, st);
+            std::vector<int> h_info((size_t)cnt * 2), h_status(cnt);
+            WS.cs_info.download(h_info.data(), (size_t)cnt * 2, st);
+            d_status.download(h_status.data(), cnt, st);
+            SA_CUDA(cudaStreamSynchronize(st));
+            for (int b = 0; b < cnt; ++b)
+                if (h_status[b])
+                    SA_FAIL("sa_gpu_local_spectral: AE %d has a non-positive diagonal "
+                            "(SA_ASSERT(diag > 0.) in mbox_snd_D_sparse_from_sparse)",
+                            h_ae[b]);
+            int failed = 0, its_max = 0;
+            for (int b = 0; b < cnt; ++b)
+            {
+                failed += h_info[2 * b] < 0;
+                its_max = std::max(its_max, h_info[2 * b + 1]);
+            }
+            if (getenv("SA_GPU_SPECTRAL_DEBUG"))
+                fprintf(stderr, "[cholsi] chunk of %d AEs (n %d..%d): %d not done, at most %d iterations\n",
+                        cnt, nAE(a1 - 1), nb0, failed, its_max);
+            if (!failed)
+            {
+                PieceResult *pr = new PieceResult;
+                pieces.push_back(pr);
+                pr->a0 = a0;
+                pr->a1 = a1;
+                pr->aes = h_ae;
+                pr->nev.resize(cnt);
+                pr->mtot.resize(cnt);
+                pr->eval_off.assign(cnt + 1, 0);
+                pr->evect_off.assign(cnt + 1, 0);
+                for (int b = 0; b < cnt; ++b)
+                {
+                    // (no eigenvalue <= theta: the lowest pair, as the reference's range 'I' 1..1
+                    // fallback, amg/src/xpacks.cpp:270-288)
+                    pr->nev[b] = pr->mtot[b] = std::max(1, h_info[2 * b]);
+                    pr->eval_off[b + 1] = pr->eval_off[b] + pr->nev[b];
+                    pr->evect_off[b + 1] = pr->evect_off[b] + (int64_t)nAE(a0 + b) * pr->nev[b];
+                }
+                pr->evals.alloc((size_t)pr->eval_off[cnt]);
+                pr->evects.alloc((size_t)pr->evect_off[cnt]);
+                staged_upload(ctx, ctx->stage, WS.nev, pr->nev.data(), cnt);
+                staged_upload(ctx, ctx->stage, WS.eval_off, pr->eval_off.data(), cnt + 1);
+                staged_upload(ctx, ctx->stage, WS.evect_off, pr->evect_off.data(), cnt + 1);
+                sa_cs_gather(ctx, (const sa_cs_mat *)WS.cs_mats.p, cnt, WS.nev.p, WS.eval_off.p,
+                             WS.evect_off.p, C.sinv, C.doff, pr->evals.p, pr->evects.p, theta,
+                             lev->borderline.p, st);
+                SA_CUDA(cudaStreamSynchronize(st));
+                if (a1 == ae_end)
+                    sa_level_host_copies(lev);
+                a0 = a1;
+                continue;
+            }
+            // (the status words are clean: the two-stage path below redoes the chunk)
+        }
         // size buckets: slots sorted by n (largest first); shared-memory tiles for
         // n <= nmax_smem with the dynamic shared size of the bucket's largest n
         // stable counting sort of the slots by n, largest first (the GPU waits for this)

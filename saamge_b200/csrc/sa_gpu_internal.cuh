@@ -224,6 +224,10 @@ struct SpectralWs
     DevBuf<int> ts_of_slot;
     DevBuf<int64_t> ts_toff, ts_mats;
     DevBuf<unsigned long long> ts_slots;
+    // large-matrix Cholesky + subspace-iteration path (cholsi.cu)
+    DevBuf<double> cs_X, cs_Z, cs_lam;
+    DevBuf<int> cs_info;
+    DevBuf<int64_t> cs_mats;
 };
 
 /* one matrix of the two-stage tridiagonalisation (twostage.cu) */

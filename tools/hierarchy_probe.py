@@ -9,6 +9,7 @@ import ctypes
 h=sab.host_lib(); h.sa_drv_gpu_profile.argtypes=[ctypes.c_int,ctypes.c_char_p,ctypes.c_int]
 h.sa_drv_problem_pin.restype=ctypes.c_double; h.sa_drv_problem_pin.argtypes=[ctypes.c_void_p,ctypes.c_int]
 if not os.environ.get('SA_NO_PIN'): print('pin %.3fs'%h.sa_drv_problem_pin(pr.handle,0))
+if os.environ.get('SA_PROBE_PROFILE'): h.sa_drv_gpu_profile(1,None,0)
 t=time.time(); H=sab.ml_build(pr,p); print("ml_build %.2fs"%(time.time()-t), flush=True)
 buf=ctypes.create_string_buffer(8192); h.sa_drv_gpu_profile(-1,buf,8192); print("PROF", buf.value.decode().replace("\n","; "))
 g=sab.gpu_lib(); clk=(ctypes.c_double*8)(); g.sa_gpu_debug_phase_clocks(clk); print("PHASE Mcycles", [round(x/1e6,1) for x in clk])
