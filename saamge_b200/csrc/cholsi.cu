@@ -31,7 +31,8 @@
 namespace
 {
 constexpr int CS_K = SA_CS_K;
-constexpr int CS_NB = 32;
+constexpr int CS_NB = 32;  // inner panel width
+constexpr int CS_OB = 128; // outer panel width (rank of the trailing update)
 constexpr int CS_NT = 512;
 constexpr int CS_NW = CS_NT / 32;
 constexpr int CS_LD = 33;
@@ -68,166 +69,216 @@ __device__ __forceinline__ void group_barrier(unsigned int *counter, int G, unsi
     }
 }
 
-/* M = T - sigma I = L L^T in the lower triangle of T (column-major, ld = n).  Returns false on a
-   non-positive pivot (decided identically by every block of the group). */
+/* one 32 x 32 tile of a trailing update: C(i0.., c0..) -= P(i0.., 0:kdim) P(c0.., 0:kdim)^T, lower
+   part only (one warp; 16 DMMA accumulators of 8 x 8; kdim a multiple of 4) */
+template <bool MULTI>
+__device__ __noinline__ void syrk_tile(double *__restrict__ T, const double *P, size_t ld, int n,
+                                       int i0, int c0, int kdim)
+{
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    double c[4][4][2];
+    double *Cp = T + (i0 + g) + ld * (size_t)(c0 + 2 * t);
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+    {
+        const int row = i0 + mi * 8 + g;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+        {
+            const int col = c0 + ni * 8 + 2 * t;
+            const double *q = Cp + mi * 8 + ld * (size_t)(ni * 8);
+            c[mi][ni][0] = (row < n && col <= row) ? (MULTI ? __ldcg(q) : __ldcs(q)) : 0.;
+            c[mi][ni][1] = (row < n && col + 1 <= row) ? (MULTI ? __ldcg(q + ld) : __ldcs(q + ld)) : 0.;
+        }
+    }
+    // operand rows clamped into the matrix (rows >= n only feed accumulators that are not stored)
+    const double *Ap = P + ld * (size_t)t;
+    int ra[4], rb[4];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+    {
+        ra[mi] = min(i0 + mi * 8 + g, n - 1);
+        rb[mi] = min(c0 + mi * 8 + g, n - 1);
+    }
+#pragma unroll 2
+    for (int kk = 0; kk < kdim; kk += 4)
+    {
+        const double *col = Ap + ld * (size_t)kk;
+        double a[4], b[4];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+        {
+            a[mi] = -ldt<MULTI>(col + ra[mi]);
+            b[mi] = ldt<MULTI>(col + rb[mi]);
+        }
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+                dmma884(c[mi][ni][0], c[mi][ni][1], a[mi], b[ni]);
+    }
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+    {
+        const int row = i0 + mi * 8 + g;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+        {
+            const int col = c0 + ni * 8 + 2 * t;
+            double *q = Cp + mi * 8 + ld * (size_t)(ni * 8);
+            if (row < n && col <= row)
+                *q = c[mi][ni][0];
+            if (row < n && col + 1 <= row)
+                q[ld] = c[mi][ni][1];
+        }
+    }
+}
+
+/* rows r0 + first, r0 + first + stride, ... of the panel: X L^T = B, one row per thread */
+template <bool MULTI>
+__device__ __noinline__ void trsm_rows(double *__restrict__ T, size_t ld, int n, int j0, int jb,
+                                       int first, int stride, const double *Ls, const double *rdiag)
+{
+    for (int r = j0 + jb + first; r < n; r += stride)
+    {
+        double x[CS_NB];
+#pragma unroll
+        for (int c = 0; c < CS_NB; ++c)
+            x[c] = (c < jb) ? ldt<MULTI>(T + r + ld * (j0 + c)) : 0.;
+#pragma unroll
+        for (int c = 0; c < CS_NB; ++c)
+        {
+            double s = x[c];
+#pragma unroll
+            for (int q = 0; q < c; ++q)
+                s -= x[q] * Ls[c * CS_LD + q];
+            x[c] = s * rdiag[c];
+        }
+#pragma unroll
+        for (int c = 0; c < CS_NB; ++c)
+            if (c < jb)
+                T[r + ld * (j0 + c)] = x[c];
+    }
+}
+
+/* trailing update by the panel columns [pc0, pc0 + kdim): the tiles of the block columns
+   [0, ntc) of the lower triangle that starts at row / column r0 (ntc >= nt: the whole triangle),
+   dealt to the warps of the group */
+template <bool MULTI>
+__device__ __forceinline__ void syrk_region(double *__restrict__ T, size_t ld, int n, int pc0, int kdim,
+                                            int r0, int ntc, int G, int gr)
+{
+    const int wid = threadIdx.x >> 5;
+    const int nt = (n - r0 + 31) >> 5;
+    ntc = min(ntc, nt);
+    // column-major enumeration of the tiles: block column tj holds nt - tj tiles
+    const int ntiles = ntc * nt - ntc * (ntc - 1) / 2;
+    const double *P = T + ld * (size_t)pc0;
+    for (int tl = gr * CS_NW + wid; tl < ntiles; tl += G * CS_NW)
+    {
+        const double bq = 2. * nt + 1.;
+        int tj = (int)((bq - sqrt(fmax(0., bq * bq - 8. * (double)tl))) * 0.5);
+        tj = max(0, min(tj, ntc - 1));
+        while (tj > 0 && tj * nt - tj * (tj - 1) / 2 > tl)
+            --tj;
+        while (tj + 1 < ntc && (tj + 1) * nt - (tj + 1) * tj / 2 <= tl)
+            ++tj;
+        const int ti = tj + (tl - (tj * nt - tj * (tj - 1) / 2));
+        syrk_tile<MULTI>(T, P, ld, n, r0 + ti * 32, r0 + tj * 32, kdim);
+    }
+}
+
+/* M = T - sigma I = L L^T in the lower triangle of T (column-major, ld = n).  Two-level blocking:
+   outer panels of CS_OB = 128 columns, factored by inner panels of 32 columns (diagonal block,
+   rows below, rank-32 update of the REST OF THE OUTER PANEL only); then ONE rank-128 update of
+   the trailing triangle per outer panel, so that the trailing matrix crosses HBM n / 128 times
+   (n^3 / 48 bytes per matrix) and every C tile that is loaded gets 128 DMMAs x 4.  Returns false
+   on a non-positive pivot (decided identically by every block of the group). */
 template <bool MULTI>
 __device__ bool chol_one(double *__restrict__ T, int n, double sigma, int G, int gr,
                          unsigned int *counter, unsigned int &target, double *Ls, double *rdiag,
                          int *flag)
 {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int g = lane >> 2, t = lane & 3;
     const size_t ld = (size_t)n;
     // shift (rows dealt to the blocks)
     for (int i = gr * CS_NT + tid; i < n; i += G * CS_NT)
         T[i + ld * i] -= sigma;
     group_barrier(counter, G, target);
-    for (int j0 = 0; j0 < n; j0 += CS_NB)
+    for (int J0 = 0; J0 < n; J0 += CS_OB)
     {
-        const int jb = min(CS_NB, n - j0);
-        // 1. diagonal block (every block of the group factors its own copy)
-        for (int idx = tid; idx < CS_NB * CS_NB; idx += CS_NT)
+        const int Jend = min(n, J0 + CS_OB);
+        for (int j0 = J0; j0 < Jend; j0 += CS_NB)
         {
-            const int i = idx & 31, c = idx >> 5;
-            double v = (i == c) ? 1. : 0.;
-            if (i < jb && c < jb && i >= c)
-                v = ldt<MULTI>(T + (j0 + i) + ld * (j0 + c));
-            Ls[i * CS_LD + c] = v;
-        }
-        if (tid == 0)
-            *flag = 0;
-        __syncthreads();
-        if (wid == 0)
-        {
-            for (int k = 0; k < CS_NB; ++k)
-            {
-                const double p = Ls[k * CS_LD + k];
-                if (!(p > 0.))
-                {
-                    if (lane == 0)
-                        *flag = 1;
-                    break;
-                }
-                const double s = sqrt(p);
-                double lik = 0.;
-                if (lane > k)
-                {
-                    lik = Ls[lane * CS_LD + k] / s;
-                    Ls[lane * CS_LD + k] = lik;
-                }
-                else if (lane == k)
-                {
-                    Ls[k * CS_LD + k] = s;
-                    rdiag[k] = 1. / s;
-                }
-                __syncwarp();
-                for (int j = k + 1; j < CS_NB; ++j)
-                    if (lane >= j)
-                        Ls[lane * CS_LD + j] -= lik * Ls[j * CS_LD + k];
-                __syncwarp();
-            }
-        }
-        __syncthreads();
-        if (*flag)
-            return false;
-        const int r0 = j0 + jb;
-        // 2. panel below the diagonal block: X L^T = B, one row per thread
-        for (int r = r0 + gr * CS_NT + tid; r < n; r += G * CS_NT)
-        {
-            double x[CS_NB];
-#pragma unroll
-            for (int c = 0; c < CS_NB; ++c)
-                x[c] = (c < jb) ? ldt<MULTI>(T + r + ld * (j0 + c)) : 0.;
-#pragma unroll
-            for (int c = 0; c < CS_NB; ++c)
-            {
-                double s = x[c];
-#pragma unroll
-                for (int q = 0; q < c; ++q)
-                    s -= x[q] * Ls[c * CS_LD + q];
-                x[c] = s * rdiag[c];
-            }
-#pragma unroll
-            for (int c = 0; c < CS_NB; ++c)
-                if (c < jb)
-                    T[r + ld * (j0 + c)] = x[c];
-        }
-        group_barrier(counter, G, target);
-        // (every block of the group has read the diagonal block by now: the factor replaces it)
-        if (gr == 0)
+            const int jb = min(CS_NB, n - j0);
+            // 1. diagonal block (every block of the group factors its own copy)
             for (int idx = tid; idx < CS_NB * CS_NB; idx += CS_NT)
             {
                 const int i = idx & 31, c = idx >> 5;
+                double v = (i == c) ? 1. : 0.;
                 if (i < jb && c < jb && i >= c)
-                    T[(j0 + i) + ld * (j0 + c)] = Ls[i * CS_LD + c];
+                    v = ldt<MULTI>(T + (j0 + i) + ld * (j0 + c));
+                Ls[i * CS_LD + c] = v;
             }
-        if (r0 >= n)
-            break;
-        // 3. trailing lower triangle -= P P^T, one warp per 32 x 32 tile (DMMA)
-        const int r = n - r0;
-        const int nt = (r + 31) >> 5;
-        const int ntiles = nt * (nt + 1) / 2;
-        const double *P = T + ld * j0; // panel columns
-        for (int tl = gr * CS_NW + wid; tl < ntiles; tl += G * CS_NW)
-        {
-            int ti = (int)((sqrt(8. * (double)tl + 1.) - 1.) * 0.5);
-            while ((ti + 1) * (ti + 2) / 2 <= tl)
-                ++ti;
-            while (ti * (ti + 1) / 2 > tl)
-                --ti;
-            const int tj = tl - ti * (ti + 1) / 2;
-            const int i0 = r0 + ti * 32, c0 = r0 + tj * 32;
-            double c[4][4][2];
-#pragma unroll
-            for (int mi = 0; mi < 4; ++mi)
+            if (tid == 0)
+                *flag = 0;
+            __syncthreads();
+            if (wid == 0)
             {
-                const int row = i0 + mi * 8 + g;
-#pragma unroll
-                for (int ni = 0; ni < 4; ++ni)
+                for (int k = 0; k < CS_NB; ++k)
                 {
-                    const int col = c0 + ni * 8 + 2 * t;
-                    c[mi][ni][0] = (row < n && col <= row) ? ldt<MULTI>(T + row + ld * col) : 0.;
-                    c[mi][ni][1] = (row < n && col + 1 <= row) ? ldt<MULTI>(T + row + ld * (col + 1)) : 0.;
+                    const double p = Ls[k * CS_LD + k];
+                    if (!(p > 0.))
+                    {
+                        if (lane == 0)
+                            *flag = 1;
+                        break;
+                    }
+                    const double s = sqrt(p);
+                    double lik = 0.;
+                    if (lane > k)
+                    {
+                        lik = Ls[lane * CS_LD + k] / s;
+                        Ls[lane * CS_LD + k] = lik;
+                    }
+                    else if (lane == k)
+                    {
+                        Ls[k * CS_LD + k] = s;
+                        rdiag[k] = 1. / s;
+                    }
+                    __syncwarp();
+                    for (int j = k + 1; j < CS_NB; ++j)
+                        if (lane >= j)
+                            Ls[lane * CS_LD + j] -= lik * Ls[j * CS_LD + k];
+                    __syncwarp();
                 }
             }
-#pragma unroll 2
-            for (int kk = 0; kk < 8; ++kk)
-            {
-                const size_t ko = ld * (size_t)(kk * 4 + t);
-                double a[4], b[4];
-#pragma unroll
-                for (int mi = 0; mi < 4; ++mi)
+            __syncthreads();
+            if (*flag)
+                return false;
+            const int r0 = j0 + jb;
+            // 2. rows below the diagonal block
+            trsm_rows<MULTI>(T, ld, n, j0, jb, gr * CS_NT + tid, G * CS_NT, Ls, rdiag);
+            group_barrier(counter, G, target);
+            // (every block of the group has read the diagonal block by now: the factor replaces it)
+            if (gr == 0)
+                for (int idx = tid; idx < CS_NB * CS_NB; idx += CS_NT)
                 {
-                    const int row = i0 + mi * 8 + g;
-                    a[mi] = (row < n) ? -ldt<MULTI>(P + row + ko) : 0.;
+                    const int i = idx & 31, c = idx >> 5;
+                    if (i < jb && c < jb && i >= c)
+                        T[(j0 + i) + ld * (j0 + c)] = Ls[i * CS_LD + c];
                 }
-#pragma unroll
-                for (int ni = 0; ni < 4; ++ni)
-                {
-                    const int row = c0 + ni * 8 + g;
-                    b[ni] = (row < n) ? ldt<MULTI>(P + row + ko) : 0.;
-                }
-#pragma unroll
-                for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-                    for (int ni = 0; ni < 4; ++ni)
-                        dmma884(c[mi][ni][0], c[mi][ni][1], a[mi], b[ni]);
-            }
-#pragma unroll
-            for (int mi = 0; mi < 4; ++mi)
-            {
-                const int row = i0 + mi * 8 + g;
-#pragma unroll
-                for (int ni = 0; ni < 4; ++ni)
-                {
-                    const int col = c0 + ni * 8 + 2 * t;
-                    if (row < n && col <= row)
-                        T[row + ld * col] = c[mi][ni][0];
-                    if (row < n && col + 1 <= row)
-                        T[row + ld * (col + 1)] = c[mi][ni][1];
-                }
-            }
+            if (r0 >= Jend)
+                break;
+            // 3. rank-32 update of the remaining columns of the outer panel (all rows below)
+            syrk_region<MULTI>(T, ld, n, j0, CS_NB, r0, (Jend - r0 + 31) >> 5, G, gr);
+            group_barrier(counter, G, target);
         }
+        if (Jend >= n)
+            break;
+        // 4. rank-128 update of the trailing triangle
+        syrk_region<MULTI>(T, ld, n, J0, CS_OB, Jend, 1 << 28, G, gr);
         group_barrier(counter, G, target);
     }
     return true;
@@ -384,144 +435,266 @@ __device__ __forceinline__ double cs_start_value(int r, int k, int salt)
     return ((double)(h & 0xffffffu) / 8388608.) - 1.;
 }
 
-__global__ void __launch_bounds__(CS_NT, 1)
-k_cs_iterate(const sa_cs_mat *mats, int nmats, double sigma, double theta, int max_its, double tol)
+/* Z = M^-1 X = L^-T L^-1 X with the K right-hand sides of every row in registers: thread t owns
+   the rows t, t + 512, ... (QMAX of them).  Per block of 32 columns the owning warp publishes its
+   entries, warps 0..K-1 solve the 32 x 32 triangle (lanes = rows, shuffles), everyone updates the
+   rows (forward) / columns (backward) it owns: L is read exactly once per solve, the vectors
+   never leave the register file in between. */
+/* generalised K x K eigenproblem H q = mu G q of the Rayleigh-Ritz step (one thread): on exit
+   S.mu ascending, S.Q the G-orthonormal eigenvectors; S.bad when G is not positive definite */
+__device__ void cs_small_solve(CsSmall &S)
 {
-    __shared__ double Ls[CS_NB * CS_LD];
-    __shared__ double rinv[CS_NB];
-    __shared__ double Ys[CS_NB][CS_K];
+    S.bad = 0;
+    // G = R^T R (upper R stored in Gm), C = R^-T H R^-1
+    double (*R)[CS_K] = S.Gm;
+    for (int j = 0; j < CS_K && !S.bad; ++j)
+    {
+        double d = R[j][j];
+        for (int k = 0; k < j; ++k)
+            d -= R[k][j] * R[k][j];
+        if (!(d > 0.))
+        {
+            S.bad = 1;
+            break;
+        }
+        d = sqrt(d);
+        R[j][j] = d;
+        for (int i = j + 1; i < CS_K; ++i)
+        {
+            double s = R[j][i];
+            for (int k = 0; k < j; ++k)
+                s -= R[k][j] * R[k][i];
+            R[j][i] = s / d;
+        }
+    }
+    if (!S.bad)
+    {
+        // Hs = symmetrised H; W = R^-T Hs (solve R^T W = Hs), C = W R^-1
+        for (int i = 0; i < CS_K; ++i)
+            for (int j = 0; j < CS_K; ++j)
+                S.Cm[i][j] = 0.5 * (S.Hm[i][j] + S.Hm[j][i]);
+        for (int col = 0; col < CS_K; ++col) // R^T W = Hs, column by column
+            for (int i = 0; i < CS_K; ++i)
+            {
+                double s = S.Cm[i][col];
+                for (int k = 0; k < i; ++k)
+                    s -= R[k][i] * S.Cm[k][col];
+                S.Cm[i][col] = s / R[i][i];
+            }
+        for (int row = 0; row < CS_K; ++row) // C R = W  =>  C = W R^-1, row by row
+            for (int j = 0; j < CS_K; ++j)
+            {
+                double s = S.Cm[row][j];
+                for (int k = 0; k < j; ++k)
+                    s -= S.Cm[row][k] * R[k][j];
+                S.Cm[row][j] = s / R[j][j];
+            }
+        for (int i = 0; i < CS_K; ++i)
+            for (int j = 0; j < i; ++j)
+            {
+                const double m = 0.5 * (S.Cm[i][j] + S.Cm[j][i]);
+                S.Cm[i][j] = S.Cm[j][i] = m;
+            }
+        jacobi_small(S.Cm, S.V);
+        for (int i = 0; i < CS_K; ++i)
+            S.perm[i] = i;
+        for (int i = 1; i < CS_K; ++i) // ascending mu
+        {
+            const int p = S.perm[i];
+            int j = i - 1;
+            while (j >= 0 && S.Cm[S.perm[j]][S.perm[j]] > S.Cm[p][p])
+            {
+                S.perm[j + 1] = S.perm[j];
+                --j;
+            }
+            S.perm[j + 1] = p;
+        }
+        // Q = R^-1 V (columns permuted)
+        for (int c = 0; c < CS_K; ++c)
+        {
+            const int pc = S.perm[c];
+            S.mu[c] = S.Cm[pc][pc];
+            for (int i = CS_K - 1; i >= 0; --i)
+            {
+                double s = S.V[i][pc];
+                for (int k = i + 1; k < CS_K; ++k)
+                    s -= R[i][k] * S.Q[k][c];
+                S.Q[i][c] = s / R[i][i];
+            }
+        }
+    }
+}
+
+/* 32 x 32 diagonal block of L at (jb, jb) into shared memory (identity beyond the matrix), with
+   the reciprocals of its diagonal */
+__device__ __forceinline__ void cs_stage_diag(const double *__restrict__ T, size_t ld, int n, int jb,
+                                              double *Ls, double *rinv)
+{
+    const int w = min(CS_NB, n - jb);
+    for (int idx = threadIdx.x; idx < CS_NB * CS_NB; idx += CS_NT)
+    {
+        const int i = idx & 31, c = idx >> 5;
+        double v = (i == c) ? 1. : 0.;
+        if (i < w && c < w && i >= c)
+            v = T[(jb + i) + ld * (jb + c)];
+        Ls[i * CS_LD + c] = v;
+        if (i == c)
+            rinv[i] = 1. / v;
+    }
+}
+
+/* Subspace iteration with M^-1 = L^-T L^-1 for one matrix by a group of G = K / KL blocks:
+   block gr solves for the KL vectors gr KL .. gr KL + KL - 1 (the triangular solves are independent
+   per right-hand side), forms its rows of G = Z^T Z and H = Z^T X, and after a group barrier every
+   block solves the same K x K problem and rotates its own vectors (ping-pong buffers X / X2: the
+   other blocks still read the old ones).  Three group barriers per iteration; G = 1 is the
+   one-block-per-matrix form used when there are enough matrices to fill the GPU. */
+template <int KL, bool MULTI>
+__global__ void __launch_bounds__(CS_NT, 1)
+k_cs_iterate(const sa_cs_mat *mats, int nmats, double sigma, double theta, int max_its, double tol,
+             unsigned int *counters)
+{
+    constexpr int G = CS_K / KL;
+    __shared__ double Lsb[2][CS_NB * CS_LD];
+    __shared__ double rinvb[2][CS_NB];
+    __shared__ double Ys[CS_NB][CS_K]; // solved block, columns >= KL stay zero
     __shared__ double red[CS_NW * 2 * CS_K];
     __shared__ double tot[2 * CS_K];
     __shared__ CsSmall S;
     __shared__ int done;
-    const int b = blockIdx.x;
+    const int b = blockIdx.x / G, gr = blockIdx.x % G;
     if (b >= nmats)
         return;
     const sa_cs_mat M = mats[b];
     const int n = M.n;
     const size_t ld = (size_t)n;
     const double *__restrict__ T = M.T;
-    double *__restrict__ X = M.X, *__restrict__ Z = M.Z;
+    double *Xc = M.X, *Xn = M.X2, *Z = M.Z;
+    double *small = M.small; // [0,64) G, [64,128) H, [128,136) residuals^2
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int k0 = gr * KL;
+    unsigned int target = 0;
+    unsigned int *counter = counters + b;
     if (M.info[0] != 0)
-        return; // factorisation failed
+        return; // factorisation failed (every block of the group sees the same word)
+    for (int idx = tid; idx < CS_NB * CS_K; idx += CS_NT)
+        Ys[idx / CS_K][idx % CS_K] = 0.;
     for (int r = tid; r < n; r += CS_NT)
 #pragma unroll
-        for (int k = 0; k < CS_K; ++k)
-            X[(size_t)k * n + r] = cs_start_value(r, k, b);
-    __syncthreads();
+        for (int k = 0; k < KL; ++k)
+            Xc[(size_t)(k0 + k) * n + r] = cs_start_value(r, k0 + k, b);
+    group_barrier(counter, G, target);
     int its = 0, result = -3; // -3: no convergence
+    int buf = 0;
     for (its = 1; its <= max_its; ++its)
     {
-        // Z = X
-        for (int idx = tid; idx < CS_K * n; idx += CS_NT)
-            Z[idx] = X[idx];
+        // own vectors: Z = X, then L Y = Z and L^T Z = Y in place
+        for (int r = tid; r < n; r += CS_NT)
+#pragma unroll
+            for (int k = 0; k < KL; ++k)
+                Z[(size_t)(k0 + k) * n + r] = Xc[(size_t)(k0 + k) * n + r];
         __syncthreads();
-        // forward: L Y = Z
-        for (int jb = 0; jb < n; jb += CS_NB)
+        for (int pass = 0; pass < 2; ++pass)
         {
-            const int w = min(CS_NB, n - jb);
-            for (int idx = tid; idx < CS_NB * CS_NB; idx += CS_NT)
+            const int nblk = (n + CS_NB - 1) / CS_NB;
+            for (int bi_ = 0; bi_ < nblk; ++bi_)
             {
-                const int i = idx & 31, c = idx >> 5;
-                double v = (i == c) ? 1. : 0.;
-                if (i < w && c < w && i >= c)
-                    v = T[(jb + i) + ld * (jb + c)];
-                Ls[i * CS_LD + c] = v;
-                if (i == c)
-                    rinv[i] = 1. / v;
-            }
-            __syncthreads();
-            if (wid < CS_K)
-            {
-                double bi = (lane < w) ? Z[(size_t)wid * n + jb + lane] : 0.;
-                for (int c = 0; c < CS_NB; ++c)
+                const int jb = (pass == 0 ? bi_ : nblk - 1 - bi_) * CS_NB;
+                const int w = min(CS_NB, n - jb);
+                // the diagonal block of this step was staged during the previous step's update
+                // (double buffer); the first one of a pass is staged here
+                if (bi_ == 0)
                 {
-                    const double tc = __shfl_sync(0xffffffffu, bi, c) * rinv[c];
-                    if (lane == c)
-                        bi = tc;
-                    else if (lane > c)
-                        bi -= Ls[lane * CS_LD + c] * tc;
+                    cs_stage_diag(T, ld, n, jb, Lsb[buf], rinvb[buf]);
+                    __syncthreads();
                 }
-                Ys[lane][wid] = bi;
-                if (lane < w)
-                    Z[(size_t)wid * n + jb + lane] = bi;
-            }
-            __syncthreads();
-            for (int r = jb + CS_NB + tid; r < n; r += CS_NT)
-            {
-                double acc[CS_K];
-#pragma unroll
-                for (int k = 0; k < CS_K; ++k)
-                    acc[k] = Z[(size_t)k * n + r];
-#pragma unroll 8
-                for (int c = 0; c < CS_NB; ++c)
+                double *Ls = Lsb[buf], *rinv = rinvb[buf];
+                if (wid < KL)
                 {
-                    const double l = T[r + ld * (jb + c)];
-#pragma unroll
-                    for (int k = 0; k < CS_K; ++k)
-                        acc[k] -= l * Ys[c][k];
+                    double bi = (lane < w) ? Z[(size_t)(k0 + wid) * n + jb + lane] : 0.;
+                    if (pass == 0)
+                    {
+                        for (int c = 0; c < CS_NB; ++c)
+                        {
+                            const double tc = __shfl_sync(0xffffffffu, bi, c) * rinv[c];
+                            if (lane == c)
+                                bi = tc;
+                            else if (lane > c)
+                                bi -= Ls[lane * CS_LD + c] * tc;
+                        }
+                    }
+                    else
+                    {
+                        for (int c = CS_NB - 1; c >= 0; --c)
+                        {
+                            const double tc = __shfl_sync(0xffffffffu, bi, c) * rinv[c];
+                            if (lane == c)
+                                bi = tc;
+                            else if (lane < c)
+                                bi -= Ls[c * CS_LD + lane] * tc;
+                        }
+                    }
+                    Ys[lane][wid] = bi;
+                    if (lane < w)
+                        Z[(size_t)(k0 + wid) * n + jb + lane] = bi;
                 }
+                __syncthreads();
+                // forward: the rows below the block; backward: the columns left of it --
+                // Z(i, :) -= sum_q L(i, q) Y(q, :) as DMMA m8n8k4 (M = 32 rows / columns per warp
+                // pass, N = the right-hand sides padded to 8, K = the 32 entries of the block);
+                // forward L(i, q) = T[i + ld (jb + q)], backward L(i, q) = T[jb + q + ld i].  All 32
+                // operand loads of a lane are in flight before the first DMMA.
+                {
+                    if (bi_ + 1 < nblk)
+                        cs_stage_diag(T, ld, n, (pass == 0 ? bi_ + 1 : nblk - 2 - bi_) * CS_NB, Lsb[buf ^ 1],
+                                      rinvb[buf ^ 1]);
+                    const int lo = (pass == 0) ? jb + CS_NB : 0, hi = (pass == 0) ? n : jb;
+                    const int g = lane >> 2, t = lane & 3;
+                    const double *base = (pass == 0) ? T + ld * (size_t)jb : T + jb;
+                    const size_t si = (pass == 0) ? 1 : ld, sq = (pass == 0) ? ld : 1;
+                    for (int i0 = lo + wid * 32; i0 < hi; i0 += CS_NW * 32)
+                    {
+                        double a[4][8], c[4][2];
 #pragma unroll
-                for (int k = 0; k < CS_K; ++k)
-                    Z[(size_t)k * n + r] = acc[k];
+                        for (int mi = 0; mi < 4; ++mi)
+                        {
+                            const int ri = min(i0 + mi * 8 + g, hi - 1);
+                            const double *row = base + si * (size_t)ri + sq * (size_t)t;
+#pragma unroll
+                            for (int kk = 0; kk < 8; ++kk)
+                                a[mi][kk] = row[sq * (size_t)(kk * 4)];
+                            c[mi][0] = (2 * t < KL) ? Z[(size_t)(k0 + 2 * t) * n + ri] : 0.;
+                            c[mi][1] = (2 * t + 1 < KL) ? Z[(size_t)(k0 + 2 * t + 1) * n + ri] : 0.;
+                        }
+#pragma unroll
+                        for (int kk = 0; kk < 8; ++kk)
+                        {
+                            const double bq = Ys[kk * 4 + t][g];
+#pragma unroll
+                            for (int mi = 0; mi < 4; ++mi)
+                                dmma884(c[mi][0], c[mi][1], -a[mi][kk], bq);
+                        }
+#pragma unroll
+                        for (int mi = 0; mi < 4; ++mi)
+                        {
+                            const int ri = i0 + mi * 8 + g;
+                            if (ri < hi)
+                            {
+                                if (2 * t < KL)
+                                    Z[(size_t)(k0 + 2 * t) * n + ri] = c[mi][0];
+                                if (2 * t + 1 < KL)
+                                    Z[(size_t)(k0 + 2 * t + 1) * n + ri] = c[mi][1];
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+                buf ^= 1;
             }
-            __syncthreads();
         }
-        // backward: L^T Z = Y
-        for (int jb = ((n - 1) / CS_NB) * CS_NB; jb >= 0; jb -= CS_NB)
-        {
-            const int w = min(CS_NB, n - jb);
-            for (int idx = tid; idx < CS_NB * CS_NB; idx += CS_NT)
-            {
-                const int i = idx & 31, c = idx >> 5;
-                double v = (i == c) ? 1. : 0.;
-                if (i < w && c < w && i >= c)
-                    v = T[(jb + i) + ld * (jb + c)];
-                Ls[i * CS_LD + c] = v;
-                if (i == c)
-                    rinv[i] = 1. / v;
-            }
-            __syncthreads();
-            if (wid < CS_K)
-            {
-                double bi = (lane < w) ? Z[(size_t)wid * n + jb + lane] : 0.;
-                for (int c = CS_NB - 1; c >= 0; --c)
-                {
-                    const double tc = __shfl_sync(0xffffffffu, bi, c) * rinv[c];
-                    if (lane == c)
-                        bi = tc;
-                    else if (lane < c)
-                        bi -= Ls[c * CS_LD + lane] * tc;
-                }
-                Ys[lane][wid] = bi;
-                if (lane < w)
-                    Z[(size_t)wid * n + jb + lane] = bi;
-            }
-            __syncthreads();
-            for (int cc = tid; cc < jb; cc += CS_NT)
-            {
-                double acc[CS_K];
-#pragma unroll
-                for (int k = 0; k < CS_K; ++k)
-                    acc[k] = Z[(size_t)k * n + cc];
-                const double *col = T + jb + ld * cc;
-#pragma unroll 8
-                for (int q = 0; q < CS_NB; ++q)
-                {
-                    const double l = (q < w) ? col[q] : 0.;
-#pragma unroll
-                    for (int k = 0; k < CS_K; ++k)
-                        acc[k] -= l * Ys[q][k];
-                }
-#pragma unroll
-                for (int k = 0; k < CS_K; ++k)
-                    Z[(size_t)k * n + cc] = acc[k];
-            }
-            __syncthreads();
-        }
-        // Rayleigh-Ritz on span(Z): G = Z^T Z, H = Z^T X (= Z^T M Z)
-        for (int a = 0; a < CS_K; ++a)
+        group_barrier(counter, G, target);
+        // Rayleigh-Ritz on span(Z): rows k0 .. k0 + KL - 1 of G = Z^T Z and H = Z^T X (= Z^T M Z)
+        for (int a = k0; a < k0 + KL; ++a)
         {
             double v[2 * CS_K];
 #pragma unroll
@@ -533,110 +706,37 @@ k_cs_iterate(const sa_cs_mat *mats, int nmats, double sigma, double theta, int m
 #pragma unroll
                 for (int k = 0; k < CS_K; ++k)
                 {
-                    v[k] += za * Z[(size_t)k * n + r];
-                    v[CS_K + k] += za * X[(size_t)k * n + r];
+                    v[k] += za * ldt<MULTI>(Z + (size_t)k * n + r);
+                    v[CS_K + k] += za * ldt<MULTI>(Xc + (size_t)k * n + r);
                 }
             }
             block_sum<2 * CS_K>(v, red, tot);
             if (tid < CS_K)
             {
-                S.Gm[a][tid] = tot[tid];
-                S.Hm[a][tid] = tot[CS_K + tid];
+                small[a * CS_K + tid] = tot[tid];
+                small[64 + a * CS_K + tid] = tot[CS_K + tid];
             }
             __syncthreads();
         }
-        if (tid == 0)
+        group_barrier(counter, G, target);
+        if (tid < 64)
         {
-            S.bad = 0;
-            // G = R^T R (upper R stored in Gm), C = R^-T H R^-1
-            double (*R)[CS_K] = S.Gm;
-            for (int j = 0; j < CS_K && !S.bad; ++j)
-            {
-                double d = R[j][j];
-                for (int k = 0; k < j; ++k)
-                    d -= R[k][j] * R[k][j];
-                if (!(d > 0.))
-                {
-                    S.bad = 1;
-                    break;
-                }
-                d = sqrt(d);
-                R[j][j] = d;
-                for (int i = j + 1; i < CS_K; ++i)
-                {
-                    double s = R[j][i];
-                    for (int k = 0; k < j; ++k)
-                        s -= R[k][j] * R[k][i];
-                    R[j][i] = s / d;
-                }
-            }
-            if (!S.bad)
-            {
-                // Hs = symmetrised H; W = R^-T Hs (solve R^T W = Hs), C = W R^-1
-                for (int i = 0; i < CS_K; ++i)
-                    for (int j = 0; j < CS_K; ++j)
-                        S.Cm[i][j] = 0.5 * (S.Hm[i][j] + S.Hm[j][i]);
-                for (int col = 0; col < CS_K; ++col) // R^T W = Hs, column by column
-                    for (int i = 0; i < CS_K; ++i)
-                    {
-                        double s = S.Cm[i][col];
-                        for (int k = 0; k < i; ++k)
-                            s -= R[k][i] * S.Cm[k][col];
-                        S.Cm[i][col] = s / R[i][i];
-                    }
-                for (int row = 0; row < CS_K; ++row) // C R = W  =>  C = W R^-1, row by row
-                    for (int j = 0; j < CS_K; ++j)
-                    {
-                        double s = S.Cm[row][j];
-                        for (int k = 0; k < j; ++k)
-                            s -= S.Cm[row][k] * R[k][j];
-                        S.Cm[row][j] = s / R[j][j];
-                    }
-                for (int i = 0; i < CS_K; ++i)
-                    for (int j = 0; j < i; ++j)
-                    {
-                        const double m = 0.5 * (S.Cm[i][j] + S.Cm[j][i]);
-                        S.Cm[i][j] = S.Cm[j][i] = m;
-                    }
-                jacobi_small(S.Cm, S.V);
-                for (int i = 0; i < CS_K; ++i)
-                    S.perm[i] = i;
-                for (int i = 1; i < CS_K; ++i) // ascending mu
-                {
-                    const int p = S.perm[i];
-                    int j = i - 1;
-                    while (j >= 0 && S.Cm[S.perm[j]][S.perm[j]] > S.Cm[p][p])
-                    {
-                        S.perm[j + 1] = S.perm[j];
-                        --j;
-                    }
-                    S.perm[j + 1] = p;
-                }
-                // Q = R^-1 V (columns permuted)
-                for (int c = 0; c < CS_K; ++c)
-                {
-                    const int pc = S.perm[c];
-                    S.mu[c] = S.Cm[pc][pc];
-                    for (int i = CS_K - 1; i >= 0; --i)
-                    {
-                        double s = S.V[i][pc];
-                        for (int k = i + 1; k < CS_K; ++k)
-                            s -= R[i][k] * S.Q[k][c];
-                        S.Q[i][c] = s / R[i][i];
-                    }
-                }
-            }
+            S.Gm[tid >> 3][tid & 7] = ldt<MULTI>(small + tid);
+            S.Hm[tid >> 3][tid & 7] = ldt<MULTI>(small + 64 + tid);
         }
+        __syncthreads();
+        if (tid == 0)
+            cs_small_solve(S);
         __syncthreads();
         if (S.bad)
         {
             result = -4; // Gram matrix not positive definite (should not happen)
             break;
         }
-        // X <- Z Q (unit vectors), residuals || X_old q - mu Z q ||
-        double rs[CS_K];
+        // own vectors: X_new = Z q (unit vectors), residuals || X_old q - mu Z q ||
+        double rs[KL];
 #pragma unroll
-        for (int k = 0; k < CS_K; ++k)
+        for (int k = 0; k < KL; ++k)
             rs[k] = 0.;
         for (int r = tid; r < n; r += CS_NT)
         {
@@ -644,41 +744,51 @@ k_cs_iterate(const sa_cs_mat *mats, int nmats, double sigma, double theta, int m
 #pragma unroll
             for (int k = 0; k < CS_K; ++k)
             {
-                zr[k] = Z[(size_t)k * n + r];
-                xr[k] = X[(size_t)k * n + r];
+                zr[k] = ldt<MULTI>(Z + (size_t)k * n + r);
+                xr[k] = ldt<MULTI>(Xc + (size_t)k * n + r);
             }
 #pragma unroll
-            for (int c = 0; c < CS_K; ++c)
+            for (int c = 0; c < KL; ++c)
             {
                 double zn = 0., xo = 0.;
 #pragma unroll
                 for (int k = 0; k < CS_K; ++k)
                 {
-                    zn += zr[k] * S.Q[k][c];
-                    xo += xr[k] * S.Q[k][c];
+                    zn += zr[k] * S.Q[k][k0 + c];
+                    xo += xr[k] * S.Q[k][k0 + c];
                 }
-                const double d = xo - S.mu[c] * zn;
+                const double d = xo - S.mu[k0 + c] * zn;
                 rs[c] += d * d;
-                X[(size_t)c * n + r] = zn;
+                Xn[(size_t)(k0 + c) * n + r] = zn;
             }
         }
-        block_sum<CS_K>(rs, red, tot);
+        block_sum<KL>(rs, red, tot);
+        if (tid < KL)
+            small[128 + k0 + tid] = tot[tid];
+        group_barrier(counter, G, target);
+        {
+            double *tmp = Xc;
+            Xc = Xn;
+            Xn = tmp;
+        }
         if (tid == 0)
         {
-            // wanted: every pair with lambda <= theta and the first one above it
+            double res2[CS_K];
+            for (int i = 0; i < CS_K; ++i)
+                res2[i] = ldt<MULTI>(small + 128 + i);
+            // wanted: every pair with lambda <= theta ...
             int m = 0;
             while (m < CS_K && S.mu[m] + sigma <= theta)
                 ++m;
             int ok = 1;
             for (int i = 0; i < max(1, m); ++i)
-                if (!(sqrt(tot[i]) <= tol))
+                if (!(sqrt(res2[i]) <= tol))
                     ok = 0;
-            // the first Ritz value above theta only has to be above it for certain: Ritz values
-            // bound the eigenvalues from above and an eigenvalue lies within the residual of it
-            if (m >= 1 && m < CS_K && !(S.mu[m] + sigma - sqrt(tot[m]) > theta))
+            // ... and the first Ritz value above theta only has to be above it for certain: Ritz
+            // values bound the eigenvalues from above and an eigenvalue lies within the residual
+            if (m >= 1 && m < CS_K && !(S.mu[m] + sigma - sqrt(res2[m]) > theta))
                 ok = 0;
-            // Ritz values bound the K lowest eigenvalues from above: all of them <= theta means
-            // the block is too small whatever the residuals are
+            // all K Ritz values <= theta: the block is too small whatever the residuals are
             done = (m == CS_K) ? 2 : ok;
         }
         __syncthreads();
@@ -687,21 +797,28 @@ k_cs_iterate(const sa_cs_mat *mats, int nmats, double sigma, double theta, int m
             result = (done == 2) ? -2 : 0;
             break;
         }
+        // (the next iteration's first group barrier separates these reads of `small` from the
+        // writes of the next Rayleigh-Ritz step)
     }
-    if (tid == 0)
+    // the final vectors live in Xc; the caller reads M.X
+    if (result == 0 && Xc != M.X)
+    {
+        for (int r = tid; r < n; r += CS_NT)
+#pragma unroll
+            for (int k = 0; k < KL; ++k)
+                M.X[(size_t)(k0 + k) * n + r] = Xc[(size_t)(k0 + k) * n + r];
+    }
+    if (tid == 0 && gr == 0)
     {
         int m = 0;
         if (result == 0)
-        {
             while (m < CS_K && S.mu[m] + sigma <= theta)
                 ++m;
-            if (m == CS_K)
-                result = -2; // the block is too small for this matrix
-        }
-        M.info[0] = (result == 0) ? m : result;
         M.info[1] = min(its, max_its);
         for (int i = 0; i < CS_K; ++i)
             M.lam[i] = (result == 0 || result == -2) ? S.mu[i] + sigma : 0.;
+        __threadfence();
+        M.info[0] = (result == 0) ? m : result;
     }
 }
 
@@ -741,7 +858,6 @@ double sa_cs_sigma(double theta) { return -std::max(0.1 * theta, 1e-6); }
 void sa_cs_factor_iterate(sa_gpu_ctx *ctx, const sa_cs_mat *d_mats, int nmats, int nmax, double theta,
                           cudaStream_t st)
 {
-    (void)nmax;
     if (nmats <= 0)
         return;
     SpectralWs &WS = ctx->sws;
@@ -773,8 +889,31 @@ void sa_cs_factor_iterate(sa_gpu_ctx *ctx, const sa_cs_mat *d_mats, int nmats, i
     ctx->launches++;
     delete pc;
     ProfScope pi(ctx, "eig.cs_iterate");
-    static const int max_its = getenv("SA_GPU_CS_MAXIT") ? atoi(getenv("SA_GPU_CS_MAXIT")) : 120;
-    k_cs_iterate<<<nmats, CS_NT, 0, st>>>(d_mats, nmats, sigma, theta, max_its, 1e-13);
+    static int max_its = getenv("SA_GPU_CS_MAXIT") ? atoi(getenv("SA_GPU_CS_MAXIT")) : 120;
+    // few matrices: G blocks per matrix, each with K / G of the vectors (co-resident: cooperative)
+    static const int force_gi = getenv("SA_GPU_CS_ITER_GROUP") ? atoi(getenv("SA_GPU_CS_ITER_GROUP")) : 0;
+    int Gi = 1;
+    while (Gi < CS_K && nmats * Gi * 2 <= ctx->num_sms)
+        Gi *= 2;
+    if (force_gi > 0)
+        Gi = force_gi;
+    const double tol = 1e-13;
+    unsigned int *cnt2 = WS.counters.p; // (k_cs_chol has finished with them: same stream)
+    SA_CUDA(cudaMemsetAsync(cnt2, 0, ((size_t)ctx->num_sms + 8) * sizeof(unsigned int), st));
+    if (Gi == 1)
+        k_cs_iterate<CS_K, false><<<nmats, CS_NT, 0, st>>>(d_mats, nmats, sigma, theta, max_its, tol, cnt2);
+    else
+    {
+        if (nmats > ctx->num_sms + 8)
+            SA_FAIL("sa_cs_factor_iterate: group counters");
+        int grid = nmats * Gi;
+        void *args[] = {(void *)&d_mats, (void *)&nmats, (void *)&sigma, (void *)&theta,
+                        (void *)&max_its, (void *)&tol, (void *)&cnt2};
+        const void *fn = (Gi == 2)   ? (const void *)k_cs_iterate<4, true>
+                         : (Gi == 4) ? (const void *)k_cs_iterate<2, true>
+                                     : (const void *)k_cs_iterate<1, true>;
+        SA_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(CS_NT), args, 0, st));
+    }
     SA_CUDA(cudaGetLastError());
     ctx->launches++;
 }
@@ -799,12 +938,14 @@ extern "C" int sa_gpu_debug_cholsi(sa_gpu_ctx *ctx, int nmats, int n, const doub
 {
     SA_API_BEGIN
     cudaStream_t st = ctx->stream;
-    DevBuf<double> T, Xd, Zd, ld;
+    DevBuf<double> T, Xd, X2d, Zd, ld, sm;
     DevBuf<int> inf;
     const size_t nn = (size_t)n * n;
     T.upload(A, nn * nmats, st);
     Xd.alloc((size_t)nmats * n * CS_K);
     Zd.alloc((size_t)nmats * n * CS_K);
+    X2d.alloc((size_t)nmats * n * CS_K);
+    sm.alloc((size_t)nmats * 160);
     ld.alloc((size_t)nmats * CS_K);
     inf.alloc((size_t)nmats * 2);
     inf.zero(st);
@@ -816,6 +957,8 @@ extern "C" int sa_gpu_debug_cholsi(sa_gpu_ctx *ctx, int nmats, int n, const doub
         hm[b].T = T.p + nn * b;
         hm[b].X = Xd.p + (size_t)b * n * CS_K;
         hm[b].Z = Zd.p + (size_t)b * n * CS_K;
+        hm[b].X2 = X2d.p + (size_t)b * n * CS_K;
+        hm[b].small = sm.p + (size_t)b * 160;
         hm[b].lam = ld.p + (size_t)b * CS_K;
         hm[b].info = inf.p + 2 * b;
     }

@@ -11,7 +11,9 @@ struct sa_cs_mat
     int slot;
     double *T;   // n x n column-major: scaled matrix on entry, L in the lower triangle on exit
     double *X;   // n x SA_CS_K: Ritz vectors (unit 2-norm, ascending Ritz value) on exit
+    double *X2;  // n x SA_CS_K: work (ping-pong partner of X)
     double *Z;   // n x SA_CS_K: work
+    double *small; // 160 doubles: Gram matrices and residuals of the Rayleigh-Ritz step
     double *lam; // SA_CS_K Ritz values
     int *info;   // [0]: number of eigenvalues <= theta (>= 0), or -1 non-positive pivot, -2 all
                  //      SA_CS_K Ritz values <= theta, -3 no convergence, -4 rank-deficient block;

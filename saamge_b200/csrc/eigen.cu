@@ -1391,6 +1391,8 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
             WS.Twork.ensure((size_t)tt);
             WS.cs_X.ensure((size_t)dofftot * SA_CS_K);
             WS.cs_Z.ensure((size_t)dofftot * SA_CS_K);
+            WS.cs_X2.ensure((size_t)dofftot * SA_CS_K);
+            WS.cs_small.ensure((size_t)cnt * 160);
             WS.cs_lam.ensure((size_t)cnt * SA_CS_K);
             WS.cs_info.ensure((size_t)cnt * 2);
             SA_CUDA(cudaMemsetAsync(WS.cs_info.p, 0, (size_t)cnt * 2 * sizeof(int), st));
@@ -1406,6 +1408,8 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
                 hm[b].T = WS.Twork.p + h_toff[b];
                 hm[b].X = WS.cs_X.p + (size_t)h_doff[b] * SA_CS_K;
                 hm[b].Z = WS.cs_Z.p + (size_t)h_doff[b] * SA_CS_K;
+                hm[b].X2 = WS.cs_X2.p + (size_t)h_doff[b] * SA_CS_K;
+                hm[b].small = WS.cs_small.p + (size_t)b * 160;
                 hm[b].lam = WS.cs_lam.p + (size_t)b * SA_CS_K;
                 hm[b].info = WS.cs_info.p + 2 * b;
             }

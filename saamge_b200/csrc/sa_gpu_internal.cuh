@@ -225,7 +225,7 @@ struct SpectralWs
     DevBuf<int64_t> ts_toff, ts_mats;
     DevBuf<unsigned long long> ts_slots;
     // large-matrix Cholesky + subspace-iteration path (cholsi.cu)
-    DevBuf<double> cs_X, cs_Z, cs_lam;
+    DevBuf<double> cs_X, cs_X2, cs_Z, cs_lam, cs_small;
     DevBuf<int> cs_info;
     DevBuf<int64_t> cs_mats;
 };

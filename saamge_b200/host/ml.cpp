@@ -721,14 +721,15 @@ void tg_build_hierarchy(const SparseMatrix *Ag, tg_data_t &tg_data,
         else
             sa_gpu_check(sa_gpu_coarse_elmats(finer->gpu, tg_data.gpu), "sa_gpu_coarse_elmats");
     }
+    // interp_sparse_tent_build (amg/src/interp.cpp:694-726)
+    interp_compute_vectors(agg_part_rels, *tg_data.interp_data, tg_data, tg_data.theta);
     {
-        // smpr_update_Dinv_neg (tg_init_data -> smpr_init_poly_data in the reference)
+        // smpr_update_Dinv_neg (tg_init_data -> smpr_init_poly_data in the reference).  After the
+        // eigen stage: it is the first stage that needs ALL rows of the operator, and with a
+        // pipelined upload of the finest level the eigen stage runs while they are in flight.
         StageTimer tm("Dinv_neg");
         sa_gpu_check(sa_gpu_build_Dinv_neg(tg_data.gpu), "sa_gpu_build_Dinv_neg");
     }
-
-    // interp_sparse_tent_build (amg/src/interp.cpp:694-726)
-    interp_compute_vectors(agg_part_rels, *tg_data.interp_data, tg_data, tg_data.theta);
     interp_sparse_tent_assemble(agg_part_rels, *tg_data.interp_data, tg_data, avoid_ess_bdr_dofs);
     // tg_smooth_interp (amg/inc/tg.hpp:678-693)
     interp_data_t &id = *tg_data.interp_data;
