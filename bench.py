@@ -13,9 +13,11 @@ lambda <= theta) over all ~40k agglomerates of the finest level.
 Extra keys: roofline (dominant kernel), roofline_spmv, cpu_baseline (the CPU oracle on
 the box's host cores, bounded sample), full-hierarchy setup and PCG solve times.
 
-Multi-GPU (torchrun, one rank per GPU): every rank owns one 128^3 subdomain (its own
-coefficient seed) -> weak scaling, no data-path collective in the stage; times are
-max-reduced over ranks.
+Multi-GPU (torchrun, one rank per GPU): STRONG scaling of ONE 128^3 problem -- the AEs of the
+level are dealt to the ranks (contiguous ranges balanced on n^3) and the per-AE results are
+exchanged device to device inside the timed region; times are max-reduced over ranks.  The
+`hierarchy` block times the whole multilevel setup (owner-sharded: sa_gpu_dist_* stages) and the
+row-partitioned PCG on the N ranks, beside the CPU path.
 
 --impl reference : the reference's CPU path (the oracle port: same algorithm, same
 LAPACK dsygvx calls) on all host cores, bounded sample per step; rank 0 only.
@@ -588,6 +590,39 @@ def main():
             "levels_rows_nnzA_nnzP": S.level_info()}
         halo = S.stats()
         hier["halo"] = {"exchanges": int(halo[2]), "doubles_sent_by_rank0": int(halo[3])} if world > 1 else None
+        if world == 1:
+            # a second, profiled build: per-kernel times of the large-AE eigensolver (levels >= 1)
+            try:
+                h.sa_drv_gpu_profile(1, None, 0)
+                H2 = sab.ml_build(pr, p, local_rank)
+                pbuf = ctypes.create_string_buffer(8192)
+                h.sa_drv_gpu_profile(0, pbuf, 8192)
+                pm = {ln.split()[0]: float(ln.split()[1]) for ln in pbuf.value.decode().splitlines() if ln.strip()}
+                n3, cnt_large = 0.0, 0
+                for l in range(1, w["levels"] - 1):
+                    nn = np.diff(H2.get("AE_to_dof.I", l)).astype(np.float64)
+                    nn = nn[nn > 208]
+                    n3 += float((nn ** 3).sum())
+                    cnt_large += int(len(nn))
+                H2.close()
+                chol_ms = pm.get("eig.cs_chol")
+                if chol_ms and n3 > 0:
+                    eig_ms = sum(v for k, v in pm.items() if k in ("eig.cs_chol", "eig.cs_iterate", "eig.large_assemble"))
+                    hier["large_AE_eigensolver"] = {
+                        "what": "levels >= 1 (n > 208): Cholesky of A^ - sigma I (DMMA) + shift-invert subspace iteration "
+                                "(cholsi.cu) instead of a tridiagonalisation",
+                        "matrices": cnt_large, "sum_n3": n3,
+                        "ms": {k: v for k, v in pm.items() if k.startswith("eig.cs_") or k == "eig.large_assemble"},
+                        "roofline": {"kernel": "k_cs_chol", "bound": "tensor",
+                                     "bound_detail": "FP64 tensor pipe (DMMA m8n8k4): n^3/3 flops per matrix executed",
+                                     "achieved": n3 / 3.0 / (chol_ms * 1e-3) / 1e12, "peak": fp64_peak,
+                                     "unit": "TFLOP/s", "frac": n3 / 3.0 / (chol_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
+                                     "peak_source": "FP64 FMA peak measured in this run (DMMA measured at 1.07x of it, tools/dmma_bench.cu)",
+                                     "traffic": None},
+                        "algorithmic_tflops_4_3_n3": (4.0 / 3.0) * n3 / (eig_ms * 1e-3) / 1e12,
+                    }
+            except Exception as ex:
+                hier["large_AE_eigensolver"] = {"error": repr(ex)}
         if rank == 0:
             t0 = time.time()
             its1 = sab.ml_pcg(H, 1000, 1e-12, 0.0)

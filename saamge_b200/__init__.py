@@ -306,12 +306,21 @@ def make_exchange(dist, group=None):
     return exchange
 
 
-def library_comm(dist, group=None):
+def library_comm(dist, group=None, device=None):
     """sa_gpu_comm (NCCL communicator owned by the CUDA library) over the ranks of `dist`:
     rank 0 makes the 128-byte unique id, the launcher's process group hands it to everyone.
-    Collective.  Returns a ctypes.c_void_p; free with gpu_lib().sa_gpu_comm_destroy."""
+    Collective.  `device`: this rank's GPU (default: torch's current device) -- the library's
+    context is created there if the process has none yet.  Returns a ctypes.c_void_p; free with
+    gpu_lib().sa_gpu_comm_destroy."""
     g, h = gpu_lib(), host_lib()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if device is None:
+        import torch
+
+        device = torch.cuda.current_device()
+    h.sa_drv_ctx_on.restype = ctypes.c_void_p
+    h.sa_drv_ctx_on.argtypes = [ctypes.c_int]
+    h.sa_drv_ctx_on(int(device))
     h.sa_drv_ctx.restype = ctypes.c_void_p
     g.sa_gpu_nccl_unique_id.argtypes = [ctypes.c_void_p]
     g.sa_gpu_comm_create.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
@@ -334,7 +343,7 @@ def library_comm(dist, group=None):
 _owner_comm = []
 
 
-def enable_sharding(dist, group=None, mode="owner"):
+def enable_sharding(dist, group=None, mode="owner", device=None):
     """Shard the setup over the ranks of `dist` (torch.distributed; NCCL on GPUs).
     mode "owner" (default with NCCL): every rank computes its AE range and keeps its
     eigenvectors; the tentative prolongator is built by the MIS owners after one all-to-all-v of
@@ -347,7 +356,7 @@ def enable_sharding(dist, group=None, mode="owner"):
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     if mode == "owner" and dist.get_backend(group) == "nccl" and world > 1 \
             and not os.environ.get("SA_SHARD_REPLICATE"):
-        comm = library_comm(dist, group)
+        comm = library_comm(dist, group, device)
         _owner_comm.append(comm)
         h.sa_drv_set_sharding_comm.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
         h.sa_drv_set_sharding_comm(comm, rank, world)

@@ -582,7 +582,7 @@ k_cs_iterate(const sa_cs_mat *mats, int nmats, double sigma, double theta, int m
     for (int r = tid; r < n; r += CS_NT)
 #pragma unroll
         for (int k = 0; k < KL; ++k)
-            Xc[(size_t)(k0 + k) * n + r] = cs_start_value(r, k0 + k, b);
+            Xc[(size_t)(k0 + k) * n + r] = cs_start_value(r, k0 + k, M.slot);
     group_barrier(counter, G, target);
     int its = 0, result = -3; // -3: no convergence
     int buf = 0;

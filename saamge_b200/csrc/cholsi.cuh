@@ -8,7 +8,7 @@
 struct sa_cs_mat
 {
     int n;
-    int slot;
+    int slot;    // seed of the start vectors (the AE id: results independent of the batching)
     double *T;   // n x n column-major: scaled matrix on entry, L in the lower triangle on exit
     double *X;   // n x SA_CS_K: Ritz vectors (unit 2-norm, ascending Ritz value) on exit
     double *X2;  // n x SA_CS_K: work (ping-pong partner of X)

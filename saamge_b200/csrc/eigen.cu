@@ -1404,7 +1404,7 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
             {
                 ident[b] = b;
                 hm[b].n = nAE(a0 + b);
-                hm[b].slot = b;
+                hm[b].slot = h_ae[b]; // (seeds the start vectors: the result does not depend on the chunking)
                 hm[b].T = WS.Twork.p + h_toff[b];
                 hm[b].X = WS.cs_X.p + (size_t)h_doff[b] * SA_CS_K;
                 hm[b].Z = WS.cs_Z.p + (size_t)h_doff[b] * SA_CS_K;

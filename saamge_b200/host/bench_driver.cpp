@@ -267,6 +267,8 @@ extern "C" int sa_drv_gpu_profile(int enable, char *buf, int buflen)
 }
 
 extern "C" void *sa_drv_ctx(void) { return proc_gpu_ctx(); }
+/* the process's context on `device` (created when there is none yet) */
+extern "C" void *sa_drv_ctx_on(int device) { return proc_gpu_init(device); }
 
 /* kind 0: SpMV with the finest operator, kind 1: fused polynomial-smoother step;
    returns milliseconds per call (device-resident vectors, CUDA events) */
