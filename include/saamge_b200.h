@@ -191,6 +191,14 @@ int sa_gpu_build_Dinv_neg(sa_gpu_level *level);
  * then restr = P^T (tg_smooth_interp, amg/inc/tg.hpp:678-693).  degree 0 => P = P_tent. */
 int sa_gpu_smooth_P(sa_gpu_level *level, int degree, const double *roots);
 /* tg_coarse_matr (amg/inc/tg.hpp:695-709): Ac = P^T A P */
+/* adapt_update_operators (amg/src/adapt.cpp:171-216): new operator values (same pattern) for a
+   level that owns its operator; afterwards sa_gpu_build_Dinv_neg (smpr_update_Dinv_neg),
+   optionally sa_gpu_smooth_P (tg_smooth_interp, from the kept tentative P) and sa_gpu_rap. */
+int sa_gpu_level_update_operator(sa_gpu_level *level, const double *A_data);
+/* AltThreshold (amg/src/interp.cpp:86-170), the drop_tol branch of interp_smooth
+   (amg/src/interp.cpp:219-228): keeps the entries of the smoothed prolongator with
+   |p_ij| > drop_tol and rebuilds R = P^T.  Call between sa_gpu_smooth_P and sa_gpu_rap. */
+int sa_gpu_threshold_P(sa_gpu_level *level, double drop_tol, int *nnz_before, int *nnz_after);
 int sa_gpu_rap(sa_gpu_level *level);
 /* ElementMatrixParallelCoarse::GetMatrix for every finer AE (amg/src/elmat.cpp:105-195):
  * coarse element matrices P_e^T A_AE(e) P_e, kept on the device of \a coarse. */

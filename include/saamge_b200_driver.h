@@ -33,6 +33,9 @@ typedef struct
     int block[3];            /* block edge in elements per direction, finest level (partition_kind 1) */
     int coarse_block;        /* fine AEs per coarse AE per direction (partition_kind 1) */
     int testmesh_inject;     /* 1 = add the all-ones vector on AE 0 (amg/src/interp.cpp:510-524) */
+    double smooth_drop_tol;  /* MultilevelParameters::smooth_drop_tol: entries of the smoothed P with
+                                |p| <= tol are dropped (AltThreshold, amg/src/interp.cpp:134-170); 0 = off */
+    int correct_nullspace;   /* --correct-nulspace: CorrectNullspace coarsest solver (amg/src/solve.cpp:52-164) */
 } sa_drv_params_t;
 
 void sa_drv_default_params(sa_drv_params_t *p);
@@ -58,6 +61,12 @@ void *sa_drv_ml_build(void *prob, const sa_drv_params_t *p, int device);
 /* Runs PCG with the V-cycle preconditioner on the device; returns iterations
  * (negative on failure, amg/src/mfem_addons.cpp:201,232). */
 int sa_drv_ml_pcg(void *hier, int maxiter, double rtol, double atol);
+/* Operator update without new eigensolves (adapt_update_operators, amg/src/adapt.cpp:171-216):
+   sa_drv_problem_set_A_values replaces the values of the problem's operator (same pattern),
+   sa_drv_ml_update_operators redoes the smoothers, (resmooth_interp) the smoothing of the kept
+   tentative prolongators, the Galerkin products and the coarsest solver on the device. */
+int sa_drv_problem_set_A_values(void *prob, const double *vals, int64_t n);
+int sa_drv_ml_update_operators(void *hier, int resmooth_interp);
 /* Pull every level's device results into the host record (for comparisons). */
 int sa_drv_ml_download(void *hier);
 void sa_drv_hier_destroy(void *hier);

@@ -848,9 +848,31 @@ SparseMatrix *interp_sparse_tent_assemble(const agg_partitioning_relations_t &ag
     return tent_interp.Finalize();
 }
 
-// amg/src/interp.cpp:64-82, 172-229 (drop_tol = 0, times_apply_smoother = 1)
+// AltThresholdLocal (amg/src/interp.cpp:86-126): keeps the entries with fabs(val) > threshold
+static SparseMatrix *AltThreshold(const SparseMatrix &mat, double val)
+{
+    SparseMatrix *out = new SparseMatrix;
+    out->h = mat.h;
+    out->w = mat.w;
+    out->I.assign((size_t)mat.h + 1, 0);
+    for (int i = 0; i < mat.h; ++i)
+    {
+        int thisrowcount = 0;
+        for (int jp = mat.I[i]; jp < mat.I[i + 1]; ++jp)
+            if (fabs(mat.A[jp]) > val)
+            {
+                ++thisrowcount;
+                out->J.push_back(mat.J[jp]);
+                out->A.push_back(mat.A[jp]);
+            }
+        out->I[i + 1] = out->I[i] + thisrowcount;
+    }
+    return out;
+}
+
+// amg/src/interp.cpp:64-82, 172-229 (times_apply_smoother = 1)
 SparseMatrix *interp_smooth(int degree, const double *roots, const SparseMatrix &A,
-                            const SparseMatrix &tent, const Vector &Dinv_neg)
+                            const SparseMatrix &tent, const Vector &Dinv_neg, double drop_tol)
 {
     // smoother_matr = diag(Dinv_neg) * A
     SparseMatrix smoother_matr = A;
@@ -873,7 +895,11 @@ SparseMatrix *interp_smooth(int degree, const double *roots, const SparseMatrix 
         delete interp;
         interp = new_interp;
     }
-    return interp;
+    if (drop_tol == 0.0)
+        return interp;
+    SparseMatrix *new_interp = AltThreshold(*interp, drop_tol);
+    delete interp;
+    return new_interp;
 }
 
 /* ---------------------------------------------------------------------- solve */
@@ -1151,7 +1177,7 @@ static void tg_build_level(oracle_level_t &L, int nu_pro, int nu_relax, double t
     t0 = now_s();
     if (nu_pro > 0)
         L.interp = interp_smooth(L.interp_smoother_degree, L.interp_smoother_roots, *L.A,
-                                 *L.ltent_interp, *L.Dinv_neg);
+                                 *L.ltent_interp, *L.Dinv_neg, L.drop_tol);
     else
         L.interp = new SparseMatrix(*L.ltent_interp);
     L.restr = new SparseMatrix;
@@ -1251,6 +1277,7 @@ extern "C" void *sa_orc_ml_build(void *prob_, const sa_drv_params_t *p)
             L->A = F->Ac;
             L->elem_data = new ElementMatrixParallelCoarse(*rels, F);
         }
+        L->drop_tol = p->smooth_drop_tol;
         tg_build_level(*L, i == 0 ? p->first_nu_pro : p->nu_pro, p->nu_relax,
                        i == 0 ? p->first_theta : p->theta, avoid, H->times, i);
     }
@@ -1388,6 +1415,7 @@ extern "C" void *sa_orc_ml_build_algebraic(void *prob_, const sa_drv_params_t *p
             L->A = F->Ac;
             L->elem_data = new ElementMatrixParallelCoarse(*rels, F);
         }
+        L->drop_tol = p->smooth_drop_tol;
         tg_build_level(*L, i == 0 ? p->first_nu_pro : p->nu_pro, p->nu_relax,
                        i == 0 ? p->first_theta : p->theta, avoid, H->times, i);
     }
@@ -1397,6 +1425,45 @@ extern "C" void *sa_orc_ml_build_algebraic(void *prob_, const sa_drv_params_t *p
     for (int i = 0; i < coarsenings; ++i)
         export_level(*ml->levels[i], H->levels[i], i + 1 < coarsenings ? ml->levels[i + 1]->elem_data : NULL);
     return H;
+}
+
+/* adapt_update_operators (amg/src/adapt.cpp:171-216) on the oracle's hierarchy, with the problem's
+   current operator values: smpr_update_Dinv_neg, tg_smooth_interp (amg/inc/tg.hpp:678-693) from
+   the kept tentative prolongator when resmooth_interp, tg_update_coarse_operator (fresh RAP), level
+   by level; then the coarsest factorisation (ml_impose_cycle). */
+extern "C" int sa_orc_ml_update_operators(void *hier, int resmooth_interp)
+{
+    sa_hierarchy_t *H = (sa_hierarchy_t *)hier;
+    oracle_ml_t *ml = (oracle_ml_t *)H->impl;
+    for (size_t i = 0; i < ml->levels.size(); ++i)
+    {
+        oracle_level_t &L = *ml->levels[i];
+        if (i > 0)
+            L.A = ml->levels[i - 1]->Ac; // Af = finer Ac
+        delete L.Dinv_neg;
+        L.Dinv_neg = mbox_build_Dinv_neg_parallel_matrix(*L.A);
+        if (resmooth_interp && L.nu_pro > 0 && L.interp_smoother_degree > 0)
+        {
+            delete L.interp;
+            delete L.restr;
+            L.interp = interp_smooth(L.interp_smoother_degree, L.interp_smoother_roots, *L.A,
+                                     *L.ltent_interp, *L.Dinv_neg, L.drop_tol);
+            L.restr = new SparseMatrix;
+            SpTranspose(*L.interp, *L.restr);
+        }
+        delete L.Ac; // tg_free_coarse_operator
+        SparseMatrix AP;
+        SpMultMat(*L.A, *L.interp, AP);
+        L.Ac = new SparseMatrix;
+        SpMultMat(*L.restr, AP, *L.Ac);
+    }
+    factor_coarsest(*ml->levels.back());
+    const int coarsenings = (int)ml->levels.size();
+    H->levels.clear();
+    H->levels.resize(coarsenings);
+    for (int i = 0; i < coarsenings; ++i)
+        export_level(*ml->levels[i], H->levels[i], i + 1 < coarsenings ? ml->levels[i + 1]->elem_data : NULL);
+    return 0;
 }
 
 extern "C" int sa_orc_ml_pcg(void *hier, int maxiter, double rtol, double atol)

@@ -113,6 +113,7 @@ struct oracle_level_t
     std::vector<double> Ac_chol;
     bool owns_A = false;
     bool testmesh_inject = false;
+    double drop_tol = 0.; // interp_data_t::drop_tol (AltThreshold on the smoothed P)
     ~oracle_level_t();
 };
 
@@ -121,7 +122,7 @@ void interp_compute_vectors(const agg_partitioning_relations_t &agg_part_rels,
 SparseMatrix *interp_sparse_tent_assemble(const agg_partitioning_relations_t &agg_part_rels,
                                           oracle_level_t &lev, bool avoid_ess_bdr_dofs);
 SparseMatrix *interp_smooth(int degree, const double *roots, const SparseMatrix &A,
-                            const SparseMatrix &tent, const Vector &Dinv_neg);
+                            const SparseMatrix &tent, const Vector &Dinv_neg, double drop_tol);
 
 /* ---- solve (amg/inc/smpr.hpp:319-339, amg/src/tg.cpp:91-132, amg/src/mfem_addons.cpp:106-248) ---- */
 void smpr_compute_poly(const SparseMatrix &A, const Vector &b, Vector &x, int degree,

@@ -39,6 +39,8 @@ class Params(ctypes.Structure):
         ("block", ctypes.c_int * 3),
         ("coarse_block", ctypes.c_int),
         ("testmesh_inject", ctypes.c_int),
+        ("smooth_drop_tol", ctypes.c_double),
+        ("correct_nullspace", ctypes.c_int),
     ]
 
 
@@ -405,6 +407,24 @@ def ml_build_algebraic(problem, params, device=0):
 
 def ml_pcg(hier, maxiter=1000, rtol=1e-12, atol=0.0):
     return host_lib().sa_drv_ml_pcg(hier.handle, maxiter, rtol, atol)
+
+
+def set_operator_values(problem, values):
+    """New values (same sparsity pattern) for the problem's operator -- the input of
+    ml_update_operators (a time-dependent coefficient)."""
+    v = np.ascontiguousarray(values, dtype=np.float64)
+    h = host_lib()
+    h.sa_drv_problem_set_A_values.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
+    rc = h.sa_drv_problem_set_A_values(problem.handle, v.ctypes.data, len(v))
+    assert rc == 0, "operator values: wrong length"
+
+
+def ml_update_operators(hier, resmooth_interp=True):
+    """adapt_update_operators (amg/src/adapt.cpp:171-216): the hierarchy follows the problem's
+    current operator values without new eigensolves."""
+    h = host_lib()
+    h.sa_drv_ml_update_operators.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    return h.sa_drv_ml_update_operators(hier.handle, 1 if resmooth_interp else 0)
 
 
 def ml_download(hier):

@@ -456,18 +456,30 @@ extern "C" int sa_gpu_comm_create(sa_gpu_ctx *ctx, const void *id128, int nranks
         }
         // NCCL connects channels lazily (first collective / first send-recv per peer: 0.5 - 2 s
         // measured): do it here, not inside the first timed stage
-        DevBuf<int> w;
-        w.alloc((size_t)2 * nranks + 2);
+        // (a few message sizes: the protocol / algorithm NCCL picks, and with it the connections
+        // it sets up on first use, depend on the size -- 8-GPU run: 40 ms inside the first small
+        // all-reduce of a level that followed a warm-up with one size only)
+        const size_t sizes[3] = {16, (size_t)1 << 15, (size_t)1 << 21}; // doubles
+        DevBuf<double> w;
+        w.alloc(sizes[2] * 2 + (size_t)nranks * sizes[1]);
         w.zero(ctx->stream);
-        SA_NCCL(nccl().AllReduce(w.p, w.p, 1, ncclInt32, ncclSum, C->comm, ctx->stream));
-        SA_NCCL(nccl().GroupStart());
-        for (int q = 0; q < nranks; ++q)
-            if (q != rank)
-            {
-                SA_NCCL(nccl().Send(w.p + 1, 1, ncclInt32, q, C->comm, ctx->stream));
-                SA_NCCL(nccl().Recv(w.p + 2 + q, 1, ncclInt32, q, C->comm, ctx->stream));
-            }
-        SA_NCCL(nccl().GroupEnd());
+        for (int si = 0; si < 3; ++si)
+        {
+            SA_NCCL(nccl().AllReduce(w.p, w.p, sizes[si], ncclDouble, ncclSum, C->comm, ctx->stream));
+            SA_NCCL(nccl().AllReduce(w.p, w.p, sizes[si], ncclInt32, ncclSum, C->comm, ctx->stream));
+        }
+        for (int si = 0; si < 2; ++si)
+        {
+            SA_NCCL(nccl().GroupStart());
+            for (int q = 0; q < nranks; ++q)
+                if (q != rank)
+                {
+                    SA_NCCL(nccl().Send(w.p, sizes[si], ncclDouble, q, C->comm, ctx->stream));
+                    SA_NCCL(nccl().Recv(w.p + sizes[2] * 2 + (size_t)q * sizes[1], sizes[si], ncclDouble, q,
+                                        C->comm, ctx->stream));
+                }
+            SA_NCCL(nccl().GroupEnd());
+        }
         SA_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     *out = C;

@@ -116,6 +116,95 @@ __global__ void k_scale_rows_add_identity_d(int rows, const int *I, const int *J
 }
 } // namespace
 
+namespace
+{
+__global__ void k_thr_count(int rows, const int *I, const double *A, double tol, int *cnt)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows)
+        return;
+    int c = 0;
+    for (int p = I[r]; p < I[r + 1]; ++p)
+        c += fabs(A[p]) > tol;
+    cnt[r] = c;
+}
+__global__ void k_thr_fill(int rows, const int *I, const int *J, const double *A, double tol,
+                           const int *In, int *Jn, double *An)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows)
+        return;
+    int o = In[r];
+    for (int p = I[r]; p < I[r + 1]; ++p)
+        if (fabs(A[p]) > tol)
+        {
+            Jn[o] = J[p];
+            An[o] = A[p];
+            ++o;
+        }
+}
+} // namespace
+
+/* AltThreshold (amg/src/interp.cpp:86-170) on the smoothed prolongator: keeps the entries with
+   |p_ij| > drop_tol (row order preserved), R = P^T is rebuilt.  interp_smooth applies it when
+   drop_tol != 0 (amg/src/interp.cpp:219-228). */
+extern "C" int sa_gpu_threshold_P(sa_gpu_level *lev, double drop_tol, int *nnz_before, int *nnz_after)
+{
+    SA_API_BEGIN
+    if (!lev->have_P)
+        SA_FAIL("sa_gpu_threshold_P: no prolongator (call sa_gpu_smooth_P)");
+    sa_gpu_ctx *ctx = lev->ctx;
+    cudaStream_t st = ctx->stream;
+    DevCsr &P = lev->P;
+    if (nnz_before)
+        *nnz_before = P.nnz;
+    DevBuf<int> cnt;
+    cnt.alloc((size_t)P.rows);
+    DevCsr Pn;
+    Pn.rows = P.rows;
+    Pn.cols = P.cols;
+    Pn.I.alloc((size_t)P.rows + 1);
+    if (P.rows)
+        SA_LAUNCH(ctx, k_thr_count, (P.rows + 255) / 256, 256, 0, P.rows, P.I.p, P.A.p, drop_tol, cnt.p);
+    dev_exclusive_scan_i32(ctx, cnt.p, Pn.I.p, P.rows);
+    int nnz = 0;
+    SA_CUDA(cudaMemcpyAsync(&nnz, Pn.I.p + P.rows, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SA_CUDA(cudaStreamSynchronize(st));
+    Pn.nnz = nnz;
+    Pn.J.alloc((size_t)nnz);
+    Pn.A.alloc((size_t)nnz);
+    if (P.rows)
+        SA_LAUNCH(ctx, k_thr_fill, (P.rows + 255) / 256, 256, 0, P.rows, P.I.p, P.J.p, P.A.p, drop_tol,
+                  Pn.I.p, Pn.J.p, Pn.A.p);
+    P.swap(Pn);
+    dev_csr_transpose(ctx, P, lev->R);
+    SA_CUDA(cudaStreamSynchronize(st));
+    lev->have_Ac = false;
+    if (nnz_after)
+        *nnz_after = nnz;
+    SA_API_END
+}
+
+/* New values for the operator of a level that owns it (the finest), same sparsity pattern:
+   smpr_update_Dinv_neg / tg_smooth_interp / tg_update_coarse_operator are then re-run by the
+   caller (adapt_update_operators, amg/src/adapt.cpp:171-216) -- the spectral data, the tentative
+   prolongator and every table stay. */
+extern "C" int sa_gpu_level_update_operator(sa_gpu_level *lev, const double *A_data)
+{
+    SA_API_BEGIN
+    sa_level_ready(lev);
+    if (lev->A != &lev->A_own || !lev->A_own.nnz)
+        SA_FAIL("sa_gpu_level_update_operator: the level does not own its operator (coarse levels "
+                "alias the finer level's Ac: redo sa_gpu_rap there)");
+    cudaStream_t st = lev->ctx->stream;
+    SA_CUDA(cudaMemcpyAsync(lev->A_own.A.p, A_data, (size_t)lev->A_own.nnz * sizeof(double),
+                            cudaMemcpyHostToDevice, st));
+    SA_CUDA(cudaStreamSynchronize(st));
+    lev->have_Dinv = false;
+    lev->have_Ac = false;
+    SA_API_END
+}
+
 extern "C" int sa_gpu_dist_rap(sa_gpu_level *lev, sa_gpu_comm *C, double *bytes_moved)
 {
     SA_API_BEGIN

@@ -100,6 +100,8 @@ extern "C" void sa_drv_default_params(sa_drv_params_t *p)
     p->block[0] = p->block[1] = p->block[2] = 4;
     p->coarse_block = 2;
     p->testmesh_inject = 0;
+    p->smooth_drop_tol = 0.0;
+    p->correct_nullspace = 0;
 }
 
 extern "C" void *sa_drv_problem_create(int dim, int nx, int ny, int nz, int order,

@@ -743,6 +743,9 @@ void tg_build_hierarchy(const SparseMatrix *Ag, tg_data_t &tg_data,
         sa_gpu_check(sa_gpu_smooth_P(tg_data.gpu, tg_data.smooth_interp ? id.interp_smoother_degree : 0,
                                      id.interp_smoother_roots),
                      "sa_gpu_smooth_P");
+    // interp_smooth's drop_tol branch (AltThreshold, amg/src/interp.cpp:219-228)
+    if (tg_data.smooth_interp && id.interp_smoother_degree > 0 && id.drop_tol != 0.0)
+        sa_gpu_check(sa_gpu_threshold_P(tg_data.gpu, id.drop_tol, NULL, NULL), "sa_gpu_threshold_P");
     tg_data.have_Ac = false;
 }
 
@@ -1271,6 +1274,7 @@ extern "C" void *sa_drv_ml_build_user(void *prob_, const sa_drv_params_t *p, int
     MultilevelParameters mlp(p->num_levels - 1, nparts_arr.data(), p->first_nu_pro, p->nu_pro,
                              p->nu_relax, p->first_theta, p->theta, -1, false, false, false);
     mlp.set_coarse_direct(true);
+    mlp.set_smooth_drop_tol(p->smooth_drop_tol);
     block_partitioner_data_t bpd = {prob, p};
     if (p->partition_kind == 1 || !prob->coarse_partitions.empty())
         mlp.set_coarse_partitioner(block_coarse_partitioner, &bpd);
@@ -1444,6 +1448,7 @@ extern "C" void *sa_drv_ml_build(void *prob_, const sa_drv_params_t *p, int devi
     MultilevelParameters mlp(p->num_levels - 1, nparts_arr.data(), p->first_nu_pro, p->nu_pro,
                              p->nu_relax, p->first_theta, p->theta, -1, false, false, false);
     mlp.set_coarse_direct(true);
+    mlp.set_smooth_drop_tol(p->smooth_drop_tol);
     mlp.testmesh_inject = p->testmesh_inject != 0;
     block_partitioner_data_t bpd = {prob, p};
     if (p->partition_kind == 1 || !prob->coarse_partitions.empty())
@@ -1480,6 +1485,7 @@ extern "C" void *sa_drv_ml_build_algebraic(void *prob_, const sa_drv_params_t *p
     MultilevelParameters mlp(p->num_levels - 1, nparts_arr.data(), p->first_nu_pro, p->nu_pro,
                              p->nu_relax, p->first_theta, p->theta, -1, false, false, false);
     mlp.set_coarse_direct(true);
+    mlp.set_smooth_drop_tol(p->smooth_drop_tol);
     pi->ml = ml_produce_data_algebraic(f.A, *prob->rels, mlp);
     sa_gpu_ctx_sync(proc_gpu_ctx());
     H->times["setup"] = now_s() - t0;
@@ -1517,6 +1523,34 @@ extern "C" int sa_drv_ml_download(void *hier)
                          "sa_gpu_get_coarse_elmats");
         }
     }
+    return 0;
+}
+
+/* New values (same pattern) for the problem's operator: the input of an operator update
+   (time-dependent coefficient); the element matrices and every relation stay. */
+extern "C" int sa_drv_problem_set_A_values(void *prob_, const double *vals, int64_t n)
+{
+    sa_problem_t *prob = (sa_problem_t *)prob_;
+    if ((int64_t)prob->fem->A.A.size() != n)
+        return 1;
+    std::copy(vals, vals + n, prob->fem->A.A.begin());
+    return 0;
+}
+
+/* adapt_update_operators (amg/src/adapt.cpp:189-216) with the problem's CURRENT operator values:
+   new weighted-l1 smoothers, (optionally) re-smoothed prolongators from the kept tentative ones,
+   fresh Galerkin products on every level, new coarsest solver -- no eigensolves. */
+extern "C" int sa_drv_ml_update_operators(void *hier, int resmooth_interp)
+{
+    sa_hierarchy_t *H = (sa_hierarchy_t *)hier;
+    product_impl_t *pi = (product_impl_t *)H->impl;
+    int one = 1;
+    MultilevelParameters mlp(1, &one, 0, 0, pi->ml->nu_relax, 0.003, 0.003, -1, false, false, false);
+    mlp.set_coarse_direct(true);
+    const double t0 = now_s();
+    adapt_update_operators(H->prob->fem->A, *pi->ml, mlp, resmooth_interp != 0);
+    sa_gpu_ctx_sync(proc_gpu_ctx());
+    H->times["update_operators"] = now_s() - t0;
     return 0;
 }
 

@@ -22,6 +22,8 @@
 #include "aggregates.hpp"
 #include "elmat.hpp"
 #include "level_results.hpp"
+#include <fstream>
+
 #include "sa_types.hpp"
 
 namespace saamge
@@ -224,6 +226,7 @@ public:
     double get_smooth_drop_tol() const { return smooth_drop_tol; }
     bool get_coarse_direct() const { return coarse_direct; }
     void set_coarse_direct(bool cd) { coarse_direct = cd; }
+    void set_smooth_drop_tol(double tol) { smooth_drop_tol = tol; }
     /* fixtures: fixed coarse partitions instead of METIS (cf. the hard-coded
        partitions of the mltest fixture, amg/src/aggregates.cpp:1777-1794) */
     typedef int *(*coarse_partition_ft)(int level, int num_elem, int *nparts, void *data);
@@ -334,6 +337,34 @@ ml_data_t *ml_produce_data_algebraic(const SparseMatrix &Ag, const agg_partition
 void ml_produce_hierarchy_from_level(int coarsenings, int starting_level, ml_data_t &ml_data,
                                      const MultilevelParameters &mlp);
 void ml_impose_cycle(ml_data_t &ml_data, bool Wcycle);
+
+/* ---- operator update without new eigensolves (amg/src/adapt.cpp:171-216, amg/inc/tg.hpp:678-693,
+   735; amg/inc/smpr.hpp:241) ---- */
+void smpr_update_Dinv_neg(tg_data_t &tg_data);
+void tg_smooth_interp(tg_data_t &tg_data);
+void tg_free_coarse_operator(tg_data_t &tg_data);
+/// \a A: the new finest operator (same pattern), or NULL on a coarse level whose operator is the
+/// finer level's Ac.
+void adapt_update_operators(const SparseMatrix *A, tg_data_t &tg_data, bool resmooth_interp);
+void adapt_update_operators(const SparseMatrix &A, ml_data_t &ml_data, const MultilevelParameters &mlp,
+                            bool resmooth_interp);
+
+/* ---- binary formats of the reference's dumps (amg/src/mbox.cpp:310-483; amg/inc/mbox.hpp:344-516):
+   caller owns what the read functions return ---- */
+Table *mbox_read_table(const char *filename);
+void mbox_write_table(const char *filename, const Table &tbl);
+SparseMatrix *mbox_read_sparse_matr(const char *filename);
+SparseMatrix *mbox_read_sparse_matr(std::ifstream &ispm);
+void mbox_write_sparse_matr(const char *filename, const SparseMatrix &spm);
+void mbox_write_sparse_matr(std::ofstream &ospm, const SparseMatrix &spm);
+DenseMatrix *mbox_read_dense_matr(const char *filename);
+DenseMatrix *mbox_read_dense_matr(std::ifstream &idem);
+void mbox_write_dense_matr(const char *filename, const DenseMatrix &dem);
+void mbox_write_dense_matr(std::ofstream &odem, const DenseMatrix &dem);
+SparseMatrix **mbox_read_sparse_matr_arr(const char *filename, int *n);
+void mbox_write_sparse_matr_arr(const char *filename, SparseMatrix **arr, int n);
+DenseMatrix **mbox_read_dense_matr_arr(const char *filename, int *n);
+void mbox_write_dense_matr_arr(const char *filename, DenseMatrix **arr, int n);
 void ml_free_data(ml_data_t *ml_data);
 levels_level_t *levels_list_get_level(const levels_list_t &list, int i);
 

@@ -47,6 +47,13 @@ def orc_pcg(hier, maxiter=1000, rtol=1e-12, atol=0.0):
     return oracle().sa_orc_ml_pcg(hier.handle, maxiter, rtol, atol)
 
 
+def orc_update_operators(hier, resmooth_interp=True):
+    """adapt_update_operators on the oracle's hierarchy (the problem's current operator values)."""
+    o = oracle()
+    o.sa_orc_ml_update_operators.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    return o.sa_orc_ml_update_operators(hier.handle, 1 if resmooth_interp else 0)
+
+
 def orc_build_algebraic(problem, params):
     o = oracle()
     o.sa_orc_ml_build_algebraic.restype = ctypes.c_void_p

@@ -409,3 +409,69 @@ def test_contexts_can_be_reopened_and_share_the_allocation_stream():
         l2.close()
         c2.close()
     pr.close()
+
+
+def test_smoothed_prolongator_drop_tolerance():
+    """AltThreshold (amg/src/interp.cpp:86-170), the drop_tol branch of interp_smooth: entries of
+    the smoothed P with |p| <= drop_tol are dropped before RAP -- same pattern and values as the
+    oracle's restatement, and the tolerance really removes entries."""
+    kw = dict(num_levels=3, first_elems_per_agg=64, elems_per_agg=8, first_nu_pro=1, nu_pro=1,
+              partition_kind=1, block=(4, 4, 4), coarse_block=2)
+    pr = sab.Problem(3, 16, coef_kind=1)
+    p0 = sab.default_params(**kw)
+    pr.partition(p0)
+    H0 = sab.ml_build(pr, p0)
+    sab.ml_download(H0)
+    nnz0 = H0.csr("interp", 0).nnz
+    H0.close()
+    p = sab.default_params(smooth_drop_tol=2e-2, **kw)
+    Hg, Ho, itg, ito = _run(pr, p)
+    assert Hg.csr("interp", 0).nnz < nnz0
+    assert np.abs(Hg.csr("interp", 0).data).min() > 2e-2
+    for l, m in enumerate(parity.compare_hierarchies(Hg, Ho, expect_levels=2)):
+        parity.assert_level_ok(m, l)
+    assert itg > 0 and abs(itg - ito) <= 1, (itg, ito)
+    for h in (Hg, Ho):
+        h.close()
+    pr.close()
+
+
+@pytest.mark.parametrize("resmooth", [True, False])
+def test_operator_update_without_eigensolves(resmooth):
+    """adapt_update_operators (amg/src/adapt.cpp:171-216): a new operator with the same pattern
+    (here A + 0.3 diag(A): a reaction term switched on) -- smoothers, smoothed prolongators (from
+    the KEPT tentative ones) and Galerkin operators of every level follow it on the device exactly
+    as in the oracle; the spectral data are untouched; PCG on the new operator converges."""
+    import scipy.sparse as sp
+
+    p = sab.default_params(num_levels=3, first_elems_per_agg=64, elems_per_agg=8, first_nu_pro=1, nu_pro=1,
+                           partition_kind=1, block=(4, 4, 4), coarse_block=2)
+    pr = sab.Problem(3, 16, coef_kind=1)
+    pr.partition(p)
+    Hg, Ho, _itg, _ito = _run(pr, p)
+    tent_before = Hg.csr("tent_interp", 0).copy()
+    interp_before = Hg.csr("interp", 0).copy()
+    I, J, A = pr.get("A.I"), pr.get("A.J"), pr.get("A.A").copy()
+    M = sp.csr_matrix((A, J, I))
+    diag = M.diagonal()
+    rows = np.repeat(np.arange(len(I) - 1), np.diff(I))
+    A2 = A + 0.3 * diag[rows] * (rows == J)
+    sab.set_operator_values(pr, A2)
+    assert sab.ml_update_operators(Hg, resmooth) == 0
+    assert ou.orc_update_operators(Ho, resmooth) == 0
+    itg, ito = sab.ml_pcg(Hg), ou.orc_pcg(Ho)
+    sab.ml_download(Hg)
+    # stage by stage against the oracle (gauge-aware: P_g = S P_o Q, Ac_g = Q^T Ac_o Q, Dinv_neg)
+    for l, m in enumerate(parity.compare_hierarchies(Hg, Ho, expect_levels=2)):
+        parity.assert_level_ok(m, l)
+    assert abs(Hg.csr("tent_interp", 0) - tent_before).max() == 0.0
+    changed = abs(Hg.csr("interp", 0) - interp_before).max()
+    assert (changed > 1e-6) if resmooth else (changed == 0.0)
+    assert itg > 0 and abs(itg - ito) <= 1, (itg, ito)
+    x = Hg.get("pcg.x")
+    b = pr.get("b")
+    M2 = sp.csr_matrix((A2, J, I))
+    assert np.linalg.norm(M2 @ x - b) <= 1e-5 * np.linalg.norm(b)
+    for h in (Hg, Ho):
+        h.close()
+    pr.close()
