@@ -275,6 +275,11 @@ int sa_gpu_debug_twostage(sa_gpu_ctx *ctx, int n, const double *A, double *T_out
 int sa_gpu_debug_twostage_back(sa_gpu_ctx *ctx, int n, int nvec, double *Y);
 /* cycle counters of the phases of the two-stage kernels since the last call (diagnostics) */
 int sa_gpu_debug_ts_clocks(double *out16);
+/* cholsi.cu on `nmats` dense symmetric n x n matrices (column-major, spectrum in [0, 1]): per matrix
+   info2 = {number of eigenvalues <= theta or a negative failure code, iterations}, 8 Ritz values
+   (ascending), the 8 Ritz vectors n x 8 (tests/test_cholsi.py) */
+int sa_gpu_debug_cholsi(sa_gpu_ctx *ctx, int nmats, int n, const double *A, double theta, int *info2,
+                        double *lam, double *X);
 
 /* ---- device-pointer entry points (row-partitioned multi-GPU solve: the caller owns the
  *      vectors on the device, e.g. torch tensors, and drives the halo exchange) ----

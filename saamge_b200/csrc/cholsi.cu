@@ -135,36 +135,73 @@ __device__ __noinline__ void syrk_tile(double *__restrict__ T, const double *P, 
     }
 }
 
-/* rows r0 + first, r0 + first + stride, ... of the panel: X L^T = B, one row per thread */
+/* rows below the diagonal block: X = B Linv^T (Linv = inverse of the 32 x 32 diagonal factor, in
+   shared memory, zero above the diagonal) as DMMA products, one warp per 32 rows, in place: the
+   warp reads its 32 x 32 piece of B completely before it writes X. */
 template <bool MULTI>
-__device__ __noinline__ void trsm_rows(double *__restrict__ T, size_t ld, int n, int j0, int jb,
-                                       int first, int stride, const double *Ls, const double *rdiag)
+__device__ __noinline__ void trsm_tiles(double *__restrict__ T, size_t ld, int n, int j0, int jb,
+                                        int first_tile, int tile_stride, const double *Li)
 {
-    for (int r = j0 + jb + first; r < n; r += stride)
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int r0 = j0 + jb;
+    for (int i0 = r0 + 32 * first_tile; i0 < n; i0 += 32 * tile_stride)
     {
-        double x[CS_NB];
+        double a[4][8], c[4][4][2];
 #pragma unroll
-        for (int c = 0; c < CS_NB; ++c)
-            x[c] = (c < jb) ? ldt<MULTI>(T + r + ld * (j0 + c)) : 0.;
-#pragma unroll
-        for (int c = 0; c < CS_NB; ++c)
+        for (int mi = 0; mi < 4; ++mi)
         {
-            double s = x[c];
+            const int row = min(i0 + mi * 8 + g, n - 1);
 #pragma unroll
-            for (int q = 0; q < c; ++q)
-                s -= x[q] * Ls[c * CS_LD + q];
-            x[c] = s * rdiag[c];
+            for (int kk = 0; kk < 8; ++kk)
+            {
+                const int col = kk * 4 + t;
+                a[mi][kk] = (col < jb) ? ldt<MULTI>(T + row + ld * (size_t)(j0 + col)) : 0.;
+            }
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+                c[mi][ni][0] = c[mi][ni][1] = 0.;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+        {
+            // B operand: (Linv^T)(k, col) = Linv(col, k)
+            double bq[4];
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+                bq[ni] = Li[(ni * 8 + g) * CS_LD + kk * 4 + t];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
+                    dmma884(c[mi][ni][0], c[mi][ni][1], a[mi][kk], bq[ni]);
         }
 #pragma unroll
-        for (int c = 0; c < CS_NB; ++c)
-            if (c < jb)
-                T[r + ld * (j0 + c)] = x[c];
+        for (int mi = 0; mi < 4; ++mi)
+        {
+            const int row = i0 + mi * 8 + g;
+            if (row < n)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
+                {
+                    const int col = ni * 8 + 2 * t;
+                    if (col < jb)
+                        T[row + ld * (size_t)(j0 + col)] = c[mi][ni][0];
+                    if (col + 1 < jb)
+                        T[row + ld * (size_t)(j0 + col + 1)] = c[mi][ni][1];
+                }
+        }
     }
 }
 
 /* trailing update by the panel columns [pc0, pc0 + kdim): the tiles of the block columns
-   [0, ntc) of the lower triangle that starts at row / column r0 (ntc >= nt: the whole triangle),
-   dealt to the warps of the group */
+   [0, ntc) of the lower triangle that starts at row / column r0 (ntc >= nt: the whole triangle).
+   The 16 warps of a block work on one SUPER-TILE of 4 x 4 tiles at a time (warp w: tile row w / 4,
+   tile column w % 4), so that the block touches 4 + 4 operand strips of the panel for 16 tiles
+   (L1 shares them) instead of 16 + 1 -- the panels of the ~148 matrices in flight do not fit L2,
+   so every operand strip that is not shared comes from HBM (ncu: 353 GB read for 132 GB of C with
+   tiles dealt one by one).  Super-tiles are dealt to the blocks of the group, column-major. */
 template <bool MULTI>
 __device__ __forceinline__ void syrk_region(double *__restrict__ T, size_t ld, int n, int pc0, int kdim,
                                             int r0, int ntc, int G, int gr)
@@ -172,20 +209,23 @@ __device__ __forceinline__ void syrk_region(double *__restrict__ T, size_t ld, i
     const int wid = threadIdx.x >> 5;
     const int nt = (n - r0 + 31) >> 5;
     ntc = min(ntc, nt);
-    // column-major enumeration of the tiles: block column tj holds nt - tj tiles
-    const int ntiles = ntc * nt - ntc * (ntc - 1) / 2;
+    const int nst = (nt + 3) >> 2, nstc = (ntc + 3) >> 2;
+    // column-major enumeration of the super-tiles: super column sj holds nst - sj of them
+    const int nsuper = nstc * nst - nstc * (nstc - 1) / 2;
     const double *P = T + ld * (size_t)pc0;
-    for (int tl = gr * CS_NW + wid; tl < ntiles; tl += G * CS_NW)
+    for (int sl = gr; sl < nsuper; sl += G)
     {
-        const double bq = 2. * nt + 1.;
-        int tj = (int)((bq - sqrt(fmax(0., bq * bq - 8. * (double)tl))) * 0.5);
-        tj = max(0, min(tj, ntc - 1));
-        while (tj > 0 && tj * nt - tj * (tj - 1) / 2 > tl)
-            --tj;
-        while (tj + 1 < ntc && (tj + 1) * nt - (tj + 1) * tj / 2 <= tl)
-            ++tj;
-        const int ti = tj + (tl - (tj * nt - tj * (tj - 1) / 2));
-        syrk_tile<MULTI>(T, P, ld, n, r0 + ti * 32, r0 + tj * 32, kdim);
+        const double bq = 2. * nst + 1.;
+        int sj = (int)((bq - sqrt(fmax(0., bq * bq - 8. * (double)sl))) * 0.5);
+        sj = max(0, min(sj, nstc - 1));
+        while (sj > 0 && sj * nst - sj * (sj - 1) / 2 > sl)
+            --sj;
+        while (sj + 1 < nstc && (sj + 1) * nst - (sj + 1) * sj / 2 <= sl)
+            ++sj;
+        const int si = sj + (sl - (sj * nst - sj * (sj - 1) / 2));
+        const int ti = 4 * si + (wid >> 2), tj = 4 * sj + (wid & 3);
+        if (ti < nt && tj < ntc && ti >= tj)
+            syrk_tile<MULTI>(T, P, ld, n, r0 + ti * 32, r0 + tj * 32, kdim);
     }
 }
 
@@ -197,8 +237,8 @@ __device__ __forceinline__ void syrk_region(double *__restrict__ T, size_t ld, i
    on a non-positive pivot (decided identically by every block of the group). */
 template <bool MULTI>
 __device__ bool chol_one(double *__restrict__ T, int n, double sigma, int G, int gr,
-                         unsigned int *counter, unsigned int &target, double *Ls, double *rdiag,
-                         int *flag)
+                         unsigned int *counter, unsigned int &target, double *Ls, double *Li,
+                         double *rdiag, int *flag)
 {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const size_t ld = (size_t)n;
@@ -257,17 +297,37 @@ __device__ bool chol_one(double *__restrict__ T, int n, double sigma, int G, int
             __syncthreads();
             if (*flag)
                 return false;
+            // inverse of the diagonal factor, column by column (lane c: Linv e_c by forward
+            // substitution); the solves of k_cs_iterate and the rows below only ever need L11^-1
+            if (wid == 0)
+            {
+                double x[CS_NB];
+#pragma unroll
+                for (int i = 0; i < CS_NB; ++i)
+                {
+                    double sacc = (i == lane) ? 1. : 0.;
+#pragma unroll
+                    for (int q = 0; q < i; ++q)
+                        sacc -= Ls[i * CS_LD + q] * x[q];
+                    x[i] = (i >= lane) ? sacc * rdiag[i] : 0.;
+                }
+#pragma unroll
+                for (int i = 0; i < CS_NB; ++i)
+                    Li[i * CS_LD + lane] = x[i];
+            }
+            __syncthreads();
             const int r0 = j0 + jb;
-            // 2. rows below the diagonal block
-            trsm_rows<MULTI>(T, ld, n, j0, jb, gr * CS_NT + tid, G * CS_NT, Ls, rdiag);
+            // 2. rows below the diagonal block: X = B Linv^T
+            trsm_tiles<MULTI>(T, ld, n, j0, jb, gr * CS_NW + wid, G * CS_NW, Li);
             group_barrier(counter, G, target);
-            // (every block of the group has read the diagonal block by now: the factor replaces it)
+            // (every block of the group has read the diagonal block by now: the INVERSE of its
+            // factor replaces it)
             if (gr == 0)
                 for (int idx = tid; idx < CS_NB * CS_NB; idx += CS_NT)
                 {
                     const int i = idx & 31, c = idx >> 5;
                     if (i < jb && c < jb && i >= c)
-                        T[(j0 + i) + ld * (j0 + c)] = Ls[i * CS_LD + c];
+                        T[(j0 + i) + ld * (j0 + c)] = Li[i * CS_LD + c];
                 }
             if (r0 >= Jend)
                 break;
@@ -290,6 +350,7 @@ k_cs_chol(const sa_cs_mat *mats, int nmats, double sigma, int G, unsigned int *c
           unsigned int *queue)
 {
     __shared__ double Ls[CS_NB * CS_LD];
+    __shared__ double Li[CS_NB * CS_LD];
     __shared__ double rdiag[CS_NB];
     __shared__ int flag;
     __shared__ int next;
@@ -307,7 +368,7 @@ k_cs_chol(const sa_cs_mat *mats, int nmats, double sigma, int G, unsigned int *c
             if (b >= nmats)
                 return;
             const sa_cs_mat M = mats[b];
-            const bool ok = chol_one<false>(M.T, M.n, sigma, 1, 0, nullptr, target, Ls, rdiag, &flag);
+            const bool ok = chol_one<false>(M.T, M.n, sigma, 1, 0, nullptr, target, Ls, Li, rdiag, &flag);
             if (threadIdx.x == 0)
                 M.info[0] = ok ? 0 : -1;
             __syncthreads();
@@ -323,7 +384,7 @@ k_cs_chol(const sa_cs_mat *mats, int nmats, double sigma, int G, unsigned int *c
         for (int b = gi; b < nmats; b += ngroups)
         {
             const sa_cs_mat M = mats[b];
-            const bool ok = chol_one<true>(M.T, M.n, sigma, G, gr, counters + gi, target, Ls, rdiag, &flag);
+            const bool ok = chol_one<true>(M.T, M.n, sigma, G, gr, counters + gi, target, Ls, Li, rdiag, &flag);
             if (threadIdx.x == 0 && gr == 0)
                 M.info[0] = ok ? 0 : -1;
             // (a failed factorisation leaves the group at the same point in every block)
@@ -525,8 +586,8 @@ __device__ void cs_small_solve(CsSmall &S)
     }
 }
 
-/* 32 x 32 diagonal block of L at (jb, jb) into shared memory (identity beyond the matrix), with
-   the reciprocals of its diagonal */
+/* 32 x 32 diagonal block at (jb, jb) -- the inverse of the diagonal factor, written by k_cs_chol --
+   into shared memory (zero above the diagonal, identity beyond the matrix) */
 __device__ __forceinline__ void cs_stage_diag(const double *__restrict__ T, size_t ld, int n, int jb,
                                               double *Ls, double *rinv)
 {
@@ -611,28 +672,21 @@ k_cs_iterate(const sa_cs_mat *mats, int nmats, double sigma, double theta, int m
                 double *Ls = Lsb[buf], *rinv = rinvb[buf];
                 if (wid < KL)
                 {
-                    double bi = (lane < w) ? Z[(size_t)(k0 + wid) * n + jb + lane] : 0.;
+                    // the diagonal block stores the INVERSE of its factor: y = Linv b (forward),
+                    // z = Linv^T y (backward) -- 32 independent products per lane, no substitution chain
+                    const double bl = (lane < w) ? Z[(size_t)(k0 + wid) * n + jb + lane] : 0.;
+                    double bi = 0.;
                     if (pass == 0)
                     {
+#pragma unroll 8
                         for (int c = 0; c < CS_NB; ++c)
-                        {
-                            const double tc = __shfl_sync(0xffffffffu, bi, c) * rinv[c];
-                            if (lane == c)
-                                bi = tc;
-                            else if (lane > c)
-                                bi -= Ls[lane * CS_LD + c] * tc;
-                        }
+                            bi += Ls[lane * CS_LD + c] * __shfl_sync(0xffffffffu, bl, c);
                     }
                     else
                     {
-                        for (int c = CS_NB - 1; c >= 0; --c)
-                        {
-                            const double tc = __shfl_sync(0xffffffffu, bi, c) * rinv[c];
-                            if (lane == c)
-                                bi = tc;
-                            else if (lane < c)
-                                bi -= Ls[c * CS_LD + lane] * tc;
-                        }
+#pragma unroll 8
+                        for (int c = 0; c < CS_NB; ++c)
+                            bi += Ls[c * CS_LD + lane] * __shfl_sync(0xffffffffu, bl, c);
                     }
                     Ys[lane][wid] = bi;
                     if (lane < w)

@@ -76,6 +76,9 @@ void dist_spgemm(sa_gpu_comm *C, const DevCsr &A, const DevCsr &B, DevCsr &out, 
     std::vector<int> hI((size_t)rows + 1);
     out.I.download(hI.data(), (size_t)rows + 1, st);
     SA_CUDA(cudaStreamSynchronize(st));
+    for (int r = 0; r < rows; ++r)
+        if (hI[r + 1] < hI[r]) // (a wrapped int32 prefix sum is not monotone)
+            SA_FAIL("dist_spgemm: the gathered product exceeds the int32 row pointers (%d rows)", rows);
     out.nnz = hI[rows];
     out.J.alloc((size_t)out.nnz);
     out.A.alloc((size_t)out.nnz);

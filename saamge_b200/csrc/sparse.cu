@@ -5,6 +5,7 @@
 //   (interp->Transpose(), amg/inc/tg.hpp:692), SpGEMM (hypre ParMult / RAP call sites
 //   amg/src/interp.cpp:77,207 and amg/inc/tg.hpp:700), prefix sums.
 #include <algorithm>
+#include <climits>
 
 #include "sa_gpu_internal.cuh"
 
@@ -561,6 +562,19 @@ void dev_csr_transpose(sa_gpu_ctx *ctx, const DevCsr &A, DevCsr &At)
     SA_CUDA(cudaStreamSynchronize(st));
 }
 
+/* total of the row counts in 64 bits (the row pointers are int32: products beyond 2^31 - 1
+   entries must fail, not wrap) */
+__global__ void k_total_i64(int n, const int *cnt, unsigned long long *total)
+{
+    unsigned long long s = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        s += (unsigned long long)cnt[i];
+    for (int o = 16; o > 0; o >>= 1)
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s)
+        atomicAdd(total, s);
+}
+
 static int pow2ceil(long long v)
 {
     long long p = 1;
@@ -669,10 +683,21 @@ void dev_spgemm(sa_gpu_ctx *ctx, const DevCsr &A, const DevCsr &B, DevCsr &C)
     {
         if (pass == 1)
         {
+            DevBuf<unsigned long long> d_total;
+            d_total.alloc(1);
+            d_total.zero(st);
+            if (rows)
+                SA_LAUNCH(ctx, k_total_i64, std::min((rows + 255) / 256, ctx->num_sms * 8), 256, 0, rows,
+                          rowcnt.p, d_total.p);
             dev_exclusive_scan_i32(ctx, rowcnt.p, C.I.p, rows);
             int nnz = 0;
+            unsigned long long total = 0;
             SA_CUDA(cudaMemcpyAsync(&nnz, C.I.p + rows, sizeof(int), cudaMemcpyDeviceToHost, st));
+            d_total.download(&total, 1, st);
             SA_CUDA(cudaStreamSynchronize(st));
+            if (total > (unsigned long long)INT_MAX)
+                SA_FAIL("dev_spgemm: the product has %llu entries, more than the int32 row pointers hold "
+                        "(%d x %d times %d x %d)", total, A.rows, A.cols, B.rows, B.cols);
             C.nnz = nnz;
             C.J.alloc(nnz);
             C.A.alloc(nnz);

@@ -58,42 +58,48 @@ def _pattern_mismatch(Mg, Mo):
     return float(worst / scale), int(only_g.nnz), int(only_o.nnz)
 
 
-def _mis_allowance(Ho, level, mis, Zo, oo, mo, AEI, AEJ):
+def _mis_allowance(Ho, level, mis, Zo, oo, mo, AEI, AEJ, input_diff=0.0):
     """How well the DATA determine the column space kept for one MIS.  The kept space consists of
     the left singular vectors with sigma_i > 1e-10 sigma_0 (amg/src/xpacks.cpp:609-610); by Wedin's
-    theorem a perturbation of size eps * sigma_0 moves it by ~ eps * sigma_0 / gap, where gap is
-    the distance from the smallest kept singular value to the next one (or to zero).  Two correct
-    SVDs (LAPACK's and ours) can therefore differ by that much: the subspace tolerance is
-    max(1e-8, 2048 eps sigma_0 / gap).  (2048 eps = 4.5e-13: the INPUT of the SVD -- the
-    eigenvectors -- is itself only determined to ~ eps ||A^|| / gap_lambda by any backward-stable
-    eigensolver, LAPACK's dsytrd path and the Cholesky / subspace-iteration path of cholsi.cu alike;
-    the accepted eigenvalues lie ~1e-3 from the rest of a spectrum in [0, 1], and
-    tests/test_cholsi.py measures 2e-12 .. 4e-12 between cholsi.cu and numpy.linalg.eigh at such
-    gaps.)
+    theorem a perturbation dM of the gathered matrix moves it by ~ ||dM|| / gap, where gap is the
+    distance from the smallest kept singular value to the next one (or to zero).  The inputs of
+    the two SVDs are the eigenvectors of the two eigensolvers, which are themselves only determined
+    to ~ eps ||A^|| / gap_lambda (the eigenvalue nearest theta is ~1e-3 from it: 1e-13 .. 1e-11
+    between two backward-stable solvers, tests/test_cholsi.py), so the subspace tolerance is
+        max(1e-8, 4 (sigma_0 / gap) amp max(2048 eps, input_diff))
+    with input_diff = the eigenspace difference actually MEASURED on this level between the CUDA
+    path and the oracle (`eigenspace_sin`, itself held to 1e-8), amp = max ||z|| / ||z restricted to
+    the MIS|| over the gathered columns (they are normalised AFTER the restriction), 4 = norm
+    conversions (several unit columns per matrix).  A MIS above 1e-8 is counted (`mis_ill_conditioned`).
     Recomputed here from the oracle's eigenvectors (the same gather / boundary filter / column
     normalisation as contrib.cpp:492-687)."""
     m2a_I, m2a_J = Ho.get("mis_to_AE.I", level), Ho.get("mis_to_AE.J", level)
     m2d_I, m2d_J = Ho.get("mis_to_dof.I", level), Ho.get("mis_to_dof.J", level)
     flags = Ho.get("agg_flags", level)
     dofs = m2d_J[m2d_I[mis] : m2d_I[mis + 1]]
-    cols = []
+    cols, full = [], []
     for ae in m2a_J[m2a_I[mis] : m2a_I[mis + 1]]:
         n = AEI[ae + 1] - AEI[ae]
         k = mo[ae]
         Z = Zo[oo[ae] : oo[ae + 1]].reshape(k, n).T
         loc = {g: i for i, g in enumerate(AEJ[AEI[ae] : AEI[ae + 1]])}
         cols.append(Z[[loc[g] for g in dofs], :])
+        full.append(np.linalg.norm(Z, axis=0))
     M = np.concatenate(cols, axis=1)
     M[(flags[dofs] & 2) != 0, :] = 0.0
     nrm = np.linalg.norm(M, axis=0)
-    M = M[:, nrm > 1e-10] / nrm[nrm > 1e-10]
+    keep = nrm > 1e-10
+    # a column is the restriction of an eigenvector to the MIS, NORMALISED: a difference of the
+    # eigenvector (relative to its own norm) is magnified by ||z|| / ||z restricted to the MIS||
+    amp = float(np.max(np.concatenate(full)[keep] / nrm[keep])) if np.any(keep) else 1.0
+    M = M[:, keep] / nrm[keep]
     if M.shape[1] == 0:
         return 1e-8
     sv = np.linalg.svd(M, compute_uv=False)
     kept = sv[sv > 1e-10 * sv[0]]
     nxt = sv[len(kept)] if len(kept) < len(sv) else 0.0
     gap = max(kept[-1] - nxt, 1e-300)
-    return max(1e-8, 2048 * np.finfo(float).eps * sv[0] / gap)
+    return max(1e-8, 4.0 * (sv[0] / gap) * amp * max(2048 * np.finfo(float).eps, input_diff))
 
 
 def compare_level(Hg, Ho, level, S_prev=None, check_celmat=True):
@@ -181,7 +187,7 @@ def compare_level(Hg, Ho, level, S_prev=None, check_celmat=True):
             Q = Uo.T @ Ug
             sin = np.linalg.norm(Ug - Uo @ Q, 2)
             if sin > 1e-8:
-                allow = _mis_allowance(Ho, level, mis, Zo, oo, mo, AEI, AEJ)
+                allow = _mis_allowance(Ho, level, mis, Zo, oo, mo, AEI, AEJ, m["eigenspace_sin"])
                 ill_conditioned += 1
                 excess = max(excess, sin / allow)
                 allowance = max(allowance, allow)

@@ -121,7 +121,9 @@ def test_atleast_one_fallback_and_tiny_theta():
 
 
 @pytest.mark.parametrize("env", [
-    {"SA_GPU_COOP_SYM": "0"},        # full-matrix cooperative kernel (k_tridiag_coop)
+    {"SA_GPU_LARGE_PATH": "twostage"},  # two-stage tridiagonalisation (the fallback of cholsi.cu) for every large AE
+    {"SA_GPU_LARGE_PATH": "coop"},      # round 1's one-stage cooperative kernel (k_tridiag_coop_sym)
+    {"SA_GPU_LARGE_PATH": "coop", "SA_GPU_COOP_SYM": "0"},  # ... its full-matrix form (k_tridiag_coop)
     {"SA_GPU_SQUARE_TILE": "1"},     # square shared-memory tile kernel (k_at_smem)
     {"SA_GPU_SMALL_PATH": "packed"}, # round 1's packed shared-memory kernel instead of k_tridiag_reg
     {"SA_GPU_NO_ASYNC_ALLOC": "1"},  # plain cudaMalloc instead of the stream-ordered pool
