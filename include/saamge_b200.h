@@ -191,6 +191,13 @@ int sa_gpu_build_Dinv_neg(sa_gpu_level *level);
  * then restr = P^T (tg_smooth_interp, amg/inc/tg.hpp:678-693).  degree 0 => P = P_tent. */
 int sa_gpu_smooth_P(sa_gpu_level *level, int degree, const double *roots);
 /* tg_coarse_matr (amg/inc/tg.hpp:695-709): Ac = P^T A P */
+/* CorrectNullspace (amg/src/solve.cpp:52-164): a level whose prolongator is given -- the
+   "scaling P" (amg/src/interp.cpp:842-909; one column per MIS of the last spectral level: the
+   coarse representation of the constant vector, amg/src/contrib.cpp:655-668).  Its operator is
+   finer's Ac; complete it with sa_gpu_build_Dinv_neg and sa_gpu_rap and pass it to
+   sa_gpu_solver_create as the last level (destroy with sa_gpu_level_destroy). */
+int sa_gpu_level_create_from_P(sa_gpu_ctx *ctx, sa_gpu_level *finer, int cols, const int *P_I,
+                               const int *P_J, const double *P_A, sa_gpu_level **out);
 /* adapt_update_operators (amg/src/adapt.cpp:171-216): new operator values (same pattern) for a
    level that owns its operator; afterwards sa_gpu_build_Dinv_neg (smpr_update_Dinv_neg),
    optionally sa_gpu_smooth_P (tg_smooth_interp, from the kept tentative P) and sa_gpu_rap. */

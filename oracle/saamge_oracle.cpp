@@ -1194,6 +1194,57 @@ static void tg_build_level(oracle_level_t &L, int nu_pro, int nu_relax, double t
     times[key] = now_s() - t0;
 }
 
+/* CorrectNullspace (amg/src/solve.cpp:52-110) below the last spectral level: scaling P from
+   local_coarse_one_representation (amg/src/contrib.cpp:655-668: per MIS with coarse dofs,
+   xpack_solve_lls of mis_tent_interps[mis] x = 1, normalised) assembled as in
+   interp_scaling_P_assemble (amg/src/interp.cpp:842-909); Ac = RAP(A, scaling P); smoother
+   smpr_init_poly_data(A, 3, 0.0) (SAS, nu = 3); its Mult is one tg_cycle_atb, i.e. one more level
+   of vcycle_mult.  The reference solves the level below with BoomerAMG; here exactly. */
+static oracle_level_t *build_correct_nullspace(oracle_level_t &last)
+{
+    oracle_level_t *N = new oracle_level_t;
+    N->A = last.Ac;
+    N->owns_A = false;
+    SparseMatrix *SP = new SparseMatrix;
+    SP->I.push_back(0);
+    int rows = 0, col = 0;
+    for (size_t mis = 0; mis < last.mis_tent_interps.size(); ++mis)
+    {
+        const DenseMatrix &V = *last.mis_tent_interps[mis];
+        if (last.mis_numcoarsedof[mis] <= 0)
+            continue;
+        SA_ASSERT(V.Width() == last.mis_numcoarsedof[mis]);
+        Vector b((size_t)V.Height(), 1.0), x;
+        xpack_solve_lls(V, b, x);
+        double norm = 0.;
+        for (size_t k = 0; k < x.size(); ++k)
+            norm += x[k] * x[k];
+        norm = sqrt(norm);
+        for (size_t k = 0; k < x.size(); ++k)
+        {
+            SP->J.push_back(col);
+            SP->A.push_back(x[k] / norm);
+            SP->I.push_back((int)SP->J.size());
+            ++rows;
+        }
+        ++col;
+    }
+    SP->h = rows;
+    SP->w = col;
+    SA_ASSERT(rows == N->A->h);
+    N->interp = SP;
+    N->restr = new SparseMatrix;
+    SpTranspose(*N->interp, *N->restr);
+    N->nu = 3;
+    N->Dinv_neg = mbox_build_Dinv_neg_parallel_matrix(*N->A);
+    N->roots = smpr_sas_poly_roots(N->nu, &N->degree);
+    SparseMatrix AP;
+    SpMultMat(*N->A, *N->interp, AP);
+    N->Ac = new SparseMatrix;
+    SpMultMat(*N->restr, AP, *N->Ac);
+    return N;
+}
+
 static void factor_coarsest(oracle_level_t &L)
 {
     const lapack_t &LP = lapack();
@@ -1280,6 +1331,12 @@ extern "C" void *sa_orc_ml_build(void *prob_, const sa_drv_params_t *p)
         L->drop_tol = p->smooth_drop_tol;
         tg_build_level(*L, i == 0 ? p->first_nu_pro : p->nu_pro, p->nu_relax,
                        i == 0 ? p->first_theta : p->theta, avoid, H->times, i);
+    }
+    if (p->correct_nullspace)
+    {
+        ml->levels.push_back(build_correct_nullspace(*ml->levels.back()));
+        H->cn_P = *ml->levels.back()->interp;
+        H->cn_Ac = *ml->levels.back()->Ac;
     }
     factor_coarsest(*ml->levels.back());
     H->times["setup"] = now_s() - tstart;
@@ -1419,6 +1476,12 @@ extern "C" void *sa_orc_ml_build_algebraic(void *prob_, const sa_drv_params_t *p
         tg_build_level(*L, i == 0 ? p->first_nu_pro : p->nu_pro, p->nu_relax,
                        i == 0 ? p->first_theta : p->theta, avoid, H->times, i);
     }
+    if (p->correct_nullspace)
+    {
+        ml->levels.push_back(build_correct_nullspace(*ml->levels.back()));
+        H->cn_P = *ml->levels.back()->interp;
+        H->cn_Ac = *ml->levels.back()->Ac;
+    }
     factor_coarsest(*ml->levels.back());
     H->times["setup"] = now_s() - tstart;
     H->levels.resize(coarsenings);
@@ -1438,6 +1501,8 @@ extern "C" int sa_orc_ml_update_operators(void *hier, int resmooth_interp)
     for (size_t i = 0; i < ml->levels.size(); ++i)
     {
         oracle_level_t &L = *ml->levels[i];
+        // (a CorrectNullspace level at the end has no tentative prolongator -- nu_pro == 0 --: only
+        // its smoother and its Galerkin operator follow the new coarsest Ac)
         if (i > 0)
             L.A = ml->levels[i - 1]->Ac; // Af = finer Ac
         delete L.Dinv_neg;
@@ -1458,7 +1523,9 @@ extern "C" int sa_orc_ml_update_operators(void *hier, int resmooth_interp)
         SpMultMat(*L.restr, AP, *L.Ac);
     }
     factor_coarsest(*ml->levels.back());
-    const int coarsenings = (int)ml->levels.size();
+    const int coarsenings = (int)H->rels.size();
+    if ((int)ml->levels.size() > coarsenings)
+        H->cn_Ac = *ml->levels.back()->Ac;
     H->levels.clear();
     H->levels.resize(coarsenings);
     for (int i = 0; i < coarsenings; ++i)

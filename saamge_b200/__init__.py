@@ -211,7 +211,7 @@ class Hierarchy:
         ncols = int(J.max()) + 1 if len(J) else 0
         if name in ("tent_interp", "interp"):
             ncols = int(self.scalar("NDc", level))
-        elif name == "Ac":
+        elif name in ("Ac", "cn_Ac"):
             ncols = len(I) - 1
         return sp.csr_matrix((A, J, I), shape=(len(I) - 1, ncols))
 

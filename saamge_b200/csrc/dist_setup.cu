@@ -188,6 +188,50 @@ extern "C" int sa_gpu_threshold_P(sa_gpu_level *lev, double drop_tol, int *nnz_b
     SA_API_END
 }
 
+/* A level below the last spectral one whose prolongator is GIVEN (CorrectNullspace,
+   amg/src/solve.cpp:52-164: the "scaling P" of interp_scaling_P_assemble, amg/src/interp.cpp:842-909
+   -- one column per MIS, the coarse representation of the constant vector): operator = the finer
+   level's Ac (alias), P from the host CSR, R = P^T.  sa_gpu_build_Dinv_neg and sa_gpu_rap complete
+   it; sa_gpu_solver_create takes it as one more level of the cycle (tg_cycle_atb with the same SAS
+   smoother, exact solve on its Ac instead of BoomerAMG). */
+extern "C" int sa_gpu_level_create_from_P(sa_gpu_ctx *ctx, sa_gpu_level *finer, int cols, const int *P_I,
+                                          const int *P_J, const double *P_A, sa_gpu_level **out)
+{
+    SA_API_BEGIN
+    *out = nullptr;
+    if (!finer || !finer->have_Ac)
+        SA_FAIL("sa_gpu_level_create_from_P: the finer level has no Ac");
+    SA_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int rows = finer->Ac.rows;
+    sa_gpu_level *L = new sa_gpu_level;
+    L->ctx = ctx;
+    L->finer = finer;
+    L->ND = rows;
+    L->A = &finer->Ac;
+    L->NDc = cols;
+    const int nnz = P_I[rows];
+    L->P.rows = rows;
+    L->P.cols = cols;
+    L->P.nnz = nnz;
+    try
+    {
+        L->P.I.upload(P_I, (size_t)rows + 1, st);
+        L->P.J.upload(P_J, (size_t)nnz, st);
+        L->P.A.upload(P_A, (size_t)nnz, st);
+        dev_csr_transpose(ctx, L->P, L->R);
+        SA_CUDA(cudaStreamSynchronize(st));
+    }
+    catch (...)
+    {
+        delete L;
+        throw;
+    }
+    L->have_P = true;
+    *out = L;
+    SA_API_END
+}
+
 /* New values for the operator of a level that owns it (the finest), same sparsity pattern:
    smpr_update_Dinv_neg / tg_smooth_interp / tg_update_coarse_operator are then re-run by the
    caller (adapt_update_operators, amg/src/adapt.cpp:171-216) -- the spectral data, the tentative

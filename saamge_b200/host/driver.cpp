@@ -356,6 +356,10 @@ extern "C" int sa_drv_get(void *obj, const char *name_, int level, const void **
         RET_ARR(keys.data(), keys.size(), char);
     }
     if (name == "pcg.x") RET_VEC(H->pcg.x);
+    if (name.compare(0, 5, "cn_P.") == 0)
+        return get_sparse(H->cn_P, name.substr(5), ptr, count, dtype);
+    if (name.compare(0, 6, "cn_Ac.") == 0)
+        return get_sparse(H->cn_Ac, name.substr(6), ptr, count, dtype);
     if (level < 0)
         return 4;
     if (name == "mis_coarsedofoffsets")

@@ -35,6 +35,8 @@ struct sa_hierarchy_t
     bool owns_rels = true;                            // rels[1..] freed with the handle
     std::vector<sa_level_results_t> levels;           // one per coarsening
     sa_pcg_results_t pcg;
+    // CorrectNullspace level (when built): scaling P and its Galerkin operator ("cn_P.*", "cn_Ac.*")
+    SparseMatrix cn_P, cn_Ac;
     std::map<std::string, double> times;
     void *impl = NULL;
     void (*impl_free)(void *) = NULL;

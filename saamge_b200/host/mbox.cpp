@@ -248,6 +248,12 @@ void adapt_update_operators(const SparseMatrix &A, ml_data_t &ml_data, const Mul
         adapt_update_operators(NULL, *level->tg_data, resmooth_interp);
         tg_update_coarse_operator(level->tg_data, NULL == level->coarser, mlp.get_coarse_direct());
     }
+    if (ml_data.correct_nullspace_level)
+    {
+        // the CorrectNullspace level's operator is the (new) coarsest Ac; the scaling P stays
+        sa_gpu_check(sa_gpu_build_Dinv_neg(ml_data.correct_nullspace_level), "sa_gpu_build_Dinv_neg");
+        sa_gpu_check(sa_gpu_rap(ml_data.correct_nullspace_level), "sa_gpu_rap");
+    }
     ml_impose_cycle(ml_data, false);
 }
 

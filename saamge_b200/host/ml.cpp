@@ -940,7 +940,72 @@ void ml_produce_hierarchy_from_level(int coarsenings, int starting_level, ml_dat
         tg_update_coarse_operator(tg_data, i + 1 == coarsenings, mlp.get_coarse_direct());
         levels_list_push_coarse_data(ml_data.levels_list, agg_part_rels, tg_data);
     }
+    // amg/src/ml.cpp:225-235: the coarsest solver becomes a CorrectNullspace two-grid cycle
+    if (mlp.get_use_correct_nullspace())
+        ml_build_correct_nullspace(ml_data);
     ml_impose_cycle(ml_data, false);
+}
+
+void ml_build_correct_nullspace(ml_data_t &ml_data)
+{
+    levels_level_t *last = ml_data.levels_list.coarsest;
+    SA_ASSERT(last && last->tg_data && last->tg_data->gpu && last->tg_data->have_Ac);
+    // the reference fixes the smoother of this cycle to smpr_init_poly_data(A, 3, 0.0)
+    // (amg/src/solve.cpp:75, amg/src/ml.cpp:233-235); the device cycle has one degree for all levels
+    SA_ASSERT(ml_data.nu_relax == 3);
+    StageTimer tm("correct_nullspace");
+    const agg_partitioning_relations_t &rels = *last->agg_part_rels;
+    const interp_data_t &id = *last->tg_data->interp_data;
+    const int nmis = rels.num_mises;
+    // MIS bases of the level (mis_tent_interps): s x k column-major blocks, MIS-major
+    std::vector<int64_t> off((size_t)nmis + 1, 0);
+    for (int mis = 0; mis < nmis; ++mis)
+        off[mis + 1] = off[mis] + (int64_t)rels.mis_to_dof->RowSize(mis) * id.mis_numcoarsedof[mis];
+    std::vector<double> tent((size_t)std::max<int64_t>(1, off[nmis]));
+    sa_gpu_check(sa_gpu_get_mis_tent(last->tg_data->gpu, tent.data()), "sa_gpu_get_mis_tent");
+    // local_coarse_one_representation (amg/src/contrib.cpp:655-668): x = argmin ||V x - 1||,
+    // normalised; V has orthonormal columns, so x = V^T 1 (what dgels returns to round-off).
+    // interp_scaling_P_assemble (amg/src/interp.cpp:842-909): coarse dof (row) -> its MIS (column,
+    // counting the MISes with coarse dofs), value = that representation
+    SparseMatrix *SP = new SparseMatrix;
+    int rows = 0, col = 0;
+    SP->I.push_back(0);
+    for (int mis = 0; mis < nmis; ++mis)
+    {
+        const int k = id.mis_numcoarsedof[mis], sz = rels.mis_to_dof->RowSize(mis);
+        if (k <= 0)
+            continue;
+        std::vector<double> x(k, 0.);
+        double norm = 0.;
+        for (int c = 0; c < k; ++c)
+        {
+            const double *v = tent.data() + off[mis] + (int64_t)sz * c;
+            for (int r = 0; r < sz; ++r)
+                x[c] += v[r];
+            norm += x[c] * x[c];
+        }
+        norm = std::sqrt(norm);
+        for (int c = 0; c < k; ++c)
+        {
+            SP->J.push_back(col);
+            SP->A.push_back(x[c] / norm);
+            SP->I.push_back((int)SP->J.size());
+            ++rows;
+        }
+        ++col;
+    }
+    SP->h = rows;
+    SP->w = col;
+    delete ml_data.scaling_P;
+    ml_data.scaling_P = SP;
+    if (ml_data.correct_nullspace_level)
+        sa_gpu_level_destroy(ml_data.correct_nullspace_level);
+    ml_data.correct_nullspace_level = NULL;
+    sa_gpu_check(sa_gpu_level_create_from_P(proc_gpu_ctx(), last->tg_data->gpu, SP->w, SP->I.data(),
+                                            SP->J.data(), SP->A.data(), &ml_data.correct_nullspace_level),
+                 "sa_gpu_level_create_from_P");
+    sa_gpu_check(sa_gpu_build_Dinv_neg(ml_data.correct_nullspace_level), "sa_gpu_build_Dinv_neg");
+    sa_gpu_check(sa_gpu_rap(ml_data.correct_nullspace_level), "sa_gpu_rap");
 }
 
 // amg/src/ml.cpp:361-377: chain the levels; coarsest level gets the exact solver
@@ -954,6 +1019,10 @@ void ml_impose_cycle(ml_data_t &ml_data, bool Wcycle)
         level->tg_data->tag = i++;
         levels.push_back(level->tg_data->gpu);
     }
+    // CorrectNullspace::Mult (amg/src/solve.cpp:137-164) is one tg_cycle_atb on the coarsest
+    // operator: one more level of the device cycle
+    if (ml_data.correct_nullspace_level)
+        levels.push_back(ml_data.correct_nullspace_level);
     if (ml_data.gpu_solver)
         sa_gpu_solver_destroy(ml_data.gpu_solver);
     ml_data.gpu_solver = NULL;
@@ -1043,6 +1112,9 @@ void ml_free_data(ml_data_t *ml_data)
         return;
     if (ml_data->gpu_solver)
         sa_gpu_solver_destroy(ml_data->gpu_solver);
+    if (ml_data->correct_nullspace_level)
+        sa_gpu_level_destroy(ml_data->correct_nullspace_level);
+    delete ml_data->scaling_P;
     // free coarse to fine: a level's operator aliases the finer level's Ac
     levels_level_t *level = ml_data->levels_list.coarsest;
     while (level)
@@ -1272,7 +1344,7 @@ extern "C" void *sa_drv_ml_build_user(void *prob_, const sa_drv_params_t *p, int
     else
         emp = new ElementMatrixDenseArray(*prob->rels, f.elmat.data(), offsets.data());
     MultilevelParameters mlp(p->num_levels - 1, nparts_arr.data(), p->first_nu_pro, p->nu_pro,
-                             p->nu_relax, p->first_theta, p->theta, -1, false, false, false);
+                             p->nu_relax, p->first_theta, p->theta, -1, p->correct_nullspace != 0, false, false);
     mlp.set_coarse_direct(true);
     mlp.set_smooth_drop_tol(p->smooth_drop_tol);
     block_partitioner_data_t bpd = {prob, p};
@@ -1446,7 +1518,7 @@ extern "C" void *sa_drv_ml_build(void *prob_, const sa_drv_params_t *p, int devi
     ElementMatrixProvider *emp =
         new ElementMatrixStandardGeometric(*prob->rels, f.A, f.elmat.data(), offsets.data());
     MultilevelParameters mlp(p->num_levels - 1, nparts_arr.data(), p->first_nu_pro, p->nu_pro,
-                             p->nu_relax, p->first_theta, p->theta, -1, false, false, false);
+                             p->nu_relax, p->first_theta, p->theta, -1, p->correct_nullspace != 0, false, false);
     mlp.set_coarse_direct(true);
     mlp.set_smooth_drop_tol(p->smooth_drop_tol);
     mlp.testmesh_inject = p->testmesh_inject != 0;
@@ -1483,7 +1555,7 @@ extern "C" void *sa_drv_ml_build_algebraic(void *prob_, const sa_drv_params_t *p
     nparts_arr[0] = prob->rels->nparts;
     const double t0 = now_s();
     MultilevelParameters mlp(p->num_levels - 1, nparts_arr.data(), p->first_nu_pro, p->nu_pro,
-                             p->nu_relax, p->first_theta, p->theta, -1, false, false, false);
+                             p->nu_relax, p->first_theta, p->theta, -1, p->correct_nullspace != 0, false, false);
     mlp.set_coarse_direct(true);
     mlp.set_smooth_drop_tol(p->smooth_drop_tol);
     pi->ml = ml_produce_data_algebraic(f.A, *prob->rels, mlp);
@@ -1522,6 +1594,22 @@ extern "C" int sa_drv_ml_download(void *hier)
             sa_gpu_check(sa_gpu_get_coarse_elmats(l->coarser->tg_data->gpu, R.celmat.data()),
                          "sa_gpu_get_coarse_elmats");
         }
+    }
+    if (pi->ml->correct_nullspace_level)
+    {
+        H->cn_P = *pi->ml->scaling_P;
+        sa_gpu_level *g = pi->ml->correct_nullspace_level;
+        int rows = 0, cols = 0, nnz = 0;
+        sa_gpu_check(sa_gpu_get_csr_sizes(g, SA_GPU_MAT_AC, &rows, &cols, &nnz), "sa_gpu_get_csr_sizes");
+        H->cn_Ac.h = rows;
+        H->cn_Ac.w = cols;
+        H->cn_Ac.I.assign((size_t)rows + 1, 0);
+        H->cn_Ac.J.assign((size_t)std::max(1, nnz), 0);
+        H->cn_Ac.A.assign((size_t)std::max(1, nnz), 0.);
+        sa_gpu_check(sa_gpu_get_csr(g, SA_GPU_MAT_AC, H->cn_Ac.I.data(), H->cn_Ac.J.data(), H->cn_Ac.A.data()),
+                     "sa_gpu_get_csr");
+        H->cn_Ac.J.resize(nnz);
+        H->cn_Ac.A.resize(nnz);
     }
     return 0;
 }

@@ -259,6 +259,11 @@ typedef struct
     levels_list_t levels_list;
     sa_gpu_solver *gpu_solver; /*!< V-cycle chain on the device (ml_impose_cycle) */
     int nu_relax;
+    /*! CorrectNullspace (amg/src/solve.cpp:52-164; ml_produce_hierarchy_from_level,
+        amg/src/ml.cpp:225-235): the level below the coarsest spectral one, prolongator =
+        scaling P (tg_data_t::scaling_P of the reference), NULL when not used. */
+    sa_gpu_level *correct_nullspace_level;
+    SparseMatrix *scaling_P; /*!< host copy of the scaling P (interp_scaling_P_assemble) */
 } ml_data_t;
 
 /* ---- the local eigensolver as a class (amg/inc/spectral.hpp:91-224) ---- */
@@ -337,6 +342,12 @@ ml_data_t *ml_produce_data_algebraic(const SparseMatrix &Ag, const agg_partition
 void ml_produce_hierarchy_from_level(int coarsenings, int starting_level, ml_data_t &ml_data,
                                      const MultilevelParameters &mlp);
 void ml_impose_cycle(ml_data_t &ml_data, bool Wcycle);
+/// interp_scaling_P_assemble (amg/src/interp.cpp:842-909) from the MIS bases of the coarsest
+/// spectral level (local_coarse_one_representation, amg/src/contrib.cpp:655-668: per MIS the
+/// least-squares representation of the constant vector in the basis, normalised) and the
+/// CorrectNullspace level built on it (amg/src/solve.cpp:52-110).  Called by ml_produce_data when
+/// MultilevelParameters::use_correct_nullspace is set; ml_impose_cycle then appends the level.
+void ml_build_correct_nullspace(ml_data_t &ml_data);
 
 /* ---- operator update without new eigensolves (amg/src/adapt.cpp:171-216, amg/inc/tg.hpp:678-693,
    735; amg/inc/smpr.hpp:241) ---- */

@@ -477,3 +477,51 @@ def test_operator_update_without_eigensolves(resmooth):
     for h in (Hg, Ho):
         h.close()
     pr.close()
+
+
+def test_correct_nullspace_coarsest_solver():
+    """CorrectNullspace (amg/src/solve.cpp:52-164; ml_produce_hierarchy_from_level,
+    amg/src/ml.cpp:225-235): below the last spectral level a two-grid cycle whose prolongator is
+    the scaling P (one column per MIS: the coarse representation of the constant,
+    amg/src/contrib.cpp:655-668, amg/src/interp.cpp:842-909).  The device builds it as one more level
+    of the cycle; against the oracle's restatement (dgels per MIS): the scaling P up to the sign
+    gauge of the coarse basis, its Galerkin operator (gauge invariant) and the PCG run."""
+    # Two-level: the last spectral level is the finest one, where "1" is the constant FUNCTION.  (On
+    # a coarser level the reference's b = 1.0 is the all-ones COEFFICIENT vector in whatever signs
+    # LAPACK gave the coarse basis functions: not a gauge-invariant quantity, there is nothing to
+    # compare entry by entry -- see the three-level run below.)
+    p = sab.default_params(num_levels=2, first_elems_per_agg=64, first_nu_pro=1, nu_pro=1,
+                           partition_kind=1, block=(4, 4, 4), correct_nullspace=1)
+    pr = sab.Problem(3, 16, coef_kind=1)
+    pr.partition(p)
+    Hg, Ho, itg, ito = _run(pr, p)
+    for l, m in enumerate(parity.compare_hierarchies(Hg, Ho, expect_levels=1)):
+        parity.assert_level_ok(m, l)
+    Pg, Po = Hg.csr("cn_P"), Ho.csr("cn_P")
+    assert Pg.shape == Po.shape and Pg.shape[0] == Hg.csr("Ac", 0).shape[0]
+    assert np.array_equal(Pg.indices, Po.indices) and np.array_equal(Pg.indptr, Po.indptr)
+    # (the entries themselves are gauge dependent: a MIS basis is fixed up to an orthogonal Q_mis, and
+    # the representation of the constant turns with it, x_g = Q_mis^T x_o -- its norm per MIS and the
+    # Galerkin operator P_s^T Ac P_s do not)
+    nrm = lambda P: np.sqrt(np.asarray(P.multiply(P).sum(axis=0)).ravel())
+    assert np.allclose(nrm(Pg), nrm(Po), atol=1e-12)
+    # every column has unit norm (the representation is normalised per MIS)
+    assert np.allclose(np.asarray(Pg.multiply(Pg).sum(axis=0)).ravel(), 1.0, atol=1e-12)
+    Ag, Ao = Hg.csr("cn_Ac"), Ho.csr("cn_Ac")
+    assert Ag.shape == Ao.shape == (Pg.shape[1], Pg.shape[1])
+    assert abs(Ag - Ao).max() <= 1e-9 * abs(Ao).max()
+    assert itg > 0 and abs(itg - ito) <= 1, (itg, ito)
+    bg, bo = Hg.get("pcg.brr"), Ho.get("pcg.brr")
+    k = min(len(bg), len(bo), 3)
+    assert np.allclose(bg[:k], bo[:k], rtol=1e-6)
+    for h in (Hg, Ho):
+        h.close()
+    # three levels: the cycle with the extra level converges like the oracle's
+    p3 = sab.default_params(num_levels=3, first_elems_per_agg=64, elems_per_agg=8, first_nu_pro=1, nu_pro=1,
+                            partition_kind=1, block=(4, 4, 4), coarse_block=2, correct_nullspace=1)
+    Hg, Ho, itg, ito = _run(pr, p3)
+    assert Hg.csr("cn_P").shape == Ho.csr("cn_P").shape
+    assert itg > 0 and abs(itg - ito) <= 2, (itg, ito)
+    for h in (Hg, Ho):
+        h.close()
+    pr.close()
