@@ -41,6 +41,8 @@ WORKLOADS = {
                    desc="3D diffusion 128^3 hex Q1, lognormal coefficient 1e6 contrast, ~40k METIS AEs (BASELINE configs[2])"),
     "c2_64": dict(n=64, levels=3, fepa=52, epa=64, tile=32,
                   desc="3D diffusion 64^3 hex Q1, lognormal coefficient 1e6 contrast, 3-level (BASELINE configs[1])"),
+    "c5_256": dict(n=256, levels=4, fepa=52, epa=64, tile=32,
+                   desc="3D diffusion 256^3 hex Q1, lognormal coefficient 1e6 contrast, 4-level, ~322k METIS AEs (BASELINE configs[4]; needs N >= 2: the owner-sharded RAP keeps nnz(A P) / N per rank)"),
     "small_32": dict(n=32, levels=3, fepa=52, epa=64, tile=32, desc="32^3 smoke workload"),
 }
 
@@ -561,6 +563,10 @@ def main():
         setup_s = max_over_ranks(time.time() - t0)
         hier = {"levels": w["levels"], "setup_s": setup_s, "setup_sharded_over_gpus": world,
                 "host_pin_s": pin_s}
+        if world > 1:
+            # bytes this rank moved in the owner-sharded stages (MIS blocks to their owners, gathered
+            # MIS bases, rows of the row-partitioned products received): the collectives of the setup
+            hier["setup_exchange_bytes_rank0"] = sab.sharding_stats()
         from saamge_b200.dist_solve import DistSolver
 
         # PCG of the library's row-partitioned solver (saamge_b200/csrc/dist.cu) on all N ranks;

@@ -102,6 +102,16 @@ void dist_spgemm(sa_gpu_comm *C, const DevCsr &A, const DevCsr &B, DevCsr &out, 
         *bytes_moved += (double)(out.nnz - loc.nnz) * 12. + (double)(rows - (r1 - r0)) * 4.;
 }
 
+/* row pointers of a rows-by-* matrix whose rows [c0, c1) are those of a local block (row pointers
+   Iloc, starting at 0) and whose other rows are empty */
+__global__ void k_place_row_ptr(int rows, int c0, int c1, const int *Iloc, int *I)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > rows)
+        return;
+    I[r] = (r <= c0) ? 0 : (r >= c1 ? Iloc[c1 - c0] : Iloc[r - c0]);
+}
+
 __global__ void k_scale_rows_add_identity_d(int rows, const int *I, const int *J, double *A,
                                             const double *dinv_neg, double mult)
 {
@@ -262,9 +272,35 @@ extern "C" int sa_gpu_dist_rap(sa_gpu_level *lev, sa_gpu_comm *C, double *bytes_
         SA_FAIL("sa_gpu_dist_rap: no prolongator (call sa_gpu_smooth_P)");
     if (bytes_moved)
         *bytes_moved = 0.;
-    DevCsr AP;
-    dist_spgemm(C, *lev->A, lev->P, AP, bytes_moved);
-    dist_spgemm(C, lev->R, AP, lev->Ac, bytes_moved);
+    // Ac by blocks of COARSE rows: rank q forms (R[q-th block, :] A) P -- both products local, the
+    // intermediate R_q A has nnz(AP) / N entries and never leaves the rank -- and only the rows of
+    // Ac are all-gathered.  (Gathering A P itself, as the first version did, moves ~40x more and
+    // overflows the int32 row pointers at 256^3: nnz(A P) ~ 2.4e9.)
+    {
+        sa_gpu_ctx *ctx = lev->ctx;
+        const DevCsr &R = lev->R;
+        const int nr = C->nranks, me = C->rank;
+        const int c0 = (int)(((int64_t)R.rows * me) / nr), c1 = (int)(((int64_t)R.rows * (me + 1)) / nr);
+        DevCsr Rv, RA;
+        Rv.rows = c1 - c0;
+        Rv.cols = R.cols;
+        Rv.nnz = R.nnz;
+        Rv.I.view(R.I.p + c0, (size_t)(c1 - c0) + 1);
+        Rv.J.view(R.J.p, (size_t)R.nnz);
+        Rv.A.view(R.A.p, (size_t)R.nnz);
+        dev_spgemm(ctx, Rv, *lev->A, RA);
+        // rows [c0, c1) of Ac = RA P: dist_spgemm deals equal row blocks of its first factor, so
+        // hand it a first factor that has rows only in this rank's block
+        DevCsr RAfull;
+        RAfull.rows = R.rows;
+        RAfull.cols = RA.cols;
+        RAfull.nnz = RA.nnz;
+        RAfull.I.alloc((size_t)R.rows + 1);
+        SA_LAUNCH(ctx, k_place_row_ptr, (R.rows + 1 + 255) / 256, 256, 0, R.rows, c0, c1, RA.I.p, RAfull.I.p);
+        RAfull.J.view(RA.J.p, (size_t)RA.nnz);
+        RAfull.A.view(RA.A.p, (size_t)RA.nnz);
+        dist_spgemm(C, RAfull, lev->P, lev->Ac, bytes_moved);
+    }
     lev->have_Ac = true;
     SA_API_END
 }
