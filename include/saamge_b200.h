@@ -337,6 +337,12 @@ void sa_gpu_comm_destroy(sa_gpu_comm *comm);
    sa_gpu_dist_smooth_P / sa_gpu_dist_rap: interp_smooth (amg/src/interp.cpp:172-229) and
    tg_coarse_matr (amg/inc/tg.hpp:695-709) as row-partitioned SpGEMM (hypre ParMult / RAP own a
    row block per rank); every rank ends with the complete P, R, Ac. */
+/* host only (no GPU): the exchange plan of sa_gpu_dist_tentative_P for one rank -- owner[mis]
+   (rank of the lowest-numbered AE containing the MIS) and the doubles sent to / received from
+   every rank; ae_m = accepted vectors of every AE */
+int sa_gpu_mis_exchange_plan(int nmis, const int *mis_to_AE_I, const int *mis_to_AE_J,
+                             const int *mis_to_dof_I, int nparts, const int *ae_m, int nranks, int rank,
+                             const int *ae_part, int *owner, int64_t *send_doubles, int64_t *recv_doubles);
 int sa_gpu_dist_tentative_P(sa_gpu_level *level, sa_gpu_comm *comm, const int *ae_part,
                             int avoid_ess_bdr_dofs, int *mis_numcoarsedof, int *NDc_out,
                             double *stats4);

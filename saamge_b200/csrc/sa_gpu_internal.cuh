@@ -4,6 +4,7 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <chrono>
 #include <cstdarg>
 #include <cstdint>
@@ -333,11 +334,36 @@ struct LevelTables
    the rows / blocks AEs [a0, a1) read and that are not queued yet (merged into at most a few
    hundred contiguous runs) and returns the index of the event that fires when they have
    arrived.  This works for any AE numbering; sa_level_queue_rest queues what is left. */
+/* Events of the upload requests of a level: appended by the helper thread of the eigen stage
+   while the main thread waits on earlier entries.  Fixed storage and an atomic count, so that
+   size() / operator[] on the reader's side never race with an append (entries below size() are
+   published by the release store). */
+struct EventList
+{
+    static const int CAP = 256;
+    cudaEvent_t e[CAP];
+    std::atomic<int> n{0};
+    size_t size() const { return (size_t)n.load(std::memory_order_acquire); }
+    bool empty() const { return size() == 0; }
+    cudaEvent_t operator[](size_t i) const { return e[i]; }
+    cudaEvent_t back() const { return e[size() - 1]; }
+    void reserve(size_t) {}
+    void clear() { n.store(0, std::memory_order_release); }
+    void push_back(cudaEvent_t ev)
+    {
+        const int k = n.load(std::memory_order_relaxed);
+        if (k >= CAP)
+            throw std::runtime_error("EventList: too many upload requests");
+        e[k] = ev;
+        n.store(k + 1, std::memory_order_release);
+    }
+};
+
 struct PendingUpload
 {
     bool active = false;
     bool complete = false; // every row / element block has been queued
-    std::vector<cudaEvent_t> ev;
+    EventList ev;
     // the caller keeps the host arrays valid while the upload is pending (API contract), so
     // the level's host-side copies of the index arrays are deferred until the GPU is busy
     sa_gpu_level_desc desc;

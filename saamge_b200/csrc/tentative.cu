@@ -522,6 +522,84 @@ extern "C" int sa_gpu_tentative_P(sa_gpu_level *lev, int avoid_ess_bdr_dofs,
 }
 
 
+/* The exchange plan of the sharded tentative prolongator for rank `me` (host; identical inputs on
+   every rank): owner of a MIS = rank of the lowest-numbered AE containing it
+   (amg/src/aggregates.cpp:583-593); a (MIS, AE) pair whose AE lives on rank src != owner moves
+   s x m_AE doubles from src to the owner (pairs of a MIS of one dof, or of an AE without vectors,
+   move nothing).  owned: the MISes of `me` ascending; pair_off[p] >= 0: offset of pair p inside the
+   piece received from its source rank; send_mis / send_ae[q]: the pairs sent to rank q, in the
+   order the receiver expects them (ascending pair index). */
+static void mis_exchange_plan(int nmis, const int *MI, const int *MJ, const int *DI, int nparts,
+                              const int *m_full, int nr, int me, const int *ae_part,
+                              std::vector<int> &owned, std::vector<int64_t> &pair_off,
+                              std::vector<std::vector<int>> &send_mis,
+                              std::vector<std::vector<int>> &send_ae, std::vector<int64_t> &send_cnt,
+                              std::vector<int64_t> &recv_cnt)
+{
+    for (int mis = 0; mis < nmis; ++mis)
+    {
+        int lowest = nparts;
+        for (int p = MI[mis]; p < MI[mis + 1]; ++p)
+            lowest = std::min(lowest, MJ[p]);
+        const int owner = (lowest < nparts) ? sa_rank_of(ae_part, nr, lowest) : 0;
+        if (owner == me)
+            owned.push_back(mis);
+        const int s = DI[mis + 1] - DI[mis];
+        if (s == 1)
+            continue; // the owner sets the single entry to 1 without looking at the vectors
+        for (int p = MI[mis]; p < MI[mis + 1]; ++p)
+        {
+            const int ae = MJ[p];
+            const int src = sa_rank_of(ae_part, nr, ae);
+            if (src == owner || m_full[ae] == 0)
+                continue;
+            const int64_t sz = (int64_t)s * m_full[ae];
+            if (src == me)
+            {
+                send_mis[owner].push_back(mis);
+                send_ae[owner].push_back(ae);
+                send_cnt[owner] += sz;
+            }
+            else if (owner == me)
+            {
+                pair_off[p] = recv_cnt[src]; // relative to the source's piece, fixed up by the caller
+                recv_cnt[src] += sz;
+            }
+        }
+    }
+}
+
+/* C ABI, host only (no GPU needed: tests/test_dist_plan.py): the plan above for one rank --
+   owner[mis] for every MIS, doubles sent to / received from every rank. */
+extern "C" int sa_gpu_mis_exchange_plan(int nmis, const int *mis_to_AE_I, const int *mis_to_AE_J,
+                                        const int *mis_to_dof_I, int nparts, const int *ae_m, int nranks,
+                                        int rank, const int *ae_part, int *owner, int64_t *send_doubles,
+                                        int64_t *recv_doubles)
+{
+    SA_API_BEGIN
+    if (ae_part[0] != 0 || ae_part[nranks] != nparts)
+        SA_FAIL("sa_gpu_mis_exchange_plan: ae_part must cover [0, nparts)");
+    std::vector<int> owned;
+    std::vector<int64_t> pair_off((size_t)std::max(1, mis_to_AE_I[nmis]), -1);
+    std::vector<std::vector<int>> send_mis(nranks), send_ae(nranks);
+    std::vector<int64_t> sc(nranks, 0), rc(nranks, 0);
+    mis_exchange_plan(nmis, mis_to_AE_I, mis_to_AE_J, mis_to_dof_I, nparts, ae_m, nranks, rank, ae_part,
+                      owned, pair_off, send_mis, send_ae, sc, rc);
+    for (int mis = 0; mis < nmis; ++mis)
+    {
+        int lowest = nparts;
+        for (int p = mis_to_AE_I[mis]; p < mis_to_AE_I[mis + 1]; ++p)
+            lowest = std::min(lowest, mis_to_AE_J[p]);
+        owner[mis] = (lowest < nparts) ? sa_rank_of(ae_part, nranks, lowest) : 0;
+    }
+    for (int q = 0; q < nranks; ++q)
+    {
+        send_doubles[q] = sc[q];
+        recv_doubles[q] = rc[q];
+    }
+    SA_API_END
+}
+
 /* Sharded tentative prolongator (SURVEY.md section 8e row "Tentative P a8-a9"; mirror of the
    reduce-to-owner exchange of ContribTent::CommunicateEigenvectors, amg/src/contrib.cpp:492-549,
    and of SharedEntityCommunication's "lowest rank owns", amg/src/aggregates.cpp:583-593):
@@ -573,37 +651,8 @@ extern "C" int sa_gpu_dist_tentative_P(sa_gpu_level *lev, sa_gpu_comm *C, const 
     std::vector<int64_t> pair_off((size_t)std::max(1, MI[nmis]), -1);
     std::vector<std::vector<int>> send_mis(nr), send_ae(nr);
     std::vector<int64_t> send_cnt(nr, 0), recv_cnt(nr, 0);
-    for (int mis = 0; mis < nmis; ++mis)
-    {
-        int lowest = nparts;
-        for (int p = MI[mis]; p < MI[mis + 1]; ++p)
-            lowest = std::min(lowest, MJ[p]);
-        const int owner = (lowest < nparts) ? sa_rank_of(ae_part, nr, lowest) : 0;
-        if (owner == me)
-            owned.push_back(mis);
-        const int s = DI[mis + 1] - DI[mis];
-        if (s == 1)
-            continue; // the owner sets the single entry to 1 without looking at the vectors
-        for (int p = MI[mis]; p < MI[mis + 1]; ++p)
-        {
-            const int ae = MJ[p];
-            const int src = sa_rank_of(ae_part, nr, ae);
-            if (src == owner || m_full[ae] == 0)
-                continue;
-            const int64_t sz = (int64_t)s * m_full[ae];
-            if (src == me)
-            {
-                send_mis[owner].push_back(mis);
-                send_ae[owner].push_back(ae);
-                send_cnt[owner] += sz;
-            }
-            else if (owner == me)
-            {
-                pair_off[p] = recv_cnt[src]; // relative to the source's piece, fixed up below
-                recv_cnt[src] += sz;
-            }
-        }
-    }
+    mis_exchange_plan(nmis, MI.data(), MJ.data(), DI.data(), nparts, m_full.data(), nr, me, ae_part, owned,
+                      pair_off, send_mis, send_ae, send_cnt, recv_cnt);
     std::vector<int64_t> send_base(nr + 1, 0), recv_base(nr + 1, 0);
     for (int q = 0; q < nr; ++q)
     {

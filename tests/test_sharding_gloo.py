@@ -87,3 +87,59 @@ def test_halo_plan_is_consistent():
                     assert np.all((recv[q] >= cp[q]) & (recv[q] < cp[q + 1]))
                     assert np.array_equal(recv[q], plans[q][0][me])  # q sends what I expect
                     assert np.all(np.diff(recv[q]) > 0)
+
+
+def test_mis_exchange_plan_is_consistent():
+    """sa_gpu_mis_exchange_plan (host side of sa_gpu_dist_tentative_P, the reduce-to-owner exchange
+    of amg/src/contrib.cpp:492-549): every MIS has one owner -- the rank of the lowest-numbered AE
+    containing it (amg/src/aggregates.cpp:583-593) --, what rank r plans to send to q is what q
+    plans to receive from r, nothing is sent to oneself, and the volume is exactly the
+    MIS-restricted blocks (s x m_AE doubles) of the pairs whose AE is not on the owner."""
+    import ctypes
+
+    g = sab.gpu_lib()
+    ip = ctypes.POINTER(ctypes.c_int)
+    lp = ctypes.POINTER(ctypes.c_int64)
+    p = sab.default_params(num_levels=2, first_elems_per_agg=27, partition_kind=0)
+    pr = sab.Problem(3, 12, coef_kind=1)
+    nparts = pr.partition(p)
+    MI, MJ = pr.get("mis_to_AE.I"), pr.get("mis_to_AE.J")
+    DI = pr.get("mis_to_dof.I")
+    nmis = len(MI) - 1
+    sizes = np.diff(pr.get("AE_to_dof.I"))
+    rng = np.random.default_rng(3)
+    ae_m = np.ascontiguousarray(rng.integers(0, 4, nparts), dtype=np.int32)
+    MI, MJ, DI = (np.ascontiguousarray(a, dtype=np.int32) for a in (MI, MJ, DI))
+    for world in (2, 3, 8):
+        part = np.ascontiguousarray([r[0] for r in sharding.shard_ranges(sizes, world)] + [nparts], dtype=np.int32)
+        rank_of = lambda ae: int(np.searchsorted(part, ae, side="right") - 1)
+        owners, S, R = [], [], []
+        for me in range(world):
+            owner = np.zeros(nmis, dtype=np.int32)
+            sd, rd = np.zeros(world, dtype=np.int64), np.zeros(world, dtype=np.int64)
+            rc = g.sa_gpu_mis_exchange_plan(nmis, MI.ctypes.data_as(ip), MJ.ctypes.data_as(ip), DI.ctypes.data_as(ip),
+                                            nparts, ae_m.ctypes.data_as(ip), world, me, part.ctypes.data_as(ip),
+                                            owner.ctypes.data_as(ip), sd.ctypes.data_as(lp), rd.ctypes.data_as(lp))
+            assert rc == 0, g.sa_gpu_last_error()
+            owners.append(owner)
+            S.append(sd)
+            R.append(rd)
+        for me in range(1, world):
+            assert np.array_equal(owners[me], owners[0])
+        expect = np.zeros((world, world), dtype=np.int64)
+        for mis in range(nmis):
+            aes = MJ[MI[mis]:MI[mis + 1]]
+            own = rank_of(aes.min())
+            assert owners[0][mis] == own
+            s = DI[mis + 1] - DI[mis]
+            if s == 1:
+                continue
+            for ae in aes:
+                if rank_of(ae) != own:
+                    expect[rank_of(ae), own] += s * ae_m[ae]
+        for r in range(world):
+            assert S[r][r] == 0 and R[r][r] == 0
+            for q in range(world):
+                assert S[r][q] == R[q][r] == expect[r, q], (world, r, q)
+        assert expect.sum() > 0
+    pr.close()
