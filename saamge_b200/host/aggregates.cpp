@@ -56,6 +56,8 @@ void agg_build_glob_to_AE_id_map(agg_partitioning_relations_t &agg_part_rels)
     const Table &dof_to_AE = *agg_part_rels.dof_to_AE;
     agg_part_rels.dof_id_inAE = new int[std::max(1, dof_to_AE.Size_of_connections())];
     const int *I = dof_to_AE.GetI();
+    // (every (AE, dof) pair writes its own slot: AEs are independent)
+#pragma omp parallel for num_threads(sa_host_threads()) schedule(dynamic, 64)
     for (int i = 0; i < agg_part_rels.nparts; ++i)
     {
         const int *row = AE_to_dof.GetRow(i);
@@ -284,6 +286,7 @@ agg_create_partitioning_coarse(const agg_partitioning_relations_t &fine,
             finedof_to_dof.I[d] + (ess ? 0 : mis_numcoarsedof[fine.mises[d]]);
     }
     finedof_to_dof.J.resize(finedof_to_dof.I[fine.ND]);
+#pragma omp parallel for num_threads(sa_host_threads()) schedule(static)
     for (int d = 0; d < fine.ND; ++d)
     {
         int q = finedof_to_dof.I[d];

@@ -821,8 +821,10 @@ struct TopologyPrefetch
         if (getenv("SA_NO_TOPOLOGY_PREFETCH"))
             return;
         src = rels;
-        fut = std::async(std::launch::async,
-                         [rels, nparts_target] { return agg_coarse_topology(*rels, nparts_target); });
+        fut = std::async(std::launch::async, [rels, nparts_target] {
+            sa_host_threads_serial_here(true); // hidden behind the GPU stages: no thread team of its own
+            return agg_coarse_topology(*rels, nparts_target);
+        });
     }
     bool take(const agg_partitioning_relations_t *rels, agg_coarse_topology_t &out)
     {

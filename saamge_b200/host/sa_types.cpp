@@ -1,7 +1,10 @@
 // Table / sparse helpers with MFEM-compatible ordering semantics (see sa_types.hpp).
 #include "sa_types.hpp"
 
+#include <omp.h>
+
 #include <algorithm>
+#include <thread>
 
 namespace saamge
 {
@@ -39,31 +42,74 @@ void TableFromArray(const int *arr, int n, int ncols, Table &T)
         T.I[i] = i;
 }
 
+static thread_local bool t_host_serial = false;
+void sa_host_threads_serial_here(bool on) { t_host_serial = on; }
+
+int sa_host_threads()
+{
+    if (t_host_serial)
+        return 1;
+    // threads for the host-side table products: SA_HOST_THREADS, else the hardware threads divided
+    // by the ranks of this node (torchrun exports LOCAL_WORLD_SIZE and sets OMP_NUM_THREADS=1)
+    static const int n = [] {
+        if (const char *e = getenv("SA_HOST_THREADS"))
+            return std::max(1, atoi(e));
+        int hw = (int)std::thread::hardware_concurrency();
+        if (hw <= 0)
+            hw = 1;
+        int ranks = 1;
+        if (const char *e = getenv("LOCAL_WORLD_SIZE"))
+            ranks = std::max(1, atoi(e));
+        return std::max(1, std::min(16, hw / ranks));
+    }();
+    return n;
+}
+
 void Mult(const Table &A, const Table &B, Table &C)
 {
-    SA_ASSERT(A.ncols == B.nrows || A.ncols <= 0 || true);
     const int nc = B.ncols;
-    C.nrows = A.nrows;
+    const int nrows = A.nrows;
+    C.nrows = nrows;
     C.ncols = nc;
-    C.I.assign((size_t)A.nrows + 1, 0);
+    C.I.assign((size_t)nrows + 1, 0);
     C.J.clear();
-    std::vector<int> marker((size_t)std::max(nc, 1), -1);
-    for (int i = 0; i < A.nrows; ++i)
+    // rows are independent and keep their first-encounter order: contiguous row blocks per thread
+    // (own marker array), concatenated afterwards -- the result is that of the sequential loop
+    const int nt = (A.Size_of_connections() < (1 << 16)) ? 1 : std::min(sa_host_threads(), std::max(1, nrows));
+    std::vector<std::vector<int>> Jt((size_t)nt);
+#pragma omp parallel num_threads(nt)
     {
-        for (int p = A.I[i]; p < A.I[i + 1]; ++p)
+        const int t = omp_get_thread_num();
+        const int r0 = (int)(((int64_t)nrows * t) / nt), r1 = (int)(((int64_t)nrows * (t + 1)) / nt);
+        std::vector<int> marker((size_t)std::max(nc, 1), -1);
+        std::vector<int> &J = Jt[t];
+        for (int i = r0; i < r1; ++i)
         {
-            const int k = A.J[p];
-            for (int q = B.I[k]; q < B.I[k + 1]; ++q)
+            const size_t before = J.size();
+            for (int p = A.I[i]; p < A.I[i + 1]; ++p)
             {
-                const int j = B.J[q];
-                if (marker[j] != i)
+                const int k = A.J[p];
+                for (int q = B.I[k]; q < B.I[k + 1]; ++q)
                 {
-                    marker[j] = i;
-                    C.J.push_back(j);
+                    const int j = B.J[q];
+                    if (marker[j] != i)
+                    {
+                        marker[j] = i;
+                        J.push_back(j);
+                    }
                 }
             }
+            C.I[i + 1] = (int)(J.size() - before); // row length; prefix sum below
         }
-        C.I[i + 1] = (int)C.J.size();
+    }
+    for (int i = 0; i < nrows; ++i)
+        C.I[i + 1] += C.I[i];
+    C.J.resize((size_t)C.I[nrows]);
+#pragma omp parallel for num_threads(nt) schedule(static, 1)
+    for (int t = 0; t < nt; ++t)
+    {
+        const int r0 = (int)(((int64_t)nrows * t) / nt);
+        std::copy(Jt[t].begin(), Jt[t].end(), C.J.begin() + C.I[r0]);
     }
 }
 

@@ -111,6 +111,12 @@ void TableFromArray(const int *arr, int n, int ncols, Table &T);
 /// C = A*B (boolean product); row i of C lists columns in first-encounter order
 /// while scanning row i of A and, for each entry, the row of B.
 void Mult(const Table &A, const Table &B, Table &C);
+/// Threads the host-side table products may use (SA_HOST_THREADS; default: hardware threads / ranks
+/// of this node, at most 16).
+int sa_host_threads();
+/// Background helper threads (the topology prefetch, which runs beside the GPU stages and their host
+/// work) keep their table products on the calling thread.
+void sa_host_threads_serial_here(bool on);
 
 /// y = A x
 void SpMult(const SparseMatrix &A, const double *x, double *y);
