@@ -1,6 +1,7 @@
 """CLI: build a hierarchy with the B200 path and with the oracle, print parity metrics.
 usage: python tests/run_parity.py dim n order coef levels first_epa epa nu_pro [kind] [--self]"""
 import json
+import os
 import sys
 import time
 
@@ -21,6 +22,8 @@ def main():
     p = sab.default_params(num_levels=levels, first_elems_per_agg=fepa, elems_per_agg=epa,
                            first_nu_pro=nupro, nu_pro=nupro, partition_kind=kind,
                            block=(blk, blk, blk), coarse_block=cblk)
+    if os.environ.get("SA_TEST_THETA"):  # spectral threshold of every level (default 0.003)
+        p.first_theta = p.theta = float(os.environ["SA_TEST_THETA"])
     pr = sab.Problem(dim, n, order=order, coef_kind=coef)
     na = pr.partition(p)
     print("AEs", na, "ND", pr.scalar("ND"), "mises", pr.scalar("num_mises"), flush=True)
@@ -48,7 +51,7 @@ def main():
     ok = True
     for l, m in enumerate(res):
         try:
-            parity.assert_level_ok(m, l)
+            parity.assert_level_ok(m, l, ac_tol=float(os.environ.get("SA_TEST_AC_TOL", "1e-9")))
         except AssertionError as e:
             ok = False
             print("FAIL", e)

@@ -146,6 +146,29 @@ def test_parity_of_alternative_kernel_paths(env):
     assert "PARITY OK" in out.stdout, out.stdout[-2000:]
 
 
+def test_large_AE_chunk_falls_back_to_the_tridiagonalisation():
+    """theta = 0.05: every coarse-level AE of the 24^3 three-level problem has 8 or more
+    eigenvalues below theta, which the 8-vector subspace iteration of cholsi.cu reports (-2) -- the
+    chunk is redone by the two-stage tridiagonalisation + Sturm counts, and the hierarchy still
+    matches the oracle (counts exactly, operators to 1e-8 with ~10 vectors per AE)."""
+    import os
+    import subprocess
+    import sys
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    e = dict(os.environ)
+    e.update({"SA_TEST_THETA": "0.05", "SA_TEST_AC_TOL": "1e-8", "SA_GPU_SPECTRAL_DEBUG": "1"})
+    out = subprocess.run([sys.executable, os.path.join(here, "run_parity.py"),
+                          "3", "24", "1", "1", "3", "52", "24", "0", "0"],
+                         env=e, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "PARITY OK" in out.stdout, out.stdout[-2000:]
+    import re
+
+    m = re.search(r"\[cholsi\] chunk of (\d+) AEs .*: (\d+) not done", out.stderr)
+    assert m and int(m.group(2)) > 0, out.stderr[-1000:]
+
+
 # ---------------------------------------------------------------- direct C ABI
 
 
