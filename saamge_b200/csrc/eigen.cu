@@ -1188,12 +1188,21 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
         const int len = ae_end - ae_begin;
         if (can_fuse && len >= 1024)
         {
-            piece_ends.push_back(ae_begin + len / 16);
-            piece_ends.push_back(ae_begin + 3 * len / 16);
+            // The upload (2.07 GB at ~52 GB/s: 40 ms at 128^3) is faster than the compute it feeds
+            // (46 ms), so the stage ends one piece's compute after the LAST piece has arrived: with
+            // pieces (1/16, 3/16, 1/2, 1) the GPU worked until 61 ms (measured), 23 ms of them on the
+            // last half after its upload.  A small first piece, then equal ones (fused pieces cost
+            // launch tails only).
+            static const int npc = getenv("SA_GPU_PIECES") ? std::max(2, atoi(getenv("SA_GPU_PIECES"))) : 8;
+            piece_ends.push_back(ae_begin + len / (2 * npc));
+            for (int k = 1; k < npc; ++k)
+                piece_ends.push_back(ae_begin + (int)(((int64_t)len * k) / npc));
         }
         else
+        {
             piece_ends.push_back(ae_begin + len / 8);
-        piece_ends.push_back(ae_begin + len / 2);
+            piece_ends.push_back(ae_begin + len / 2);
+        }
     }
     piece_ends.push_back(ae_end);
     // The first piece's request is queued here; marking and queueing the others costs the host
