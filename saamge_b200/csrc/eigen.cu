@@ -1186,7 +1186,15 @@ extern "C" int sa_gpu_local_spectral(sa_gpu_level *lev, double theta, int ae_beg
     if (lev->pending.active && !lev->pending.complete && ae_end - ae_begin >= 64)
     {
         const int len = ae_end - ae_begin;
-        if (can_fuse && len >= 1024)
+        if (can_fuse && len >= 1024 && lev->pending.lazy_rest)
+        {
+            // (one rank of a sharded stage, only its own inputs are uploaded: growing pieces --
+            // measured on 2 GPUs: 39.8 ms per step against 44.2 ms with the equal pieces below)
+            piece_ends.push_back(ae_begin + len / 16);
+            piece_ends.push_back(ae_begin + 3 * len / 16);
+            piece_ends.push_back(ae_begin + len / 2);
+        }
+        else if (can_fuse && len >= 1024)
         {
             // The upload (2.07 GB at ~52 GB/s: 40 ms at 128^3) is faster than the compute it feeds
             // (46 ms), so the stage ends one piece's compute after the LAST piece has arrived: with
