@@ -611,6 +611,13 @@ def main():
                     n3 += float((nn ** 3).sum())
                     cnt_large += int(len(nn))
                 H2.close()
+                chol_traffic = None
+                try:
+                    tj2 = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+                    if tj2.get("workload") == args.workload:
+                        chol_traffic = tj2["k_cs_chol"]["dram_bytes_per_launch"]
+                except Exception:
+                    chol_traffic = None
                 chol_ms = pm.get("eig.cs_chol")
                 if chol_ms and n3 > 0:
                     eig_ms = sum(v for k, v in pm.items() if k in ("eig.cs_chol", "eig.cs_iterate", "eig.large_assemble"))
@@ -624,7 +631,8 @@ def main():
                                      "achieved": n3 / 3.0 / (chol_ms * 1e-3) / 1e12, "peak": fp64_peak,
                                      "unit": "TFLOP/s", "frac": n3 / 3.0 / (chol_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
                                      "peak_source": "FP64 FMA peak measured in this run (DMMA measured at 1.07x of it, tools/dmma_bench.cu)",
-                                     "traffic": None},
+                                     "traffic": chol_traffic,
+                                     "traffic_source": "profiles/r02_traffic.json: ncu DRAM bytes of the level-1 launch (630 of the %d matrices)" % cnt_large if chol_traffic else None},
                         "algorithmic_tflops_4_3_n3": (4.0 / 3.0) * n3 / (eig_ms * 1e-3) / 1e12,
                     }
             except Exception as ex:
