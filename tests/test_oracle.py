@@ -171,3 +171,19 @@ def test_algebraic_ctest_pin():
     assert np.linalg.norm(P @ coef - ones) <= 1e-8 * np.linalg.norm(ones)
     Ho.close()
     pr.close()
+
+
+def test_fine_relations_with_the_threaded_table_products():
+    """40^3: elem_to_dof has 512 000 entries, so Transpose / Mult of the host mirror take their
+    multi-threaded forms (row blocks per thread, saamge_b200/host/sa_types.cpp) -- every table must
+    still equal the oracle's own sequential construction (first-encounter / ascending orders)."""
+    import ctypes
+
+    o = ou.oracle()
+    o.sa_orc_check_relations.argtypes = [ctypes.c_void_p]
+    p = sab.default_params(num_levels=2, first_elems_per_agg=52, partition_kind=0)
+    pr = sab.Problem(3, 40, coef_kind=1)
+    pr.partition(p)
+    assert len(pr.get("elem_to_dof.J")) >= (1 << 18)
+    assert o.sa_orc_check_relations(pr.handle) == 0
+    pr.close()
