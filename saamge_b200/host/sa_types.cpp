@@ -22,61 +22,14 @@ void Transpose(const Table &A, Table &At, int ncols_A)
     At.ncols = A.nrows;
     At.I.assign((size_t)nc + 1, 0);
     At.J.resize(nnz);
-    const int nrows = A.nrows;
-    // counting sort by column.  Large tables: row blocks per thread with their own histograms
-    // (the slots of a column are handed out block by block, so every row of At still lists the rows
-    // of A in ascending order -- the result of the sequential loop)
-    int nt = (nnz < (1 << 18)) ? 1 : std::min(sa_host_threads(), std::max(1, nrows));
-    while (nt > 1 && (size_t)nt * (size_t)nc > ((size_t)1 << 27)) // histograms: at most 512 MB
-        nt /= 2;
-    if (nt <= 1)
-    {
-        for (int p = 0; p < nnz; ++p)
-            At.I[A.J[p] + 1]++;
-        for (int i = 0; i < nc; ++i)
-            At.I[i + 1] += At.I[i];
-        std::vector<int> pos(At.I.begin(), At.I.end() - 1);
-        for (int i = 0; i < nrows; ++i)
-            for (int p = A.I[i]; p < A.I[i + 1]; ++p)
-                At.J[pos[A.J[p]]++] = i;
-        return;
-    }
-    std::vector<int> hist((size_t)nt * nc, 0);
-#pragma omp parallel num_threads(nt)
-    {
-        const int t = omp_get_thread_num();
-        const int r0 = (int)(((int64_t)nrows * t) / nt), r1 = (int)(((int64_t)nrows * (t + 1)) / nt);
-        int *h = hist.data() + (size_t)t * nc;
-        for (int p = A.I[r0]; p < A.I[r1]; ++p)
-            h[A.J[p]]++;
-    }
-    // per column: exclusive prefix over the threads, total into At.I
-#pragma omp parallel for num_threads(nt) schedule(static)
-    for (int c = 0; c < nc; ++c)
-    {
-        int acc = 0;
-        for (int t = 0; t < nt; ++t)
-        {
-            const int v = hist[(size_t)t * nc + c];
-            hist[(size_t)t * nc + c] = acc;
-            acc += v;
-        }
-        At.I[c + 1] = acc;
-    }
-    for (int c = 0; c < nc; ++c)
-        At.I[c + 1] += At.I[c];
-#pragma omp parallel num_threads(nt)
-    {
-        const int t = omp_get_thread_num();
-        const int r0 = (int)(((int64_t)nrows * t) / nt), r1 = (int)(((int64_t)nrows * (t + 1)) / nt);
-        int *h = hist.data() + (size_t)t * nc;
-        for (int i = r0; i < r1; ++i)
-            for (int p = A.I[i]; p < A.I[i + 1]; ++p)
-            {
-                const int c = A.J[p];
-                At.J[At.I[c] + h[c]++] = i;
-            }
-    }
+    for (int p = 0; p < nnz; ++p)
+        At.I[A.J[p] + 1]++;
+    for (int i = 0; i < nc; ++i)
+        At.I[i + 1] += At.I[i];
+    std::vector<int> pos(At.I.begin(), At.I.end() - 1);
+    for (int i = 0; i < A.nrows; ++i)
+        for (int p = A.I[i]; p < A.I[i + 1]; ++p)
+            At.J[pos[A.J[p]]++] = i;
 }
 
 void TableFromArray(const int *arr, int n, int ncols, Table &T)

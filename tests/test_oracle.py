@@ -174,9 +174,11 @@ def test_algebraic_ctest_pin():
 
 
 def test_fine_relations_with_the_threaded_table_products():
-    """40^3: elem_to_dof has 512 000 entries, so Transpose / Mult of the host mirror take their
-    multi-threaded forms (row blocks per thread, saamge_b200/host/sa_types.cpp) -- every table must
-    still equal the oracle's own sequential construction (first-encounter / ascending orders)."""
+    """40^3: elem_to_dof has 512 000 entries, so the table products (Mult) of the host mirror take
+    their multi-threaded form (row blocks per thread, saamge_b200/host/sa_types.cpp) -- every table
+    must still equal the oracle's own sequential construction (first-encounter order).  (A threaded
+    Transpose with per-thread histograms was measured and dropped: the tables here have about as many
+    columns as entries, the histograms cost more than the sequential counting sort.)"""
     import ctypes
 
     o = ou.oracle()
