@@ -8,6 +8,7 @@
 // and adapt_update_operators (amg/src/adapt.cpp:171-216): a new operator with the same pattern
 // re-uses the spectral data -- only the weighted-l1 smoother, the smoothing of P and the Galerkin
 // products are redone, on the device.
+#include <algorithm>
 #include <fstream>
 
 #include "saamge.hpp"
@@ -15,171 +16,175 @@
 namespace saamge
 {
 
+namespace
+{
+/* raw native-endian records, the whole format: counts as int32, then the arrays */
+template <class T> void get(std::istream &in, T *dst, size_t count = 1)
+{
+    in.read(reinterpret_cast<char *>(dst), (std::streamsize)(sizeof(T) * count));
+    SA_ASSERT(in);
+}
+template <class T> void put(std::ostream &out, const T *src, size_t count = 1)
+{
+    out.write(reinterpret_cast<const char *>(src), (std::streamsize)(sizeof(T) * count));
+    SA_ASSERT(out);
+}
+int get_count(std::istream &in)
+{
+    int v = 0;
+    get(in, &v);
+    SA_ASSERT(v >= 0);
+    return v;
+}
+std::ifstream open_in(const char *filename)
+{
+    std::ifstream in(filename, std::ios::binary);
+    SA_ASSERT(in);
+    return in;
+}
+std::ofstream open_out(const char *filename)
+{
+    std::ofstream out(filename, std::ios::binary);
+    SA_ASSERT(out);
+    return out;
+}
+} // namespace
+
+// amg/src/mbox.cpp:310-329: [rows][connections][I: rows + 1][J: connections]
 Table *mbox_read_table(const char *filename)
 {
-    int size = 0, j_size = 0;
-    std::ifstream itbl(filename, std::ifstream::binary);
-    SA_ASSERT(itbl);
-    itbl.read((char *)&size, sizeof(size));
-    itbl.read((char *)&j_size, sizeof(j_size));
-    SA_ASSERT(itbl && size >= 0 && j_size >= 0);
-    Table *tbl = new Table;
-    tbl->nrows = size;
-    tbl->I.resize((size_t)size + 1);
-    tbl->J.resize((size_t)j_size);
-    itbl.read((char *)tbl->I.data(), sizeof(int) * ((size_t)size + 1));
-    itbl.read((char *)tbl->J.data(), sizeof(int) * (size_t)j_size);
-    SA_ASSERT(itbl);
-    SA_ASSERT(j_size == tbl->I[size]);
-    int w = 0;
-    for (int j = 0; j < j_size; ++j)
-        w = tbl->J[j] + 1 > w ? tbl->J[j] + 1 : w;
-    tbl->ncols = w;
-    return tbl;
+    std::ifstream in = open_in(filename);
+    Table *t = new Table;
+    t->nrows = get_count(in);
+    const int conn = get_count(in);
+    t->I.resize((size_t)t->nrows + 1);
+    t->J.resize((size_t)conn);
+    get(in, t->I.data(), t->I.size());
+    get(in, t->J.data(), t->J.size());
+    SA_ASSERT(t->I[t->nrows] == conn);
+    t->ncols = conn ? 1 + *std::max_element(t->J.begin(), t->J.end()) : 0;
+    return t;
 }
 
+// amg/src/mbox.cpp:331-344
 void mbox_write_table(const char *filename, const Table &tbl)
 {
-    std::ofstream otbl(filename, std::ofstream::binary);
-    SA_ASSERT(otbl);
-    const int size = tbl.Size(), j_size = tbl.Size_of_connections();
-    otbl.write((const char *)&size, sizeof(size));
-    otbl.write((const char *)&j_size, sizeof(j_size));
-    otbl.write((const char *)tbl.GetI(), sizeof(int) * ((size_t)size + 1));
-    otbl.write((const char *)tbl.GetJ(), sizeof(int) * (size_t)j_size);
-    SA_ASSERT(otbl);
+    std::ofstream out = open_out(filename);
+    const int rows = tbl.Size(), conn = tbl.Size_of_connections();
+    put(out, &rows);
+    put(out, &conn);
+    put(out, tbl.GetI(), (size_t)rows + 1);
+    put(out, tbl.GetJ(), (size_t)conn);
 }
 
-SparseMatrix *mbox_read_sparse_matr(std::ifstream &ispm)
+// amg/src/mbox.cpp:355-375: [rows][cols][nnz][I][J][data]
+SparseMatrix *mbox_read_sparse_matr(std::ifstream &in)
 {
-    int size = 0, width = 0, j_size = 0;
-    SA_ASSERT(ispm);
-    ispm.read((char *)&size, sizeof(size));
-    ispm.read((char *)&width, sizeof(width));
-    ispm.read((char *)&j_size, sizeof(j_size));
-    SA_ASSERT(ispm && size >= 0 && width >= 0 && j_size >= 0);
-    SparseMatrix *spm = new SparseMatrix;
-    spm->h = size;
-    spm->w = width;
-    spm->I.resize((size_t)size + 1);
-    spm->J.resize((size_t)j_size);
-    spm->A.resize((size_t)j_size);
-    ispm.read((char *)spm->I.data(), sizeof(int) * ((size_t)size + 1));
-    ispm.read((char *)spm->J.data(), sizeof(int) * (size_t)j_size);
-    ispm.read((char *)spm->A.data(), sizeof(double) * (size_t)j_size);
-    SA_ASSERT(ispm);
-    SA_ASSERT(j_size == spm->I[size]);
-    return spm;
+    SparseMatrix *m = new SparseMatrix;
+    m->h = get_count(in);
+    m->w = get_count(in);
+    const int nnz = get_count(in);
+    m->I.resize((size_t)m->h + 1);
+    m->J.resize((size_t)nnz);
+    m->A.resize((size_t)nnz);
+    get(in, m->I.data(), m->I.size());
+    get(in, m->J.data(), m->J.size());
+    get(in, m->A.data(), m->A.size());
+    SA_ASSERT(m->I[m->h] == nnz);
+    return m;
 }
 
 SparseMatrix *mbox_read_sparse_matr(const char *filename)
 {
-    std::ifstream ispm(filename, std::ifstream::binary);
-    SA_ASSERT(ispm);
-    return mbox_read_sparse_matr(ispm);
+    std::ifstream in = open_in(filename);
+    return mbox_read_sparse_matr(in);
 }
 
-void mbox_write_sparse_matr(std::ofstream &ospm, const SparseMatrix &spm)
+// amg/src/mbox.cpp:378-395
+void mbox_write_sparse_matr(std::ofstream &out, const SparseMatrix &spm)
 {
-    SA_ASSERT(ospm);
-    const int size = spm.Size(), width = spm.Width(), j_size = spm.NumNonZeroElems();
-    ospm.write((const char *)&size, sizeof(size));
-    ospm.write((const char *)&width, sizeof(width));
-    ospm.write((const char *)&j_size, sizeof(j_size));
-    ospm.write((const char *)spm.GetI(), sizeof(int) * ((size_t)size + 1));
-    ospm.write((const char *)spm.GetJ(), sizeof(int) * (size_t)j_size);
-    ospm.write((const char *)spm.GetData(), sizeof(double) * (size_t)j_size);
-    SA_ASSERT(ospm);
+    const int rows = spm.Size(), cols = spm.Width(), nnz = spm.NumNonZeroElems();
+    put(out, &rows);
+    put(out, &cols);
+    put(out, &nnz);
+    put(out, spm.GetI(), (size_t)rows + 1);
+    put(out, spm.GetJ(), (size_t)nnz);
+    put(out, spm.GetData(), (size_t)nnz);
 }
 
 void mbox_write_sparse_matr(const char *filename, const SparseMatrix &spm)
 {
-    std::ofstream ospm(filename, std::ofstream::binary);
-    SA_ASSERT(ospm);
-    mbox_write_sparse_matr(ospm, spm);
+    std::ofstream out = open_out(filename);
+    mbox_write_sparse_matr(out, spm);
 }
 
-DenseMatrix *mbox_read_dense_matr(std::ifstream &idem)
+// amg/src/mbox.cpp:406-419: [rows][cols][column-major data]
+DenseMatrix *mbox_read_dense_matr(std::ifstream &in)
 {
-    int height = 0, width = 0;
-    SA_ASSERT(idem);
-    idem.read((char *)&height, sizeof(height));
-    idem.read((char *)&width, sizeof(width));
-    SA_ASSERT(idem && height >= 0 && width >= 0);
-    DenseMatrix *dem = new DenseMatrix(height, width);
-    idem.read((char *)dem->Data(), sizeof(double) * (size_t)height * width);
-    SA_ASSERT(idem);
-    return dem;
+    const int rows = get_count(in), cols = get_count(in);
+    DenseMatrix *m = new DenseMatrix(rows, cols);
+    get(in, m->Data(), (size_t)rows * cols);
+    return m;
 }
 
 DenseMatrix *mbox_read_dense_matr(const char *filename)
 {
-    std::ifstream idem(filename, std::ifstream::binary);
-    SA_ASSERT(idem);
-    return mbox_read_dense_matr(idem);
+    std::ifstream in = open_in(filename);
+    return mbox_read_dense_matr(in);
 }
 
-void mbox_write_dense_matr(std::ofstream &odem, const DenseMatrix &dem)
+// amg/src/mbox.cpp:438-446
+void mbox_write_dense_matr(std::ofstream &out, const DenseMatrix &dem)
 {
-    SA_ASSERT(odem);
-    const int height = dem.Height(), width = dem.Width();
-    odem.write((const char *)&height, sizeof(height));
-    odem.write((const char *)&width, sizeof(width));
-    odem.write((const char *)dem.Data(), sizeof(double) * (size_t)height * width);
-    SA_ASSERT(odem);
+    const int rows = dem.Height(), cols = dem.Width();
+    put(out, &rows);
+    put(out, &cols);
+    put(out, dem.Data(), (size_t)rows * cols);
 }
 
 void mbox_write_dense_matr(const char *filename, const DenseMatrix &dem)
 {
-    std::ofstream odem(filename, std::ofstream::binary);
-    SA_ASSERT(odem);
-    mbox_write_dense_matr(odem, dem);
+    std::ofstream out = open_out(filename);
+    mbox_write_dense_matr(out, dem);
 }
 
+// amg/src/mbox.cpp:448-481: [n] followed by n matrices back to back
 SparseMatrix **mbox_read_sparse_matr_arr(const char *filename, int *n)
 {
-    std::ifstream ispm(filename, std::ifstream::binary);
-    SA_ASSERT(ispm);
-    ispm.read((char *)n, sizeof(*n));
-    SA_ASSERT(ispm && *n >= 0);
-    SparseMatrix **arr = new SparseMatrix *[*n > 0 ? *n : 1];
-    for (int i = 0; i < *n; ++i)
-        arr[i] = mbox_read_sparse_matr(ispm);
+    std::ifstream in = open_in(filename);
+    *n = get_count(in);
+    SparseMatrix **arr = new SparseMatrix *[std::max(1, *n)];
+    for (int k = 0; k < *n; ++k)
+        arr[k] = mbox_read_sparse_matr(in);
     return arr;
 }
 
 void mbox_write_sparse_matr_arr(const char *filename, SparseMatrix **arr, int n)
 {
-    SA_ASSERT(arr);
-    SA_ASSERT(n > 0);
-    std::ofstream ospm(filename, std::ofstream::binary);
-    SA_ASSERT(ospm);
-    ospm.write((const char *)&n, sizeof(n));
-    for (int i = 0; i < n; ++i)
-        mbox_write_sparse_matr(ospm, *(arr[i]));
+    SA_ASSERT(arr && n > 0);
+    std::ofstream out = open_out(filename);
+    put(out, &n);
+    for (int k = 0; k < n; ++k)
+        mbox_write_sparse_matr(out, *arr[k]);
 }
 
 DenseMatrix **mbox_read_dense_matr_arr(const char *filename, int *n)
 {
-    std::ifstream idem(filename, std::ifstream::binary);
-    SA_ASSERT(idem);
-    idem.read((char *)n, sizeof(*n));
-    SA_ASSERT(idem && *n >= 0);
-    DenseMatrix **arr = new DenseMatrix *[*n > 0 ? *n : 1];
-    for (int i = 0; i < *n; ++i)
-        arr[i] = mbox_read_dense_matr(idem);
+    std::ifstream in = open_in(filename);
+    *n = get_count(in);
+    DenseMatrix **arr = new DenseMatrix *[std::max(1, *n)];
+    for (int k = 0; k < *n; ++k)
+        arr[k] = mbox_read_dense_matr(in);
     return arr;
 }
 
 void mbox_write_dense_matr_arr(const char *filename, DenseMatrix **arr, int n)
 {
-    SA_ASSERT(arr);
-    SA_ASSERT(n > 0);
-    std::ofstream odem(filename, std::ofstream::binary);
-    SA_ASSERT(odem);
-    odem.write((const char *)&n, sizeof(n));
-    for (int i = 0; i < n; ++i)
-        mbox_write_dense_matr(odem, *(arr[i]));
+    SA_ASSERT(arr && n > 0);
+    std::ofstream out = open_out(filename);
+    put(out, &n);
+    for (int k = 0; k < n; ++k)
+        mbox_write_dense_matr(out, *arr[k]);
 }
 
 /* ---- adapt_update_operators ---------------------------------------------------------------- */
